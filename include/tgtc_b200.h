@@ -1,0 +1,176 @@
+/*
+ * tgtc_b200.h -- C ABI of the B200-native NeRF ray-render hot path of TGTC-Style.
+ *
+ * One shared library (libtgtc_b200.so, built by nvcc for sm_100a), plain
+ * pointers and sizes, no torch types.  Every entry point that launches work
+ * takes a CUDA stream (passed as void*), is asynchronous and stream-ordered,
+ * and returns an int status; tgtc_last_error() gives the thread-local message
+ * of the last non-zero status.  The library allocates nothing the caller sees:
+ * inputs, outputs and workspaces are caller-owned device memory (the *_host
+ * entry points own a private staging arena inside the context).
+ *
+ * The reference (/root/reference, pure Python/PyTorch) has no FFI; the seam this
+ * ABI replaces is the set of four Python callables that the reference injects
+ * into its render loops plus the ray generation that
+ * feeds them.  Each entry point cites the reference interface it replaces.
+ * The Python-side binding a maintainer adds is shown in INTEGRATION.md.
+ */
+#ifndef TGTC_B200_H
+#define TGTC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGTC_ABI_VERSION 1
+
+typedef struct tgtc_ctx tgtc_ctx;
+typedef void* tgtc_stream; /* cudaStream_t */
+
+enum {
+  TGTC_OK = 0,
+  TGTC_ERR_ARG = 1,         /* null / misaligned pointer, bad size, bad enum */
+  TGTC_ERR_CUDA = 2,        /* a CUDA runtime call or launch failed */
+  TGTC_ERR_STATE = 3,       /* weights not set, workspace too small, ... */
+  TGTC_ERR_UNSUPPORTED = 4  /* shape outside what the kernel handles */
+};
+
+enum { TGTC_NET_COARSE = 0, TGTC_NET_FINE = 1 };
+
+/* arithmetic of the MLP (K3+K4).  FP32: CUDA-core FFMA, reference-grade
+ * (<=1e-3 end to end).  BF16: bf16 operands on tcgen05 tensor cores, fp32
+ * accumulation in TMEM, fp32 sigma/rgb heads (<=1e-2 teacher-forced). */
+enum { TGTC_MLP_FP32 = 0, TGTC_MLP_BF16 = 1 };
+
+#define TGTC_NUM_PARAMS 24 /* 12 layers x (weight, bias) */
+
+const char* tgtc_last_error(void);
+int tgtc_abi_version(void);
+
+/* One context per device (not shared between threads without a lock).
+ * Owns the packed weights of both nets and small tables. */
+int tgtc_create(int device, tgtc_ctx** out);
+int tgtc_destroy(tgtc_ctx* ctx);
+
+/* Network parameters.  Replaces: nn.Module state of models.StyleNerf
+ * (models.py:182-223; MLP_style.__init__ models.py:63-93).
+ * params[2*i], params[2*i+1] = weight [out,in] row-major fp32, bias [out] of
+ * layer i in the order base_layers[0..7], sigma_layer, base_remap_layer,
+ * rgb_layers[0], rgb_layers[1] (shapes: 256x63, 5x 256x256 with layer 5
+ * 256x319, 1x256, 256x256, 128x283, 3x128).  Device pointers; packed on
+ * `stream` into the fp32-transposed and bf16-swizzled images the kernels read.
+ * Call again after every optimizer step / load_state_dict. */
+int tgtc_set_weights(tgtc_ctx* ctx, int net, const float* const* params, tgtc_stream stream);
+
+/* K1 -- ray generation + NDC warp.  Replaces dataset.get_rays_np
+ * (dataset.py:33-42) and dataset.ndc_rays_np (dataset.py:44-61) followed by
+ * the cast to fp32 rays.  fp64 arithmetic in the reference's operation order
+ * (bit-exact), K row-major 3x3, c2w row-major 3x4 (host pointers, copied by
+ * value).  Writes rays for pixels [pix_begin, pix_begin+n) of the H x W frame
+ * (row-major, pixel p = row*W+col) to rays_o / rays_d ([n,3] fp32, device). */
+int tgtc_raygen(tgtc_ctx* ctx, int H, int W, const double* K, const double* c2w, int ndc, double ndc_near,
+                int pixel_alignment, int64_t pix_begin, int64_t n, float* rays_o, float* rays_d,
+                tgtc_stream stream);
+
+/* K2 -- stratified sample positions.  Replaces utils.sampling_pts_uniform
+ * (utils.py:509-531, harmony=False).  rand: NULL for perturb=False, else [n,S]
+ * uniforms replaying utils.py:518-524.  pts [n,S,3] may be NULL. ts [n,S]. */
+int tgtc_sample_uniform(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n, int n_samples,
+                        double near, double far, const float* rand, float* pts, float* ts, tgtc_stream stream);
+
+/* K3+K4 -- positional encoding + MLP on explicit points.  Replaces
+ * models.StyleNerf.forward (models.py:216-223) = Embedder x2 (models.py:46-60)
+ * + MLP_style.forward (models.py:95-117), including utils.batchify
+ * (utils.py:435-456; chunking is internal).  pts [n_rays*S,3]; dirs is [n_rays,3]
+ * when dirs_per_ray (the reference passes a stride-0 expand, rendering.py:30)
+ * else [n_rays*S,3].  Outputs: rgb [M,3], sigma [M]; optional (NULL to skip)
+ * base_remap [M,256], pts_embed [M,63], dirs_embed [M,27] -- the other keys of
+ * the reference's returned dict.  BF16 mode needs dirs_per_ray and
+ * S in {32,64,128} or a multiple of 128, and no optional outputs. */
+int tgtc_nerf_forward(tgtc_ctx* ctx, int net, int mode, const float* pts, const float* dirs, int dirs_per_ray,
+                      int64_t n_rays, int S, float* rgb, float* sigma, float* base_remap, float* pts_embed,
+                      float* dirs_embed, tgtc_stream stream);
+
+/* K2+K3+K4 fused -- sample points are formed in-kernel from rays and t values
+ * (pts = o + t*d never touches HBM).  ts: [n_rays,S] or NULL for the uniform
+ * coarse positions linspace(0,1,S)*(far-near)+near.  Output rgbsigma
+ * [n_rays,S,4] = (r,g,b,sigma). */
+int tgtc_nerf_forward_rays(tgtc_ctx* ctx, int net, int mode, const float* rays_o, const float* rays_d,
+                           const float* ts, int64_t n_rays, int S, double near, double far, float* rgbsigma,
+                           tgtc_stream stream);
+
+/* K5 -- alpha compositing.  Replaces utils.alpha_composition (utils.py:354-386).
+ * Either (rgb [n,S,3], sigma [n,S]) or rgbsigma [n,S,4] (the other NULL).
+ * ts [n,S] with ts_ray_stride = S, or one shared row with ts_ray_stride = 0
+ * (the reference's expanded view).  noise: NULL or [n,S] = randn*sigma_noise_std.
+ * Outputs (each may be NULL): rgb_out [n,3], depth_out [n], acc_out [n]
+ * (the reference computes and drops it, utils.py:382), weights_out [n,S]. */
+int tgtc_composite(tgtc_ctx* ctx, const float* rgb, const float* sigma, const float* rgbsigma, const float* ts,
+                   int64_t ts_ray_stride, const float* noise, int white_bkgd, int64_t n, int S, float* rgb_out,
+                   float* depth_out, float* acc_out, float* weights_out, tgtc_stream stream);
+
+/* K6+K7 -- hierarchical inverse-CDF resampling + sorted union.  Replaces
+ * utils.sampling_pts_fine_torch (utils.py:573-580) and utils.sample_pdf
+ * (utils.py:583-609, det=True).  Bin selection is bit-exact with CPU torch
+ * (sum in ATen's vector order, fp64 cdf).  ts [n,S] (ts_ray_stride S or 0),
+ * weights [n,S].  Outputs: ts_out [n,S+n_fine]; optional pts_out
+ * [n,S+n_fine,3] (needs rays_o/rays_d), inds_out [n,n_fine] int64 (the
+ * searchsorted result), samples_out [n,n_fine] (unsorted new samples). */
+int tgtc_sample_fine(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, const float* ts,
+                     int64_t ts_ray_stride, const float* weights, int64_t n, int S, int n_fine, float* pts_out,
+                     float* ts_out, int64_t* inds_out, float* samples_out, tgtc_stream stream);
+
+/* The fused operator (north-star surface):
+ *   render(rays_o, rays_d, near, far, chunk) -> {rgb, depth, acc, weights}
+ * = the loop body of rendering.py:27-51 (cal_geometry) for one batch of rays:
+ * coarse MLP -> compositing -> resampling -> fine MLP -> compositing.
+ * Any output pointer may be NULL.  All device memory. */
+typedef struct tgtc_render_out {
+  float* rgb;            /* [n,3]   fine */
+  float* depth;          /* [n]     fine, NDC t units (t_exp) */
+  float* acc;            /* [n]     fine */
+  float* weights;        /* [n,S+F] fine */
+  float* rgb_coarse;     /* [n,3] */
+  float* depth_coarse;   /* [n] */
+  float* acc_coarse;     /* [n] */
+  float* weights_coarse; /* [n,S] */
+  float* ts_fine;        /* [n,S+F] */
+} tgtc_render_out;
+
+/* bytes of device workspace tgtc_render needs for a call with these sizes
+ * (chunk <= 0 means "all rays in one pass") */
+size_t tgtc_render_workspace_bytes(int64_t n_rays, int n_samples, int n_fine, int64_t chunk);
+
+int tgtc_render(tgtc_ctx* ctx, int mode, const float* rays_o, const float* rays_d, int64_t n_rays, double near,
+                double far, int n_samples, int n_fine, int64_t chunk, int white_bkgd, const tgtc_render_out* out,
+                void* workspace, size_t workspace_bytes, tgtc_stream stream);
+
+/* Same operator with HOST buffers (pinned or pageable): copies rays H2D,
+ * renders, copies the requested outputs D2H and synchronises `stream` before
+ * returning.  Staging memory lives in the context.  This is the end-to-end
+ * entry bench.py times as `e2e`. */
+int tgtc_render_host(tgtc_ctx* ctx, int mode, const float* rays_o, const float* rays_d, int64_t n_rays, double near,
+                     double far, int n_samples, int n_fine, int64_t chunk, int white_bkgd,
+                     const tgtc_render_out* host_out, tgtc_stream stream);
+
+/* Frame operator: K1 fused in front of tgtc_render for pixels
+ * [pix_begin, pix_begin+n) of an H x W pinhole frame (replaces the
+ * RaySampler precompute dataset.py:105-118 + the cal_geometry batch loop).
+ * Device outputs; workspace as for tgtc_render plus 24*n bytes for the rays. */
+size_t tgtc_render_frame_workspace_bytes(int64_t n_rays, int n_samples, int n_fine, int64_t chunk);
+int tgtc_render_frame(tgtc_ctx* ctx, int mode, int H, int W, const double* K, const double* c2w, int ndc,
+                      double ndc_near, int64_t pix_begin, int64_t n, double near, double far, int n_samples,
+                      int n_fine, int64_t chunk, int white_bkgd, const tgtc_render_out* out, void* workspace,
+                      size_t workspace_bytes, tgtc_stream stream);
+
+/* number of kernel launches issued by this context so far (bench.py's
+ * gpu_launches claim is counted here, not estimated) */
+int64_t tgtc_launch_count(const tgtc_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGTC_B200_H */

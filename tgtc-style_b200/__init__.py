@@ -1,0 +1,16 @@
+"""tgtc-style_b200 -- B200-native (sm_100a) NeRF ray-render hot path of TGTC-Style.
+
+Public surface:
+  NerfRenderer            render(rays_o, rays_d, near, far, chunk) -> {rgb, depth, acc, weights}
+  make_callables / patch  the reference's four injected callables, B200-backed
+  shard_range / gather_tiles / render_frame_sharded   multi-GPU ray sharding
+The directory name contains a hyphen; import it as `tgtc_style_b200` (root-level loader module).
+"""
+from . import _lib
+from ._lib import MLP_BF16, MLP_FP32, NET_COARSE, NET_FINE, TgtcError
+from .dist import gather_tiles, render_frame_sharded, shard_range, shard_sizes
+from .render import LAYER_NAMES, LAYER_SHAPES, NerfRenderer
+from .shims import make_callables, patch
+
+__all__ = ["NerfRenderer", "make_callables", "patch", "shard_range", "shard_sizes", "gather_tiles", "render_frame_sharded",
+           "TgtcError", "MLP_FP32", "MLP_BF16", "NET_COARSE", "NET_FINE", "LAYER_NAMES", "LAYER_SHAPES"]

@@ -1,0 +1,380 @@
+// C-ABI entry points of libtgtc_b200 (declared in include/tgtc_b200.h):
+// argument validation, error plumbing, and the render pipeline that strings the
+// kernels together in the order of the reference's loop body (rendering.py:27-51).
+#include "common.cuh"
+
+#include <string.h>
+
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void tgtc_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int tgtc_cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  tgtc_set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  return TGTC_ERR_CUDA;
+}
+
+extern "C" const char* tgtc_last_error(void) { return g_err; }
+extern "C" int tgtc_abi_version(void) { return TGTC_ABI_VERSION; }
+
+#define CHECK_CTX(ctx)                                                  \
+  TGTC_REQUIRE((ctx) != nullptr, TGTC_ERR_ARG, "null context");         \
+  DeviceGuard _guard((ctx)->device);                                    \
+  TGTC_REQUIRE(_guard.ok, TGTC_ERR_CUDA, "cannot select device %d", (ctx)->device)
+
+#define CHECK_NET(ctx, which)                                                               \
+  TGTC_REQUIRE((which) == TGTC_NET_COARSE || (which) == TGTC_NET_FINE, TGTC_ERR_ARG, "bad net id %d", (which)); \
+  TGTC_REQUIRE((ctx)->net[(which)].set, TGTC_ERR_STATE, "weights of net %d not set (call tgtc_set_weights)", (which))
+
+#define CHECK_MODE(mode) \
+  TGTC_REQUIRE((mode) == TGTC_MLP_FP32 || (mode) == TGTC_MLP_BF16, TGTC_ERR_ARG, "bad MLP mode %d", (mode))
+
+#define CHECK_PTR(p, name) TGTC_REQUIRE((p) != nullptr && aligned4(p), TGTC_ERR_ARG, "%s is null or misaligned", name)
+
+// ---------------------------------------------------------------------------
+extern "C" int tgtc_create(int device, tgtc_ctx** out) {
+  TGTC_REQUIRE(out != nullptr, TGTC_ERR_ARG, "out is null");
+  *out = nullptr;
+  int count = 0;
+  TGTC_CUDA(cudaGetDeviceCount(&count));
+  TGTC_REQUIRE(device >= 0 && device < count, TGTC_ERR_ARG, "device %d out of range (%d visible)", device, count);
+  cudaDeviceProp prop;
+  TGTC_CUDA(cudaGetDeviceProperties(&prop, device));
+  TGTC_REQUIRE(prop.major == 10, TGTC_ERR_UNSUPPORTED,
+               "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+  tgtc_ctx* c = new tgtc_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  *out = c;
+  return TGTC_OK;
+}
+
+extern "C" int tgtc_destroy(tgtc_ctx* ctx) {
+  if (ctx == nullptr) return TGTC_OK;
+  DeviceGuard g(ctx->device);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->net[i].f32_gemm) cudaFree(ctx->net[i].f32_gemm);
+    if (ctx->net[i].smalls) cudaFree(ctx->net[i].smalls);
+    if (ctx->net[i].tc_blob) cudaFree(ctx->net[i].tc_blob);
+  }
+  if (ctx->arena) cudaFree(ctx->arena);
+  delete ctx;
+  return TGTC_OK;
+}
+
+extern "C" int64_t tgtc_launch_count(const tgtc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int tgtc_set_weights(tgtc_ctx* ctx, int net, const float* const* params, tgtc_stream stream) {
+  CHECK_CTX(ctx);
+  TGTC_REQUIRE(net == TGTC_NET_COARSE || net == TGTC_NET_FINE, TGTC_ERR_ARG, "bad net id %d", net);
+  TGTC_REQUIRE(params != nullptr, TGTC_ERR_ARG, "params is null");
+  for (int i = 0; i < TGTC_NUM_PARAMS; ++i)
+    TGTC_REQUIRE(params[i] != nullptr && aligned4(params[i]), TGTC_ERR_ARG, "params[%d] is null or misaligned", i);
+  return pack_weights(ctx, net, params, (cudaStream_t)stream);
+}
+
+extern "C" int tgtc_raygen(tgtc_ctx* ctx, int H, int W, const double* K, const double* c2w, int ndc, double ndc_near,
+                           int pixel_alignment, int64_t pix_begin, int64_t n, float* rays_o, float* rays_d,
+                           tgtc_stream stream) {
+  CHECK_CTX(ctx);
+  TGTC_REQUIRE(H > 0 && W > 0, TGTC_ERR_ARG, "bad frame size %dx%d", H, W);
+  TGTC_REQUIRE(K != nullptr && c2w != nullptr, TGTC_ERR_ARG, "K / c2w is null");
+  TGTC_REQUIRE(n >= 0 && pix_begin >= 0 && pix_begin + n <= (int64_t)H * W, TGTC_ERR_ARG,
+               "pixel range [%lld,%lld) outside the %dx%d frame", (long long)pix_begin, (long long)(pix_begin + n), H, W);
+  if (n == 0) return TGTC_OK;
+  CHECK_PTR(rays_o, "rays_o");
+  CHECK_PTR(rays_d, "rays_d");
+  return launch_raygen(ctx, H, W, K, c2w, ndc, ndc_near, pixel_alignment, pix_begin, n, rays_o, rays_d, (cudaStream_t)stream);
+}
+
+extern "C" int tgtc_sample_uniform(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n, int n_samples,
+                                   double near, double far, const float* rnd, float* pts, float* ts, tgtc_stream stream) {
+  CHECK_CTX(ctx);
+  TGTC_REQUIRE(n >= 0 && n_samples >= 1, TGTC_ERR_ARG, "bad sizes n=%lld S=%d", (long long)n, n_samples);
+  if (n == 0) return TGTC_OK;
+  CHECK_PTR(ts, "ts");
+  if (pts != nullptr) { CHECK_PTR(rays_o, "rays_o"); CHECK_PTR(rays_d, "rays_d"); }
+  return launch_sample_uniform(ctx, rays_o, rays_d, n, n_samples, near, far, rnd, pts, ts, (cudaStream_t)stream);
+}
+
+static int run_mlp(tgtc_ctx* ctx, int net, int mode, const MlpIO& io, cudaStream_t st) {
+  if (mode == TGTC_MLP_BF16) {
+    TGTC_REQUIRE(mlp_tc_supports(io), TGTC_ERR_UNSUPPORTED,
+                 "bf16 MLP needs per-ray view dirs, S in {32,64,128} or a multiple of 128, and no feature outputs (S=%d)", io.S);
+    return launch_mlp_tc(ctx, net, io, st);
+  }
+  return launch_mlp_fp32(ctx, net, io, st);
+}
+
+extern "C" int tgtc_nerf_forward(tgtc_ctx* ctx, int net, int mode, const float* pts, const float* dirs, int dirs_per_ray,
+                                 int64_t n_rays, int S, float* rgb, float* sigma, float* base_remap, float* pts_embed,
+                                 float* dirs_embed, tgtc_stream stream) {
+  CHECK_CTX(ctx);
+  CHECK_NET(ctx, net);
+  CHECK_MODE(mode);
+  TGTC_REQUIRE(n_rays >= 0 && S >= 1, TGTC_ERR_ARG, "bad sizes n_rays=%lld S=%d", (long long)n_rays, S);
+  if (n_rays == 0) return TGTC_OK;
+  CHECK_PTR(pts, "pts");
+  CHECK_PTR(dirs, "dirs");
+  CHECK_PTR(rgb, "rgb");
+  CHECK_PTR(sigma, "sigma");
+  MlpIO io;
+  io.pts = pts; io.dirs = dirs; io.dirs_per_ray = dirs_per_ray ? 1 : 0;
+  io.n_rays = n_rays; io.S = S;
+  io.rgb = rgb; io.sigma = sigma; io.base_remap = base_remap; io.pts_embed = pts_embed; io.dirs_embed = dirs_embed;
+  return run_mlp(ctx, net, mode, io, (cudaStream_t)stream);
+}
+
+extern "C" int tgtc_nerf_forward_rays(tgtc_ctx* ctx, int net, int mode, const float* rays_o, const float* rays_d,
+                                      const float* ts, int64_t n_rays, int S, double near, double far, float* rgbsigma,
+                                      tgtc_stream stream) {
+  CHECK_CTX(ctx);
+  CHECK_NET(ctx, net);
+  CHECK_MODE(mode);
+  TGTC_REQUIRE(n_rays >= 0 && S >= 1, TGTC_ERR_ARG, "bad sizes n_rays=%lld S=%d", (long long)n_rays, S);
+  if (n_rays == 0) return TGTC_OK;
+  CHECK_PTR(rays_o, "rays_o");
+  CHECK_PTR(rays_d, "rays_d");
+  TGTC_REQUIRE(rgbsigma != nullptr && aligned16(rgbsigma), TGTC_ERR_ARG, "rgbsigma is null or not 16-byte aligned");
+  MlpIO io;
+  io.rays_o = rays_o; io.rays_d = rays_d; io.ts = ts;
+  io.t_scale = (float)(far - near); io.t_near = (float)near;
+  io.n_rays = n_rays; io.S = S; io.rgbsigma = rgbsigma;
+  return run_mlp(ctx, net, mode, io, (cudaStream_t)stream);
+}
+
+extern "C" int tgtc_composite(tgtc_ctx* ctx, const float* rgb, const float* sigma, const float* rgbsigma, const float* ts,
+                              int64_t ts_ray_stride, const float* noise, int white_bkgd, int64_t n, int S, float* rgb_out,
+                              float* depth_out, float* acc_out, float* weights_out, tgtc_stream stream) {
+  CHECK_CTX(ctx);
+  TGTC_REQUIRE(n >= 0 && S >= 1, TGTC_ERR_ARG, "bad sizes n=%lld S=%d", (long long)n, S);
+  if (n == 0) return TGTC_OK;
+  TGTC_REQUIRE((rgbsigma != nullptr) != (rgb != nullptr && sigma != nullptr), TGTC_ERR_ARG,
+               "pass either rgbsigma or (rgb and sigma)");
+  if (rgbsigma != nullptr) TGTC_REQUIRE(aligned16(rgbsigma), TGTC_ERR_ARG, "rgbsigma not 16-byte aligned");
+  CHECK_PTR(ts, "ts");
+  TGTC_REQUIRE(ts_ray_stride == 0 || ts_ray_stride >= S, TGTC_ERR_ARG, "bad ts_ray_stride %lld", (long long)ts_ray_stride);
+  return launch_composite(ctx, rgb, sigma, rgbsigma, ts, ts_ray_stride, noise, white_bkgd, n, S, rgb_out, depth_out, acc_out,
+                          weights_out, (cudaStream_t)stream);
+}
+
+extern "C" int tgtc_sample_fine(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, const float* ts,
+                                int64_t ts_ray_stride, const float* weights, int64_t n, int S, int n_fine, float* pts_out,
+                                float* ts_out, int64_t* inds_out, float* samples_out, tgtc_stream stream) {
+  CHECK_CTX(ctx);
+  TGTC_REQUIRE(n >= 0, TGTC_ERR_ARG, "bad n=%lld", (long long)n);
+  if (n == 0) return TGTC_OK;
+  CHECK_PTR(ts, "ts");
+  CHECK_PTR(weights, "weights");
+  CHECK_PTR(ts_out, "ts_out");
+  TGTC_REQUIRE(ts_ray_stride == 0 || ts_ray_stride >= S, TGTC_ERR_ARG, "bad ts_ray_stride %lld", (long long)ts_ray_stride);
+  if (pts_out != nullptr) { CHECK_PTR(rays_o, "rays_o"); CHECK_PTR(rays_d, "rays_d"); }
+  return launch_sample_fine(ctx, rays_o, rays_d, ts, ts_ray_stride, weights, n, S, n_fine, pts_out, ts_out, inds_out,
+                            samples_out, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------
+// the fused operator
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct RenderWs {
+  size_t off_rs_c, off_rs_f, off_w_c, off_ts_f, off_ts_c, total;
+};
+
+static RenderWs render_ws_layout(int64_t pass_rays, int S, int F) {
+  RenderWs w;
+  size_t o = 0;
+  w.off_rs_c = o; o = align_up(o + (size_t)pass_rays * S * 16, 256);
+  w.off_rs_f = o; o = align_up(o + (size_t)pass_rays * (S + F) * 16, 256);
+  w.off_w_c = o;  o = align_up(o + (size_t)pass_rays * S * 4, 256);
+  w.off_ts_f = o; o = align_up(o + (size_t)pass_rays * (S + F) * 4, 256);
+  w.off_ts_c = o; o = align_up(o + (size_t)S * 4, 256);
+  w.total = o;
+  return w;
+}
+
+static inline int64_t pass_size(int64_t n, int64_t chunk) { return (chunk <= 0 || chunk > n) ? n : chunk; }
+
+extern "C" size_t tgtc_render_workspace_bytes(int64_t n_rays, int n_samples, int n_fine, int64_t chunk) {
+  if (n_rays <= 0 || n_samples <= 0 || n_fine < 0) return 0;
+  return render_ws_layout(pass_size(n_rays, chunk), n_samples, n_fine).total;
+}
+
+static int check_render_args(tgtc_ctx* ctx, int mode, int64_t n, int S, int F) {
+  CHECK_MODE(mode);
+  CHECK_NET(ctx, TGTC_NET_COARSE);
+  TGTC_REQUIRE(n >= 0, TGTC_ERR_ARG, "bad n_rays=%lld", (long long)n);
+  TGTC_REQUIRE(S >= 10 && S <= 128, TGTC_ERR_UNSUPPORTED, "n_samples=%d outside [10,128]", S);
+  TGTC_REQUIRE(F >= 0 && S + F <= 256, TGTC_ERR_UNSUPPORTED, "n_samples+n_fine=%d > 256", S + F);
+  if (F > 0) { CHECK_NET(ctx, TGTC_NET_FINE); }
+  return TGTC_OK;
+}
+
+// rendering.py:27-51 for rays [0,n): passes of `chunk` rays, six launches per pass
+static int render_impl(tgtc_ctx* ctx, int mode, const float* rays_o, const float* rays_d, int64_t n, double near, double far,
+                       int S, int F, int64_t chunk, int white_bkgd, const tgtc_render_out& out, void* workspace,
+                       size_t workspace_bytes, cudaStream_t st) {
+  if (n == 0) return TGTC_OK;
+  const int64_t pass = pass_size(n, chunk);
+  const RenderWs ws = render_ws_layout(pass, S, F);
+  TGTC_REQUIRE(workspace != nullptr && aligned16(workspace) && workspace_bytes >= ws.total, TGTC_ERR_STATE,
+               "workspace too small or misaligned: need %zu bytes, got %zu", ws.total, workspace_bytes);
+  uint8_t* base = static_cast<uint8_t*>(workspace);
+  float* rs_c = reinterpret_cast<float*>(base + ws.off_rs_c);
+  float* rs_f = reinterpret_cast<float*>(base + ws.off_rs_f);
+  float* ts_c = reinterpret_cast<float*>(base + ws.off_ts_c);
+  const int T = S + F;
+  // the shared coarse t row (utils.py:512-516; the reference expands it with stride 0 over rays)
+  int rc = launch_sample_uniform(ctx, nullptr, nullptr, 1, S, near, far, nullptr, nullptr, ts_c, st);
+  if (rc) return rc;
+  for (int64_t r0 = 0; r0 < n; r0 += pass) {
+    const int64_t m = (n - r0 < pass) ? (n - r0) : pass;
+    const float* o = rays_o + r0 * 3;
+    const float* d = rays_d + r0 * 3;
+    float* w_c = out.weights_coarse ? out.weights_coarse + r0 * S : reinterpret_cast<float*>(base + ws.off_w_c);
+    float* ts_f = out.ts_fine ? out.ts_fine + r0 * T : reinterpret_cast<float*>(base + ws.off_ts_f);
+    // coarse: sampling_pts_uniform + StyleNerf('coarse') fused (rendering.py:27-34)
+    MlpIO ic;
+    ic.rays_o = o; ic.rays_d = d; ic.ts = nullptr;
+    ic.t_scale = (float)(far - near); ic.t_near = (float)near;
+    ic.n_rays = m; ic.S = S; ic.rgbsigma = rs_c;
+    rc = run_mlp(ctx, TGTC_NET_COARSE, mode, ic, st);
+    if (rc) return rc;
+    // alpha_composition(coarse) (rendering.py:36)
+    const bool last = (F == 0);
+    rc = launch_composite(ctx, nullptr, nullptr, rs_c, ts_c, 0, nullptr, white_bkgd, m, S,
+                          out.rgb_coarse ? out.rgb_coarse + r0 * 3 : (last && out.rgb ? out.rgb + r0 * 3 : nullptr),
+                          out.depth_coarse ? out.depth_coarse + r0 : (last && out.depth ? out.depth + r0 : nullptr),
+                          out.acc_coarse ? out.acc_coarse + r0 : (last && out.acc ? out.acc + r0 : nullptr), w_c, st);
+    if (rc) return rc;
+    if (last) continue;
+    // sampling_pts_fine_torch (rendering.py:43)
+    rc = launch_sample_fine(ctx, nullptr, nullptr, ts_c, 0, w_c, m, S, F, nullptr, ts_f, nullptr, nullptr, st);
+    if (rc) return rc;
+    // fine MLP on the sorted union (rendering.py:44-46)
+    MlpIO fi;
+    fi.rays_o = o; fi.rays_d = d; fi.ts = ts_f;
+    fi.n_rays = m; fi.S = T; fi.rgbsigma = rs_f;
+    rc = run_mlp(ctx, TGTC_NET_FINE, mode, fi, st);
+    if (rc) return rc;
+    // alpha_composition(fine) (rendering.py:51)
+    rc = launch_composite(ctx, nullptr, nullptr, rs_f, ts_f, T, nullptr, white_bkgd, m, T,
+                          out.rgb ? out.rgb + r0 * 3 : nullptr, out.depth ? out.depth + r0 : nullptr,
+                          out.acc ? out.acc + r0 : nullptr, out.weights ? out.weights + r0 * T : nullptr, st);
+    if (rc) return rc;
+  }
+  return TGTC_OK;
+}
+
+extern "C" int tgtc_render(tgtc_ctx* ctx, int mode, const float* rays_o, const float* rays_d, int64_t n_rays, double near,
+                           double far, int n_samples, int n_fine, int64_t chunk, int white_bkgd, const tgtc_render_out* out,
+                           void* workspace, size_t workspace_bytes, tgtc_stream stream) {
+  CHECK_CTX(ctx);
+  int rc = check_render_args(ctx, mode, n_rays, n_samples, n_fine);
+  if (rc) return rc;
+  TGTC_REQUIRE(out != nullptr, TGTC_ERR_ARG, "out is null");
+  if (n_rays == 0) return TGTC_OK;
+  CHECK_PTR(rays_o, "rays_o");
+  CHECK_PTR(rays_d, "rays_d");
+  return render_impl(ctx, mode, rays_o, rays_d, n_rays, near, far, n_samples, n_fine, chunk, white_bkgd, *out, workspace,
+                     workspace_bytes, (cudaStream_t)stream);
+}
+
+static int ensure_arena(tgtc_ctx* ctx, size_t bytes, cudaStream_t st) {
+  if (ctx->arena_bytes >= bytes) return TGTC_OK;
+  if (ctx->arena) {
+    TGTC_CUDA(cudaStreamSynchronize(st));
+    TGTC_CUDA(cudaFree(ctx->arena));
+    ctx->arena = nullptr;
+    ctx->arena_bytes = 0;
+  }
+  TGTC_CUDA(cudaMalloc(&ctx->arena, bytes));
+  ctx->arena_bytes = bytes;
+  return TGTC_OK;
+}
+
+extern "C" int tgtc_render_host(tgtc_ctx* ctx, int mode, const float* rays_o, const float* rays_d, int64_t n_rays,
+                                double near, double far, int n_samples, int n_fine, int64_t chunk, int white_bkgd,
+                                const tgtc_render_out* host_out, tgtc_stream stream) {
+  CHECK_CTX(ctx);
+  int rc = check_render_args(ctx, mode, n_rays, n_samples, n_fine);
+  if (rc) return rc;
+  TGTC_REQUIRE(host_out != nullptr, TGTC_ERR_ARG, "host_out is null");
+  if (n_rays == 0) return TGTC_OK;
+  TGTC_REQUIRE(rays_o != nullptr && rays_d != nullptr, TGTC_ERR_ARG, "rays_o / rays_d is null");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = n_rays;
+  const int S = n_samples, F = n_fine, T = S + F;
+  // arena: rays | requested outputs | render workspace
+  struct Slot { float* const* hostp; size_t bytes; size_t off; };
+  const tgtc_render_out& h = *host_out;
+  Slot slots[9] = {
+      {&h.rgb, (size_t)n * 12, 0},           {&h.depth, (size_t)n * 4, 0},        {&h.acc, (size_t)n * 4, 0},
+      {&h.weights, (size_t)n * T * 4, 0},    {&h.rgb_coarse, (size_t)n * 12, 0},  {&h.depth_coarse, (size_t)n * 4, 0},
+      {&h.acc_coarse, (size_t)n * 4, 0},     {&h.weights_coarse, (size_t)n * S * 4, 0}, {&h.ts_fine, (size_t)n * T * 4, 0}};
+  size_t o = 0;
+  const size_t off_o = o; o = align_up(o + (size_t)n * 12, 256);
+  const size_t off_d = o; o = align_up(o + (size_t)n * 12, 256);
+  for (auto& s : slots) {
+    if (*s.hostp != nullptr) { s.off = o; o = align_up(o + s.bytes, 256); }
+  }
+  const size_t off_ws = o;
+  const size_t ws_bytes = tgtc_render_workspace_bytes(n, S, F, chunk);
+  o += ws_bytes;
+  rc = ensure_arena(ctx, o, st);
+  if (rc) return rc;
+  uint8_t* base = static_cast<uint8_t*>(ctx->arena);
+  TGTC_CUDA(cudaMemcpyAsync(base + off_o, rays_o, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+  TGTC_CUDA(cudaMemcpyAsync(base + off_d, rays_d, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+  tgtc_render_out dev;
+  memset(&dev, 0, sizeof(dev));
+  float** devp[9] = {&dev.rgb, &dev.depth, &dev.acc, &dev.weights, &dev.rgb_coarse, &dev.depth_coarse,
+                     &dev.acc_coarse, &dev.weights_coarse, &dev.ts_fine};
+  for (int i = 0; i < 9; ++i)
+    if (*slots[i].hostp != nullptr) *devp[i] = reinterpret_cast<float*>(base + slots[i].off);
+  rc = render_impl(ctx, mode, reinterpret_cast<const float*>(base + off_o), reinterpret_cast<const float*>(base + off_d), n, near,
+                   far, S, F, chunk, white_bkgd, dev, base + off_ws, ws_bytes, st);
+  if (rc) return rc;
+  for (int i = 0; i < 9; ++i)
+    if (*slots[i].hostp != nullptr)
+      TGTC_CUDA(cudaMemcpyAsync(*slots[i].hostp, *devp[i], slots[i].bytes, cudaMemcpyDeviceToHost, st));
+  TGTC_CUDA(cudaStreamSynchronize(st));
+  return TGTC_OK;
+}
+
+extern "C" size_t tgtc_render_frame_workspace_bytes(int64_t n_rays, int n_samples, int n_fine, int64_t chunk) {
+  if (n_rays <= 0) return 0;
+  return align_up((size_t)n_rays * 12, 256) * 2 + tgtc_render_workspace_bytes(n_rays, n_samples, n_fine, chunk);
+}
+
+extern "C" int tgtc_render_frame(tgtc_ctx* ctx, int mode, int H, int W, const double* K, const double* c2w, int ndc,
+                                 double ndc_near, int64_t pix_begin, int64_t n, double near, double far, int n_samples,
+                                 int n_fine, int64_t chunk, int white_bkgd, const tgtc_render_out* out, void* workspace,
+                                 size_t workspace_bytes, tgtc_stream stream) {
+  CHECK_CTX(ctx);
+  int rc = check_render_args(ctx, mode, n, n_samples, n_fine);
+  if (rc) return rc;
+  TGTC_REQUIRE(out != nullptr, TGTC_ERR_ARG, "out is null");
+  TGTC_REQUIRE(H > 0 && W > 0 && K != nullptr && c2w != nullptr, TGTC_ERR_ARG, "bad camera");
+  TGTC_REQUIRE(pix_begin >= 0 && pix_begin + n <= (int64_t)H * W, TGTC_ERR_ARG, "pixel range outside the frame");
+  if (n == 0) return TGTC_OK;
+  const size_t need = tgtc_render_frame_workspace_bytes(n, n_samples, n_fine, chunk);
+  TGTC_REQUIRE(workspace != nullptr && aligned16(workspace) && workspace_bytes >= need, TGTC_ERR_STATE,
+               "workspace too small or misaligned: need %zu bytes, got %zu", need, workspace_bytes);
+  uint8_t* base = static_cast<uint8_t*>(workspace);
+  const size_t ray_bytes = align_up((size_t)n * 12, 256);
+  float* ro = reinterpret_cast<float*>(base);
+  float* rd = reinterpret_cast<float*>(base + ray_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = launch_raygen(ctx, H, W, K, c2w, ndc, ndc_near, 0, pix_begin, n, ro, rd, st);
+  if (rc) return rc;
+  return render_impl(ctx, mode, ro, rd, n, near, far, n_samples, n_fine, chunk, white_bkgd, *out, base + 2 * ray_bytes,
+                     workspace_bytes - 2 * ray_bytes, st);
+}

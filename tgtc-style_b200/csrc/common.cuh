@@ -1,0 +1,178 @@
+// Shared declarations of libtgtc_b200 (internal; the public ABI is include/tgtc_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/tgtc_b200.h"
+
+// ---------------------------------------------------------------------------
+// network geometry (models.py:63-117 with D=8, W=256, skips=[4], L_pts=10, L_dir=4)
+constexpr int kHidden = 256;
+constexpr int kPtsEmb = 63;      // 3 + 3*2*10
+constexpr int kPtsEmbPad = 64;
+constexpr int kDirEmb = 27;      // 3 + 3*2*4
+constexpr int kDirEmbPad = 32;
+constexpr int kRgbHidden = 128;
+constexpr int kNumLayers = 12;   // base 0..7, sigma, remap, rgb0, rgb1
+
+// ---- fp32 image (mlp_fp32.cu): every GEMM layer transposed to [Kpad][N] fp32
+// order: L0 (64x256), L1..L4 (256x256), L5 (320x256: 64 PE rows then 256 hidden),
+//        L6, L7, remap (256x256), rgb0 (288x128: 256 remap rows then 32 dir-PE rows)
+constexpr int kF32NumGemm = 10;
+__host__ __device__ constexpr int f32_layer_k(int l) { return l == 0 ? 64 : (l == 5 ? 320 : (l == 9 ? 288 : 256)); }
+__host__ __device__ constexpr int f32_layer_n(int l) { return l == 9 ? 128 : 256; }
+__host__ __device__ constexpr size_t f32_layer_off(int l) {
+  size_t o = 0;
+  for (int i = 0; i < l; ++i) o += (size_t)f32_layer_k(i) * f32_layer_n(i);
+  return o;
+}
+constexpr size_t kF32GemmFloats = f32_layer_off(kF32NumGemm);
+
+// small fp32 vectors shared by both MLP kernels ("smalls"), offsets in floats
+constexpr int kSmBias = 0;                       // 9 x 256: bias of L0..L7, remap
+constexpr int kSmBiasRgb0 = 9 * 256;             // 128
+constexpr int kSmWSigma = kSmBiasRgb0 + 128;     // 256
+constexpr int kSmWRgb1 = kSmWSigma + 256;        // 3 x 128
+constexpr int kSmBSigma = kSmWRgb1 + 384;        // 1
+constexpr int kSmBRgb1 = kSmBSigma + 1;          // 3
+constexpr int kSmWDir = kSmBRgb1 + 3 + 0;        // 32 x 128 (dir-PE rows of rgb0, transposed, rows 27..31 zero)
+constexpr int kSmallFloats = kSmWDir + 32 * 128;
+static_assert(kSmWDir % 4 == 0, "WDir must stay float4 aligned");
+
+// ---- bf16 image (mlp_tc.cu): chunks of [N rows x 32 K] bf16 in the 64B-swizzled
+// K-major UMMA shared-memory layout, in consumption order (see mlp_tc.cu)
+constexpr int kTcChunkK = 32;
+constexpr int kTcNumGemm = 10;  // L0..L7, remap, rgb0
+__host__ __device__ constexpr int tc_layer_k(int l) { return l == 0 ? 64 : (l == 5 ? 320 : 256); }
+__host__ __device__ constexpr int tc_layer_n(int l) { return l == 9 ? 128 : 256; }
+__host__ __device__ constexpr int tc_layer_chunks(int l) { return tc_layer_k(l) / kTcChunkK; }
+__host__ __device__ constexpr size_t tc_layer_off_bytes(int l) {
+  size_t o = 0;
+  for (int i = 0; i < l; ++i) o += (size_t)tc_layer_k(i) * tc_layer_n(i) * 2;
+  return o;
+}
+constexpr size_t kTcBlobBytes = tc_layer_off_bytes(kTcNumGemm);
+
+struct NetImage {
+  float* f32_gemm = nullptr;   // kF32GemmFloats
+  float* smalls = nullptr;     // kSmallFloats
+  uint8_t* tc_blob = nullptr;  // kTcBlobBytes
+  bool set = false;
+};
+
+struct tgtc_ctx {
+  int device = 0;
+  int num_sms = 0;
+  NetImage net[2];
+  int64_t launches = 0;
+  // staging arena for the *_host entry points
+  void* arena = nullptr;
+  size_t arena_bytes = 0;
+};
+
+// ---------------------------------------------------------------------------
+// error plumbing
+void tgtc_set_error(const char* fmt, ...);
+int tgtc_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define TGTC_CUDA(expr)                                                      \
+  do {                                                                       \
+    cudaError_t _e = (expr);                                                 \
+    if (_e != cudaSuccess) return tgtc_cuda_fail(_e, #expr, __FILE__, __LINE__); \
+  } while (0)
+
+#define TGTC_REQUIRE(cond, code, ...)  \
+  do {                                 \
+    if (!(cond)) {                     \
+      tgtc_set_error(__VA_ARGS__);     \
+      return (code);                   \
+    }                                  \
+  } while (0)
+
+#define TGTC_LAUNCH_CHECK(ctx)                                                      \
+  do {                                                                              \
+    (ctx)->launches++;                                                              \
+    cudaError_t _e = cudaGetLastError();                                            \
+    if (_e != cudaSuccess) return tgtc_cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3) == 0; }
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ---------------------------------------------------------------------------
+// internal launchers (one per .cu file)
+
+// pack.cu
+int pack_weights(tgtc_ctx* ctx, int net, const float* const* params, cudaStream_t st);
+
+// raygen.cu
+int launch_raygen(tgtc_ctx* ctx, int H, int W, const double* K, const double* c2w, int ndc, double ndc_near,
+                  int pixel_alignment, int64_t pix_begin, int64_t n, float* rays_o, float* rays_d, cudaStream_t st);
+
+// sampling.cu
+int launch_sample_uniform(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n, int S, double near,
+                          double far, const float* rnd, float* pts, float* ts, cudaStream_t st);
+int launch_sample_fine(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, const float* ts, int64_t ts_stride,
+                       const float* weights, int64_t n, int S, int n_fine, float* pts_out, float* ts_out,
+                       int64_t* inds_out, float* samples_out, cudaStream_t st);
+
+// composite.cu
+int launch_composite(tgtc_ctx* ctx, const float* rgb, const float* sigma, const float* rgbsigma, const float* ts,
+                     int64_t ts_stride, const float* noise, int white_bkgd, int64_t n, int S, float* rgb_out,
+                     float* depth_out, float* acc_out, float* weights_out, cudaStream_t st);
+
+// how the MLP kernels get their per-sample inputs and where results go
+struct MlpIO {
+  // explicit-points mode (rays_o == nullptr): pts [M,3]; dirs [n_rays,3] if dirs_per_ray else [M,3]
+  const float* pts = nullptr;
+  const float* dirs = nullptr;
+  int dirs_per_ray = 1;
+  // ray mode: rays_o/rays_d [n_rays,3]; ts [n_rays,S] or nullptr -> uniform(t_scale, t_near)
+  const float* rays_o = nullptr;
+  const float* rays_d = nullptr;
+  const float* ts = nullptr;
+  float t_scale = 1.f;  // (float)(far-near)
+  float t_near = 0.f;   // (float)near
+  int64_t n_rays = 0;
+  int S = 0;
+  // outputs (rgbsigma packed, or rgb+sigma split; optional extras)
+  float* rgbsigma = nullptr;
+  float* rgb = nullptr;
+  float* sigma = nullptr;
+  float* base_remap = nullptr;
+  float* pts_embed = nullptr;
+  float* dirs_embed = nullptr;
+};
+
+// mlp_fp32.cu / mlp_tc.cu
+int launch_mlp_fp32(tgtc_ctx* ctx, int net, const MlpIO& io, cudaStream_t st);
+int launch_mlp_tc(tgtc_ctx* ctx, int net, const MlpIO& io, cudaStream_t st);
+bool mlp_tc_supports(const MlpIO& io);
+
+// ---------------------------------------------------------------------------
+// device helpers shared by kernels
+
+// torch.linspace(0,1,steps)[i] in fp32, bit for bit (fma form, symmetric halves)
+__device__ __forceinline__ float linspace01(int i, int steps) {
+  if (steps == 1) return 0.f;
+  const float step = __fdiv_rn(1.0f, (float)(steps - 1));
+  return (i < steps / 2) ? __fmaf_rn(step, (float)i, 0.0f) : __fmaf_rn(-step, (float)(steps - 1 - i), 1.0f);
+}
+
+// ts = linspace*(far-near)+near exactly as torch evaluates it (mul, then add)
+__device__ __forceinline__ float coarse_t(int i, int steps, float t_scale, float t_near) {
+  return __fadd_rn(__fmul_rn(linspace01(i, steps), t_scale), t_near);
+}

@@ -1,0 +1,564 @@
+// K3+K4, bf16 mode -- positional encoding + the 8x256 NeRF MLP as ONE persistent,
+// warp-specialised tcgen05 kernel.  Replaces models.Embedder.forward
+// (models.py:46-60), models.MLP_style.forward (models.py:95-117) and
+// models.StyleNerf.forward (models.py:216-223); utils.batchify (utils.py:435-456)
+// disappears (the CTA streams 128-sample tiles).
+//
+// Per CTA (1 per SM, 448 threads):
+//   warp 0      weight producer: cp.async.bulk (TMA engine, UBLKCP) of pre-swizzled
+//               [N x 32] bf16 chunks from the packed blob (L2-resident) into a
+//               3-stage shared-memory ring, mbarrier complete_tx
+//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=256|128, K=16,
+//               bf16 x bf16 -> fp32) with A = activations in shared memory
+//               (128B-swizzled K-major), B = weight chunk (64B-swizzled K-major),
+//               D = a 128x256 fp32 accumulator in TMEM; tcgen05.commit -> mbarriers
+//   warps 2-5   input producers: pts = o + t*d, precise sin/cos positional encoding
+//               written as the bf16 A operand of layer 0 / the skip of layer 5,
+//               and the per-ray view-direction term of rgb0 (fp32, CUDA cores)
+//   warps 6-13  epilogue: tcgen05.ld the accumulator, +bias, ReLU, bf16, store as
+//               the next layer's A operand (in place); fp32 sigma head at layer 7,
+//               fp32 rgb1 head + sigmoid at rgb0; float4 (r,g,b,sigma) to HBM
+// Two 128-row tiles are in flight per CTA (TMEM columns [0,256) and [256,512)):
+// while the tensor core runs layer l of one tile, the epilogue warps turn the
+// other tile's accumulator into its next A operand, so activations never leave
+// the SM between layers.
+//
+// Tensor-roofline kernel: 1 186 816 algorithmic FLOP per sample; HBM traffic is
+// 24 B/ray in + 16 B/sample out.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kStages = 3;
+constexpr int kStageBytes = 256 * kTcChunkK * 2;  // 16384
+constexpr int kNumThreads = 448;
+constexpr int kPeWarp0 = 2, kEpiWarp0 = 6;
+constexpr int kNumEpiThreads = 256;
+constexpr int kNumPeThreads = 128;
+constexpr int kMaxRaysPerTile = 2;  // S >= 64
+
+// ---- shared memory map (bytes from a 1024-aligned base)
+constexpr int kOffAct = 0;                                   // 2 x [4 kblocks][128 rows x 128 B]  SW128
+constexpr int kActBytes = kTileM * 256 * 2;                  // 65536
+constexpr int kOffPe = kOffAct + 2 * kActBytes;              // 2 x [128 rows x 128 B]             SW128
+constexpr int kPeBytes = kTileM * 64 * 2;                    // 16384
+constexpr int kOffW = kOffPe + 2 * kPeBytes;                 // 3 x 16384                          SW64
+constexpr int kOffBias = kOffW + kStages * kStageBytes;      // 9 x 256 fp32
+constexpr int kOffWSig = kOffBias + 9 * 256 * 4;             // 256 fp32
+constexpr int kOffWRgb1 = kOffWSig + 256 * 4;                // 3 x 128 fp32
+constexpr int kOffDirBias = kOffWRgb1 + 384 * 4;             // [2 slots][2 bufs][2 rays][128] fp32
+constexpr int kOffSigPart = kOffDirBias + 2 * 2 * kMaxRaysPerTile * 128 * 4;  // [2 slots][128] fp32
+constexpr int kOffRgbPart = kOffSigPart + 2 * 128 * 4;       // [128][4] fp32
+constexpr int kOffBars = kOffRgbPart + 128 * 4 * 4;          // mbarriers
+constexpr int kNumBars = 2 * kStages + 8;
+constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
+constexpr int kSmemBytes = kOffTmemPtr + 16;
+static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
+
+// barrier indices
+constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarPeReady = 2 * kStages, kBarPeFree = kBarPeReady + 2,
+              kBarActReady = kBarPeFree + 2, kBarAccFull = kBarActReady + 2;
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (visible as a launch failure) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s
+      printf("tgtc mlp_tc: mbarrier timeout (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): K-major, swizzled.
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major; 1 as CUTLASS) | [32,46) SBO>>4 |
+//   [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t hi) {
+  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+  return ((uint64_t)hi << 32) | lo;
+}
+constexpr uint32_t kDescHiSW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t kDescHiSW64 = (512u >> 4) | (1u << 14) | (4u << 29);
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
+
+struct TcParams {
+  const uint8_t* blob;
+  const float* smalls;
+  MlpIO io;
+  int64_t M;        // samples
+  int64_t ntiles;
+  int rays_per_tile;  // 128/S when S<128 else 1
+  int dbg_layers;     // >0: stop after this many GEMM layers and dump the fp32 accumulator (tests)
+  float* dbg_out;     // [ntiles*128, 256]
+};
+
+// which tile does (cta, j) own, and is it valid
+__device__ __forceinline__ int64_t my_tile(int64_t j) { return (int64_t)blockIdx.x + j * gridDim.x; }
+
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t bars = sbase + kOffBars;
+  auto bar = [&](int i) { return bars + 8u * i; };
+
+  const int64_t n_my = (P.ntiles > (int64_t)blockIdx.x) ? (P.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t iters = (n_my + 1) / 2;
+  const int nlayers = P.dbg_layers > 0 ? P.dbg_layers : kTcNumGemm;
+
+  // ---- one-time setup
+  if (threadIdx.x == 0) {
+    if ((sbase & 1023u) != 0) { printf("tgtc mlp_tc: shared memory base not 1024-aligned\n"); __trap(); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarWFull + s), 1); mbar_init(bar(kBarWEmpty + s), 1); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(bar(kBarPeReady + t), kNumPeThreads);
+      mbar_init(bar(kBarPeFree + t), 1);
+      mbar_init(bar(kBarActReady + t), kNumEpiThreads);
+      mbar_init(bar(kBarAccFull + t), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {  // TMEM: all 512 columns (two 128x256 fp32 accumulators)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(sbase + kOffTmemPtr), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+  }
+  // biases / head weights -> shared memory (fp32), once per CTA
+  {
+    float* dst = reinterpret_cast<float*>(smem + kOffBias);
+    for (int i = threadIdx.x; i < 9 * 256; i += kNumThreads) dst[i] = P.smalls[kSmBias + i];
+    float* ws = reinterpret_cast<float*>(smem + kOffWSig);
+    for (int i = threadIdx.x; i < 256; i += kNumThreads) ws[i] = P.smalls[kSmWSigma + i];
+    float* wr = reinterpret_cast<float*>(smem + kOffWRgb1);
+    for (int i = threadIdx.x; i < 384; i += kNumThreads) wr[i] = P.smalls[kSmWRgb1 + i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
+
+  if (warp == 0) {
+    // =====================================================================
+    // weight producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t it = 0; it < iters; ++it) {
+        const int nslots = (2 * it + 1 < n_my) ? 2 : 1;
+        for (int l = 0; l < nlayers; ++l) {
+          const uint8_t* src = P.blob + tc_layer_off_bytes(l);
+          const uint32_t cbytes = (uint32_t)tc_layer_n(l) * kTcChunkK * 2;
+          const int nch = tc_layer_chunks(l);
+          for (int t = 0; t < nslots; ++t) {
+            for (int c = 0; c < nch; ++c) {
+              mbar_wait(bar(kBarWEmpty + stage), phase ^ 1);
+              mbar_arrive_expect_tx(bar(kBarWFull + stage), cbytes);
+              bulk_g2s(sbase + kOffW + stage * kStageBytes, src + (size_t)c * cbytes, cbytes, bar(kBarWFull + stage));
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =====================================================================
+    // MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t act_par[2] = {0, 0}, pe_par[2] = {0, 0};
+      for (int64_t it = 0; it < iters; ++it) {
+        const int nslots = (2 * it + 1 < n_my) ? 2 : 1;
+        for (int l = 0; l < nlayers; ++l) {
+          const int N = tc_layer_n(l);
+          const uint32_t idesc = make_idesc(kTileM, N);
+          const int nch = tc_layer_chunks(l);
+          for (int t = 0; t < nslots; ++t) {
+            // A operand ready?  (also: accumulator of this slot drained by the epilogue)
+            if (l == 0) {
+              mbar_wait(bar(kBarPeReady + t), pe_par[t]); pe_par[t] ^= 1;
+              if (it > 0) { mbar_wait(bar(kBarActReady + t), act_par[t]); act_par[t] ^= 1; }
+            } else {
+              mbar_wait(bar(kBarActReady + t), act_par[t]); act_par[t] ^= 1;
+            }
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(256 * t);
+            const uint32_t act = sbase + kOffAct + t * kActBytes;
+            const uint32_t pe = sbase + kOffPe + t * kPeBytes;
+            for (int c = 0; c < nch; ++c) {
+              mbar_wait(bar(kBarWFull + stage), phase);
+              tc_fence_after();
+              const uint32_t wst = sbase + kOffW + stage * kStageBytes;
+#pragma unroll
+              for (int s = 0; s < 2; ++s) {
+                const int ks = 2 * c + s;  // 16-wide K step within the layer
+                uint32_t a_addr;
+                if (l == 0) {
+                  a_addr = pe + ks * 32;
+                } else if (l == 5) {
+                  a_addr = ks < 4 ? pe + ks * 32 : act + ((ks - 4) >> 2) * 16384 + ((ks - 4) & 3) * 32;
+                } else {
+                  a_addr = act + (ks >> 2) * 16384 + (ks & 3) * 32;
+                }
+                umma_bf16(d_tmem, make_desc(a_addr, kDescHiSW128), make_desc(wst + s * 32, kDescHiSW64), idesc, ks > 0 ? 1u : 0u);
+              }
+              umma_commit(bar(kBarWEmpty + stage));  // frees the weight stage when these MMAs retire
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            if (l == 5 || (l == nlayers - 1 && nlayers <= 5)) umma_commit(bar(kBarPeFree + t));
+            umma_commit(bar(kBarAccFull + t));
+          }
+        }
+      }
+    }
+  } else if (warp < kEpiWarp0) {
+    // =====================================================================
+    // input producers: one thread per tile row
+    const int r = (warp - kPeWarp0) * 32 + lane;
+    const MlpIO& io = P.io;
+    const int S = io.S;
+    for (int64_t it = 0; it < iters; ++it) {
+      const int nslots = (2 * it + 1 < n_my) ? 2 : 1;
+      for (int t = 0; t < nslots; ++t) {
+        const int64_t tile = my_tile(2 * it + t);
+        if (it > 0) mbar_wait(bar(kBarPeFree + t), (uint32_t)((it - 1) & 1));
+        // ---- sample position of this row
+        int64_t m = tile * kTileM + r;
+        if (m >= P.M) m = P.M - 1;  // padding rows of the last tile: recompute a valid sample, never stored
+        const int64_t ray = m / S;
+        float x[3];
+        if (io.rays_o != nullptr) {
+          const int k = (int)(m - ray * S);
+          const float tt = io.ts != nullptr ? io.ts[m] : coarse_t(k, S, io.t_scale, io.t_near);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(io.rays_o[ray * 3 + c], __fmul_rn(tt, io.rays_d[ray * 3 + c]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) x[c] = io.pts[m * 3 + c];
+        }
+        // ---- positional encoding row (63 values + zero pad) -> bf16, SW128 K-major
+        const uint32_t prow = sbase + kOffPe + t * kPeBytes + (r >> 3) * 1024 + (r & 7) * 128;
+        float e[64];
+        e[0] = x[0]; e[1] = x[1]; e[2] = x[2];
+#pragma unroll
+        for (int f = 0; f < 10; ++f) {
+          const float fr = (float)(1 << f);
+#pragma unroll
+          for (int a = 0; a < 3; ++a) sincosf(__fmul_rn(x[a], fr), &e[3 + 6 * f + a], &e[3 + 6 * f + 3 + a]);
+        }
+        e[63] = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+          st_shared_v4(prow + ((ch ^ (r & 7)) << 4), pack_bf16(e[8 * ch + 0], e[8 * ch + 1]), pack_bf16(e[8 * ch + 2], e[8 * ch + 3]),
+                       pack_bf16(e[8 * ch + 4], e[8 * ch + 5]), pack_bf16(e[8 * ch + 6], e[8 * ch + 7]));
+        // ---- per-ray view-direction term of rgb0: b_rgb0[j] + sum_k W_dir[k][j] * dirPE[k]   (j = r)
+        {
+          float* db = reinterpret_cast<float*>(smem + kOffDirBias) + ((t * 2 + (int)(it & 1)) * kMaxRaysPerTile) * 128;
+          const float* wd = P.smalls + kSmWDir;
+          const int64_t ray0 = (tile * kTileM) / S;
+          for (int rs = 0; rs < P.rays_per_tile; ++rs) {
+            int64_t rr = ray0 + rs;
+            if (rr >= io.n_rays) rr = io.n_rays - 1;
+            const float* dsrc = io.rays_o != nullptr ? io.rays_d : io.dirs;
+            const float v[3] = {dsrc[rr * 3 + 0], dsrc[rr * 3 + 1], dsrc[rr * 3 + 2]};
+            float acc = P.smalls[kSmBiasRgb0 + r];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) acc = fmaf(wd[a * 128 + r], v[a], acc);
+#pragma unroll 1
+            for (int f = 0; f < 4; ++f) {
+              const float fr = (float)(1 << f);
+#pragma unroll
+              for (int a = 0; a < 3; ++a) {
+                float sn, cs;
+                sincosf(__fmul_rn(v[a], fr), &sn, &cs);
+                acc = fmaf(wd[(3 + 6 * f + a) * 128 + r], sn, acc);
+                acc = fmaf(wd[(3 + 6 * f + 3 + a) * 128 + r], cs, acc);
+              }
+            }
+            db[rs * 128 + r] = acc;
+          }
+        }
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(bar(kBarPeReady + t));
+      }
+    }
+  } else {
+    // =====================================================================
+    // epilogue warps
+    const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    const int hc = (warp - kEpiWarp0) >> 2;   // which half of the columns
+    const int row = q * 32 + lane;
+    const float* bias_s = reinterpret_cast<const float*>(smem + kOffBias);
+    const float* wsig_s = reinterpret_cast<const float*>(smem + kOffWSig);
+    const float* wrgb_s = reinterpret_cast<const float*>(smem + kOffWRgb1);
+    float* sigpart_s = reinterpret_cast<float*>(smem + kOffSigPart);
+    float* rgbpart_s = reinterpret_cast<float*>(smem + kOffRgbPart);
+    const float b_sigma = P.smalls[kSmBSigma];
+    const float b_rgb[3] = {P.smalls[kSmBRgb1 + 0], P.smalls[kSmBRgb1 + 1], P.smalls[kSmBRgb1 + 2]};
+    uint32_t acc_par[2] = {0, 0};
+    float sig_keep[2] = {0.f, 0.f};
+    const int S = P.io.S;
+
+    for (int64_t it = 0; it < iters; ++it) {
+      const int nslots = (2 * it + 1 < n_my) ? 2 : 1;
+      for (int l = 0; l < nlayers; ++l) {
+        for (int t = 0; t < nslots; ++t) {
+          if (l == 0) mbar_wait(bar(kBarPeReady + t), (uint32_t)(it & 1));  // acquire the producers' dir-bias writes
+          mbar_wait(bar(kBarAccFull + t), acc_par[t]); acc_par[t] ^= 1;
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 * t);
+          const int64_t tile = my_tile(2 * it + t);
+          const int64_t m = tile * kTileM + row;
+
+          if (P.dbg_layers > 0 && l == nlayers - 1) {
+            // test hook: dump the raw fp32 accumulator of the last executed layer
+            const int ncols = tc_layer_n(l) / 2;
+            for (int b = 0; b < ncols / 32; ++b) {
+              uint32_t v[32];
+              const int c0 = hc * ncols + b * 32;
+              tmem_ld32(taddr + c0, v);
+              tmem_ld_wait();
+              if (m < P.M)
+                for (int j = 0; j < 32; ++j) P.dbg_out[m * 256 + c0 + j] = __uint_as_float(v[j]);
+            }
+            tc_fence_before();
+            mbar_arrive(bar(kBarActReady + t));
+            continue;
+          }
+
+          if (l < 9) {
+            // hidden layer: bias + ReLU -> bf16 A operand of the next layer (in place)
+            const float* bl = bias_s + l * 256;
+            const uint32_t arow = sbase + kOffAct + t * kActBytes + (row >> 3) * 1024 + (row & 7) * 128;
+            float sig = 0.f;
+#pragma unroll 1
+            for (int b = 0; b < 4; ++b) {
+              uint32_t v[32];
+              const int c0 = hc * 128 + b * 32;
+              tmem_ld32(taddr + c0, v);
+              tmem_ld_wait();
+              const uint32_t kb = arow + (c0 >> 6) * 16384;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int c = c0 + 8 * j;
+                const float4 b0 = *reinterpret_cast<const float4*>(bl + c);
+                const float4 b1 = *reinterpret_cast<const float4*>(bl + c + 4);
+                float h[8];
+                h[0] = fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x, 0.f);
+                h[1] = fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y, 0.f);
+                h[2] = fmaxf(__uint_as_float(v[8 * j + 2]) + b0.z, 0.f);
+                h[3] = fmaxf(__uint_as_float(v[8 * j + 3]) + b0.w, 0.f);
+                h[4] = fmaxf(__uint_as_float(v[8 * j + 4]) + b1.x, 0.f);
+                h[5] = fmaxf(__uint_as_float(v[8 * j + 5]) + b1.y, 0.f);
+                h[6] = fmaxf(__uint_as_float(v[8 * j + 6]) + b1.z, 0.f);
+                h[7] = fmaxf(__uint_as_float(v[8 * j + 7]) + b1.w, 0.f);
+                if (l == 7) {  // fp32 sigma head on the un-rounded activations (models.py:103)
+                  const float4 w0 = *reinterpret_cast<const float4*>(wsig_s + c);
+                  const float4 w1 = *reinterpret_cast<const float4*>(wsig_s + c + 4);
+                  sig = fmaf(h[0], w0.x, sig); sig = fmaf(h[1], w0.y, sig); sig = fmaf(h[2], w0.z, sig); sig = fmaf(h[3], w0.w, sig);
+                  sig = fmaf(h[4], w1.x, sig); sig = fmaf(h[5], w1.y, sig); sig = fmaf(h[6], w1.z, sig); sig = fmaf(h[7], w1.w, sig);
+                }
+                const int c16 = (c & 63) >> 3;
+                st_shared_v4(kb + ((c16 ^ (row & 7)) << 4), pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]),
+                             pack_bf16(h[6], h[7]));
+              }
+            }
+            if (l == 7) {
+              if (hc == 1) sigpart_s[t * 128 + row] = sig; else sig_keep[t] = sig;
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(bar(kBarActReady + t));
+          } else {
+            // rgb0 (N=128): + per-ray dir term, ReLU, then the 3x128 rgb1 head + sigmoid in fp32 (models.py:108-111)
+            const float* db = reinterpret_cast<const float*>(smem + kOffDirBias) + ((t * 2 + (int)(it & 1)) * kMaxRaysPerTile) * 128;
+            const int rs = (S < kTileM) ? (row / S) : 0;
+            const float* dbr = db + rs * 128;
+            float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#pragma unroll 1
+            for (int b = 0; b < 2; ++b) {
+              uint32_t v[32];
+              const int c0 = hc * 64 + b * 32;
+              tmem_ld32(taddr + c0, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const int c = c0 + j;
+                const float4 bb = *reinterpret_cast<const float4*>(dbr + c);
+                const float4 w0 = *reinterpret_cast<const float4*>(wrgb_s + c);
+                const float4 w1 = *reinterpret_cast<const float4*>(wrgb_s + 128 + c);
+                const float4 w2 = *reinterpret_cast<const float4*>(wrgb_s + 256 + c);
+                const float f0 = fmaxf(__uint_as_float(v[j + 0]) + bb.x, 0.f);
+                const float f1 = fmaxf(__uint_as_float(v[j + 1]) + bb.y, 0.f);
+                const float f2 = fmaxf(__uint_as_float(v[j + 2]) + bb.z, 0.f);
+                const float f3 = fmaxf(__uint_as_float(v[j + 3]) + bb.w, 0.f);
+                p0 = fmaf(f0, w0.x, p0); p0 = fmaf(f1, w0.y, p0); p0 = fmaf(f2, w0.z, p0); p0 = fmaf(f3, w0.w, p0);
+                p1 = fmaf(f0, w1.x, p1); p1 = fmaf(f1, w1.y, p1); p1 = fmaf(f2, w1.z, p1); p1 = fmaf(f3, w1.w, p1);
+                p2 = fmaf(f0, w2.x, p2); p2 = fmaf(f1, w2.y, p2); p2 = fmaf(f2, w2.z, p2); p2 = fmaf(f3, w2.w, p2);
+              }
+            }
+            tc_fence_before();
+            mbar_arrive(bar(kBarActReady + t));  // accumulator drained: the next tile's layer 0 may start
+            if (hc == 1) *reinterpret_cast<float4*>(rgbpart_s + row * 4) = make_float4(p0, p1, p2, 0.f);
+            named_bar_sync(1, kNumEpiThreads);
+            if (hc == 0) {
+              const float4 o = *reinterpret_cast<const float4*>(rgbpart_s + row * 4);
+              const float z0 = p0 + o.x + b_rgb[0], z1 = p1 + o.y + b_rgb[1], z2 = p2 + o.z + b_rgb[2];
+              const float sg = sig_keep[t] + sigpart_s[t * 128 + row] + b_sigma;
+              if (m < P.M) {
+                const float r0 = 1.0f / (1.0f + expf(-z0)), r1 = 1.0f / (1.0f + expf(-z1)), r2 = 1.0f / (1.0f + expf(-z2));
+                if (P.io.rgbsigma != nullptr) {
+                  reinterpret_cast<float4*>(P.io.rgbsigma)[m] = make_float4(r0, r1, r2, sg);
+                } else {
+                  P.io.rgb[m * 3 + 0] = r0; P.io.rgb[m * 3 + 1] = r1; P.io.rgb[m * 3 + 2] = r2;
+                  P.io.sigma[m] = sg;
+                }
+              }
+            }
+            named_bar_sync(2, kNumEpiThreads);  // partial buffers free for the next tile
+          }
+        }
+      }
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+}  // namespace
+
+bool mlp_tc_supports(const MlpIO& io) {
+  if (io.base_remap || io.pts_embed || io.dirs_embed) return false;
+  if (io.rays_o == nullptr && !io.dirs_per_ray) return false;
+  const int S = io.S;
+  if (!(S == 64 || S == 128 || (S > 128 && S % 128 == 0))) return false;
+  if (io.rgbsigma != nullptr && !aligned16(io.rgbsigma)) return false;
+  return true;
+}
+
+static int launch_tc_common(tgtc_ctx* ctx, int net, const MlpIO& io, int dbg_layers, float* dbg_out, cudaStream_t st) {
+  const NetImage& im = ctx->net[net];
+  TcParams P;
+  P.blob = im.tc_blob;
+  P.smalls = im.smalls;
+  P.io = io;
+  P.M = io.n_rays * io.S;
+  if (P.M == 0) return TGTC_OK;
+  P.ntiles = (P.M + kTileM - 1) / kTileM;
+  P.rays_per_tile = io.S < kTileM ? kTileM / io.S : 1;
+  P.dbg_layers = dbg_layers;
+  P.dbg_out = dbg_out;
+  static bool attr_set[64] = {};
+  if (!attr_set[ctx->device & 63]) {
+    TGTC_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set[ctx->device & 63] = true;
+  }
+  const int grid = (int)(P.ntiles < ctx->num_sms ? P.ntiles : ctx->num_sms);
+  mlp_tc_kernel<<<grid, kNumThreads, kSmemBytes, st>>>(P);
+  TGTC_LAUNCH_CHECK(ctx);
+  return TGTC_OK;
+}
+
+int launch_mlp_tc(tgtc_ctx* ctx, int net, const MlpIO& io, cudaStream_t st) {
+  return launch_tc_common(ctx, net, io, 0, nullptr, st);
+}
+
+// test hook (not part of the public header): run the first `layers` GEMM layers of the bf16 kernel and dump
+// the raw fp32 accumulator of the last one ([n_rays*S, 256], columns >= N untouched)
+extern "C" int tgtc_debug_tc_layers(tgtc_ctx* ctx, int net, const float* rays_o, const float* rays_d, const float* ts,
+                                    int64_t n_rays, int S, double near, double far, int layers, float* acc_out, void* stream) {
+  if (ctx == nullptr || !ctx->net[net].set || layers < 1 || layers > kTcNumGemm) { tgtc_set_error("bad debug args"); return TGTC_ERR_ARG; }
+  DeviceGuard g(ctx->device);
+  MlpIO io;
+  io.rays_o = rays_o; io.rays_d = rays_d; io.ts = ts;
+  io.t_scale = (float)(far - near); io.t_near = (float)near;
+  io.n_rays = n_rays; io.S = S;
+  if (!mlp_tc_supports(io)) { tgtc_set_error("unsupported S"); return TGTC_ERR_UNSUPPORTED; }
+  return launch_tc_common(ctx, net, io, layers, acc_out, (cudaStream_t)stream);
+}

@@ -1,0 +1,121 @@
+// Weight packer: fp32 nn.Linear tensors ([out,in] row-major, the reference's
+// state_dict layout, models.py:75-91) -> the three device images the kernels read.
+//   f32_gemm : per GEMM layer, transposed [Kpad][N] fp32        (mlp_fp32.cu)
+//   tc_blob  : per GEMM layer, chunks of [N x 32] bf16 in the 64B-swizzled
+//              K-major UMMA shared-memory layout, consumption order (mlp_tc.cu)
+//   smalls   : biases, sigma head, rgb1 head, dir-PE slice of rgb0 (fp32)
+// K padding: PE 63->64 (zero column 63; layer 5 = [PE(64) | hidden(256)]),
+// dir-PE 27->32.
+#include "common.cuh"
+
+namespace {
+
+struct Params24 { const float* p[TGTC_NUM_PARAMS]; };
+
+// param index of GEMM layer l (0..9): L0..L7 -> 0..7, remap -> 9, rgb0 -> 10
+__device__ __forceinline__ int gemm_param(int l) { return l < 8 ? l : l + 1; }
+
+// value of GEMM layer l's weight at (n, k) in the padded-K numbering
+__device__ __forceinline__ float gemm_w(const Params24& P, int l, int n, int k, bool with_dir) {
+  const float* W = P.p[2 * gemm_param(l)];
+  if (l == 0) return k < kPtsEmb ? W[n * kPtsEmb + k] : 0.f;
+  if (l == 5) {
+    if (k < kPtsEmb) return W[n * 319 + k];
+    if (k < kPtsEmbPad) return 0.f;
+    return W[n * 319 + kPtsEmb + (k - kPtsEmbPad)];
+  }
+  if (l == 9) {
+    if (k < 256) return W[n * 283 + k];
+    if (with_dir && k < 256 + kDirEmb) return W[n * 283 + k];
+    return 0.f;
+  }
+  return W[n * 256 + k];
+}
+
+__global__ void pack_f32_kernel(Params24 P, float* __restrict__ out) {
+  const size_t total = kF32GemmFloats;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    int l = 0;
+    size_t off = 0;
+    while (l + 1 < kF32NumGemm && idx >= off + (size_t)f32_layer_k(l) * f32_layer_n(l)) {
+      off += (size_t)f32_layer_k(l) * f32_layer_n(l);
+      ++l;
+    }
+    const size_t r = idx - off;
+    const int N = f32_layer_n(l);
+    const int k = (int)(r / N), n = (int)(r % N);
+    out[idx] = gemm_w(P, l, n, k, /*with_dir=*/true);
+  }
+}
+
+__global__ void pack_tc_kernel(Params24 P, __nv_bfloat16* __restrict__ out) {
+  const size_t total = kTcBlobBytes / 2;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    int l = 0;
+    size_t off = 0;  // in elements
+    while (l + 1 < kTcNumGemm && idx >= off + (size_t)tc_layer_k(l) * tc_layer_n(l)) {
+      off += (size_t)tc_layer_k(l) * tc_layer_n(l);
+      ++l;
+    }
+    const size_t r = idx - off;
+    const int N = tc_layer_n(l);
+    const size_t chunk_elems = (size_t)N * kTcChunkK;
+    const int chunk = (int)(r / chunk_elems);
+    const int e = (int)(r % chunk_elems);       // element offset inside the chunk image
+    const int byte = e * 2;
+    // invert: byte = (n/8)*512 + (n%8)*64 + (((kk/8) ^ ((n%8)>>1)) * 16) + (kk%8)*2
+    const int grp = byte >> 9, rem = byte & 511;
+    const int rr = rem >> 6, inrow = rem & 63;
+    const int c16p = inrow >> 4, within = (inrow & 15) >> 1;
+    const int c16 = c16p ^ (rr >> 1);
+    const int n = grp * 8 + rr;
+    const int k = chunk * kTcChunkK + c16 * 8 + within;
+    out[idx] = __float2bfloat16_rn(gemm_w(P, l, n, k, /*with_dir=*/false));
+  }
+}
+
+__global__ void pack_smalls_kernel(Params24 P, float* __restrict__ out) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < kSmallFloats; idx += gridDim.x * blockDim.x) {
+    float v;
+    if (idx < kSmBiasRgb0) {
+      const int j = idx / 256, c = idx % 256;           // L0..L7, remap
+      v = P.p[2 * (j < 8 ? j : 9) + 1][c];
+    } else if (idx < kSmWSigma) {
+      v = P.p[2 * 10 + 1][idx - kSmBiasRgb0];
+    } else if (idx < kSmWRgb1) {
+      v = P.p[2 * 8][idx - kSmWSigma];
+    } else if (idx < kSmBSigma) {
+      v = P.p[2 * 11][idx - kSmWRgb1];
+    } else if (idx < kSmBRgb1) {
+      v = P.p[2 * 8 + 1][0];
+    } else if (idx < kSmWDir) {
+      v = P.p[2 * 11 + 1][idx - kSmBRgb1];
+    } else {
+      const int r = idx - kSmWDir;
+      const int k = r / 128, n = r % 128;
+      v = k < kDirEmb ? P.p[2 * 10][n * 283 + 256 + k] : 0.f;
+    }
+    out[idx] = v;
+  }
+}
+
+}  // namespace
+
+int pack_weights(tgtc_ctx* ctx, int net, const float* const* params, cudaStream_t st) {
+  NetImage& im = ctx->net[net];
+  if (im.f32_gemm == nullptr) {
+    TGTC_CUDA(cudaMalloc(&im.f32_gemm, kF32GemmFloats * sizeof(float)));
+    TGTC_CUDA(cudaMalloc(&im.smalls, kSmallFloats * sizeof(float)));
+    TGTC_CUDA(cudaMalloc(&im.tc_blob, kTcBlobBytes));
+  }
+  Params24 P;
+  for (int i = 0; i < TGTC_NUM_PARAMS; ++i) P.p[i] = params[i];
+  pack_f32_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(P, im.f32_gemm);
+  TGTC_LAUNCH_CHECK(ctx);
+  pack_tc_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(P, reinterpret_cast<__nv_bfloat16*>(im.tc_blob));
+  TGTC_LAUNCH_CHECK(ctx);
+  pack_smalls_kernel<<<32, 256, 0, st>>>(P, im.smalls);
+  TGTC_LAUNCH_CHECK(ctx);
+  im.set = true;
+  return TGTC_OK;
+}

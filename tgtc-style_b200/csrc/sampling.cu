@@ -1,0 +1,214 @@
+// K2 -- stratified sample positions (utils.py:509-531)
+// K6+K7 -- inverse-CDF importance resampling + sorted union (utils.py:573-609)
+//
+// Both are HBM-bound when run stand-alone (sample_fine: read w 4S + write
+// ts_fine 4(S+F) bytes per ray = 768 B/ray at S=F=64).  One warp per ray.
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// K2
+__global__ void __launch_bounds__(256) sample_uniform_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                             int64_t n, int S, float t_scale, float t_near,
+                                                             const float* __restrict__ rnd, float* __restrict__ pts,
+                                                             float* __restrict__ ts) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * S) return;
+  const int64_t ray = idx / S;
+  const int k = (int)(idx - ray * S);
+  float t = coarse_t(k, S, t_scale, t_near);
+  if (rnd != nullptr) {
+    // utils.py:518-524: mid=(ts[1:]+ts[:-1])/2; upper=[mid, ts[-1]]; lower=[ts[0], mid]; ts=lower+(upper-lower)*rand
+    const float tp = coarse_t(k > 0 ? k - 1 : 0, S, t_scale, t_near);
+    const float tn = coarse_t(k < S - 1 ? k + 1 : S - 1, S, t_scale, t_near);
+    const float lower = (k == 0) ? t : __fdiv_rn(__fadd_rn(t, tp), 2.0f);
+    const float upper = (k == S - 1) ? t : __fdiv_rn(__fadd_rn(tn, t), 2.0f);
+    t = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), rnd[idx]));
+  }
+  ts[idx] = t;
+  if (pts != nullptr) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)  // pts = rays_o + ts*rays_d : separate mul and add
+      pts[idx * 3 + c] = __fadd_rn(rays_o[ray * 3 + c], __fmul_rn(t, rays_d[ray * 3 + c]));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K6+K7
+constexpr int kMaxS = 128;       // coarse samples per ray
+constexpr int kMaxOut = 256;     // S + n_fine, padded to a power of two for the sort
+constexpr int kWarpsPerBlock = 4;
+
+struct FineSmem {
+  float ts[kMaxS];
+  float w[kMaxS];        // weights[1:-1] + 1e-5, later pdf
+  float cdf[kMaxS];      // S-1 entries
+  float out[kMaxOut];    // union to sort
+};
+
+__device__ __forceinline__ double shfl_up_f64(double v, int delta) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_up_sync(0xffffffffu, lo, delta);
+  hi = __shfl_up_sync(0xffffffffu, hi, delta);
+  return __hiloint2double(hi, lo);
+}
+__global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_fine_kernel(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ ts_in,
+    int64_t ts_stride, const float* __restrict__ weights, int64_t n, int S, int F, int sort_n,
+    float* __restrict__ pts_out, float* __restrict__ ts_out, int64_t* __restrict__ inds_out,
+    float* __restrict__ samples_out) {
+  __shared__ FineSmem smem[kWarpsPerBlock];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  FineSmem& sm = smem[wib];
+  const int nw = S - 2;    // pdf entries
+  const int nb = S - 1;    // bins (midpoints) == cdf entries
+  const int total = S + F;
+
+  for (int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + wib; ray < n; ray += (int64_t)gridDim.x * kWarpsPerBlock) {
+    // ---- stage the ray: ts[S], w[j] = weights[j+1] + 1e-5
+    for (int i = lane; i < S; i += 32) sm.ts[i] = ts_in[ray * ts_stride + i];
+    for (int i = lane; i < nw; i += 32) sm.w[i] = __fadd_rn(weights[ray * S + 1 + i], 1e-5f);
+    __syncwarp();
+
+    // ---- normaliser: torch.sum(-1) in ATen's order (vectorized_inner_sum, 8 lanes, ILP 4)
+    const int nvec = nw >> 3, nilp = nvec >> 2;
+    float acc0 = 0.f;
+    if (lane < 8) {
+      float a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int i = 0; i < nilp; ++i) {
+        acc0 = __fadd_rn(acc0, sm.w[8 * (4 * i + 0) + lane]);
+        a1 = __fadd_rn(a1, sm.w[8 * (4 * i + 1) + lane]);
+        a2 = __fadd_rn(a2, sm.w[8 * (4 * i + 2) + lane]);
+        a3 = __fadd_rn(a3, sm.w[8 * (4 * i + 3) + lane]);
+      }
+      for (int j = 4 * nilp; j < nvec; ++j) acc0 = __fadd_rn(acc0, sm.w[8 * j + lane]);
+      acc0 = __fadd_rn(acc0, a1);
+      acc0 = __fadd_rn(acc0, a2);
+      acc0 = __fadd_rn(acc0, a3);
+    }
+    float fin = 0.f;
+    for (int k = 8 * nvec; k < nw; ++k) fin = __fadd_rn(fin, sm.w[k]);   // every lane, same value
+#pragma unroll
+    for (int l = 0; l < 8; ++l) fin = __fadd_rn(fin, __shfl_sync(0xffffffffu, acc0, l));
+    __syncwarp();
+
+    // ---- pdf = w / sum ; cdf = [0, cumsum(pdf)] with an fp64 accumulator rounded per prefix.
+    // Every partial sum of these <=126 non-negative fp32 values in [~1e-7, 1] is exactly
+    // representable in fp64 (span < 53 bits), so the warp-parallel scan is bit-identical to
+    // torch's sequential fp64 accumulation.
+    const int per = (nw + 31) >> 5;            // contiguous elements per lane
+    const int j0 = lane * per;
+    double run = 0.0;
+    for (int q = 0; q < per; ++q) {
+      const int j = j0 + q;
+      if (j < nw) {
+        const float pdf = __fdiv_rn(sm.w[j], fin);
+        run += (double)pdf;
+      }
+    }
+    double incl = run;
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+      const double o = shfl_up_f64(incl, dlt);
+      if (lane >= dlt) incl += o;
+    }
+    double pre = incl - run;                   // exclusive prefix of this lane (exact)
+    if (lane == 0) sm.cdf[0] = 0.f;
+    for (int q = 0; q < per; ++q) {
+      const int j = j0 + q;
+      if (j < nw) {
+        pre += (double)__fdiv_rn(sm.w[j], fin);
+        sm.cdf[j + 1] = (float)pre;
+      }
+    }
+    __syncwarp();
+
+    // ---- inverse CDF for u = linspace(0,1,F)
+    for (int k = lane; k < F; k += 32) {
+      const float u = linspace01(k, F);
+      // searchsorted(cdf, u, right=True) = #{cdf <= u}; cdf is non-decreasing
+      int lo = 0, hi = nb;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sm.cdf[mid] <= u) lo = mid + 1; else hi = mid;
+      }
+      const int ind = lo;
+      const int below = max(0, ind - 1);
+      const int above = min(nb - 1, ind);
+      const float cb = sm.cdf[below], ca = sm.cdf[above];
+      const float bb = __fmul_rn(0.5f, __fadd_rn(sm.ts[below + 1], sm.ts[below]));
+      const float ba = __fmul_rn(0.5f, __fadd_rn(sm.ts[above + 1], sm.ts[above]));
+      float denom = __fsub_rn(ca, cb);
+      if (denom < 1e-5f) denom = 1.0f;
+      const float t = __fdiv_rn(__fsub_rn(u, cb), denom);
+      const float s = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
+      sm.out[S + k] = s;
+      if (inds_out != nullptr) inds_out[ray * F + k] = ind;
+      if (samples_out != nullptr) samples_out[ray * F + k] = s;
+    }
+    for (int i = lane; i < S; i += 32) sm.out[i] = sm.ts[i];
+    for (int i = total + lane; i < sort_n; i += 32) sm.out[i] = __int_as_float(0x7f800000);  // +inf padding
+    __syncwarp();
+
+    // ---- torch.sort(cat(ts, t_samples)): bitonic network over sort_n (power of two) in shared memory
+    for (int k = 2; k <= sort_n; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = lane; i < sort_n; i += 32) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const float a = sm.out[i], b = sm.out[ixj];
+            const bool up = ((i & k) == 0);
+            if ((a > b) == up) { sm.out[i] = b; sm.out[ixj] = a; }
+          }
+        }
+        __syncwarp();
+      }
+    }
+
+    // ---- write ts_fine (coalesced) and optionally pts = o + d*t
+    for (int i = lane; i < total; i += 32) ts_out[ray * total + i] = sm.out[i];
+    if (pts_out != nullptr) {
+      const float ox = rays_o[ray * 3 + 0], oy = rays_o[ray * 3 + 1], oz = rays_o[ray * 3 + 2];
+      const float dx = rays_d[ray * 3 + 0], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
+      for (int i = lane; i < total; i += 32) {
+        const float t = sm.out[i];
+        float* p = pts_out + (ray * total + i) * 3;
+        p[0] = __fadd_rn(ox, __fmul_rn(dx, t));
+        p[1] = __fadd_rn(oy, __fmul_rn(dy, t));
+        p[2] = __fadd_rn(oz, __fmul_rn(dz, t));
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+int launch_sample_uniform(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n, int S, double near,
+                          double far, const float* rnd, float* pts, float* ts, cudaStream_t st) {
+  const int64_t total = n * S;
+  const int block = 256;
+  const int64_t grid = (total + block - 1) / block;
+  TGTC_REQUIRE(grid <= 0x7fffffff, TGTC_ERR_UNSUPPORTED, "sample_uniform: too many samples in one call");
+  sample_uniform_kernel<<<(unsigned)grid, block, 0, st>>>(rays_o, rays_d, n, S, (float)(far - near), (float)near, rnd, pts, ts);
+  TGTC_LAUNCH_CHECK(ctx);
+  return TGTC_OK;
+}
+
+int launch_sample_fine(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, const float* ts, int64_t ts_stride,
+                       const float* weights, int64_t n, int S, int n_fine, float* pts_out, float* ts_out,
+                       int64_t* inds_out, float* samples_out, cudaStream_t st) {
+  TGTC_REQUIRE(S >= 10 && S <= kMaxS, TGTC_ERR_UNSUPPORTED, "sample_fine: S=%d outside [10,%d]", S, kMaxS);
+  TGTC_REQUIRE(n_fine >= 1 && S + n_fine <= kMaxOut, TGTC_ERR_UNSUPPORTED, "sample_fine: S+n_fine=%d > %d", S + n_fine, kMaxOut);
+  int sort_n = 2;
+  while (sort_n < S + n_fine) sort_n <<= 1;
+  const int64_t blocks_needed = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const int64_t cap = (int64_t)ctx->num_sms * 16;   // 16 resident 128-thread CTAs per SM
+  const int64_t grid = blocks_needed < cap ? blocks_needed : cap;
+  sample_fine_kernel<<<(unsigned)grid, 32 * kWarpsPerBlock, 0, st>>>(rays_o, rays_d, ts, ts_stride, weights, n, S, n_fine,
+                                                                    sort_n, pts_out, ts_out, inds_out, samples_out);
+  TGTC_LAUNCH_CHECK(ctx);
+  return TGTC_OK;
+}

@@ -1,0 +1,327 @@
+"""Host side of the B200 ray-render path: a thin Python layer over the C ABI.
+
+`NerfRenderer` owns one library context (one per device/process) and exposes
+  * the fused operator   render(rays_o, rays_d, near, far, chunk) -> {rgb, depth, acc, weights}
+    (= the loop body of the reference's rendering.py:27-51),
+  * the stage operators that mirror the reference's four injected callables
+    (utils.sampling_pts_uniform, models.StyleNerf.forward via utils.batchify,
+    utils.alpha_composition, utils.sampling_pts_fine_torch) and its ray generation
+    (dataset.get_rays_np + ndc_rays_np).
+torch supplies device memory and the stream; all arithmetic happens in
+libtgtc_b200.so.  No CPU fallback exists.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+LAYER_NAMES = (["net.base_layers.%d" % i for i in range(8)]
+               + ["net.sigma_layer", "net.base_remap_layer", "net.rgb_layers.0", "net.rgb_layers.1"])
+LAYER_SHAPES = ([(256, 63)] + [(256, 256)] * 4 + [(256, 319)] + [(256, 256)] * 2
+                + [(1, 256), (256, 256), (128, 283), (3, 128)])
+
+_MODES = {"fp32": _lib.MLP_FP32, "bf16": _lib.MLP_BF16, _lib.MLP_FP32: _lib.MLP_FP32, _lib.MLP_BF16: _lib.MLP_BF16}
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _dptr(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_lib.c_double_p)
+
+
+class NerfRenderer:
+    """B200 drop-in for the NeRF ray-render chain of TGTC-Style (coarse + fine StyleNerf)."""
+
+    def __init__(self, device=None, mode="bf16"):
+        if not torch.cuda.is_available():
+            raise _lib.TgtcError("tgtc-style_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.mode = _MODES[mode]
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.tgtc_create(self.device.index, ctypes.byref(h)))
+        self._h = h
+        self._ws = None
+        self._weights_src = [None, None]   # keeps packed-from tensors alive / version-tracked
+        self._versions = [None, None]
+        self._keep = [None, None]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.tgtc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, t, dtype=torch.float32):
+        t = torch.as_tensor(t)
+        if t.device != self.device or t.dtype != dtype:
+            t = t.to(device=self.device, dtype=dtype)
+        return t.contiguous()
+
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def launch_count(self):
+        return int(self.lib.tgtc_launch_count(self._h))
+
+    # ------------------------------------------------------------------ weights
+    def set_weights(self, coarse=None, fine=None):
+        """coarse / fine: a models.StyleNerf (or any nn.Module / state_dict) whose parameters are named
+        net.base_layers.{0..7}, net.sigma_layer, net.base_remap_layer, net.rgb_layers.{0,1} (models.py:75-91)."""
+        for which, src in ((_lib.NET_COARSE, coarse), (_lib.NET_FINE, fine)):
+            if src is None:
+                continue
+            sd = src.state_dict() if hasattr(src, "state_dict") else src
+            tensors = []
+            for name, (o, i) in zip(LAYER_NAMES, LAYER_SHAPES):
+                w = sd[name + ".weight"]
+                b = sd[name + ".bias"]
+                if tuple(w.shape) != (o, i) or tuple(b.shape) != (o,):
+                    raise ValueError("%s has shape %s/%s, expected %s/%s" % (name, tuple(w.shape), tuple(b.shape), (o, i), (o,)))
+                tensors += [self._dev(w.detach()), self._dev(b.detach())]
+            arr = (ctypes.c_void_p * _lib.NUM_PARAMS)(*[t.data_ptr() for t in tensors])
+            _lib.check(self.lib.tgtc_set_weights(self._h, which, arr, self._stream))
+            self._weights_src[which] = src
+            self._versions[which] = self._version_of(src)
+            self._keep[which] = tensors
+
+    @staticmethod
+    def _version_of(src):
+        if hasattr(src, "parameters"):
+            return tuple(p._version for p in src.parameters())
+        return None
+
+    def refresh_weights(self):
+        """Re-pack any nn.Module source whose parameters changed in place (optimizer step, load_state_dict)."""
+        for which in (0, 1):
+            src = self._weights_src[which]
+            if src is not None and hasattr(src, "parameters") and self._version_of(src) != self._versions[which]:
+                self.set_weights(**{("coarse" if which == 0 else "fine"): src})
+
+    # ------------------------------------------------------------------ K1
+    def raygen(self, H, W, K, c2w, ndc=True, ndc_near=1.0, pix_begin=0, n=None, pixel_alignment=False):
+        """dataset.get_rays_np + ndc_rays_np (dataset.py:33-61) for pixels [pix_begin, pix_begin+n) -> fp32 [n,3] x2."""
+        n = H * W - pix_begin if n is None else n
+        ro = torch.empty(n, 3, dtype=torch.float32, device=self.device)
+        rd = torch.empty(n, 3, dtype=torch.float32, device=self.device)
+        Ka, Kp = _dptr(np.asarray(K, np.float64).reshape(9))
+        Ca, Cp = _dptr(np.asarray(c2w, np.float64)[:3, :4].reshape(12))
+        _lib.check(self.lib.tgtc_raygen(self._h, H, W, Kp, Cp, int(ndc), float(ndc_near), int(pixel_alignment), pix_begin, n,
+                                        _ptr(ro), _ptr(rd), self._stream))
+        return ro, rd
+
+    # ------------------------------------------------------------------ K2
+    def sample_uniform(self, rays_o, rays_d, n_samples=64, near=0., far=1.05, rand=None, want_pts=True):
+        """utils.sampling_pts_uniform (utils.py:509-531).  Returns (pts [N,S,3], ts [N,S])."""
+        ro, rd = self._dev(rays_o), self._dev(rays_d)
+        n = ro.shape[0]
+        ts = torch.empty(n, n_samples, dtype=torch.float32, device=self.device)
+        pts = torch.empty(n, n_samples, 3, dtype=torch.float32, device=self.device) if want_pts else None
+        rnd = self._dev(rand) if rand is not None else None
+        _lib.check(self.lib.tgtc_sample_uniform(self._h, _ptr(ro), _ptr(rd), n, n_samples, float(near), float(far), _ptr(rnd),
+                                                _ptr(pts), _ptr(ts), self._stream))
+        return pts, ts
+
+    # ------------------------------------------------------------------ K3+K4
+    def nerf_forward(self, net, pts, dirs, want_features=True, mode=None):
+        """models.StyleNerf.forward(pts=[N,S,3], dirs=[N,S,3]) through utils.batchify (models.py:216-223).
+        Returns the reference's dict: rgb, base_remap, pts (embedded), sigma, dirs (embedded)."""
+        mode = self.mode if mode is None else _MODES[mode]
+        pts_t = torch.as_tensor(pts)
+        dirs_t = torch.as_tensor(dirs)
+        if pts_t.dim() != 3 or pts_t.shape[-1] != 3:
+            raise ValueError("pts must be [N,S,3]")
+        n, S = pts_t.shape[0], pts_t.shape[1]
+        # the reference passes rays_d.unsqueeze(1).expand(N,S,3) (rendering.py:30): a stride-0 view
+        per_ray = dirs_t.dim() == 2 or (dirs_t.dim() == 3 and (dirs_t.stride(1) == 0 or S == 1))
+        d = self._dev(dirs_t[:, 0, :] if (per_ray and dirs_t.dim() == 3) else dirs_t)
+        p = self._dev(pts_t)
+        rgb = torch.empty(n, S, 3, dtype=torch.float32, device=self.device)
+        sigma = torch.empty(n, S, dtype=torch.float32, device=self.device)
+        if want_features and mode == _lib.MLP_BF16:
+            mode = _lib.MLP_FP32  # feature outputs exist on the general path only
+        remap = torch.empty(n, S, 256, dtype=torch.float32, device=self.device) if want_features else None
+        pe = torch.empty(n, S, 63, dtype=torch.float32, device=self.device) if want_features else None
+        de = torch.empty(n, S, 27, dtype=torch.float32, device=self.device) if want_features else None
+        _lib.check(self.lib.tgtc_nerf_forward(self._h, net, mode, _ptr(p), _ptr(d), int(per_ray), n, S, _ptr(rgb), _ptr(sigma),
+                                              _ptr(remap), _ptr(pe), _ptr(de), self._stream))
+        out = {"rgb": rgb, "sigma": sigma}
+        if want_features:
+            out.update(base_remap=remap, pts=pe, dirs=de)
+        return out
+
+    def nerf_forward_rays(self, net, rays_o, rays_d, ts=None, n_samples=64, near=0., far=1., mode=None):
+        """Fused K2+K3+K4: rgbsigma [N,S,4] for samples o + t*d (ts=None -> uniform coarse positions)."""
+        mode = self.mode if mode is None else _MODES[mode]
+        ro, rd = self._dev(rays_o), self._dev(rays_d)
+        n = ro.shape[0]
+        tsd = self._dev(ts) if ts is not None else None
+        S = tsd.shape[1] if tsd is not None else n_samples
+        out = torch.empty(n, S, 4, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.tgtc_nerf_forward_rays(self._h, net, mode, _ptr(ro), _ptr(rd), _ptr(tsd), n, S, float(near), float(far),
+                                                   _ptr(out), self._stream))
+        return out
+
+    # ------------------------------------------------------------------ K5
+    def composite(self, pts_rgb=None, pts_sigma=None, t_values=None, noise=None, white_bkgd=False, rgbsigma=None):
+        """utils.alpha_composition (utils.py:354-386).  Returns (rgb [N,3], depth [N], weights [N,S], acc [N])."""
+        ts_t = torch.as_tensor(t_values)
+        if rgbsigma is not None:
+            rs = self._dev(rgbsigma)
+            n, S = rs.shape[0], rs.shape[1]
+            rgb = sig = None
+        else:
+            rgb, sig = self._dev(pts_rgb), self._dev(pts_sigma)
+            n, S = sig.shape[0], sig.shape[1]
+            rs = None
+        if ts_t.dim() == 2 and ts_t.shape[0] == n and ts_t.stride(0) == 0 and n > 1:
+            tsd, stride = self._dev(ts_t[0]), 0     # the reference's expanded coarse ts (utils.py:512)
+        elif ts_t.dim() == 1:
+            tsd, stride = self._dev(ts_t), 0
+        else:
+            tsd, stride = self._dev(ts_t), S
+        nz = self._dev(noise) if noise is not None else None
+        o_rgb = torch.empty(n, 3, dtype=torch.float32, device=self.device)
+        o_d = torch.empty(n, dtype=torch.float32, device=self.device)
+        o_a = torch.empty(n, dtype=torch.float32, device=self.device)
+        o_w = torch.empty(n, S, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.tgtc_composite(self._h, _ptr(rgb), _ptr(sig), _ptr(rs), _ptr(tsd), stride, _ptr(nz), int(white_bkgd), n, S,
+                                           _ptr(o_rgb), _ptr(o_d), _ptr(o_a), _ptr(o_w), self._stream))
+        return o_rgb, o_d, o_w, o_a
+
+    # ------------------------------------------------------------------ K6+K7
+    def sample_fine(self, rays_o, rays_d, ts, weights, n_fine=64, want_pts=True, return_aux=False):
+        """utils.sampling_pts_fine_torch (utils.py:573-580).  Returns (pts [N,S+F,3], ts [N,S+F]) and, with
+        return_aux, also (t_samples [N,F], inds [N,F] int64)."""
+        w = self._dev(weights)
+        n, S = w.shape
+        ts_t = torch.as_tensor(ts)
+        if ts_t.dim() == 1 or (ts_t.stride(0) == 0 and n > 1):
+            tsd, stride = self._dev(ts_t if ts_t.dim() == 1 else ts_t[0]), 0
+        else:
+            tsd, stride = self._dev(ts_t), S
+        T = S + n_fine
+        ts_out = torch.empty(n, T, dtype=torch.float32, device=self.device)
+        ro = self._dev(rays_o) if want_pts else None
+        rd = self._dev(rays_d) if want_pts else None
+        pts = torch.empty(n, T, 3, dtype=torch.float32, device=self.device) if want_pts else None
+        inds = torch.empty(n, n_fine, dtype=torch.int64, device=self.device) if return_aux else None
+        smp = torch.empty(n, n_fine, dtype=torch.float32, device=self.device) if return_aux else None
+        _lib.check(self.lib.tgtc_sample_fine(self._h, _ptr(ro), _ptr(rd), _ptr(tsd), stride, _ptr(w), n, S, n_fine, _ptr(pts),
+                                             _ptr(ts_out), _ptr(inds), _ptr(smp), self._stream))
+        if return_aux:
+            return pts, ts_out, smp, inds
+        return pts, ts_out
+
+    # ------------------------------------------------------------------ the fused operator
+    def _alloc_out(self, n, S, F, extras, device, pin=False):
+        kw = dict(dtype=torch.float32, device=device)
+        if pin:
+            kw["pin_memory"] = True
+        T = S + F
+        out = {"rgb": torch.empty(n, 3, **kw), "depth": torch.empty(n, **kw), "acc": torch.empty(n, **kw),
+               "weights": torch.empty(n, T, **kw)}
+        if extras:
+            out.update(rgb_coarse=torch.empty(n, 3, **kw), depth_coarse=torch.empty(n, **kw), acc_coarse=torch.empty(n, **kw),
+                       weights_coarse=torch.empty(n, S, **kw), ts_fine=torch.empty(n, T, **kw))
+        return out
+
+    @staticmethod
+    def _out_struct(out):
+        s = _lib.RenderOut()
+        for name in _lib.OUT_FIELDS:
+            t = out.get(name)
+            setattr(s, name, t.data_ptr() if t is not None else None)
+        return s
+
+    def render(self, rays_o, rays_d, near=0., far=1., chunk=None, n_samples=64, n_fine=64, white_bkgd=False, extras=False,
+               want_weights=True, mode=None, out=None):
+        """render(rays_o [N,3], rays_d [N,3], near, far, chunk) -> {rgb [N,3], depth [N], acc [N], weights [N,S+F]}
+        (+ rgb_coarse, depth_coarse, acc_coarse, weights_coarse, ts_fine when extras).  Device tensors in and out."""
+        self.refresh_weights()
+        mode = self.mode if mode is None else _MODES[mode]
+        ro, rd = self._dev(rays_o), self._dev(rays_d)
+        n = ro.shape[0]
+        if out is None:
+            out = self._alloc_out(n, n_samples, n_fine, extras, self.device)
+            if not want_weights:
+                out.pop("weights")
+        ck = int(chunk) if chunk else 0
+        wsb = self.lib.tgtc_render_workspace_bytes(n, n_samples, n_fine, ck)
+        ws = self._workspace(wsb)
+        s = self._out_struct(out)
+        _lib.check(self.lib.tgtc_render(self._h, mode, _ptr(ro), _ptr(rd), n, float(near), float(far), n_samples, n_fine, ck,
+                                        int(white_bkgd), ctypes.byref(s), _ptr(ws), wsb, self._stream))
+        return out
+
+    def render_host(self, rays_o, rays_d, near=0., far=1., chunk=None, n_samples=64, n_fine=64, white_bkgd=False, extras=False,
+                    want_weights=False, mode=None, out=None):
+        """Same operator with HOST tensors (pinned recommended): H2D of the rays, render, D2H of the results,
+        synchronous.  This is the call the reference's loop makes per batch (rendering.py:20-21, :53-54)."""
+        self.refresh_weights()
+        mode = self.mode if mode is None else _MODES[mode]
+        ro = torch.as_tensor(rays_o, dtype=torch.float32).contiguous()
+        rd = torch.as_tensor(rays_d, dtype=torch.float32).contiguous()
+        if ro.is_cuda or rd.is_cuda:
+            raise ValueError("render_host takes host tensors")
+        n = ro.shape[0]
+        if out is None:
+            out = self._alloc_out(n, n_samples, n_fine, extras, "cpu", pin=True)
+            if not want_weights:
+                out.pop("weights")
+        s = self._out_struct(out)
+        _lib.check(self.lib.tgtc_render_host(self._h, mode, _ptr(ro), _ptr(rd), n, float(near), float(far), n_samples, n_fine,
+                                             int(chunk) if chunk else 0, int(white_bkgd), ctypes.byref(s), self._stream))
+        return out
+
+    def render_frame(self, H, W, K, c2w, pix_begin=0, n=None, near=0., far=1., chunk=None, n_samples=64, n_fine=64, ndc=True,
+                     ndc_near=1.0, white_bkgd=False, extras=False, want_weights=False, mode=None, out=None):
+        """Ray generation (K1) fused in front of render() for pixels [pix_begin, pix_begin+n) of an HxW frame."""
+        self.refresh_weights()
+        mode = self.mode if mode is None else _MODES[mode]
+        n = H * W - pix_begin if n is None else n
+        if out is None:
+            out = self._alloc_out(n, n_samples, n_fine, extras, self.device)
+            if not want_weights:
+                out.pop("weights")
+        ck = int(chunk) if chunk else 0
+        wsb = self.lib.tgtc_render_frame_workspace_bytes(n, n_samples, n_fine, ck)
+        ws = self._workspace(wsb)
+        Ka, Kp = _dptr(np.asarray(K, np.float64).reshape(9))
+        Ca, Cp = _dptr(np.asarray(c2w, np.float64)[:3, :4].reshape(12))
+        s = self._out_struct(out)
+        _lib.check(self.lib.tgtc_render_frame(self._h, mode, H, W, Kp, Cp, int(ndc), float(ndc_near), pix_begin, n, float(near),
+                                              float(far), n_samples, n_fine, ck, int(white_bkgd), ctypes.byref(s), _ptr(ws), wsb,
+                                              self._stream))
+        return out
+
+    # ------------------------------------------------------------------ test hook
+    def debug_tc_layers(self, net, rays_o, rays_d, ts, n_samples, near, far, layers):
+        ro, rd = self._dev(rays_o), self._dev(rays_d)
+        n = ro.shape[0]
+        tsd = self._dev(ts) if ts is not None else None
+        S = tsd.shape[1] if tsd is not None else n_samples
+        acc = torch.zeros(n * S, 256, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.tgtc_debug_tc_layers(self._h, net, _ptr(ro), _ptr(rd), _ptr(tsd), n, S, float(near), float(far), layers,
+                                                 _ptr(acc), self._stream))
+        return acc
