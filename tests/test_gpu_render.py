@@ -1,0 +1,134 @@
+"""GPU parity of the fused operator render(rays_o, rays_d, near, far, chunk) -> {rgb, depth, acc, weights}
+against the golden chain vectors (produced by the real reference) and the oracle; size-independent
+properties at the full 1008x756 frame; host-buffer entry; chunk / shard invariance; the reference-signature shims."""
+import numpy as np
+import pytest
+import torch
+
+import render_oracle as O
+import tgtc_style_b200 as T
+from helpers import FERN_FULL, golden, knife_edge_mask, small_rays, weights
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("kind", ["w1", "w0"])
+def test_render_fp32_end_to_end_vs_reference_vectors(renderer_fp32, kind):
+    """fp32 mode: strict max <= 1e-3 on rgb/depth/acc, END TO END (not teacher-forced), vs the reference."""
+    g = golden("chain_" + kind)
+    wc, wf = weights(kind)
+    renderer_fp32.set_weights(wc, wf)
+    out = renderer_fp32.render(g["rays_o"], g["rays_d"], 0., 1., n_samples=64, n_fine=64, extras=True)
+    tol = 1e-3
+    assert np.abs(out["rgb"].cpu().numpy() - g["rgb"]).max() <= tol
+    assert np.abs(out["depth"].cpu().numpy() - g["depth"]).max() <= tol
+    assert np.abs(out["acc"].cpu().numpy() - g["acc"]).max() <= tol
+    assert np.abs(out["rgb_coarse"].cpu().numpy() - g["rgb_coarse"]).max() <= tol
+    assert np.abs(out["weights"].cpu().numpy() - g["weights"]).max() <= tol
+    assert np.abs(out["ts_fine"].cpu().numpy() - g["ts_fine"]).max() <= 1e-4
+
+
+def test_render_bf16_teacher_forced_protocol(renderer_bf16):
+    """bf16 mode, SURVEY H1 protocol: fine pass teacher-forced on the reference's ts_fine; max <= 1e-2 over rays
+    not flagged knife-edge (alpha_last is a step function of sigma_last), flagged fraction small; end-to-end
+    mean error reported and bounded."""
+    g = golden("chain_w1")
+    wc, wf = weights("w1")
+    renderer_bf16.set_weights(wc, wf)
+    rs = renderer_bf16.nerf_forward_rays(T.NET_FINE, g["rays_o"], g["rays_d"], g["ts_fine"], 128, 0., 1.)
+    rgb, depth, w, acc = renderer_bf16.composite(t_values=g["ts_fine"], rgbsigma=rs)
+    flagged = knife_edge_mask(torch.from_numpy(g["sigma_fine"]), torch.from_numpy(g["ts_fine"])).numpy()
+    ok = ~flagged
+    assert flagged.mean() <= 0.05
+    assert np.abs(rgb.cpu().numpy() - g["rgb"])[ok].max() <= 1e-2
+    assert np.abs(acc.cpu().numpy() - g["acc"])[ok].max() <= 1e-2
+    assert np.abs(depth.cpu().numpy() - g["depth"])[ok].max() <= 1e-2
+    out = renderer_bf16.render(g["rays_o"], g["rays_d"], 0., 1., n_samples=64, n_fine=64)
+    assert np.abs(out["rgb"].cpu().numpy() - g["rgb"]).mean() <= 5e-3
+
+
+def test_render_host_chunk_and_shard_invariance(renderer_fp32):
+    """rays are independent: chunked passes, host-buffer entry and 2/3/8-way ray shards all give the same BITS."""
+    wc, wf = weights("w1")
+    renderer_fp32.set_weights(wc, wf)
+    ro, rd = small_rays()
+    sel = np.arange(0, ro.shape[0], 331)[:500]
+    o, d = torch.from_numpy(ro[sel]), torch.from_numpy(rd[sel])
+    full = renderer_fp32.render(o, d, 0., 1., extras=True)
+    chunked = renderer_fp32.render(o, d, 0., 1., chunk=128, extras=True)
+    host = renderer_fp32.render_host(o.pin_memory(), d.pin_memory(), 0., 1., extras=True, want_weights=True)
+    for k in full:
+        assert torch.equal(full[k], chunked[k]), k
+        assert torch.equal(full[k].cpu(), host[k]), k
+    for world in (2, 3, 8):
+        parts = []
+        for r in range(world):
+            b, e = T.shard_range(500, r, world)
+            parts.append(renderer_fp32.render(o[b:e], d[b:e], 0., 1.))
+        for k in ("rgb", "depth", "acc", "weights"):
+            assert torch.equal(torch.cat([p[k] for p in parts], 0), full[k]), (world, k)
+
+
+def test_render_frame_properties_full_size(renderer_bf16):
+    """1008x756 (BASELINE config 2) through render_frame (ray-gen fused): properties the domain offers."""
+    H, W, f = FERN_FULL
+    wc, wf = weights("w1")
+    renderer_bf16.set_weights(wc, wf)
+    K = np.array([[f, 0, 0.5 * W], [0, f, 0.5 * H], [0, 0, 1]])
+    n = 1008 * 96                                          # 96 image rows (the whole frame is timed in bench.py)
+    out = renderer_bf16.render_frame(H, W, K, np.eye(4)[:3, :4], pix_begin=1008 * 300, n=n, extras=True, want_weights=True)
+    ts = out["ts_fine"]
+    assert (ts[:, 1:] >= ts[:, :-1]).all() and (ts[:, 0] == 0).all() and (ts[:, -1] == 1).all()
+    assert torch.isfinite(out["rgb"]).all() and (out["rgb"] >= 0).all() and (out["rgb"] <= 1 + 1e-5).all()
+    assert (out["weights"] >= 0).all() and (out["acc"] <= 1 + 1e-4).all()
+    assert torch.allclose(out["weights"].sum(-1), out["acc"], atol=1e-5)
+    assert (out["depth"] >= -1e-6).all() and (out["depth"] <= 1 + 1e-4).all()
+    # same pixels through explicit rays: identical bits
+    ro, rd = renderer_bf16.raygen(H, W, K, np.eye(4)[:3, :4], pix_begin=1008 * 300, n=n)
+    out2 = renderer_bf16.render(ro, rd, 0., 1.)
+    assert torch.equal(out2["rgb"], out["rgb"]) and torch.equal(out2["depth"], out["depth"])
+
+
+def test_empty_and_tiny_inputs(renderer_fp32):
+    wc, wf = weights("w1")
+    renderer_fp32.set_weights(wc, wf)
+    out = renderer_fp32.render(torch.zeros(0, 3), torch.zeros(0, 3), 0., 1.)
+    assert out["rgb"].shape == (0, 3)
+    ro, rd = small_rays()
+    one = renderer_fp32.render(ro[:1], rd[:1], 0., 1.)
+    three = renderer_fp32.render(ro[:3], rd[:3], 0., 1.)
+    assert torch.equal(one["rgb"][0], three["rgb"][0])
+    coarse_only = renderer_fp32.render(ro[:3], rd[:3], 0., 1., n_fine=0, extras=True)
+    assert torch.equal(coarse_only["rgb"], coarse_only["rgb_coarse"])
+
+
+def test_unset_weights_fail_loudly():
+    r = T.NerfRenderer(device="cuda:0", mode="fp32")
+    with pytest.raises(T.TgtcError, match="weights"):
+        r.render(torch.zeros(4, 3), torch.ones(4, 3), 0., 1.)
+    r.close()
+
+
+def test_reference_signature_shims(renderer_fp32):
+    """the four injected callables driven exactly as rendering.py:27-51 drives them."""
+    g = golden("chain_w1")
+    wc, wf = weights("w1")
+    renderer_fp32.set_weights(wc, wf)
+    fns = T.make_callables(renderer_fp32)
+    dev = renderer_fp32.device
+    rays_o, rays_d = torch.from_numpy(g["rays_o"]).to(dev), torch.from_numpy(g["rays_d"]).to(dev)
+    n = rays_o.shape[0]
+    pts, ts = fns["sampling_pts_uniform"](rays_o=rays_o, rays_d=rays_d, N_samples=64, near=0., far=1.)
+    ret = fns["model_forward"](pts=pts, dirs=rays_d.unsqueeze(1).expand([n, 64, 3]))
+    assert set(ret) == {"rgb", "base_remap", "pts", "sigma", "dirs"}
+    rgb_exp, t_exp, weights_c = fns["alpha_composition"](ret["rgb"], ret["sigma"], ts, 0)
+    pts_fine, ts_fine = fns["sampling_pts_fine_torch"](rays_o, rays_d, ts, weights_c, 64)
+    ret_f = fns["model_forward_fine"](pts=pts_fine, dirs=rays_d.unsqueeze(1).expand([n, 128, 3]))
+    rgb_f, t_f, _ = fns["alpha_composition"](ret_f["rgb"], ret_f["sigma"], ts_fine, 0)
+    assert np.abs(rgb_f.cpu().numpy() - g["rgb"]).max() <= 1e-3
+    assert np.abs(t_f.cpu().numpy() - g["depth"]).max() <= 1e-3
+    assert ret_f["base_remap"].shape == (n, 128, 256) and ret_f["pts"].shape == (n, 128, 63) and ret_f["dirs"].shape == (n, 128, 27)
+    # sigma_noise_std > 0 draws from torch's generator like utils.py:372-374 and still composites
+    torch.manual_seed(0)
+    noisy = fns["alpha_composition"](ret["rgb"], ret["sigma"], ts, 1.0)
+    assert torch.isfinite(noisy[0]).all()
