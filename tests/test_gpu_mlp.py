@@ -77,8 +77,8 @@ def test_tc_accumulators_layer_by_layer(renderer_bf16, layers):
     err = (acc[:, :N] - ref).abs().max().item()
     scale = ref.abs().max().item()
     # fp32 accumulation-order noise + rare bf16 rounding flips of upstream activations
-    assert err <= 2e-2 * max(scale, 1.0), (layers, err, scale)
-    assert (acc[:, :N] - ref).abs().mean().item() <= 2e-3 * max(scale, 1.0)
+    assert err <= 3e-2 * scale, (layers, err, scale)
+    assert (acc[:, :N] - ref).abs().mean().item() <= 2e-3 * scale
 
 
 @pytest.mark.parametrize("n,S", [(300, 64), (301, 64), (77, 128), (1, 64), (3, 256)])
