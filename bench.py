@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement of the B200 NeRF ray-render path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torch.distributed.run)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" renders one fern-shaped 1008x756 frame (BASELINE config 2: 762 048 rays, 64 coarse + 128 fine
+network samples per ray, NDC rays, perturb=0, random-init weights W0) per GPU.  With N GPUs every rank
+renders its own frame of the synthetic spiral per step (weak scaling, rays never cross ranks) and the
+rendered tiles {rgb, depth, acc} are all-gathered over NCCL -- the path's only exchange (config 3).
+
+Printed JSON (rank 0): value = whole-job rays/s with the rays resident in HBM; e2e = the same metric through
+the public host-buffer API (pinned rays H2D, rgb/depth/acc D2H inside the timed region); roofline = the
+fused tcgen05 MLP kernel's achieved algorithmic TFLOP/s (CUDA events around every launch, on its stream)
+against the measured bf16 peak; cpu_baseline = the oracle's CPU chain on this box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, FOCAL = 756, 1008, 815.13
+N_SAMPLES, N_FINE = 64, 64
+FLOP_PER_SAMPLE = 1186816.0          # 2 x 593 408 MAC, un-padded
+SAMPLES_PER_RAY = N_SAMPLES + (N_SAMPLES + N_FINE)
+WORKLOAD = "fern-shaped 1008x756 single-view render, 64 coarse + 128 fine samples/ray, NDC rays, perturb=0, random-init (seed 0) NeRF MLPs"
+
+
+def spiral_poses(n=120):
+    """load_llff.render_path_spiral (load_llff.py:145-154) for the synthetic camera of SURVEY 8d: c2w = I,
+    up=[0,1,0], rads=[0.3,0.3,0.05], focal=3.9, zrate=.5, rots=2 (restated: viewmatrix/normalize are 10 lines)."""
+    import numpy as np
+
+    def normalize(x):
+        return x / np.linalg.norm(x)
+
+    def viewmatrix(z, up, pos):
+        vec2 = normalize(z)
+        vec0 = normalize(np.cross(up, vec2))
+        vec1 = normalize(np.cross(vec2, vec0))
+        return np.stack([vec0, vec1, vec2, pos], 1)
+
+    c2w = np.eye(4)[:3, :4]
+    up = np.array([0., 1., 0.])
+    rads = np.array([0.3, 0.3, 0.05, 1.])
+    poses = []
+    for theta in np.linspace(0., 2. * np.pi * 2, n + 1)[:-1]:
+        c = np.dot(c2w, np.array([np.cos(theta), -np.sin(theta), -np.sin(theta * .5), 1.]) * rads)
+        z = normalize(c - np.dot(c2w, np.array([0, 0, -3.9, 1.])))
+        poses.append(viewmatrix(z, up, c))
+    return np.stack(poses, 0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        for t, line in self.lines:
+            if t < t0 or t > t1 + 0.15:
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+
+def cpu_chain_rays_per_s(n_rays, chunk=1024, min_seconds=8.0, max_chunks=16):
+    """The oracle's CPU chain (oracle/render_oracle.py = the reference's arithmetic, rendering.py:27-51) on a
+    bounded sample of the SAME workload: chunks of `chunk` rays spread over the frame, all host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import torch
+    import render_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wc, wf = O.init_linear_like_reference(0)
+    ro, rd = O.make_rays(H, W, FOCAL, np.eye(4)[:3, :4])
+    sel = np.linspace(0, H * W - 1, chunk * (max_chunks + 1)).astype(np.int64)
+    O.render_chain(wc, wf, ro[sel[:chunk]], rd[sel[:chunk]], 0., 1., N_SAMPLES, N_FINE, chunk)   # warm-up chunk
+    done, t0 = 0, time.perf_counter()
+    while done < max_chunks and (done < 3 or time.perf_counter() - t0 < min_seconds) and done * chunk < n_rays:
+        s = sel[(done + 1) * chunk:(done + 2) * chunk]
+        O.render_chain(wc, wf, ro[s], rd[s], 0., 1., N_SAMPLES, N_FINE, chunk)
+        done += 1
+    dt = time.perf_counter() - t0
+    return done * chunk / dt, cores, "%d chunks of %d rays of the 1008x756 frame, chunk=%d, %.1f s" % (done, chunk, chunk, dt)
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path (its arithmetic restated in
+    oracle/render_oracle.py, pinned bit-for-bit to /root/reference in the build container; the reference tree
+    itself cannot travel to the GPU box), timed on the host cores.  Each step = a bounded sample of the frame."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import torch
+    import render_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wc, wf = O.init_linear_like_reference(0)
+    ro, rd = O.make_rays(H, W, FOCAL, np.eye(4)[:3, :4])
+    per_step = 2048
+    sel = np.linspace(0, H * W - 1, per_step * (args.steps + args.warmup)).astype(np.int64)
+    t_steps = []
+    for i in range(args.warmup + args.steps):
+        s = sel[i * per_step:(i + 1) * per_step]
+        t0 = time.perf_counter()
+        O.render_chain(wc, wf, ro[s], rd[s], 0., 1., N_SAMPLES, N_FINE, 1024)
+        if i >= args.warmup:
+            t_steps.append(time.perf_counter() - t0)
+    total = sum(t_steps)
+    value = per_step * args.steps / total
+    sample = "%d rays per step spread over the 1008x756 frame, chunk 1024, torch CPU fp32, %d threads" % (per_step, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "rays/s", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "mlp_samples_per_s": value * SAMPLES_PER_RAY,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    import tgtc_style_b200 as T
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run --nproc-per-node %d" % (args.gpus, world, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import render_oracle as O   # only for the synthetic weight set W0 (input synthesis) and the cpu_baseline leg
+    wc, wf = O.init_linear_like_reference(0)
+    r = T.NerfRenderer(device=dev, mode=args.mode)
+    r.set_weights(wc, wf)
+    K = np.array([[FOCAL, 0, 0.5 * W], [0, FOCAL, 0.5 * H], [0, 0, 1]])
+    poses = spiral_poses(120)
+    n = H * W
+    total_steps = args.warmup + args.steps
+
+    # rays of this rank's frames: generated on device (K1) -> resident in HBM before the timed region
+    def pose_of(step):
+        return np.eye(4)[:3, :4] if world == 1 else poses[(step * world + rank) % 120]
+    rays = [r.raygen(H, W, K, pose_of(s)) for s in range(min(total_steps, 4))]
+    out = r._alloc_out(n, N_SAMPLES, N_FINE, False, dev)
+    out.pop("weights")
+
+    def gather(o):
+        if world > 1:
+            T.gather_tiles({"rgb": o["rgb"], "depth": o["depth"], "acc": o["acc"]}, n * world)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_dev(s):
+        ro, rd = rays[s % len(rays)]
+        r.render(ro, rd, 0., 1., n_samples=N_SAMPLES, n_fine=N_FINE, out=out)
+        gather(out)
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+
+    # ---------------- arm 1: inputs resident in HBM
+    for s in range(args.warmup):
+        step_dev(s)
+    sync_all()
+    r.profile_enable(True)
+    l0 = r.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for s in range(args.steps):
+        step_dev(args.warmup + s)
+    e1.record()
+    sync_all()
+    t_wall1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = ms.item()
+    launches = r.launch_count() - l0
+    mlp_launches, mlp_ms, mlp_flops = r.profile_read()
+    r.profile_enable(False)
+
+    # ---------------- arm 2: end to end through the host-buffer API (pinned rays in, rgb/depth/acc out)
+    h_rays = [(a.cpu().pin_memory(), b.cpu().pin_memory()) for a, b in rays[:2]]
+    h_out = r._alloc_out(n, N_SAMPLES, N_FINE, False, "cpu", pin=True)
+    h_out.pop("weights")
+
+    def step_host(s):
+        ro, rd = h_rays[s % len(h_rays)]
+        r.render_host(ro, rd, 0., 1., n_samples=N_SAMPLES, n_fine=N_FINE, out=h_out)
+
+    for s in range(args.warmup):
+        step_host(s)
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for s in range(args.steps):
+        step_host(s)
+    e3.record()
+    sync_all()
+    ms2 = torch.tensor([e2.elapsed_time(e3)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    checksum = float(h_out["rgb"].double().sum())
+
+    if rank == 0:
+        clocks.stop()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops_sustained")
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+        if peak is None:
+            peak, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained figure)"
+        rays_total = n * world * args.steps
+        value = rays_total / (ms_total * 1e-3)
+        achieved = (mlp_flops / (mlp_ms * 1e-3)) / 1e12 if mlp_ms > 0 else None
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "mlp_tc_traffic.json"))).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        res = {
+            "metric": "rays/s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.mode if args.mode != "fp32" else "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n, "samples_per_ray": SAMPLES_PER_RAY,
+                       "parallelism": "ray-sharded, one frame per GPU per step, NCCL all-gather of rgb/depth/acc tiles" if world > 1 else "1 GPU",
+                       "l2_policy": "per-step working set 2.4 GB (rgb-sigma workspace) >> 126 MB L2; no flush needed"},
+            "mlp_samples_per_s": value * SAMPLES_PER_RAY,
+            "e2e": {"value": rays_total / (ms2.item() * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 20 * n,
+                    "ms_per_step": ms2.item() / args.steps, "api": "NerfRenderer.render_host -> tgtc_render_host", "checksum": checksum},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+                         "traffic": traffic, "kernel": "mlp_tc_kernel" if args.mode == "bf16" else "mlp_fp32_kernel",
+                         "launches_timed": int(mlp_launches), "avg_launch_ms": mlp_ms / max(mlp_launches, 1),
+                         "flop_per_launch_avg": mlp_flops / max(mlp_launches, 1), "peak_source": peak_src,
+                         "frac_of_burst_peak": (achieved / peaks["bf16_tflops"]) if (achieved and peaks.get("bf16_tflops")) else None,
+                         "mlp_share_of_step": mlp_ms / ms_total if ms_total > 0 else None},
+            "clocks": clocks.window(t_wall0, t_wall1),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample = cpu_chain_rays_per_s(16 * 1024)
+            res["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(res))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -166,6 +166,13 @@ int tgtc_render_frame(tgtc_ctx* ctx, int mode, int H, int W, const double* K, co
                       int n_fine, int64_t chunk, int white_bkgd, const tgtc_render_out* out, void* workspace,
                       size_t workspace_bytes, tgtc_stream stream);
 
+/* Per-kernel device timing of the MLP launches (the dominant kernel), for the roofline line of bench.py:
+ * while enabled, every MLP launch is bracketed by cudaEvents on its stream (no host sync).
+ * tgtc_profile_read synchronises those events and returns, since the last read/enable: the number of MLP
+ * launches, their summed device time in ms, and their summed algorithmic FLOPs (1 186 816 per sample). */
+int tgtc_profile_enable(tgtc_ctx* ctx, int on);
+int tgtc_profile_read(tgtc_ctx* ctx, int64_t* launches, double* ms, double* flops);
+
 /* number of kernel launches issued by this context so far (bench.py's
  * gpu_launches claim is counted here, not estimated) */
 int64_t tgtc_launch_count(const tgtc_ctx* ctx);

@@ -94,8 +94,13 @@ def test_tc_forward_vs_emulation_and_oracle(renderer_bf16, n, S):
     ref = O.nerf_forward(wf, pts, d.unsqueeze(1).expand(n, S, 3))
     # per-sample accuracy of the bf16 path against the fp32 oracle (|drgb| ~1.5e-4, |dsigma|/|sigma| ~1%)
     assert (rs[..., :3] - ref["rgb"]).abs().max().item() <= 1e-2
-    rel = (rs[..., 3] - ref["sigma"]).abs() / ref["sigma"].abs().clamp_min(1.0)
-    assert rel.median().item() <= 2e-2 and rel.max().item() <= 0.5
+    # sigma: bf16 operands cost ~1% of the sigma scale; the kernel must be as close to the oracle as the
+    # bf16-operand emulation is (same arithmetic, different summation order)
+    scale = ref["sigma"].abs().max().item()
+    err_k = (rs[..., 3] - ref["sigma"]).abs()
+    err_e = (sig_e - ref["sigma"]).abs()
+    assert err_k.median().item() <= 1e-2 * scale and err_k.max().item() <= 5e-2 * scale
+    assert err_k.max().item() <= 1.25 * err_e.max().item() + 1e-3 * scale
     # explicit-points entry (the model_forward shim) gives the same numbers as the fused ray entry
     got = renderer_bf16.nerf_forward(T.NET_FINE, pts, d.unsqueeze(1).expand(n, S, 3), want_features=False, mode="bf16")
     assert torch.allclose(got["rgb"].cpu(), rs[..., :3], atol=1e-6) and torch.allclose(got["sigma"].cpu(), rs[..., 3], atol=1e-4)

@@ -64,6 +64,7 @@ extern "C" int tgtc_destroy(tgtc_ctx* ctx) {
     if (ctx->net[i].tc_blob) cudaFree(ctx->net[i].tc_blob);
   }
   if (ctx->arena) cudaFree(ctx->arena);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   delete ctx;
   return TGTC_OK;
 }
@@ -104,12 +105,56 @@ extern "C" int tgtc_sample_uniform(tgtc_ctx* ctx, const float* rays_o, const flo
 }
 
 static int run_mlp(tgtc_ctx* ctx, int net, int mode, const MlpIO& io, cudaStream_t st) {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->profile) {
+    if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
+      for (int i = 0; i < 2; ++i) {
+        cudaEvent_t e;
+        TGTC_CUDA(cudaEventCreate(&e));
+        ctx->ev_pool.push_back(e);
+      }
+    }
+    e0 = ctx->ev_pool[ctx->ev_used++];
+    e1 = ctx->ev_pool[ctx->ev_used++];
+    ctx->prof_flops += (double)io.n_rays * io.S * 1186816.0;
+    TGTC_CUDA(cudaEventRecord(e0, st));
+  }
+  int rc;
   if (mode == TGTC_MLP_BF16) {
     TGTC_REQUIRE(mlp_tc_supports(io), TGTC_ERR_UNSUPPORTED,
-                 "bf16 MLP needs per-ray view dirs, S in {32,64,128} or a multiple of 128, and no feature outputs (S=%d)", io.S);
-    return launch_mlp_tc(ctx, net, io, st);
+                 "bf16 MLP needs per-ray view dirs, S in {64,128} or a multiple of 128, and no feature outputs (S=%d)", io.S);
+    rc = launch_mlp_tc(ctx, net, io, st);
+  } else {
+    rc = launch_mlp_fp32(ctx, net, io, st);
   }
-  return launch_mlp_fp32(ctx, net, io, st);
+  if (rc) return rc;
+  if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
+  return TGTC_OK;
+}
+
+extern "C" int tgtc_profile_enable(tgtc_ctx* ctx, int on) {
+  CHECK_CTX(ctx);
+  ctx->profile = on != 0;
+  ctx->ev_used = 0;
+  ctx->prof_flops = 0.0;
+  return TGTC_OK;
+}
+
+extern "C" int tgtc_profile_read(tgtc_ctx* ctx, int64_t* launches, double* ms, double* flops) {
+  CHECK_CTX(ctx);
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+    TGTC_CUDA(cudaEventSynchronize(ctx->ev_pool[i + 1]));
+    float t = 0.f;
+    TGTC_CUDA(cudaEventElapsedTime(&t, ctx->ev_pool[i], ctx->ev_pool[i + 1]));
+    total += t;
+  }
+  if (launches) *launches = (int64_t)(ctx->ev_used / 2);
+  if (ms) *ms = total;
+  if (flops) *flops = ctx->prof_flops;
+  ctx->ev_used = 0;
+  ctx->prof_flops = 0.0;
+  return TGTC_OK;
 }
 
 extern "C" int tgtc_nerf_forward(tgtc_ctx* ctx, int net, int mode, const float* pts, const float* dirs, int dirs_per_ray,
@@ -254,7 +299,15 @@ static int render_impl(tgtc_ctx* ctx, int mode, const float* rays_o, const float
                           out.depth_coarse ? out.depth_coarse + r0 : (last && out.depth ? out.depth + r0 : nullptr),
                           out.acc_coarse ? out.acc_coarse + r0 : (last && out.acc ? out.acc + r0 : nullptr), w_c, st);
     if (rc) return rc;
-    if (last) continue;
+    if (last) {
+      // coarse-only render: the coarse result IS the result; mirror it into the fine slots when both were asked for
+      if (out.rgb && out.rgb_coarse) TGTC_CUDA(cudaMemcpyAsync(out.rgb + r0 * 3, out.rgb_coarse + r0 * 3, (size_t)m * 12, cudaMemcpyDeviceToDevice, st));
+      if (out.depth && out.depth_coarse) TGTC_CUDA(cudaMemcpyAsync(out.depth + r0, out.depth_coarse + r0, (size_t)m * 4, cudaMemcpyDeviceToDevice, st));
+      if (out.acc && out.acc_coarse) TGTC_CUDA(cudaMemcpyAsync(out.acc + r0, out.acc_coarse + r0, (size_t)m * 4, cudaMemcpyDeviceToDevice, st));
+      if (out.weights) TGTC_CUDA(cudaMemcpyAsync(out.weights + r0 * S, w_c, (size_t)m * S * 4, cudaMemcpyDeviceToDevice, st));
+      if (out.ts_fine) { rc = launch_sample_uniform(ctx, nullptr, nullptr, m, S, near, far, nullptr, nullptr, out.ts_fine + r0 * S, st); if (rc) return rc; }
+      continue;
+    }
     // sampling_pts_fine_torch (rendering.py:43)
     rc = launch_sample_fine(ctx, nullptr, nullptr, ts_c, 0, w_c, m, S, F, nullptr, ts_f, nullptr, nullptr, st);
     if (rc) return rc;

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <vector>
 
 #include "../../include/tgtc_b200.h"
 
@@ -71,6 +72,11 @@ struct tgtc_ctx {
   // staging arena for the *_host entry points
   void* arena = nullptr;
   size_t arena_bytes = 0;
+  // optional per-launch timing of the MLP kernel (tgtc_profile_*)
+  bool profile = false;
+  std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
+  size_t ev_used = 0;                 // events handed out since the last read
+  double prof_flops = 0.0;
 };
 
 // ---------------------------------------------------------------------------

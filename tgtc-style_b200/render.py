@@ -84,6 +84,16 @@ class NerfRenderer:
     def launch_count(self):
         return int(self.lib.tgtc_launch_count(self._h))
 
+    def profile_enable(self, on=True):
+        """bracket every MLP launch with CUDA events on its stream (see tgtc_profile_enable)."""
+        _lib.check(self.lib.tgtc_profile_enable(self._h, int(on)))
+
+    def profile_read(self):
+        """-> (mlp launches, summed device ms, summed algorithmic FLOPs) since the last read."""
+        n, ms, fl = _lib.c_i64(0), ctypes.c_double(0), ctypes.c_double(0)
+        _lib.check(self.lib.tgtc_profile_read(self._h, ctypes.byref(n), ctypes.byref(ms), ctypes.byref(fl)))
+        return n.value, ms.value, fl.value
+
     # ------------------------------------------------------------------ weights
     def set_weights(self, coarse=None, fine=None):
         """coarse / fine: a models.StyleNerf (or any nn.Module / state_dict) whose parameters are named
