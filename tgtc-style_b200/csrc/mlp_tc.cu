@@ -97,6 +97,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// same, for roles that are far off the critical path: sleep between probes so the spin does not steal issue slots
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (clock64() - t0 > 4000000000LL) {
+      printf("tgtc mlp_tc: mbarrier timeout (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
@@ -134,6 +146,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+// wait::ld that also "defines" the 32 destination registers, so no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                 "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                 "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                 "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+// packed fp32x2 add (sm_100 FADD2): {x0,x1} += {b0,b1}
+__device__ __forceinline__ void add2(uint32_t& x0, uint32_t& x1, float b0, float b1) {
+  asm("{\n.reg .b64 a, b, d;\nmov.b64 a, {%0, %1};\nmov.b64 b, {%2, %3};\nadd.rn.f32x2 d, a, b;\nmov.b64 {%0, %1}, d;\n}\n"
+      : "+r"(x0), "+r"(x1)
+      : "f"(b0), "f"(b1));
+}
+// relu + round-to-nearest bf16 + pack in one instruction (F2FP.RELU)
+__device__ __forceinline__ uint32_t pack_bf16_relu(uint32_t lo, uint32_t hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return r;
+}
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): K-major, swizzled.
 //   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major; 1 as CUTLASS) | [32,46) SBO>>4 |
@@ -160,6 +194,65 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 }
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
 
+// one 32-column block of a hidden-layer epilogue: +bias, ReLU, bf16, 4 x 16-byte swizzled stores.
+// blk = 32-column block index inside this thread's 128 columns; kb = row base of the 64-column K block.
+template <bool kSigma>
+__device__ __forceinline__ void epi_block(uint32_t (&v)[32], const float* bl, const float* wsig, uint32_t kb, uint32_t rx, int blk,
+                                          float& sig) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = blk * 32 + 8 * j;  // column inside the 128-column half
+    const float4 b0 = *reinterpret_cast<const float4*>(bl + c);
+    const float4 b1 = *reinterpret_cast<const float4*>(bl + c + 4);
+    const uint32_t dst = kb + ((uint32_t)((((blk & 1) * 4) + j) << 4) ^ rx);
+    if constexpr (kSigma) {
+      float h[8];
+      h[0] = fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x, 0.f);
+      h[1] = fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y, 0.f);
+      h[2] = fmaxf(__uint_as_float(v[8 * j + 2]) + b0.z, 0.f);
+      h[3] = fmaxf(__uint_as_float(v[8 * j + 3]) + b0.w, 0.f);
+      h[4] = fmaxf(__uint_as_float(v[8 * j + 4]) + b1.x, 0.f);
+      h[5] = fmaxf(__uint_as_float(v[8 * j + 5]) + b1.y, 0.f);
+      h[6] = fmaxf(__uint_as_float(v[8 * j + 6]) + b1.z, 0.f);
+      h[7] = fmaxf(__uint_as_float(v[8 * j + 7]) + b1.w, 0.f);
+      // fp32 sigma head on the un-rounded activations (models.py:103)
+      const float4 w0 = *reinterpret_cast<const float4*>(wsig + c);
+      const float4 w1 = *reinterpret_cast<const float4*>(wsig + c + 4);
+      sig = fmaf(h[0], w0.x, sig); sig = fmaf(h[1], w0.y, sig); sig = fmaf(h[2], w0.z, sig); sig = fmaf(h[3], w0.w, sig);
+      sig = fmaf(h[4], w1.x, sig); sig = fmaf(h[5], w1.y, sig); sig = fmaf(h[6], w1.z, sig); sig = fmaf(h[7], w1.w, sig);
+      st_shared_v4(dst, pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+    } else {
+      add2(v[8 * j + 0], v[8 * j + 1], b0.x, b0.y);
+      add2(v[8 * j + 2], v[8 * j + 3], b0.z, b0.w);
+      add2(v[8 * j + 4], v[8 * j + 5], b1.x, b1.y);
+      add2(v[8 * j + 6], v[8 * j + 7], b1.z, b1.w);
+      st_shared_v4(dst, pack_bf16_relu(v[8 * j + 0], v[8 * j + 1]), pack_bf16_relu(v[8 * j + 2], v[8 * j + 3]),
+                   pack_bf16_relu(v[8 * j + 4], v[8 * j + 5]), pack_bf16_relu(v[8 * j + 6], v[8 * j + 7]));
+    }
+  }
+}
+
+// this thread's 128 columns of one hidden layer: TMEM loads software-pipelined against the math
+// (the load of block b+1 is in flight while block b is converted and stored)
+template <bool kSigma>
+__device__ __forceinline__ float hidden_epilogue(uint32_t tcol, const float* bl, const float* wsig, uint32_t arow, uint32_t rx) {
+  float sig = 0.f;
+  uint32_t va[32], vb[32];
+  tmem_ld32(tcol, va);
+  tmem_ld_wait_dep(va);
+  tmem_ld32(tcol + 32, vb);
+  epi_block<kSigma>(va, bl, wsig, arow, rx, 0, sig);
+  tmem_ld_wait_dep(vb);
+  tmem_ld32(tcol + 64, va);
+  epi_block<kSigma>(vb, bl, wsig, arow, rx, 1, sig);
+  tmem_ld_wait_dep(va);
+  tmem_ld32(tcol + 96, vb);
+  epi_block<kSigma>(va, bl, wsig, arow + 16384, rx, 2, sig);
+  tmem_ld_wait_dep(vb);
+  epi_block<kSigma>(vb, bl, wsig, arow + 16384, rx, 3, sig);
+  return sig;
+}
+
 struct TcParams {
   const uint8_t* blob;
   const float* smalls;
@@ -167,9 +260,16 @@ struct TcParams {
   int64_t M;        // samples
   int64_t ntiles;
   int rays_per_tile;  // 128/S when S<128 else 1
+  int dbg_flags;      // timing experiments: 1 = skip MMA issue, 2 = skip epilogue math, 4 = skip weight copies, 8 = skip PE math
   int dbg_layers;     // >0: stop after this many GEMM layers and dump the fp32 accumulator (tests)
   float* dbg_out;     // [ntiles*128, 256]
+  long long* dbg_trace;  // timing experiments: clock64 stamps of CTA 0's roles, [4 roles][4 iters][10 layers][2 slots][2]
 };
+#define TC_TRACE(role, it, l, t, k)                                                                              \
+  do {                                                                                                           \
+    if (P.dbg_trace != nullptr && blockIdx.x == 0 && (it) < 4)                                                   \
+      P.dbg_trace[(((((role)*4 + (int)(it)) * 10 + (l)) * 2 + (t)) * 2) + (k)] = clock64();                      \
+  } while (0)
 
 // which tile does (cta, j) own, and is it valid
 __device__ __forceinline__ int64_t my_tile(int64_t j) { return (int64_t)blockIdx.x + j * gridDim.x; }
@@ -220,7 +320,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
   if (warp == 0) {
     // =====================================================================
     // weight producer
-    if (lane == 0) {
+    if (lane == 0 && !(P.dbg_flags & 16)) {
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t it = 0; it < iters; ++it) {
@@ -231,9 +331,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
           const int nch = tc_layer_chunks(l);
           for (int t = 0; t < nslots; ++t) {
             for (int c = 0; c < nch; ++c) {
-              mbar_wait(bar(kBarWEmpty + stage), phase ^ 1);
-              mbar_arrive_expect_tx(bar(kBarWFull + stage), cbytes);
-              bulk_g2s(sbase + kOffW + stage * kStageBytes, src + (size_t)c * cbytes, cbytes, bar(kBarWFull + stage));
+              mbar_wait_relaxed(bar(kBarWEmpty + stage), phase ^ 1, 64);
+              if (P.dbg_flags & 4) {
+                mbar_arrive(bar(kBarWFull + stage));
+              } else {
+                mbar_arrive_expect_tx(bar(kBarWFull + stage), cbytes);
+                bulk_g2s(sbase + kOffW + stage * kStageBytes, src + (size_t)c * cbytes, cbytes, bar(kBarWFull + stage));
+              }
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
           }
@@ -262,12 +366,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
               mbar_wait(bar(kBarActReady + t), act_par[t]); act_par[t] ^= 1;
             }
             tc_fence_after();
+            TC_TRACE(0, it, l, t, 0);
             const uint32_t d_tmem = tmem_base + (uint32_t)(256 * t);
             const uint32_t act = sbase + kOffAct + t * kActBytes;
             const uint32_t pe = sbase + kOffPe + t * kPeBytes;
             for (int c = 0; c < nch; ++c) {
-              mbar_wait(bar(kBarWFull + stage), phase);
-              tc_fence_after();
+              if (!(P.dbg_flags & 16)) { mbar_wait(bar(kBarWFull + stage), phase); tc_fence_after(); }
               const uint32_t wst = sbase + kOffW + stage * kStageBytes;
 #pragma unroll
               for (int s = 0; s < 2; ++s) {
@@ -280,13 +384,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
                 } else {
                   a_addr = act + (ks >> 2) * 16384 + (ks & 3) * 32;
                 }
-                umma_bf16(d_tmem, make_desc(a_addr, kDescHiSW128), make_desc(wst + s * 32, kDescHiSW64), idesc, ks > 0 ? 1u : 0u);
+                if (!(P.dbg_flags & 1)) umma_bf16(d_tmem, make_desc(a_addr, kDescHiSW128), make_desc(wst + s * 32, kDescHiSW64), idesc, ks > 0 ? 1u : 0u);
               }
-              umma_commit(bar(kBarWEmpty + stage));  // frees the weight stage when these MMAs retire
+              if (!(P.dbg_flags & 16)) umma_commit(bar(kBarWEmpty + stage));  // frees the weight stage when these MMAs retire
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
             if (l == 5 || (l == nlayers - 1 && nlayers <= 5)) umma_commit(bar(kBarPeFree + t));
             umma_commit(bar(kBarAccFull + t));
+            TC_TRACE(0, it, l, t, 1);
           }
         }
       }
@@ -301,7 +406,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
       const int nslots = (2 * it + 1 < n_my) ? 2 : 1;
       for (int t = 0; t < nslots; ++t) {
         const int64_t tile = my_tile(2 * it + t);
-        if (it > 0) mbar_wait(bar(kBarPeFree + t), (uint32_t)((it - 1) & 1));
+        if (it > 0) mbar_wait_relaxed(bar(kBarPeFree + t), (uint32_t)((it - 1) & 1), 512);
+        if (r == 0) TC_TRACE(3, it, 0, t, 0);
         // ---- sample position of this row
         int64_t m = tile * kTileM + r;
         if (m >= P.M) m = P.M - 1;  // padding rows of the last tile: recompute a valid sample, never stored
@@ -324,7 +430,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
         for (int f = 0; f < 10; ++f) {
           const float fr = (float)(1 << f);
 #pragma unroll
-          for (int a = 0; a < 3; ++a) sincosf(__fmul_rn(x[a], fr), &e[3 + 6 * f + a], &e[3 + 6 * f + 3 + a]);
+          for (int a = 0; a < 3; ++a) {
+            if (P.dbg_flags & 8) { e[3 + 6 * f + a] = x[a]; e[3 + 6 * f + 3 + a] = fr; }
+            else sincosf(__fmul_rn(x[a], fr), &e[3 + 6 * f + a], &e[3 + 6 * f + 3 + a]);
+          }
         }
         e[63] = 0.f;
 #pragma unroll
@@ -360,6 +469,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
         mbar_arrive(bar(kBarPeReady + t));
+        if (r == 0) TC_TRACE(3, it, 0, t, 1);
       }
     }
   } else {
@@ -386,6 +496,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
           if (l == 0) mbar_wait(bar(kBarPeReady + t), (uint32_t)(it & 1));  // acquire the producers' dir-bias writes
           mbar_wait(bar(kBarAccFull + t), acc_par[t]); acc_par[t] ^= 1;
           tc_fence_after();
+          if (lane == 0 && q == 2) TC_TRACE(1 + hc, it, l, t, 0);
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 * t);
           const int64_t tile = my_tile(2 * it + t);
           const int64_t m = tile * kTileM + row;
@@ -408,47 +519,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
 
           if (l < 9) {
             // hidden layer: bias + ReLU -> bf16 A operand of the next layer (in place)
-            const float* bl = bias_s + l * 256;
-            const uint32_t arow = sbase + kOffAct + t * kActBytes + (row >> 3) * 1024 + (row & 7) * 128;
-            float sig = 0.f;
-#pragma unroll 1
-            for (int b = 0; b < 4; ++b) {
-              uint32_t v[32];
-              const int c0 = hc * 128 + b * 32;
-              tmem_ld32(taddr + c0, v);
-              tmem_ld_wait();
-              const uint32_t kb = arow + (c0 >> 6) * 16384;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int c = c0 + 8 * j;
-                const float4 b0 = *reinterpret_cast<const float4*>(bl + c);
-                const float4 b1 = *reinterpret_cast<const float4*>(bl + c + 4);
-                float h[8];
-                h[0] = fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x, 0.f);
-                h[1] = fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y, 0.f);
-                h[2] = fmaxf(__uint_as_float(v[8 * j + 2]) + b0.z, 0.f);
-                h[3] = fmaxf(__uint_as_float(v[8 * j + 3]) + b0.w, 0.f);
-                h[4] = fmaxf(__uint_as_float(v[8 * j + 4]) + b1.x, 0.f);
-                h[5] = fmaxf(__uint_as_float(v[8 * j + 5]) + b1.y, 0.f);
-                h[6] = fmaxf(__uint_as_float(v[8 * j + 6]) + b1.z, 0.f);
-                h[7] = fmaxf(__uint_as_float(v[8 * j + 7]) + b1.w, 0.f);
-                if (l == 7) {  // fp32 sigma head on the un-rounded activations (models.py:103)
-                  const float4 w0 = *reinterpret_cast<const float4*>(wsig_s + c);
-                  const float4 w1 = *reinterpret_cast<const float4*>(wsig_s + c + 4);
-                  sig = fmaf(h[0], w0.x, sig); sig = fmaf(h[1], w0.y, sig); sig = fmaf(h[2], w0.z, sig); sig = fmaf(h[3], w0.w, sig);
-                  sig = fmaf(h[4], w1.x, sig); sig = fmaf(h[5], w1.y, sig); sig = fmaf(h[6], w1.z, sig); sig = fmaf(h[7], w1.w, sig);
-                }
-                const int c16 = (c & 63) >> 3;
-                st_shared_v4(kb + ((c16 ^ (row & 7)) << 4), pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]),
-                             pack_bf16(h[6], h[7]));
-              }
-            }
-            if (l == 7) {
+            const float* bl = bias_s + l * 256 + hc * 128;
+            const uint32_t arow = sbase + kOffAct + t * kActBytes + (row >> 3) * 1024 + (row & 7) * 128 + hc * 2 * 16384;
+            const uint32_t tcol = taddr + hc * 128;
+            const uint32_t rx = (uint32_t)(row & 7) << 4;
+            if (P.dbg_flags & 2) {
+            } else if (l == 7) {
+              const float sig = hidden_epilogue<true>(tcol, bl, wsig_s + hc * 128, arow, rx);
               if (hc == 1) sigpart_s[t * 128 + row] = sig; else sig_keep[t] = sig;
+            } else {
+              hidden_epilogue<false>(tcol, bl, nullptr, arow, rx);
             }
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(bar(kBarActReady + t));
+            if (lane == 0 && q == 2) TC_TRACE(1 + hc, it, l, t, 1);
           } else {
             // rgb0 (N=128): + per-ray dir term, ReLU, then the 3x128 rgb1 head + sigmoid in fp32 (models.py:108-111)
             const float* db = reinterpret_cast<const float*>(smem + kOffDirBias) + ((t * 2 + (int)(it & 1)) * kMaxRaysPerTile) * 128;
@@ -479,6 +564,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
             }
             tc_fence_before();
             mbar_arrive(bar(kBarActReady + t));  // accumulator drained: the next tile's layer 0 may start
+            if (lane == 0 && q == 2) TC_TRACE(1 + hc, it, l, t, 1);
             if (hc == 1) *reinterpret_cast<float4*>(rgbpart_s + row * 4) = make_float4(p0, p1, p2, 0.f);
             named_bar_sync(1, kNumEpiThreads);
             if (hc == 0) {
@@ -522,6 +608,11 @@ bool mlp_tc_supports(const MlpIO& io) {
   return true;
 }
 
+static int g_dbg_flags = 0;
+static long long* g_dbg_trace = nullptr;
+extern "C" void tgtc_debug_tc_flags(int f) { g_dbg_flags = f; }
+extern "C" void tgtc_debug_tc_trace(long long* dev_buf) { g_dbg_trace = dev_buf; }
+
 static int launch_tc_common(tgtc_ctx* ctx, int net, const MlpIO& io, int dbg_layers, float* dbg_out, cudaStream_t st) {
   const NetImage& im = ctx->net[net];
   TcParams P;
@@ -533,6 +624,8 @@ static int launch_tc_common(tgtc_ctx* ctx, int net, const MlpIO& io, int dbg_lay
   P.ntiles = (P.M + kTileM - 1) / kTileM;
   P.rays_per_tile = io.S < kTileM ? kTileM / io.S : 1;
   P.dbg_layers = dbg_layers;
+  P.dbg_flags = g_dbg_flags;
+  P.dbg_trace = g_dbg_trace;
   P.dbg_out = dbg_out;
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
