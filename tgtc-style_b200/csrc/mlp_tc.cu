@@ -130,6 +130,44 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// tcgen05.mma with the descriptors given as (lo, hi) halves: the hi halves are compile-time constants and the lo
+// halves advance by (byte offset >> 4), so one K step costs one integer add per operand
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// one lane of a converged warp (the same lane every time for a full mask)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xFFFFFFFF;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred));
+  return pred != 0;
+}
+// sin/cos for the bf16 operand path: two-constant Cody-Waite reduction to [-pi, pi] (exact to ~2e-7 for |a| < 4096),
+// then the SFU approximations (abs error 2^-21.4 on that interval) -- three orders below a bf16 ulp
+__device__ __forceinline__ void fast_sincos(float a, float* s, float* c) {
+  const float n = rintf(a * 0.15915494309189535f);
+  float r = fmaf(n, -6.2831854820251465f, a);
+  r = fmaf(n, 1.7484555e-7f, r);
+  *s = __sinf(r);
+  *c = __cosf(r);
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
 }
@@ -260,7 +298,7 @@ struct TcParams {
   int64_t M;        // samples
   int64_t ntiles;
   int rays_per_tile;  // 128/S when S<128 else 1
-  int dbg_flags;      // timing experiments: 1 = skip MMA issue, 2 = skip epilogue math, 4 = skip weight copies, 8 = skip PE math
+  int dbg_flags;      // reserved for timing experiments
   int dbg_layers;     // >0: stop after this many GEMM layers and dump the fp32 accumulator (tests)
   float* dbg_out;     // [ntiles*128, 256]
   long long* dbg_trace;  // timing experiments: clock64 stamps of CTA 0's roles, [4 roles][4 iters][10 layers][2 slots][2]
@@ -315,82 +353,89 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
+  // the CTA owns all 512 columns of its SM's tensor memory, so the allocation starts at lane 0 / column 0; using the
+  // literal keeps every TMEM address a compile-time/uniform value in the issue loops
+  if (*reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr) != 0u) {
+    if (threadIdx.x == 0) printf("tgtc mlp_tc: unexpected TMEM base\n");
+    __trap();
+  }
+  constexpr uint32_t tmem_base = 0u;
 
   if (warp == 0) {
     // =====================================================================
-    // weight producer
-    if (lane == 0 && !(P.dbg_flags & 16)) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int64_t it = 0; it < iters; ++it) {
-        const int nslots = (2 * it + 1 < n_my) ? 2 : 1;
-        for (int l = 0; l < nlayers; ++l) {
-          const uint8_t* src = P.blob + tc_layer_off_bytes(l);
-          const uint32_t cbytes = (uint32_t)tc_layer_n(l) * kTcChunkK * 2;
-          const int nch = tc_layer_chunks(l);
-          for (int t = 0; t < nslots; ++t) {
-            for (int c = 0; c < nch; ++c) {
-              mbar_wait_relaxed(bar(kBarWEmpty + stage), phase ^ 1, 64);
-              if (P.dbg_flags & 4) {
-                mbar_arrive(bar(kBarWFull + stage));
-              } else {
-                mbar_arrive_expect_tx(bar(kBarWFull + stage), cbytes);
-                bulk_g2s(sbase + kOffW + stage * kStageBytes, src + (size_t)c * cbytes, cbytes, bar(kBarWFull + stage));
-              }
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
+    // weight producer (whole warp converged, one elected lane issues the bulk copies)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t it = 0; it < iters; ++it) {
+      const int nslots = (2 * it + 1 < n_my) ? 2 : 1;
+      for (int l = 0; l < nlayers; ++l) {
+        const uint8_t* src = P.blob + tc_layer_off_bytes(l);
+        const uint32_t cbytes = (uint32_t)tc_layer_n(l) * kTcChunkK * 2;
+        const int nch = tc_layer_chunks(l);
+        for (int t = 0; t < nslots; ++t) {
+          for (int c = 0; c < nch; ++c) {
+            mbar_wait(bar(kBarWEmpty + stage), phase ^ 1);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(bar(kBarWFull + stage), cbytes);
+              bulk_g2s(sbase + kOffW + stage * kStageBytes, src + (size_t)c * cbytes, cbytes, bar(kBarWFull + stage));
             }
+            __syncwarp();
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // =====================================================================
-    // MMA issuer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t act_par[2] = {0, 0}, pe_par[2] = {0, 0};
-      for (int64_t it = 0; it < iters; ++it) {
-        const int nslots = (2 * it + 1 < n_my) ? 2 : 1;
-        for (int l = 0; l < nlayers; ++l) {
-          const int N = tc_layer_n(l);
-          const uint32_t idesc = make_idesc(kTileM, N);
-          const int nch = tc_layer_chunks(l);
-          for (int t = 0; t < nslots; ++t) {
+    // MMA issuer: the warp runs converged (uniform registers), one elected lane issues tcgen05.mma / commit.
+    // Descriptor low words advance by (bytes >> 4); everything per K step is an integer add.
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t act_par0 = 0, act_par1 = 0, pe_par0 = 0, pe_par1 = 0;
+    const uint32_t w_lo0 = (((sbase + kOffW) & 0x3FFFFu) >> 4) | (1u << 16);
+    for (int64_t it = 0; it < iters; ++it) {
+      const int nslots = (2 * it + 1 < n_my) ? 2 : 1;
+      for (int l = 0; l < nlayers; ++l) {
+        const uint32_t idesc = make_idesc(kTileM, tc_layer_n(l));
+        const int nch = tc_layer_chunks(l);
+        const int npe = (l == 0 || l == 5) ? 2 : 0;  // leading chunks whose A operand is the positional encoding
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (t < nslots) {
             // A operand ready?  (also: accumulator of this slot drained by the epilogue)
+            uint32_t& act_par = t ? act_par1 : act_par0;
+            uint32_t& pe_par = t ? pe_par1 : pe_par0;
             if (l == 0) {
-              mbar_wait(bar(kBarPeReady + t), pe_par[t]); pe_par[t] ^= 1;
-              if (it > 0) { mbar_wait(bar(kBarActReady + t), act_par[t]); act_par[t] ^= 1; }
+              mbar_wait(bar(kBarPeReady + t), pe_par); pe_par ^= 1;
+              if (it > 0) { mbar_wait(bar(kBarActReady + t), act_par); act_par ^= 1; }
             } else {
-              mbar_wait(bar(kBarActReady + t), act_par[t]); act_par[t] ^= 1;
+              mbar_wait(bar(kBarActReady + t), act_par); act_par ^= 1;
             }
             tc_fence_after();
             TC_TRACE(0, it, l, t, 0);
             const uint32_t d_tmem = tmem_base + (uint32_t)(256 * t);
-            const uint32_t act = sbase + kOffAct + t * kActBytes;
-            const uint32_t pe = sbase + kOffPe + t * kPeBytes;
+            const uint32_t pe_lo = (((sbase + kOffPe + t * kPeBytes) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t act_lo = (((sbase + kOffAct + t * kActBytes) & 0x3FFFFu) >> 4) | (1u << 16);
             for (int c = 0; c < nch; ++c) {
-              if (!(P.dbg_flags & 16)) { mbar_wait(bar(kBarWFull + stage), phase); tc_fence_after(); }
-              const uint32_t wst = sbase + kOffW + stage * kStageBytes;
-#pragma unroll
-              for (int s = 0; s < 2; ++s) {
-                const int ks = 2 * c + s;  // 16-wide K step within the layer
-                uint32_t a_addr;
-                if (l == 0) {
-                  a_addr = pe + ks * 32;
-                } else if (l == 5) {
-                  a_addr = ks < 4 ? pe + ks * 32 : act + ((ks - 4) >> 2) * 16384 + ((ks - 4) & 3) * 32;
-                } else {
-                  a_addr = act + (ks >> 2) * 16384 + (ks & 3) * 32;
-                }
-                if (!(P.dbg_flags & 1)) umma_bf16(d_tmem, make_desc(a_addr, kDescHiSW128), make_desc(wst + s * 32, kDescHiSW64), idesc, ks > 0 ? 1u : 0u);
+              mbar_wait(bar(kBarWFull + stage), phase);
+              tc_fence_after();
+              // chunk c covers K columns [32c, 32c+32): byte offset inside a 128 B swizzled row = 64*(c&1), K block = c>>1
+              const int ca = c - npe;
+              const uint32_t a_lo = c < npe ? pe_lo + 4u * (uint32_t)c : act_lo + 1024u * (uint32_t)(ca >> 1) + 4u * (uint32_t)(ca & 1);
+              const uint32_t b_lo = w_lo0 + (uint32_t)stage * (kStageBytes >> 4);
+              if (elect_one()) {
+                umma_bf16_lohi(d_tmem, a_lo, kDescHiSW128, b_lo, kDescHiSW64, idesc, c > 0 ? 1u : 0u);
+                umma_bf16_lohi(d_tmem, a_lo + 2u, kDescHiSW128, b_lo + 2u, kDescHiSW64, idesc, 1u);
+                umma_commit(bar(kBarWEmpty + stage));  // frees the weight stage when these MMAs retire
               }
-              if (!(P.dbg_flags & 16)) umma_commit(bar(kBarWEmpty + stage));  // frees the weight stage when these MMAs retire
+              __syncwarp();
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            if (l == 5 || (l == nlayers - 1 && nlayers <= 5)) umma_commit(bar(kBarPeFree + t));
-            umma_commit(bar(kBarAccFull + t));
+            if (elect_one()) {
+              if (l == 5 || (l == nlayers - 1 && nlayers <= 5)) umma_commit(bar(kBarPeFree + t));
+              umma_commit(bar(kBarAccFull + t));
+            }
+            __syncwarp();
             TC_TRACE(0, it, l, t, 1);
           }
         }
@@ -406,7 +451,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
       const int nslots = (2 * it + 1 < n_my) ? 2 : 1;
       for (int t = 0; t < nslots; ++t) {
         const int64_t tile = my_tile(2 * it + t);
-        if (it > 0) mbar_wait_relaxed(bar(kBarPeFree + t), (uint32_t)((it - 1) & 1), 512);
+        if (it > 0) mbar_wait_relaxed(bar(kBarPeFree + t), (uint32_t)((it - 1) & 1), 128);
         if (r == 0) TC_TRACE(3, it, 0, t, 0);
         // ---- sample position of this row
         int64_t m = tile * kTileM + r;
@@ -430,10 +475,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
         for (int f = 0; f < 10; ++f) {
           const float fr = (float)(1 << f);
 #pragma unroll
-          for (int a = 0; a < 3; ++a) {
-            if (P.dbg_flags & 8) { e[3 + 6 * f + a] = x[a]; e[3 + 6 * f + 3 + a] = fr; }
-            else sincosf(__fmul_rn(x[a], fr), &e[3 + 6 * f + a], &e[3 + 6 * f + 3 + a]);
-          }
+          for (int a = 0; a < 3; ++a) fast_sincos(__fmul_rn(x[a], fr), &e[3 + 6 * f + a], &e[3 + 6 * f + 3 + a]);
         }
         e[63] = 0.f;
 #pragma unroll
@@ -459,7 +501,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
 #pragma unroll
               for (int a = 0; a < 3; ++a) {
                 float sn, cs;
-                sincosf(__fmul_rn(v[a], fr), &sn, &cs);
+                fast_sincos(__fmul_rn(v[a], fr), &sn, &cs);
                 acc = fmaf(wd[(3 + 6 * f + a) * 128 + r], sn, acc);
                 acc = fmaf(wd[(3 + 6 * f + 3 + a) * 128 + r], cs, acc);
               }
@@ -523,8 +565,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
             const uint32_t arow = sbase + kOffAct + t * kActBytes + (row >> 3) * 1024 + (row & 7) * 128 + hc * 2 * 16384;
             const uint32_t tcol = taddr + hc * 128;
             const uint32_t rx = (uint32_t)(row & 7) << 4;
-            if (P.dbg_flags & 2) {
-            } else if (l == 7) {
+            if (l == 7) {
               const float sig = hidden_epilogue<true>(tcol, bl, wsig_s + hc * 128, arow, rx);
               if (hc == 1) sigpart_s[t * 128 + row] = sig; else sig_keep[t] = sig;
             } else {
