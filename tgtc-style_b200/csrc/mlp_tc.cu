@@ -1,27 +1,31 @@
 // K3+K4, bf16 mode -- positional encoding + the 8x256 NeRF MLP as ONE persistent,
-// warp-specialised tcgen05 kernel.  Replaces models.Embedder.forward
-// (models.py:46-60), models.MLP_style.forward (models.py:95-117) and
-// models.StyleNerf.forward (models.py:216-223); utils.batchify (utils.py:435-456)
-// disappears (the CTA streams 128-sample tiles).
+// warp-specialised tcgen05 kernel running on CTA PAIRS (cta_group::2).  Replaces
+// models.Embedder.forward (models.py:46-60), models.MLP_style.forward
+// (models.py:95-117) and models.StyleNerf.forward (models.py:216-223);
+// utils.batchify (utils.py:435-456) disappears (the CTAs stream 128-sample tiles).
+//
+// A cluster of two CTAs (the two SMs of a TPC) works on four 128-sample tiles at a
+// time: each CTA owns two tiles ("slots").  One tcgen05.mma.cta_group::2
+// (M=256, N=256|128, K=16, bf16 x bf16 -> fp32) multiplies slot t of BOTH CTAs
+// by the same weight slice: every CTA stages only HALF of the weight rows
+// (N/2) in its shared memory, which halves the L2->SMEM weight stream and the
+// operand-read pressure per SM -- the limiter of the single-CTA version.
 //
 // Per CTA (1 per SM, 448 threads):
-//   warp 0      weight producer: cp.async.bulk (TMA engine, UBLKCP) of pre-swizzled
-//               [N x 32] bf16 chunks from the packed blob (L2-resident) into a
-//               3-stage shared-memory ring, mbarrier complete_tx
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (M=128, N=256|128, K=16,
-//               bf16 x bf16 -> fp32) with A = activations in shared memory
-//               (128B-swizzled K-major), B = weight chunk (64B-swizzled K-major),
-//               D = a 128x256 fp32 accumulator in TMEM; tcgen05.commit -> mbarriers
-//   warps 2-5   input producers: pts = o + t*d, precise sin/cos positional encoding
-//               written as the bf16 A operand of layer 0 / the skip of layer 5,
+//   warp 0      weight producer: cp.async.bulk (UBLKCP) of this CTA's half of each
+//               pre-swizzled [N x 32] bf16 chunk (L2-resident blob) into a 6-stage ring
+//   warp 1      leader CTA: MMA issuer -- the warp runs converged, one elected lane
+//               issues tcgen05.mma / tcgen05.commit (multicast to both CTAs' barriers);
+//               peer CTA: forwards "my half of the stage has landed" to the leader
+//   warps 2-5   input producers: pts = o + t*d, positional encoding written as the
+//               bf16 A operand of layer 0 / the skip of layer 5 (128B-swizzled K-major),
 //               and the per-ray view-direction term of rgb0 (fp32, CUDA cores)
 //   warps 6-13  epilogue: tcgen05.ld the accumulator, +bias, ReLU, bf16, store as
 //               the next layer's A operand (in place); fp32 sigma head at layer 7,
 //               fp32 rgb1 head + sigmoid at rgb0; float4 (r,g,b,sigma) to HBM
-// Two 128-row tiles are in flight per CTA (TMEM columns [0,256) and [256,512)):
-// while the tensor core runs layer l of one tile, the epilogue warps turn the
-// other tile's accumulator into its next A operand, so activations never leave
-// the SM between layers.
+// While the tensor cores run layer l of slot 0, the epilogue warps turn slot 1's
+// accumulator (TMEM columns [256,512)) into its next A operand and vice versa, so
+// activations never leave the SM between layers.
 //
 // Tensor-roofline kernel: 1 186 816 algorithmic FLOP per sample; HBM traffic is
 // 24 B/ray in + 16 B/sample out.
@@ -30,8 +34,8 @@
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kStages = 3;
-constexpr int kStageBytes = 256 * kTcChunkK * 2;  // 16384
+constexpr int kStages = 6;
+constexpr int kStageBytes = 128 * kTcChunkK * 2;  // 8192: this CTA's half (N/2 rows) of a [256 x 32] chunk
 constexpr int kNumThreads = 448;
 constexpr int kPeWarp0 = 2, kEpiWarp0 = 6;
 constexpr int kNumEpiThreads = 256;
@@ -43,7 +47,7 @@ constexpr int kOffAct = 0;                                   // 2 x [4 kblocks][
 constexpr int kActBytes = kTileM * 256 * 2;                  // 65536
 constexpr int kOffPe = kOffAct + 2 * kActBytes;              // 2 x [128 rows x 128 B]             SW128
 constexpr int kPeBytes = kTileM * 64 * 2;                    // 16384
-constexpr int kOffW = kOffPe + 2 * kPeBytes;                 // 3 x 16384                          SW64
+constexpr int kOffW = kOffPe + 2 * kPeBytes;                 // 6 x 8192                           SW64
 constexpr int kOffBias = kOffW + kStages * kStageBytes;      // 9 x 256 fp32
 constexpr int kOffWSig = kOffBias + 9 * 256 * 4;             // 256 fp32
 constexpr int kOffWRgb1 = kOffWSig + 256 * 4;                // 3 x 128 fp32
@@ -51,14 +55,21 @@ constexpr int kOffDirBias = kOffWRgb1 + 384 * 4;             // [2 slots][2 bufs
 constexpr int kOffSigPart = kOffDirBias + 2 * 2 * kMaxRaysPerTile * 128 * 4;  // [2 slots][128] fp32
 constexpr int kOffRgbPart = kOffSigPart + 2 * 128 * 4;       // [128][4] fp32
 constexpr int kOffBars = kOffRgbPart + 128 * 4 * 4;          // mbarriers
-constexpr int kNumBars = 2 * kStages + 8;
+constexpr int kNumBars = 2 * kStages + 10;
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 
 // barrier indices
+//   WFull[s]    this CTA's half of ring stage s landed (leader: + the peer's half, forwarded)      leader count 2, peer 1
+//   WEmpty[s]   the MMAs that read stage s retired (commit, multicast to both CTAs)                  count 1
+//   PeReady[t]  slot t's PE tile + dir term written by this CTA's producers (local: epilogue waits)  count 128
+//   PePair[t]   leader only: both CTAs' PE tiles of slot t written                                   count 8 (warps)
+//   PeFree[t]   layer 5 of slot t retired: PE tile reusable (commit, multicast)                      count 1
+//   ActReady[t] leader only: both CTAs' epilogues stored slot t's next A operand / drained TMEM      count 16 (warps)
+//   AccFull[t]  slot t's accumulator complete (commit, multicast)                                    count 1
 constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarPeReady = 2 * kStages, kBarPeFree = kBarPeReady + 2,
-              kBarActReady = kBarPeFree + 2, kBarAccFull = kBarActReady + 2;
+              kBarActReady = kBarPeFree + 2, kBarAccFull = kBarActReady + 2, kBarPePair = kBarAccFull + 2;
 
 // ---------------------------------------------------------------------------
 // PTX wrappers
@@ -120,15 +131,25 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                : "memory");
 }
 
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// address of a shared-memory object of CTA `rank` of this cluster, in the shared::cluster window
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default semantics (.release at CTA scope), as cutlass::arch::ClusterBarrier::arrive(cta_id): a cluster-scope release would
+  // make ptxas emit an L1 invalidate + membar on every arrive (measured: ~1 us per arrive)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
 }
 // tcgen05.mma with the descriptors given as (lo, hi) halves: the hi halves are compile-time constants and the lo
 // halves advance by (byte offset >> 4), so one K step costs one integer add per operand
@@ -141,7 +162,7 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, u
       "setp.ne.b32 p, %6, 0;\n"
       "mov.b64 da, {%1, %2};\n"
       "mov.b64 db, {%3, %4};\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
       "}\n" ::"r"(d_tmem),
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
@@ -168,8 +189,11 @@ __device__ __forceinline__ void fast_sincos(float a, float* s, float* c) {
   *s = __sinf(r);
   *c = __cosf(r);
 }
+// arrive (once the MMAs issued so far by this thread retire) on the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -298,7 +322,7 @@ struct TcParams {
   int64_t M;        // samples
   int64_t ntiles;
   int rays_per_tile;  // 128/S when S<128 else 1
-  int dbg_flags;      // reserved for timing experiments
+  int dbg_flags;      // timing experiments (results garbage): 16 = no weight ring at all, 16|64 = no ring but per-stage commits, 4 = ring handshakes without the copies
   int dbg_layers;     // >0: stop after this many GEMM layers and dump the fp32 accumulator (tests)
   float* dbg_out;     // [ntiles*128, 256]
   long long* dbg_trace;  // timing experiments: clock64 stamps of CTA 0's roles, [4 roles][4 iters][10 layers][2 slots][2]
@@ -309,37 +333,56 @@ struct TcParams {
       P.dbg_trace[(((((role)*4 + (int)(it)) * 10 + (l)) * 2 + (t)) * 2) + (k)] = clock64();                      \
   } while (0)
 
-// which tile does (cta, j) own, and is it valid
-__device__ __forceinline__ int64_t my_tile(int64_t j) { return (int64_t)blockIdx.x + j * gridDim.x; }
+// ring-path trace (cluster 0 only, both CTAs): %globaltimer stamps of chunk numbers [kRingTraceBase, +64) per role
+//   role 0 leader MMA (WFull wake), 1 leader producer (WEmpty wake), 2 peer producer (WEmpty wake), 3 peer forwarder (WFull wake)
+constexpr int kRingTraceBase = 100;
+#define TC_RTRACE(role, j)                                                                                       \
+  do {                                                                                                           \
+    if (P.dbg_trace != nullptr && (blockIdx.x >> 1) == 0 && (j) >= kRingTraceBase && (j) < kRingTraceBase + 64 && lane == 0) { \
+      unsigned long long _g;                                                                                     \
+      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(_g));                                                   \
+      P.dbg_trace[640 + (role)*64 + ((j)-kRingTraceBase)] = (long long)_g;                                       \
+    }                                                                                                            \
+  } while (0)
+
+// tile of (cluster iteration it, slot t) for this CTA: a cluster works on 4 consecutive tiles per iteration
+// (CTA rank r owns tiles 4q+2r and 4q+2r+1); tiles >= ntiles are padding (computed on clamped samples, never stored)
+__device__ __forceinline__ int64_t my_tile(int64_t it, int t, uint32_t rank) {
+  const int64_t quad = (int64_t)(blockIdx.x >> 1) + it * (int64_t)(gridDim.x >> 1);
+  return quad * 4 + 2 * (int64_t)rank + t;
+}
 
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t bars = sbase + kOffBars;
   auto bar = [&](int i) { return bars + 8u * i; };
+  const uint32_t rank = cluster_ctarank();   // 0 = leader (issues the MMAs of the pair)
 
-  const int64_t n_my = (P.ntiles > (int64_t)blockIdx.x) ? (P.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const int64_t iters = (n_my + 1) / 2;
+  const int64_t nquads = (P.ntiles + 3) / 4;
+  const int64_t ncl = gridDim.x >> 1, cid = blockIdx.x >> 1;
+  const int64_t iters = nquads > cid ? (nquads - cid + ncl - 1) / ncl : 0;   // identical in both CTAs of the pair
   const int nlayers = P.dbg_layers > 0 ? P.dbg_layers : kTcNumGemm;
 
   // ---- one-time setup
   if (threadIdx.x == 0) {
     if ((sbase & 1023u) != 0) { printf("tgtc mlp_tc: shared memory base not 1024-aligned\n"); __trap(); }
-    for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarWFull + s), 1); mbar_init(bar(kBarWEmpty + s), 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarWFull + s), rank == 0 ? 2 : 1); mbar_init(bar(kBarWEmpty + s), 1); }
     for (int t = 0; t < 2; ++t) {
       mbar_init(bar(kBarPeReady + t), kNumPeThreads);
+      mbar_init(bar(kBarPePair + t), 2 * (kNumPeThreads / 32));
       mbar_init(bar(kBarPeFree + t), 1);
-      mbar_init(bar(kBarActReady + t), kNumEpiThreads);
+      mbar_init(bar(kBarActReady + t), 2 * (kNumEpiThreads / 32));
       mbar_init(bar(kBarAccFull + t), 1);
     }
     fence_barrier_init();
   }
-  if (warp == 1) {  // TMEM: all 512 columns (two 128x256 fp32 accumulators)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(sbase + kOffTmemPtr), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+  if (warp == 1) {  // TMEM: all 512 columns in both CTAs of the pair (two 128x256 fp32 accumulators per CTA)
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(sbase + kOffTmemPtr), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
   }
   // biases / head weights -> shared memory (fp32), once per CTA
   {
@@ -352,8 +395,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
-  // the CTA owns all 512 columns of its SM's tensor memory, so the allocation starts at lane 0 / column 0; using the
+  // the pair owns all 512 columns of both SMs' tensor memory, so the allocation starts at lane 0 / column 0; using the
   // literal keeps every TMEM address a compile-time/uniform value in the issue loops
   if (*reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr) != 0u) {
     if (threadIdx.x == 0) printf("tgtc mlp_tc: unexpected TMEM base\n");
@@ -363,21 +407,26 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
 
   if (warp == 0) {
     // =====================================================================
-    // weight producer (whole warp converged, one elected lane issues the bulk copies)
+    // weight producer (whole warp converged, one elected lane issues the bulk copies): this CTA's half of the rows
     int stage = 0;
     uint32_t phase = 0;
-    for (int64_t it = 0; it < iters; ++it) {
-      const int nslots = (2 * it + 1 < n_my) ? 2 : 1;
+    int jchunk = 0;
+    for (int64_t it = 0; it < ((P.dbg_flags & 16) ? 0 : iters); ++it) {
       for (int l = 0; l < nlayers; ++l) {
-        const uint8_t* src = P.blob + tc_layer_off_bytes(l);
-        const uint32_t cbytes = (uint32_t)tc_layer_n(l) * kTcChunkK * 2;
+        const uint32_t hbytes = (uint32_t)tc_layer_n(l) * kTcChunkK;   // half of a [N x 32] bf16 chunk
+        const uint8_t* src = P.blob + tc_layer_off_bytes(l) + (size_t)rank * hbytes;
         const int nch = tc_layer_chunks(l);
-        for (int t = 0; t < nslots; ++t) {
+        for (int t = 0; t < 2; ++t) {
           for (int c = 0; c < nch; ++c) {
             mbar_wait(bar(kBarWEmpty + stage), phase ^ 1);
+            TC_RTRACE(1 + (int)rank, jchunk); ++jchunk;
             if (elect_one()) {
-              mbar_arrive_expect_tx(bar(kBarWFull + stage), cbytes);
-              bulk_g2s(sbase + kOffW + stage * kStageBytes, src + (size_t)c * cbytes, cbytes, bar(kBarWFull + stage));
+              if (P.dbg_flags & 4) {
+                mbar_arrive(bar(kBarWFull + stage));
+              } else {
+                mbar_arrive_expect_tx(bar(kBarWFull + stage), hbytes);
+                bulk_g2s(sbase + kOffW + stage * kStageBytes, src + (size_t)c * 2 * hbytes, hbytes, bar(kBarWFull + stage));
+              }
             }
             __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -385,59 +434,76 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
         }
       }
     }
+  } else if (warp == 1 && rank != 0) {
+    // =====================================================================
+    // peer CTA: tell the leader's MMA warp when this CTA's half of each ring stage has landed
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t leader_wfull = mapa_cluster(bar(kBarWFull), 0);
+    int jchunk = 0;
+    for (int64_t it = 0; it < ((P.dbg_flags & 16) ? 0 : iters); ++it) {
+      for (int l = 0; l < nlayers; ++l) {
+        const int nch = 2 * tc_layer_chunks(l);
+        for (int c = 0; c < nch; ++c) {
+          mbar_wait(bar(kBarWFull + stage), phase);
+          TC_RTRACE(3, jchunk); ++jchunk;
+          if (elect_one()) mbar_arrive_cluster(leader_wfull + 8u * stage);
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
   } else if (warp == 1) {
     // =====================================================================
-    // MMA issuer: the warp runs converged (uniform registers), one elected lane issues tcgen05.mma / commit.
-    // Descriptor low words advance by (bytes >> 4); everything per K step is an integer add.
+    // leader CTA: MMA issuer for the pair.  The warp runs converged (uniform registers), one elected lane issues
+    // tcgen05.mma / commit.  Descriptor low words advance by (bytes >> 4); everything per K step is an integer add.
     int stage = 0;
     uint32_t phase = 0;
     uint32_t act_par0 = 0, act_par1 = 0, pe_par0 = 0, pe_par1 = 0;
+    int jchunk = 0;
     const uint32_t w_lo0 = (((sbase + kOffW) & 0x3FFFFu) >> 4) | (1u << 16);
     for (int64_t it = 0; it < iters; ++it) {
-      const int nslots = (2 * it + 1 < n_my) ? 2 : 1;
       for (int l = 0; l < nlayers; ++l) {
-        const uint32_t idesc = make_idesc(kTileM, tc_layer_n(l));
+        const uint32_t idesc = make_idesc(2 * kTileM, tc_layer_n(l));
         const int nch = tc_layer_chunks(l);
         const int npe = (l == 0 || l == 5) ? 2 : 0;  // leading chunks whose A operand is the positional encoding
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
-          if (t < nslots) {
-            // A operand ready?  (also: accumulator of this slot drained by the epilogue)
-            uint32_t& act_par = t ? act_par1 : act_par0;
-            uint32_t& pe_par = t ? pe_par1 : pe_par0;
-            if (l == 0) {
-              mbar_wait(bar(kBarPeReady + t), pe_par); pe_par ^= 1;
-              if (it > 0) { mbar_wait(bar(kBarActReady + t), act_par); act_par ^= 1; }
-            } else {
-              mbar_wait(bar(kBarActReady + t), act_par); act_par ^= 1;
-            }
-            tc_fence_after();
-            TC_TRACE(0, it, l, t, 0);
-            const uint32_t d_tmem = tmem_base + (uint32_t)(256 * t);
-            const uint32_t pe_lo = (((sbase + kOffPe + t * kPeBytes) & 0x3FFFFu) >> 4) | (1u << 16);
-            const uint32_t act_lo = (((sbase + kOffAct + t * kActBytes) & 0x3FFFFu) >> 4) | (1u << 16);
-            for (int c = 0; c < nch; ++c) {
-              mbar_wait(bar(kBarWFull + stage), phase);
-              tc_fence_after();
-              // chunk c covers K columns [32c, 32c+32): byte offset inside a 128 B swizzled row = 64*(c&1), K block = c>>1
-              const int ca = c - npe;
-              const uint32_t a_lo = c < npe ? pe_lo + 4u * (uint32_t)c : act_lo + 1024u * (uint32_t)(ca >> 1) + 4u * (uint32_t)(ca & 1);
-              const uint32_t b_lo = w_lo0 + (uint32_t)stage * (kStageBytes >> 4);
-              if (elect_one()) {
-                umma_bf16_lohi(d_tmem, a_lo, kDescHiSW128, b_lo, kDescHiSW64, idesc, c > 0 ? 1u : 0u);
-                umma_bf16_lohi(d_tmem, a_lo + 2u, kDescHiSW128, b_lo + 2u, kDescHiSW64, idesc, 1u);
-                umma_commit(bar(kBarWEmpty + stage));  // frees the weight stage when these MMAs retire
-              }
-              __syncwarp();
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
-            }
+          // A operands of both CTAs ready?  (also: this slot's accumulators drained by both epilogues)
+          uint32_t& act_par = t ? act_par1 : act_par0;
+          uint32_t& pe_par = t ? pe_par1 : pe_par0;
+          if (l == 0) {
+            mbar_wait(bar(kBarPePair + t), pe_par); pe_par ^= 1;
+            if (it > 0) { mbar_wait(bar(kBarActReady + t), act_par); act_par ^= 1; }
+          } else {
+            mbar_wait(bar(kBarActReady + t), act_par); act_par ^= 1;
+          }
+          tc_fence_after();
+          TC_TRACE(0, it, l, t, 0);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(256 * t);
+          const uint32_t pe_lo = (((sbase + kOffPe + t * kPeBytes) & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t act_lo = (((sbase + kOffAct + t * kActBytes) & 0x3FFFFu) >> 4) | (1u << 16);
+          for (int c = 0; c < nch; ++c) {
+            if (!(P.dbg_flags & 16)) { mbar_wait(bar(kBarWFull + stage), phase); tc_fence_after(); }
+            TC_RTRACE(0, jchunk); ++jchunk;
+            // chunk c covers K columns [32c, 32c+32): byte offset inside a 128 B swizzled row = 64*(c&1), K block = c>>1
+            const int ca = c - npe;
+            const uint32_t a_lo = c < npe ? pe_lo + 4u * (uint32_t)c : act_lo + 1024u * (uint32_t)(ca >> 1) + 4u * (uint32_t)(ca & 1);
+            const uint32_t b_lo = w_lo0 + (uint32_t)stage * (kStageBytes >> 4);
             if (elect_one()) {
-              if (l == 5 || (l == nlayers - 1 && nlayers <= 5)) umma_commit(bar(kBarPeFree + t));
-              umma_commit(bar(kBarAccFull + t));
+              umma_bf16_lohi(d_tmem, a_lo, kDescHiSW128, b_lo, kDescHiSW64, idesc, c > 0 ? 1u : 0u);
+              umma_bf16_lohi(d_tmem, a_lo + 2u, kDescHiSW128, b_lo + 2u, kDescHiSW64, idesc, 1u);
+              if ((P.dbg_flags & 80) != 16) umma_commit(bar(kBarWEmpty + stage));  // frees the ring stage in both CTAs when these MMAs retire
             }
             __syncwarp();
-            TC_TRACE(0, it, l, t, 1);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
+          if (elect_one()) {
+            if (l == 5 || (l == nlayers - 1 && nlayers <= 5)) umma_commit(bar(kBarPeFree + t));
+            umma_commit(bar(kBarAccFull + t));
+          }
+          __syncwarp();
+          TC_TRACE(0, it, l, t, 1);
         }
       }
     }
@@ -447,10 +513,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
     const int r = (warp - kPeWarp0) * 32 + lane;
     const MlpIO& io = P.io;
     const int S = io.S;
+    const uint32_t leader_pepair = mapa_cluster(bar(kBarPePair), 0);
     for (int64_t it = 0; it < iters; ++it) {
-      const int nslots = (2 * it + 1 < n_my) ? 2 : 1;
-      for (int t = 0; t < nslots; ++t) {
-        const int64_t tile = my_tile(2 * it + t);
+      for (int t = 0; t < 2; ++t) {
+        const int64_t tile = my_tile(it, t, rank);
         if (it > 0) mbar_wait_relaxed(bar(kBarPeFree + t), (uint32_t)((it - 1) & 1), 128);
         if (r == 0) TC_TRACE(3, it, 0, t, 0);
         // ---- sample position of this row
@@ -510,7 +576,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
           }
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        mbar_arrive(bar(kBarPeReady + t));
+        mbar_arrive(bar(kBarPeReady + t));          // local: this CTA's epilogue acquires the dir term
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(leader_pepair + 8u * t);   // pair: the leader's MMA warp
         if (r == 0) TC_TRACE(3, it, 0, t, 1);
       }
     }
@@ -531,16 +599,21 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
     float sig_keep[2] = {0.f, 0.f};
     const int S = P.io.S;
 
+    const uint32_t leader_actready = mapa_cluster(bar(kBarActReady), 0);
+    // per-warp arrival on the leader's barrier: every lane has fenced its own writes / TMEM loads before the warp sync
+    auto act_arrive = [&](int t) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_actready + 8u * t);
+    };
     for (int64_t it = 0; it < iters; ++it) {
-      const int nslots = (2 * it + 1 < n_my) ? 2 : 1;
       for (int l = 0; l < nlayers; ++l) {
-        for (int t = 0; t < nslots; ++t) {
+        for (int t = 0; t < 2; ++t) {
           if (l == 0) mbar_wait(bar(kBarPeReady + t), (uint32_t)(it & 1));  // acquire the producers' dir-bias writes
           mbar_wait(bar(kBarAccFull + t), acc_par[t]); acc_par[t] ^= 1;
           tc_fence_after();
           if (lane == 0 && q == 2) TC_TRACE(1 + hc, it, l, t, 0);
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 * t);
-          const int64_t tile = my_tile(2 * it + t);
+          const int64_t tile = my_tile(it, t, rank);
           const int64_t m = tile * kTileM + row;
 
           if (P.dbg_layers > 0 && l == nlayers - 1) {
@@ -555,7 +628,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
                 for (int j = 0; j < 32; ++j) P.dbg_out[m * 256 + c0 + j] = __uint_as_float(v[j]);
             }
             tc_fence_before();
-            mbar_arrive(bar(kBarActReady + t));
+            act_arrive(t);
             continue;
           }
 
@@ -573,7 +646,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
             }
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(bar(kBarActReady + t));
+            act_arrive(t);
             if (lane == 0 && q == 2) TC_TRACE(1 + hc, it, l, t, 1);
           } else {
             // rgb0 (N=128): + per-ray dir term, ReLU, then the 3x128 rgb1 head + sigmoid in fp32 (models.py:108-111)
@@ -604,7 +677,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
               }
             }
             tc_fence_before();
-            mbar_arrive(bar(kBarActReady + t));  // accumulator drained: the next tile's layer 0 may start
+            act_arrive(t);  // accumulator drained: the next tile's layer 0 may start
             if (lane == 0 && q == 2) TC_TRACE(1 + hc, it, l, t, 1);
             if (hc == 1) *reinterpret_cast<float4*>(rgbpart_s + row * 4) = make_float4(p0, p1, p2, 0.f);
             named_bar_sync(1, kNumEpiThreads);
@@ -632,9 +705,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P
   // ---- teardown
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();   // neither CTA may exit (or free TMEM) while the other can still signal it / read its shared memory
   if (warp == 1) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -673,7 +747,9 @@ static int launch_tc_common(tgtc_ctx* ctx, int net, const MlpIO& io, int dbg_lay
     TGTC_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set[ctx->device & 63] = true;
   }
-  const int grid = (int)(P.ntiles < ctx->num_sms ? P.ntiles : ctx->num_sms);
+  const int64_t nquads = (P.ntiles + 3) / 4;
+  const int64_t max_pairs = ctx->num_sms / 2;
+  const int grid = 2 * (int)(nquads < max_pairs ? nquads : max_pairs);   // CTA pairs (clusters of 2)
   mlp_tc_kernel<<<grid, kNumThreads, kSmemBytes, st>>>(P);
   TGTC_LAUNCH_CHECK(ctx);
   return TGTC_OK;

@@ -27,14 +27,16 @@ def main():
     for _ in range(2):
         r.nerf_forward_rays(net, ro, rd, ts, S, 0., 1.)
     torch.cuda.synchronize()
-    buf = torch.zeros(4 * 4 * 10 * 2 * 2, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(4 * 4 * 10 * 2 * 2 + 4 * 64, dtype=torch.int64, device="cuda")
     lib.tgtc_debug_tc_flags(fl)
     lib.tgtc_debug_tc_trace(buf.data_ptr())
     r.nerf_forward_rays(net, ro, rd, ts, S, 0., 1.)
     torch.cuda.synchronize()
     lib.tgtc_debug_tc_trace(None)
     lib.tgtc_debug_tc_flags(0)
-    tr = buf.cpu().numpy().reshape(4, 4, 10, 2, 2)
+    full = buf.cpu().numpy()
+    tr = full[:640].reshape(4, 4, 10, 2, 2)
+    ring = full[640:].reshape(4, 64)
     t0 = tr[tr > 0].min()
     names = ["MMA ", "EPI0", "EPI1", "PE  "]
     ev = []
@@ -60,6 +62,24 @@ def main():
     print("AccFull wake - MMA issue end per layer (MMA exec + signal latency):", gap.mean(axis=(0, 2)).astype(int).tolist())
     w = tr[0, 1:3, :, :, 1] - tr[0, 1:3, :, :, 0]
     print("MMA issue duration per layer:", w.mean(axis=(0, 2)).astype(int).tolist())
+    ring_report(ring)
+
+
+def ring_report(ring, stages=6):
+    if ring.max() == 0:
+        return
+    r0 = ring[ring > 0].min()
+    r = ring - r0
+    print("ring path (ns, %globaltimer): chunk | MMA WFull wake | leader prod WEmpty wake | peer prod WEmpty wake | peer fwd WFull wake")
+    for j in range(64):
+        print("%3d  %7d %7d %7d %7d" % (j, r[0, j], r[1, j], r[2, j], r[3, j]))
+    j = np.arange(8, 56)
+    print("mean period per chunk (MMA wake to wake): %.1f ns" % np.diff(r[0, 8:56]).mean())
+    print("MMA wake(j) -> leader producer WEmpty wake(j+%d): %.1f ns" % (stages, (r[1, j + stages] - r[0, j]).mean()))
+    print("MMA wake(j) -> peer   producer WEmpty wake(j+%d): %.1f ns" % (stages, (r[2, j + stages] - r[0, j]).mean()))
+    print("peer producer wake(j) -> peer forwarder wake(j): %.1f ns" % (r[3, j] - r[2, j]).mean())
+    print("peer forwarder wake(j) -> MMA wake(j): %.1f ns" % (r[0, j] - r[3, j]).mean())
+    print("leader producer wake(j) -> MMA wake(j): %.1f ns" % (r[0, j] - r[1, j]).mean())
 
 
 if __name__ == "__main__":
