@@ -43,9 +43,10 @@ constexpr int kSmWDir = kSmBRgb1 + 3 + 0;        // 32 x 128 (dir-PE rows of rgb
 constexpr int kSmallFloats = kSmWDir + 32 * 128;
 static_assert(kSmWDir % 4 == 0, "WDir must stay float4 aligned");
 
-// ---- bf16 image (mlp_tc.cu): chunks of [N rows x 32 K] bf16 in the 64B-swizzled
-// K-major UMMA shared-memory layout, in consumption order (see mlp_tc.cu)
-constexpr int kTcChunkK = 32;
+// ---- bf16 image (mlp_tc.cu): chunks of [N rows x 64 K] bf16 in the 128B-swizzled
+// K-major UMMA shared-memory layout, in consumption order (see mlp_tc.cu); the first
+// half of a chunk's bytes holds rows [0, N/2) (CTA 0 of a pair), the second half the rest
+constexpr int kTcChunkK = 64;
 constexpr int kTcNumGemm = 10;  // L0..L7, remap, rgb0
 __host__ __device__ constexpr int tc_layer_k(int l) { return l == 0 ? 64 : (l == 5 ? 320 : 256); }
 __host__ __device__ constexpr int tc_layer_n(int l) { return l == 9 ? 128 : 256; }

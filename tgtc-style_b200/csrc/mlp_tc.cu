@@ -13,7 +13,7 @@
 //
 // Per CTA (1 per SM, 448 threads):
 //   warp 0      weight producer: cp.async.bulk (UBLKCP) of this CTA's half of each
-//               pre-swizzled [N x 32] bf16 chunk (L2-resident blob) into a 6-stage ring
+//               pre-swizzled [N x 64] bf16 chunk (L2-resident blob) into a 3-stage ring
 //   warp 1      leader CTA: MMA issuer -- the warp runs converged, one elected lane
 //               issues tcgen05.mma / tcgen05.commit (multicast to both CTAs' barriers);
 //               peer CTA: forwards "my half of the stage has landed" to the leader
@@ -34,8 +34,8 @@
 namespace {
 
 constexpr int kTileM = 128;
-constexpr int kStages = 6;
-constexpr int kStageBytes = 128 * kTcChunkK * 2;  // 8192: this CTA's half (N/2 rows) of a [256 x 32] chunk
+constexpr int kStages = 3;
+constexpr int kStageBytes = 128 * kTcChunkK * 2;  // 16384: this CTA's half (N/2 rows) of a [256 x 64] chunk
 constexpr int kNumThreads = 448;
 constexpr int kPeWarp0 = 2, kEpiWarp0 = 6;
 constexpr int kNumEpiThreads = 256;
@@ -47,7 +47,7 @@ constexpr int kOffAct = 0;                                   // 2 x [4 kblocks][
 constexpr int kActBytes = kTileM * 256 * 2;                  // 65536
 constexpr int kOffPe = kOffAct + 2 * kActBytes;              // 2 x [128 rows x 128 B]             SW128
 constexpr int kPeBytes = kTileM * 64 * 2;                    // 16384
-constexpr int kOffW = kOffPe + 2 * kPeBytes;                 // 6 x 8192                           SW64
+constexpr int kOffW = kOffPe + 2 * kPeBytes;                 // 3 x 16384                          SW128
 constexpr int kOffBias = kOffW + kStages * kStageBytes;      // 9 x 256 fp32
 constexpr int kOffWSig = kOffBias + 9 * 256 * 4;             // 256 fp32
 constexpr int kOffWRgb1 = kOffWSig + 256 * 4;                // 3 x 128 fp32
@@ -104,6 +104,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {  // ~2 s
       printf("tgtc mlp_tc: mbarrier timeout (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+// warp-uniform wait for converged single-issuer warps: the loop condition is a vote, so control flow stays uniform and
+// ptxas can keep descriptors / barrier addresses in uniform registers across the wait
+__device__ __forceinline__ void mbar_wait_uniform(uint32_t bar, uint32_t parity) {
+  if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
+  const long long t0 = clock64();
+  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+    if (clock64() - t0 > 4000000000LL) {
+      if ((threadIdx.x & 31) == 0) printf("tgtc mlp_tc: mbarrier timeout (block %d warp %d bar@%u parity %u)\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), bar, parity);
       __trap();
     }
   }
@@ -233,13 +245,12 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(uint32_t lo, uint32_t hi) {
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): K-major, swizzled.
 //   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major; 1 as CUTLASS) | [32,46) SBO>>4 |
-//   [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
+//   [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t hi) {
   const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
   return ((uint64_t)hi << 32) | lo;
 }
 constexpr uint32_t kDescHiSW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
-constexpr uint32_t kDescHiSW64 = (512u >> 4) | (1u << 14) | (4u << 29);
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
@@ -322,7 +333,7 @@ struct TcParams {
   int64_t M;        // samples
   int64_t ntiles;
   int rays_per_tile;  // 128/S when S<128 else 1
-  int dbg_flags;      // timing experiments (results garbage): 16 = no weight ring at all, 16|64 = no ring but per-stage commits, 4 = ring handshakes without the copies
+  int dbg_flags;      // timing experiments (results garbage): 16 = no weight ring at all
   int dbg_layers;     // >0: stop after this many GEMM layers and dump the fp32 accumulator (tests)
   float* dbg_out;     // [ntiles*128, 256]
   long long* dbg_trace;  // timing experiments: clock64 stamps of CTA 0's roles, [4 roles][4 iters][10 layers][2 slots][2]
@@ -331,18 +342,6 @@ struct TcParams {
   do {                                                                                                           \
     if (P.dbg_trace != nullptr && blockIdx.x == 0 && (it) < 4)                                                   \
       P.dbg_trace[(((((role)*4 + (int)(it)) * 10 + (l)) * 2 + (t)) * 2) + (k)] = clock64();                      \
-  } while (0)
-
-// ring-path trace (cluster 0 only, both CTAs): %globaltimer stamps of chunk numbers [kRingTraceBase, +64) per role
-//   role 0 leader MMA (WFull wake), 1 leader producer (WEmpty wake), 2 peer producer (WEmpty wake), 3 peer forwarder (WFull wake)
-constexpr int kRingTraceBase = 100;
-#define TC_RTRACE(role, j)                                                                                       \
-  do {                                                                                                           \
-    if (P.dbg_trace != nullptr && (blockIdx.x >> 1) == 0 && (j) >= kRingTraceBase && (j) < kRingTraceBase + 64 && lane == 0) { \
-      unsigned long long _g;                                                                                     \
-      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(_g));                                                   \
-      P.dbg_trace[640 + (role)*64 + ((j)-kRingTraceBase)] = (long long)_g;                                       \
-    }                                                                                                            \
   } while (0)
 
 // tile of (cluster iteration it, slot t) for this CTA: a cluster works on 4 consecutive tiles per iteration
@@ -410,23 +409,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
     // weight producer (whole warp converged, one elected lane issues the bulk copies): this CTA's half of the rows
     int stage = 0;
     uint32_t phase = 0;
-    int jchunk = 0;
     for (int64_t it = 0; it < ((P.dbg_flags & 16) ? 0 : iters); ++it) {
       for (int l = 0; l < nlayers; ++l) {
-        const uint32_t hbytes = (uint32_t)tc_layer_n(l) * kTcChunkK;   // half of a [N x 32] bf16 chunk
+        const uint32_t hbytes = (uint32_t)tc_layer_n(l) * kTcChunkK;   // half of a [N x 64] bf16 chunk
         const uint8_t* src = P.blob + tc_layer_off_bytes(l) + (size_t)rank * hbytes;
         const int nch = tc_layer_chunks(l);
         for (int t = 0; t < 2; ++t) {
           for (int c = 0; c < nch; ++c) {
             mbar_wait(bar(kBarWEmpty + stage), phase ^ 1);
-            TC_RTRACE(1 + (int)rank, jchunk); ++jchunk;
             if (elect_one()) {
-              if (P.dbg_flags & 4) {
-                mbar_arrive(bar(kBarWFull + stage));
-              } else {
-                mbar_arrive_expect_tx(bar(kBarWFull + stage), hbytes);
-                bulk_g2s(sbase + kOffW + stage * kStageBytes, src + (size_t)c * 2 * hbytes, hbytes, bar(kBarWFull + stage));
-              }
+              mbar_arrive_expect_tx(bar(kBarWFull + stage), hbytes);
+              bulk_g2s(sbase + kOffW + stage * kStageBytes, src + (size_t)c * 2 * hbytes, hbytes, bar(kBarWFull + stage));
             }
             __syncwarp();
             if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -440,13 +433,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t leader_wfull = mapa_cluster(bar(kBarWFull), 0);
-    int jchunk = 0;
     for (int64_t it = 0; it < ((P.dbg_flags & 16) ? 0 : iters); ++it) {
       for (int l = 0; l < nlayers; ++l) {
         const int nch = 2 * tc_layer_chunks(l);
         for (int c = 0; c < nch; ++c) {
           mbar_wait(bar(kBarWFull + stage), phase);
-          TC_RTRACE(3, jchunk); ++jchunk;
           if (elect_one()) mbar_arrive_cluster(leader_wfull + 8u * stage);
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -455,48 +446,54 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
     }
   } else if (warp == 1) {
     // =====================================================================
-    // leader CTA: MMA issuer for the pair.  The warp runs converged (uniform registers), one elected lane issues
-    // tcgen05.mma / commit.  Descriptor low words advance by (bytes >> 4); everything per K step is an integer add.
+    // leader CTA: MMA issuer for the pair.  The warp runs converged with warp-uniform control flow (vote-based waits), so
+    // descriptors and barrier addresses live in uniform registers; one elected lane issues tcgen05.mma / commit.
+    // Descriptor low words advance by (bytes >> 4); everything per K step is an integer add.
     int stage = 0;
     uint32_t phase = 0;
     uint32_t act_par0 = 0, act_par1 = 0, pe_par0 = 0, pe_par1 = 0;
-    int jchunk = 0;
     const uint32_t w_lo0 = (((sbase + kOffW) & 0x3FFFFu) >> 4) | (1u << 16);
+    const bool ring = !(P.dbg_flags & 16);
+    // one K=64 chunk: wait for the ring stage, four MMAs (K=16 each: +32 B inside the 128 B swizzled rows), release the stage
+    auto issue_chunk = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t idesc, uint32_t accumulate) {
+      if (ring) { mbar_wait_uniform(bar(kBarWFull + stage), phase); tc_fence_after(); }
+      const uint32_t b_lo = w_lo0 + (uint32_t)stage * (kStageBytes >> 4);
+      if (elect_one()) {
+        umma_bf16_lohi(d_tmem, a_lo, kDescHiSW128, b_lo, kDescHiSW128, idesc, accumulate);
+        umma_bf16_lohi(d_tmem, a_lo + 2u, kDescHiSW128, b_lo + 2u, kDescHiSW128, idesc, 1u);
+        umma_bf16_lohi(d_tmem, a_lo + 4u, kDescHiSW128, b_lo + 4u, kDescHiSW128, idesc, 1u);
+        umma_bf16_lohi(d_tmem, a_lo + 6u, kDescHiSW128, b_lo + 6u, kDescHiSW128, idesc, 1u);
+        if (ring) umma_commit(bar(kBarWEmpty + stage));  // frees the ring stage in both CTAs when these MMAs retire
+      }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    };
     for (int64_t it = 0; it < iters; ++it) {
       for (int l = 0; l < nlayers; ++l) {
         const uint32_t idesc = make_idesc(2 * kTileM, tc_layer_n(l));
-        const int nch = tc_layer_chunks(l);
-        const int npe = (l == 0 || l == 5) ? 2 : 0;  // leading chunks whose A operand is the positional encoding
+        const bool has_pe = (l == 0 || l == 5);
+        const bool has_act = (l != 0);
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
           // A operands of both CTAs ready?  (also: this slot's accumulators drained by both epilogues)
           uint32_t& act_par = t ? act_par1 : act_par0;
           uint32_t& pe_par = t ? pe_par1 : pe_par0;
           if (l == 0) {
-            mbar_wait(bar(kBarPePair + t), pe_par); pe_par ^= 1;
-            if (it > 0) { mbar_wait(bar(kBarActReady + t), act_par); act_par ^= 1; }
+            mbar_wait_uniform(bar(kBarPePair + t), pe_par); pe_par ^= 1;
+            if (it > 0) { mbar_wait_uniform(bar(kBarActReady + t), act_par); act_par ^= 1; }
           } else {
-            mbar_wait(bar(kBarActReady + t), act_par); act_par ^= 1;
+            mbar_wait_uniform(bar(kBarActReady + t), act_par); act_par ^= 1;
           }
           tc_fence_after();
           TC_TRACE(0, it, l, t, 0);
           const uint32_t d_tmem = tmem_base + (uint32_t)(256 * t);
           const uint32_t pe_lo = (((sbase + kOffPe + t * kPeBytes) & 0x3FFFFu) >> 4) | (1u << 16);
           const uint32_t act_lo = (((sbase + kOffAct + t * kActBytes) & 0x3FFFFu) >> 4) | (1u << 16);
-          for (int c = 0; c < nch; ++c) {
-            if (!(P.dbg_flags & 16)) { mbar_wait(bar(kBarWFull + stage), phase); tc_fence_after(); }
-            TC_RTRACE(0, jchunk); ++jchunk;
-            // chunk c covers K columns [32c, 32c+32): byte offset inside a 128 B swizzled row = 64*(c&1), K block = c>>1
-            const int ca = c - npe;
-            const uint32_t a_lo = c < npe ? pe_lo + 4u * (uint32_t)c : act_lo + 1024u * (uint32_t)(ca >> 1) + 4u * (uint32_t)(ca & 1);
-            const uint32_t b_lo = w_lo0 + (uint32_t)stage * (kStageBytes >> 4);
-            if (elect_one()) {
-              umma_bf16_lohi(d_tmem, a_lo, kDescHiSW128, b_lo, kDescHiSW64, idesc, c > 0 ? 1u : 0u);
-              umma_bf16_lohi(d_tmem, a_lo + 2u, kDescHiSW128, b_lo + 2u, kDescHiSW64, idesc, 1u);
-              if ((P.dbg_flags & 80) != 16) umma_commit(bar(kBarWEmpty + stage));  // frees the ring stage in both CTAs when these MMAs retire
-            }
-            __syncwarp();
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          // chunk = one 64-column K block: the PE tile (layers 0 and 5) or K block c of the activations (16 KB apart)
+          if (has_pe) issue_chunk(d_tmem, pe_lo, idesc, 0u);
+          if (has_act) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) issue_chunk(d_tmem, act_lo + 1024u * (uint32_t)c, idesc, (has_pe || c > 0) ? 1u : 0u);
           }
           if (elect_one()) {
             if (l == 5 || (l == nlayers - 1 && nlayers <= 5)) umma_commit(bar(kBarPeFree + t));

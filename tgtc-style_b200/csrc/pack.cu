@@ -1,7 +1,7 @@
 // Weight packer: fp32 nn.Linear tensors ([out,in] row-major, the reference's
 // state_dict layout, models.py:75-91) -> the three device images the kernels read.
 //   f32_gemm : per GEMM layer, transposed [Kpad][N] fp32        (mlp_fp32.cu)
-//   tc_blob  : per GEMM layer, chunks of [N x 32] bf16 in the 64B-swizzled
+//   tc_blob  : per GEMM layer, chunks of [N x 64] bf16 in the 128B-swizzled
 //              K-major UMMA shared-memory layout, consumption order (mlp_tc.cu)
 //   smalls   : biases, sigma head, rgb1 head, dir-PE slice of rgb0 (fp32)
 // K padding: PE 63->64 (zero column 63; layer 5 = [PE(64) | hidden(256)]),
@@ -63,11 +63,11 @@ __global__ void pack_tc_kernel(Params24 P, __nv_bfloat16* __restrict__ out) {
     const int chunk = (int)(r / chunk_elems);
     const int e = (int)(r % chunk_elems);       // element offset inside the chunk image
     const int byte = e * 2;
-    // invert: byte = (n/8)*512 + (n%8)*64 + (((kk/8) ^ ((n%8)>>1)) * 16) + (kk%8)*2
-    const int grp = byte >> 9, rem = byte & 511;
-    const int rr = rem >> 6, inrow = rem & 63;
+    // invert: byte = (n/8)*1024 + (n%8)*128 + (((kk/8) ^ (n%8)) * 16) + (kk%8)*2
+    const int grp = byte >> 10, rem = byte & 1023;
+    const int rr = rem >> 7, inrow = rem & 127;
     const int c16p = inrow >> 4, within = (inrow & 15) >> 1;
-    const int c16 = c16p ^ (rr >> 1);
+    const int c16 = c16p ^ rr;
     const int n = grp * 8 + rr;
     const int k = chunk * kTcChunkK + c16 * 8 + within;
     out[idx] = __float2bfloat16_rn(gemm_w(P, l, n, k, /*with_dir=*/false));

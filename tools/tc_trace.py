@@ -62,7 +62,6 @@ def main():
     print("AccFull wake - MMA issue end per layer (MMA exec + signal latency):", gap.mean(axis=(0, 2)).astype(int).tolist())
     w = tr[0, 1:3, :, :, 1] - tr[0, 1:3, :, :, 0]
     print("MMA issue duration per layer:", w.mean(axis=(0, 2)).astype(int).tolist())
-    ring_report(ring)
 
 
 def ring_report(ring, stages=6):
