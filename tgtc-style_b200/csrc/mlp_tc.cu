@@ -333,7 +333,7 @@ struct TcParams {
   int64_t M;        // samples
   int64_t ntiles;
   int rays_per_tile;  // 128/S when S<128 else 1
-  int dbg_flags;      // timing experiments (results garbage): 16 = no weight ring at all
+  int dbg_flags;      // timing experiments (results garbage): 2 = skip the hidden-layer epilogue work, 16 = no weight ring at all
   int dbg_layers;     // >0: stop after this many GEMM layers and dump the fp32 accumulator (tests)
   float* dbg_out;     // [ntiles*128, 256]
   long long* dbg_trace;  // timing experiments: clock64 stamps of CTA 0's roles, [4 roles][4 iters][10 layers][2 slots][2]
@@ -635,7 +635,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
             const uint32_t arow = sbase + kOffAct + t * kActBytes + (row >> 3) * 1024 + (row & 7) * 128 + hc * 2 * 16384;
             const uint32_t tcol = taddr + hc * 128;
             const uint32_t rx = (uint32_t)(row & 7) << 4;
-            if (l == 7) {
+            if (P.dbg_flags & 2) {
+            } else if (l == 7) {
               const float sig = hidden_epilogue<true>(tcol, bl, wsig_s + hc * 128, arow, rx);
               if (hc == 1) sigpart_s[t * 128 + row] = sig; else sig_keep[t] = sig;
             } else {
