@@ -112,6 +112,14 @@ int tgtc_composite(tgtc_ctx* ctx, const float* rgb, const float* sigma, const fl
                    int64_t ts_ray_stride, const float* noise, int white_bkgd, int64_t n, int S, float* rgb_out,
                    float* depth_out, float* acc_out, float* weights_out, tgtc_stream stream);
 
+/* K5 backward -- gradient of alpha_composition for the training step (the autograd graph of
+ * train_tgtcs.py:236-255 restricted to utils.py:354-386).  rgbsigma [n,S,4] and ts as in the forward; g_rgb [n,3] =
+ * dL/d(rgb map); g_depth [n], g_acc [n] may be NULL.  Writes d_rgbsigma [n,S,4] = dL/d(r,g,b,sigma) per sample.
+ * No gradient flows to ts (utils.py:576-579).  S <= 256. */
+int tgtc_composite_backward(tgtc_ctx* ctx, const float* rgbsigma, const float* ts, int64_t ts_ray_stride, const float* noise,
+                            int white_bkgd, int64_t n, int S, const float* g_rgb, const float* g_depth, const float* g_acc,
+                            float* d_rgbsigma, tgtc_stream stream);
+
 /* K6+K7 -- hierarchical inverse-CDF resampling + sorted union.  Replaces
  * utils.sampling_pts_fine_torch (utils.py:573-580) and utils.sample_pdf
  * (utils.py:583-609, det=True).  Bin selection is bit-exact with CPU torch

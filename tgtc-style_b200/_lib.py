@@ -44,6 +44,8 @@ PROTOTYPES = {
                                               ctypes.c_double, ctypes.c_double, c_void_p, c_void_p]),
     "tgtc_composite": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, ctypes.c_int, c_i64,
                                       ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tgtc_composite_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, ctypes.c_int, c_i64, ctypes.c_int,
+                                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tgtc_sample_fine": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, ctypes.c_int, ctypes.c_int,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tgtc_render_workspace_bytes": (ctypes.c_size_t, [c_i64, ctypes.c_int, ctypes.c_int, c_i64]),

@@ -209,6 +209,22 @@ extern "C" int tgtc_composite(tgtc_ctx* ctx, const float* rgb, const float* sigm
                           weights_out, (cudaStream_t)stream);
 }
 
+extern "C" int tgtc_composite_backward(tgtc_ctx* ctx, const float* rgbsigma, const float* ts, int64_t ts_ray_stride,
+                                       const float* noise, int white_bkgd, int64_t n, int S, const float* g_rgb,
+                                       const float* g_depth, const float* g_acc, float* d_rgbsigma, tgtc_stream stream) {
+  CHECK_CTX(ctx);
+  TGTC_REQUIRE(n >= 0 && S >= 1, TGTC_ERR_ARG, "bad sizes n=%lld S=%d", (long long)n, S);
+  if (n == 0) return TGTC_OK;
+  CHECK_PTR(rgbsigma, "rgbsigma");
+  CHECK_PTR(ts, "ts");
+  CHECK_PTR(g_rgb, "g_rgb");
+  CHECK_PTR(d_rgbsigma, "d_rgbsigma");
+  TGTC_REQUIRE(aligned16(rgbsigma) && aligned16(d_rgbsigma), TGTC_ERR_ARG, "rgbsigma / d_rgbsigma not 16-byte aligned");
+  TGTC_REQUIRE(ts_ray_stride == 0 || ts_ray_stride >= S, TGTC_ERR_ARG, "bad ts_ray_stride %lld", (long long)ts_ray_stride);
+  return launch_composite_backward(ctx, rgbsigma, ts, ts_ray_stride, noise, white_bkgd, n, S, g_rgb, g_depth, g_acc, d_rgbsigma,
+                                   (cudaStream_t)stream);
+}
+
 extern "C" int tgtc_sample_fine(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, const float* ts,
                                 int64_t ts_ray_stride, const float* weights, int64_t n, int S, int n_fine, float* pts_out,
                                 float* ts_out, int64_t* inds_out, float* samples_out, tgtc_stream stream) {

@@ -141,6 +141,10 @@ int launch_composite(tgtc_ctx* ctx, const float* rgb, const float* sigma, const 
                      int64_t ts_stride, const float* noise, int white_bkgd, int64_t n, int S, float* rgb_out,
                      float* depth_out, float* acc_out, float* weights_out, cudaStream_t st);
 
+int launch_composite_backward(tgtc_ctx* ctx, const float* rgbsigma, const float* ts, int64_t ts_stride, const float* noise,
+                              int white_bkgd, int64_t n, int S, const float* g_rgb, const float* g_depth, const float* g_acc,
+                              float* d_rgbsigma, cudaStream_t st);
+
 // how the MLP kernels get their per-sample inputs and where results go
 struct MlpIO {
   // explicit-points mode (rays_o == nullptr): pts [M,3]; dirs [n_rays,3] if dirs_per_ray else [M,3]

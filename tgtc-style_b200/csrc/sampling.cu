@@ -45,6 +45,7 @@ struct FineSmem {
   float w[kMaxS];        // weights[1:-1] + 1e-5, later pdf
   float cdf[kMaxS];      // S-1 entries
   float out[kMaxOut];    // union to sort
+  float smp[kMaxOut];    // the new inverse-CDF samples (F entries)
 };
 
 __device__ __forceinline__ double shfl_up_f64(double v, int delta) {
@@ -144,16 +145,28 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_fine_kernel(
       if (denom < 1e-5f) denom = 1.0f;
       const float t = __fdiv_rn(__fsub_rn(u, cb), denom);
       const float s = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
-      sm.out[S + k] = s;
+      sm.smp[k] = s;
       if (inds_out != nullptr) inds_out[ray * F + k] = ind;
       if (samples_out != nullptr) samples_out[ray * F + k] = s;
     }
-    for (int i = lane; i < S; i += 32) sm.out[i] = sm.ts[i];
-    for (int i = total + lane; i < sort_n; i += 32) sm.out[i] = __int_as_float(0x7f800000);  // +inf padding
     __syncwarp();
-
-    // ---- torch.sort(cat(ts, t_samples)): bitonic network over sort_n (power of two) in shared memory
-    for (int k = 2; k <= sort_n; k <<= 1) {
+    // ---- torch.sort(cat(ts, t_samples)) (utils.py:577), values only.  ts is ascending by construction; the new
+    // samples are non-decreasing except in rare fp32 corner cases.  When they are (warp vote) and S+F is a power of
+    // two, asc(ts) ++ reversed(samples) is a bitonic sequence and ONE bitonic merge (log2 n steps) sorts it;
+    // otherwise fall back to the full bitonic network (log2^2 n steps).
+    bool mono = true;
+    for (int k = lane; k + 1 < F; k += 32) mono = mono && (sm.smp[k] <= sm.smp[k + 1]);
+    for (int i = lane; i + 1 < S; i += 32) mono = mono && (sm.ts[i] <= sm.ts[i + 1]);
+    const bool merge_only = __all_sync(0xffffffffu, mono) && (total == sort_n);
+    for (int i = lane; i < S; i += 32) sm.out[i] = sm.ts[i];
+    if (merge_only) {
+      for (int k = lane; k < F; k += 32) sm.out[S + (F - 1 - k)] = sm.smp[k];
+    } else {
+      for (int k = lane; k < F; k += 32) sm.out[S + k] = sm.smp[k];
+      for (int i = total + lane; i < sort_n; i += 32) sm.out[i] = __int_as_float(0x7f800000);  // +inf padding
+    }
+    __syncwarp();
+    for (int k = merge_only ? sort_n : 2; k <= sort_n; k <<= 1) {
       for (int j = k >> 1; j > 0; j >>= 1) {
         for (int i = lane; i < sort_n; i += 32) {
           const int ixj = i ^ j;

@@ -219,6 +219,25 @@ class NerfRenderer:
                                            _ptr(o_rgb), _ptr(o_d), _ptr(o_a), _ptr(o_w), self._stream))
         return o_rgb, o_d, o_w, o_a
 
+    def composite_backward(self, rgbsigma, t_values, g_rgb, g_depth=None, g_acc=None, noise=None, white_bkgd=False):
+        """Gradient of utils.alpha_composition (utils.py:354-386) w.r.t. the per-sample (r,g,b,sigma): rgbsigma [N,S,4],
+        g_rgb [N,3] = dL/d(rgb map) (+ optional dL/d(depth), dL/d(acc)) -> d_rgbsigma [N,S,4]."""
+        rs = self._dev(rgbsigma)
+        n, S = rs.shape[0], rs.shape[1]
+        ts_t = torch.as_tensor(t_values)
+        if ts_t.dim() == 1 or (ts_t.dim() == 2 and ts_t.stride(0) == 0 and n > 1):
+            tsd, stride = self._dev(ts_t if ts_t.dim() == 1 else ts_t[0]), 0
+        else:
+            tsd, stride = self._dev(ts_t), S
+        g = self._dev(g_rgb)
+        gd = self._dev(g_depth) if g_depth is not None else None
+        ga = self._dev(g_acc) if g_acc is not None else None
+        nz = self._dev(noise) if noise is not None else None
+        out = torch.empty(n, S, 4, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.tgtc_composite_backward(self._h, _ptr(rs), _ptr(tsd), stride, _ptr(nz), int(white_bkgd), n, S, _ptr(g),
+                                                    _ptr(gd), _ptr(ga), _ptr(out), self._stream))
+        return out
+
     # ------------------------------------------------------------------ K6+K7
     def sample_fine(self, rays_o, rays_d, ts, weights, n_fine=64, want_pts=True, return_aux=False):
         """utils.sampling_pts_fine_torch (utils.py:573-580).  Returns (pts [N,S+F,3], ts [N,S+F]) and, with
