@@ -174,6 +174,22 @@ int tgtc_render_frame(tgtc_ctx* ctx, int mode, int H, int W, const double* K, co
                       int n_fine, int64_t chunk, int white_bkgd, const tgtc_render_out* out, void* workspace,
                       size_t workspace_bytes, tgtc_stream stream);
 
+/* Training step (replaces the autograd graph of Origin_train, train_tgtcs.py:228-255, for one batch
+ * of rays with perturb=0 / sigma_noise_std=0): forward of both nets with the activations stashed, the two MSE losses
+ * against rgb_gt [n,3], and the full backward.  grads: flat fp32 buffer of 2 * tgtc_num_params() values -- coarse net
+ * then fine net, each in the order of tgtc_set_weights (weight [out,in] row-major, bias) -- so one all-reduce covers
+ * both nets; accumulate != 0 adds to it (ray chunks of one step).  The loss is
+ * mean((rgb_coarse-gt)^2) + mean((rgb_fine-gt)^2) over n_rays_total*3 values (pass the whole step's ray count when
+ * the step is split into chunks / ranks); loss_sums (device float[2], may be NULL) is incremented by the two
+ * un-normalised squared-error sums.  rgb_coarse / rgb_fine [n,3] may be NULL.  bf16 tcgen05 path;
+ * n_samples = n_fine = 64.  No gradient flows through the resampling (utils.py:576-579). */
+size_t tgtc_train_workspace_bytes(tgtc_ctx* ctx, int64_t n_rays, int n_samples, int n_fine);
+int64_t tgtc_num_params(void); /* 595 844 per net */
+int tgtc_train_step(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, const float* rgb_gt, int64_t n_rays,
+                    int64_t n_rays_total, double near, double far, int n_samples, int n_fine, float* grads, int accumulate,
+                    float* loss_sums, float* rgb_coarse, float* rgb_fine, void* workspace, size_t workspace_bytes,
+                    tgtc_stream stream);
+
 /* Per-kernel device timing of the MLP launches (the dominant kernel), for the roofline line of bench.py:
  * while enabled, every MLP launch is bracketed by cudaEvents on its stream (no host sync).
  * tgtc_profile_read synchronises those events and returns, since the last read/enable: the number of MLP

@@ -334,3 +334,25 @@ def render_chain(sd_coarse, sd_fine, rays_o, rays_d, near=0., far=1., n_samples=
     if keep_intermediates:
         out.update(pts_fine=pts_f, rgb_pts_fine=ret_f["rgb"], sigma_fine=ret_f["sigma"], t_samples=t_samples, cdf=cdf)
     return out
+
+
+def train_step_reference(sd_coarse, sd_fine, rays_o, rays_d, rgb_gt, near=0., far=1., n_samples=64, n_fine=64):
+    """train_tgtcs.py:228-255 (Origin_train's step) with perturb=0 and sigma_noise_std=0, through torch.autograd:
+    loss = mse(rgb_gt, rgb_coarse) + mse(rgb_gt, rgb_fine)  (utils.py:460).  No gradient flows through the
+    resampling (utils.py:576-579).  Returns (loss, grads_coarse, grads_fine, rgb_coarse, rgb_fine, ts_fine)."""
+    ro = torch.as_tensor(rays_o, dtype=torch.float32)
+    rd = torch.as_tensor(rays_d, dtype=torch.float32)
+    gt = torch.as_tensor(rgb_gt, dtype=torch.float32)
+    n = ro.shape[0]
+    pc = {k: v.detach().clone().requires_grad_(True) for k, v in sd_coarse.items()}
+    pf = {k: v.detach().clone().requires_grad_(True) for k, v in sd_fine.items()}
+    pts, ts = sample_uniform(ro, rd, n_samples, near, far)
+    ret = nerf_forward(pc, pts, rd.unsqueeze(1).expand(n, n_samples, 3))
+    rgb_c, _, w_c, _ = alpha_composition(ret["rgb"], ret["sigma"], ts)
+    pts_f, ts_f = sample_fine(ro, rd, ts, w_c.detach(), n_fine)
+    ret_f = nerf_forward(pf, pts_f.detach(), rd.unsqueeze(1).expand(n, n_samples + n_fine, 3))
+    rgb_f = alpha_composition(ret_f["rgb"], ret_f["sigma"], ts_f)[0]
+    loss = torch.mean((rgb_c - gt) ** 2) + torch.mean((rgb_f - gt) ** 2)
+    loss.backward()
+    return (loss.detach(), {k: v.grad for k, v in pc.items()}, {k: v.grad for k, v in pf.items()}, rgb_c.detach(), rgb_f.detach(),
+            ts_f.detach())

@@ -62,6 +62,7 @@ extern "C" int tgtc_destroy(tgtc_ctx* ctx) {
     if (ctx->net[i].f32_gemm) cudaFree(ctx->net[i].f32_gemm);
     if (ctx->net[i].smalls) cudaFree(ctx->net[i].smalls);
     if (ctx->net[i].tc_blob) cudaFree(ctx->net[i].tc_blob);
+    if (ctx->net[i].tc_blobT) cudaFree(ctx->net[i].tc_blobT);
   }
   if (ctx->arena) cudaFree(ctx->arena);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
@@ -447,3 +448,113 @@ extern "C" int tgtc_render_frame(tgtc_ctx* ctx, int mode, int H, int W, const do
   return render_impl(ctx, mode, ro, rd, n, near, far, n_samples, n_fine, chunk, white_bkgd, *out, base + 2 * ray_bytes,
                      workspace_bytes - 2 * ray_bytes, st);
 }
+
+// ---------------------------------------------------------------------------
+// training step: forward with activation stash + backward, both nets
+
+struct TrainWs {
+  size_t off_stash_h, off_stash_f, off_stash_pe, off_dz, off_dzf, off_dhead, off_rs, off_drs, off_w_c, off_ts_f, off_ts_c,
+      off_rgb, off_g, off_partial, total;
+};
+
+static TrainWs train_ws_layout(tgtc_ctx* ctx, int64_t n, int S, int F) {
+  TrainWs w;
+  const int64_t Mf = n * (S + F), Mc = n * S;
+  const int64_t Mmax = Mf > Mc ? Mf : Mc;
+  const size_t tiles = (size_t)((Mmax + 127) / 128);
+  size_t o = 0;
+  w.off_stash_h = o;  o = align_up(o + tiles * kStashHBytesPerTile, 1024);
+  w.off_stash_f = o;  o = align_up(o + tiles * kStashFBytesPerTile, 1024);
+  w.off_stash_pe = o; o = align_up(o + tiles * kStashPeBytesPerTile, 1024);
+  w.off_dz = o;       o = align_up(o + tiles * kStashHBytesPerTile, 1024);
+  w.off_dzf = o;      o = align_up(o + tiles * kStashFBytesPerTile, 1024);
+  w.off_dhead = o;    o = align_up(o + tiles * kStashPeBytesPerTile, 1024);
+  w.off_rs = o;       o = align_up(o + (size_t)Mmax * 16, 256);
+  w.off_drs = o;      o = align_up(o + (size_t)Mmax * 16, 256);
+  w.off_w_c = o;      o = align_up(o + (size_t)n * S * 4, 256);
+  w.off_ts_f = o;     o = align_up(o + (size_t)n * (S + F) * 4, 256);
+  w.off_ts_c = o;     o = align_up(o + (size_t)S * 4, 256);
+  w.off_rgb = o;      o = align_up(o + (size_t)n * 12, 256);
+  w.off_g = o;        o = align_up(o + (size_t)n * 12, 256);
+  w.off_partial = o;  o = align_up(o + (size_t)ctx->num_sms * bwd_partial_floats() * 4, 256);
+  w.total = o;
+  return w;
+}
+
+extern "C" size_t tgtc_train_workspace_bytes(tgtc_ctx* ctx, int64_t n_rays, int n_samples, int n_fine) {
+  if (ctx == nullptr || n_rays <= 0 || n_samples <= 0 || n_fine < 0) return 0;
+  return train_ws_layout(ctx, n_rays, n_samples, n_fine).total;
+}
+
+extern "C" int64_t tgtc_num_params(void) { return (int64_t)bwd_flat_floats(); }
+
+// one network pass: forward (stash) -> compositing -> [caller hook: resampling] -> loss gradient -> compositing backward ->
+// activation gradients -> weight gradients
+static int train_pass(tgtc_ctx* ctx, int net, const float* rays_o, const float* rays_d, const float* ts, int64_t ts_stride, int64_t n,
+                      int S, double near, double far, const float* rgb_gt, float scale, const TrainWs& ws, uint8_t* base,
+                      float* grads, int accumulate, float* sq_sum, float* rgb_out, float* weights_out, cudaStream_t st) {
+  TcStash stash;
+  stash.h = base + ws.off_stash_h; stash.f = base + ws.off_stash_f; stash.pe = base + ws.off_stash_pe;
+  TcDz dz;
+  dz.dz = base + ws.off_dz; dz.dzf = base + ws.off_dzf; dz.dhead = base + ws.off_dhead;
+  float* rs = reinterpret_cast<float*>(base + ws.off_rs);
+  float* drs = reinterpret_cast<float*>(base + ws.off_drs);
+  float* rgb = rgb_out != nullptr ? rgb_out : reinterpret_cast<float*>(base + ws.off_rgb);
+  float* g = reinterpret_cast<float*>(base + ws.off_g);
+  float* partial = reinterpret_cast<float*>(base + ws.off_partial);
+  MlpIO io;
+  io.rays_o = rays_o; io.rays_d = rays_d; io.ts = ts_stride == 0 ? nullptr : ts;
+  io.t_scale = (float)(far - near); io.t_near = (float)near;
+  io.n_rays = n; io.S = S; io.rgbsigma = rs;
+  TGTC_REQUIRE(mlp_tc_supports(io), TGTC_ERR_UNSUPPORTED, "training needs n_samples in {64,128} (tcgen05 path)");
+  int rc = launch_mlp_tc_train(ctx, net, io, stash, st);
+  if (rc) return rc;
+  rc = launch_composite(ctx, nullptr, nullptr, rs, ts, ts_stride, nullptr, 0, n, S, rgb, nullptr, nullptr, weights_out, st);
+  if (rc) return rc;
+  rc = launch_mse_grad(ctx, rgb, rgb_gt, n, scale, g, sq_sum, st);
+  if (rc) return rc;
+  rc = launch_composite_backward(ctx, rs, ts, ts_stride, nullptr, 0, n, S, g, nullptr, nullptr, drs, st);
+  if (rc) return rc;
+  rc = launch_mlp_dgrad(ctx, net, rs, drs, stash, dz, n * S, st);
+  if (rc) return rc;
+  return launch_mlp_wgrad(ctx, stash, dz, rays_d, n * S, S, partial, grads, accumulate, st);
+}
+
+extern "C" int tgtc_train_step(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, const float* rgb_gt, int64_t n_rays,
+                               int64_t n_rays_total, double near, double far, int n_samples, int n_fine, float* grads,
+                               int accumulate, float* loss_sums, float* rgb_coarse, float* rgb_fine, void* workspace,
+                               size_t workspace_bytes, tgtc_stream stream) {
+  CHECK_CTX(ctx);
+  CHECK_NET(ctx, TGTC_NET_COARSE);
+  CHECK_NET(ctx, TGTC_NET_FINE);
+  TGTC_REQUIRE(n_rays >= 0 && n_rays_total >= n_rays, TGTC_ERR_ARG, "bad n_rays=%lld / n_rays_total=%lld", (long long)n_rays,
+               (long long)n_rays_total);
+  if (n_rays == 0) return TGTC_OK;
+  const int S = n_samples, F = n_fine;
+  TGTC_REQUIRE(S == 64 && (S + F) == 128, TGTC_ERR_UNSUPPORTED,
+               "training supports n_samples=64, n_fine=64 (configs/fern.txt:16-17); got %d+%d", S, F);
+  CHECK_PTR(rays_o, "rays_o"); CHECK_PTR(rays_d, "rays_d"); CHECK_PTR(rgb_gt, "rgb_gt"); CHECK_PTR(grads, "grads");
+  const TrainWs ws = train_ws_layout(ctx, n_rays, S, F);
+  TGTC_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0 && workspace_bytes >= ws.total,
+               TGTC_ERR_STATE, "training workspace too small or not 1024-byte aligned: need %zu bytes, got %zu", ws.total,
+               workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* base = static_cast<uint8_t*>(workspace);
+  float* ts_c = reinterpret_cast<float*>(base + ws.off_ts_c);
+  float* ts_f = reinterpret_cast<float*>(base + ws.off_ts_f);
+  float* w_c = reinterpret_cast<float*>(base + ws.off_w_c);
+  const size_t np = bwd_flat_floats();
+  // loss = mse(rgb_gt, rgb_coarse) + mse(rgb_gt, rgb_fine), each a mean over n_rays_total*3 values (train_tgtcs.py:238-251)
+  const float scale = 2.0f / (3.0f * (float)n_rays_total);
+  int rc = launch_sample_uniform(ctx, nullptr, nullptr, 1, S, near, far, nullptr, nullptr, ts_c, st);
+  if (rc) return rc;
+  rc = train_pass(ctx, TGTC_NET_COARSE, rays_o, rays_d, ts_c, 0, n_rays, S, near, far, rgb_gt, scale, ws, base, grads, accumulate,
+                  loss_sums, rgb_coarse, w_c, st);
+  if (rc) return rc;
+  // no gradient flows through the resampling (utils.py:576-579): the two nets' backward passes are independent
+  rc = launch_sample_fine(ctx, nullptr, nullptr, ts_c, 0, w_c, n_rays, S, F, nullptr, ts_f, nullptr, nullptr, st);
+  if (rc) return rc;
+  return train_pass(ctx, TGTC_NET_FINE, rays_o, rays_d, ts_f, S + F, n_rays, S + F, near, far, rgb_gt, scale, ws, base, grads + np,
+                    accumulate, loss_sums != nullptr ? loss_sums + 1 : nullptr, rgb_fine, nullptr, st);
+}
+

@@ -62,6 +62,7 @@ struct NetImage {
   float* f32_gemm = nullptr;   // kF32GemmFloats
   float* smalls = nullptr;     // kSmallFloats
   uint8_t* tc_blob = nullptr;  // kTcBlobBytes
+  uint8_t* tc_blobT = nullptr; // transposed weights for the activation-gradient kernel (mlp_bwd.cu), bwd_blobT_bytes()
   bool set = false;
 };
 
@@ -168,9 +169,38 @@ struct MlpIO {
   float* dirs_embed = nullptr;
 };
 
+// Activation stash of the training forward (mlp_tc.cu writes, mlp_bwd.cu reads).  Every array is a sequence of
+// "tile images": per 128-sample tile and per 64-column block, [128 rows x 128 B] bf16 in the 128-byte-swizzled
+// layout of the kernels' shared-memory operand tiles (byte = (row>>3)*1024 + (row&7)*128 + ((chunk ^ (row&7))<<4)),
+// so a bulk copy brings a ready tcgen05 operand (K-major as [sample x feature], MN-major as [feature x sample]).
+struct TcStash {
+  uint8_t* h = nullptr;    // [ntiles][9][4 blocks][16 KB]  post-ReLU outputs of L0..L7 and remap
+  uint8_t* f = nullptr;    // [ntiles][2 blocks][16 KB]     post-ReLU output of rgb0
+  uint8_t* pe = nullptr;   // [ntiles][16 KB]               positional encoding (column 63 = 0)
+};
+constexpr size_t kStashHBytesPerTile = 9 * 65536, kStashFBytesPerTile = 32768, kStashPeBytesPerTile = 16384;
+
+// gradients of the pre-activations, written by the dgrad kernel and read by the wgrad kernel (tile images like TcStash)
+struct TcDz {
+  uint8_t* dz = nullptr;     // [ntiles][9][64 KB]  dz_0..dz_7, dz_remap
+  uint8_t* dzf = nullptr;    // [ntiles][32 KB]     dz of rgb0
+  uint8_t* dhead = nullptr;  // [ntiles][16 KB]     columns 0..2 = dz of rgb1, column 3 = d_sigma
+};
+
+// mlp_bwd.cu
+size_t bwd_partial_floats();
+size_t bwd_blobT_bytes();
+size_t bwd_flat_floats();
+int launch_mlp_dgrad(tgtc_ctx* ctx, int net, const float* rgbsigma, const float* d_rgbsigma, const TcStash& stash, const TcDz& dz,
+                     int64_t M, cudaStream_t st);
+int launch_mlp_wgrad(tgtc_ctx* ctx, const TcStash& stash, const TcDz& dz, const float* rays_d, int64_t M, int S, float* partial,
+                     float* grads, int accumulate, cudaStream_t st);
+int launch_mse_grad(tgtc_ctx* ctx, const float* rgb, const float* gt, int64_t n, float scale, float* g, float* sq_sum, cudaStream_t st);
+
 // mlp_fp32.cu / mlp_tc.cu
 int launch_mlp_fp32(tgtc_ctx* ctx, int net, const MlpIO& io, cudaStream_t st);
 int launch_mlp_tc(tgtc_ctx* ctx, int net, const MlpIO& io, cudaStream_t st);
+int launch_mlp_tc_train(tgtc_ctx* ctx, int net, const MlpIO& io, const TcStash& stash, cudaStream_t st);
 bool mlp_tc_supports(const MlpIO& io);
 
 // ---------------------------------------------------------------------------

@@ -30,6 +30,7 @@
 // Tensor-roofline kernel: 1 186 816 algorithmic FLOP per sample; HBM traffic is
 // 24 B/ray in + 16 B/sample out.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
@@ -71,213 +72,25 @@ static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarPeReady = 2 * kStages, kBarPeFree = kBarPeReady + 2,
               kBarActReady = kBarPeFree + 2, kBarAccFull = kBarActReady + 2, kBarPePair = kBarAccFull + 2;
 
-// ---------------------------------------------------------------------------
-// PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// bounded wait: a protocol bug traps (visible as a launch failure) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s
-      printf("tgtc mlp_tc: mbarrier timeout (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-// warp-uniform wait for converged single-issuer warps: the loop condition is a vote, so control flow stays uniform and
-// ptxas can keep descriptors / barrier addresses in uniform registers across the wait
-__device__ __forceinline__ void mbar_wait_uniform(uint32_t bar, uint32_t parity) {
-  if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
-  const long long t0 = clock64();
-  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
-    if (clock64() - t0 > 4000000000LL) {
-      if ((threadIdx.x & 31) == 0) printf("tgtc mlp_tc: mbarrier timeout (block %d warp %d bar@%u parity %u)\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), bar, parity);
-      __trap();
-    }
-  }
-}
-// same, for roles that are far off the critical path: sleep between probes so the spin does not steal issue slots
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(ns);
-    if (clock64() - t0 > 4000000000LL) {
-      printf("tgtc mlp_tc: mbarrier timeout (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar)
-               : "memory");
-}
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-}
-// address of a shared-memory object of CTA `rank` of this cluster, in the shared::cluster window
-__device__ __forceinline__ uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  // default semantics (.release at CTA scope), as cutlass::arch::ClusterBarrier::arrive(cta_id): a cluster-scope release would
-  // make ptxas emit an L1 invalidate + membar on every arrive (measured: ~1 us per arrive)
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
-}
-// tcgen05.mma with the descriptors given as (lo, hi) halves: the hi halves are compile-time constants and the lo
-// halves advance by (byte offset >> 4), so one K step costs one integer add per operand
-__device__ __forceinline__ void umma_bf16_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
-                                               uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      ".reg .b64 da, db;\n"
-      "setp.ne.b32 p, %6, 0;\n"
-      "mov.b64 da, {%1, %2};\n"
-      "mov.b64 db, {%3, %4};\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// one lane of a converged warp (the same lane every time for a full mask)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n"
-      ".reg .b32 rx;\n"
-      ".reg .pred px;\n"
-      "elect.sync rx|px, 0xFFFFFFFF;\n"
-      "@px mov.s32 %0, 1;\n"
-      "}\n"
-      : "+r"(pred));
-  return pred != 0;
-}
-// sin/cos for the bf16 operand path: two-constant Cody-Waite reduction to [-pi, pi] (exact to ~2e-7 for |a| < 4096),
-// then the SFU approximations (abs error 2^-21.4 on that interval) -- three orders below a bf16 ulp
-__device__ __forceinline__ void fast_sincos(float a, float* s, float* c) {
-  const float n = rintf(a * 0.15915494309189535f);
-  float r = fmaf(n, -6.2831854820251465f, a);
-  r = fmaf(n, 1.7484555e-7f, r);
-  *s = __sinf(r);
-  *c = __cosf(r);
-}
-// arrive (once the MMAs issued so far by this thread retire) on the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
-               "h"((uint16_t)3)
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
-// wait::ld that also "defines" the 32 destination registers, so no use of them can be scheduled above the wait
-__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
-               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
-                 "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
-                 "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
-                 "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
-               :
-               : "memory");
-}
-// packed fp32x2 add (sm_100 FADD2): {x0,x1} += {b0,b1}
-__device__ __forceinline__ void add2(uint32_t& x0, uint32_t& x1, float b0, float b1) {
-  asm("{\n.reg .b64 a, b, d;\nmov.b64 a, {%0, %1};\nmov.b64 b, {%2, %3};\nadd.rn.f32x2 d, a, b;\nmov.b64 {%0, %1}, d;\n}\n"
-      : "+r"(x0), "+r"(x1)
-      : "f"(b0), "f"(b1));
-}
-// relu + round-to-nearest bf16 + pack in one instruction (F2FP.RELU)
-__device__ __forceinline__ uint32_t pack_bf16_relu(uint32_t lo, uint32_t hi) {
-  uint32_t r;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
-  return r;
-}
-
-// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): K-major, swizzled.
-//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major; 1 as CUTLASS) | [32,46) SBO>>4 |
-//   [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t hi) {
-  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
-  return ((uint64_t)hi << 32) | lo;
-}
-constexpr uint32_t kDescHiSW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
-
-// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
+using namespace tcptx;
 
 // one 32-column block of a hidden-layer epilogue: +bias, ReLU, bf16, 4 x 16-byte swizzled stores.
 // blk = 32-column block index inside this thread's 128 columns; kb = row base of the 64-column K block.
+// gk: when training, the same 16-byte chunk also goes to the activation stash in HBM (tile image = the shared-memory
+// layout verbatim), at the address that corresponds to kb; nullptr otherwise.
+__device__ __forceinline__ void st_global_v4(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
+}
 template <bool kSigma>
 __device__ __forceinline__ void epi_block(uint32_t (&v)[32], const float* bl, const float* wsig, uint32_t kb, uint32_t rx, int blk,
-                                          float& sig) {
+                                          float& sig, uint8_t* gk) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int c = blk * 32 + 8 * j;  // column inside the 128-column half
     const float4 b0 = *reinterpret_cast<const float4*>(bl + c);
     const float4 b1 = *reinterpret_cast<const float4*>(bl + c + 4);
-    const uint32_t dst = kb + ((uint32_t)((((blk & 1) * 4) + j) << 4) ^ rx);
+    const uint32_t coff = (uint32_t)((((blk & 1) * 4) + j) << 4) ^ rx;
+    const uint32_t dst = kb + coff;
     if constexpr (kSigma) {
       float h[8];
       h[0] = fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x, 0.f);
@@ -293,14 +106,18 @@ __device__ __forceinline__ void epi_block(uint32_t (&v)[32], const float* bl, co
       const float4 w1 = *reinterpret_cast<const float4*>(wsig + c + 4);
       sig = fmaf(h[0], w0.x, sig); sig = fmaf(h[1], w0.y, sig); sig = fmaf(h[2], w0.z, sig); sig = fmaf(h[3], w0.w, sig);
       sig = fmaf(h[4], w1.x, sig); sig = fmaf(h[5], w1.y, sig); sig = fmaf(h[6], w1.z, sig); sig = fmaf(h[7], w1.w, sig);
-      st_shared_v4(dst, pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+      const uint32_t q0 = pack_bf16(h[0], h[1]), q1 = pack_bf16(h[2], h[3]), q2 = pack_bf16(h[4], h[5]), q3 = pack_bf16(h[6], h[7]);
+      st_shared_v4(dst, q0, q1, q2, q3);
+      if (gk != nullptr) st_global_v4(gk + coff, q0, q1, q2, q3);
     } else {
       add2(v[8 * j + 0], v[8 * j + 1], b0.x, b0.y);
       add2(v[8 * j + 2], v[8 * j + 3], b0.z, b0.w);
       add2(v[8 * j + 4], v[8 * j + 5], b1.x, b1.y);
       add2(v[8 * j + 6], v[8 * j + 7], b1.z, b1.w);
-      st_shared_v4(dst, pack_bf16_relu(v[8 * j + 0], v[8 * j + 1]), pack_bf16_relu(v[8 * j + 2], v[8 * j + 3]),
-                   pack_bf16_relu(v[8 * j + 4], v[8 * j + 5]), pack_bf16_relu(v[8 * j + 6], v[8 * j + 7]));
+      const uint32_t q0 = pack_bf16_relu(v[8 * j + 0], v[8 * j + 1]), q1 = pack_bf16_relu(v[8 * j + 2], v[8 * j + 3]),
+                     q2 = pack_bf16_relu(v[8 * j + 4], v[8 * j + 5]), q3 = pack_bf16_relu(v[8 * j + 6], v[8 * j + 7]);
+      st_shared_v4(dst, q0, q1, q2, q3);
+      if (gk != nullptr) st_global_v4(gk + coff, q0, q1, q2, q3);
     }
   }
 }
@@ -308,21 +125,23 @@ __device__ __forceinline__ void epi_block(uint32_t (&v)[32], const float* bl, co
 // this thread's 128 columns of one hidden layer: TMEM loads software-pipelined against the math
 // (the load of block b+1 is in flight while block b is converted and stored)
 template <bool kSigma>
-__device__ __forceinline__ float hidden_epilogue(uint32_t tcol, const float* bl, const float* wsig, uint32_t arow, uint32_t rx) {
+__device__ __forceinline__ float hidden_epilogue(uint32_t tcol, const float* bl, const float* wsig, uint32_t arow, uint32_t rx,
+                                                 uint8_t* grow) {
+  uint8_t* const grow1 = grow != nullptr ? grow + 16384 : nullptr;
   float sig = 0.f;
   uint32_t va[32], vb[32];
   tmem_ld32(tcol, va);
   tmem_ld_wait_dep(va);
   tmem_ld32(tcol + 32, vb);
-  epi_block<kSigma>(va, bl, wsig, arow, rx, 0, sig);
+  epi_block<kSigma>(va, bl, wsig, arow, rx, 0, sig, grow);
   tmem_ld_wait_dep(vb);
   tmem_ld32(tcol + 64, va);
-  epi_block<kSigma>(vb, bl, wsig, arow, rx, 1, sig);
+  epi_block<kSigma>(vb, bl, wsig, arow, rx, 1, sig, grow);
   tmem_ld_wait_dep(va);
   tmem_ld32(tcol + 96, vb);
-  epi_block<kSigma>(va, bl, wsig, arow + 16384, rx, 2, sig);
+  epi_block<kSigma>(va, bl, wsig, arow + 16384, rx, 2, sig, grow1);
   tmem_ld_wait_dep(vb);
-  epi_block<kSigma>(vb, bl, wsig, arow + 16384, rx, 3, sig);
+  epi_block<kSigma>(vb, bl, wsig, arow + 16384, rx, 3, sig, grow1);
   return sig;
 }
 
@@ -333,6 +152,10 @@ struct TcParams {
   int64_t M;        // samples
   int64_t ntiles;
   int rays_per_tile;  // 128/S when S<128 else 1
+  // training: activation stash (tile images, see mlp_bwd.cu); all nullptr for inference
+  uint8_t* stash_h;   // [ntiles][9][128 x 256 bf16]  post-ReLU outputs of L0..L7 and remap
+  uint8_t* stash_f;   // [ntiles][128 x 128 bf16]      post-ReLU output of rgb0
+  uint8_t* stash_pe;  // [ntiles][128 x 64 bf16]       positional encoding tile
   int dbg_flags;      // timing experiments (results garbage): 2 = skip the hidden-layer epilogue work, 16 = no weight ring at all
   int dbg_layers;     // >0: stop after this many GEMM layers and dump the fp32 accumulator (tests)
   float* dbg_out;     // [ntiles*128, 256]
@@ -541,10 +364,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
           for (int a = 0; a < 3; ++a) fast_sincos(__fmul_rn(x[a], fr), &e[3 + 6 * f + a], &e[3 + 6 * f + 3 + a]);
         }
         e[63] = 0.f;
+        uint8_t* const gpe = (P.stash_pe != nullptr && tile < P.ntiles) ? P.stash_pe + (size_t)tile * 16384 + (r >> 3) * 1024 + (r & 7) * 128 : nullptr;
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch)
-          st_shared_v4(prow + ((ch ^ (r & 7)) << 4), pack_bf16(e[8 * ch + 0], e[8 * ch + 1]), pack_bf16(e[8 * ch + 2], e[8 * ch + 3]),
-                       pack_bf16(e[8 * ch + 4], e[8 * ch + 5]), pack_bf16(e[8 * ch + 6], e[8 * ch + 7]));
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint32_t q0 = pack_bf16(e[8 * ch + 0], e[8 * ch + 1]), q1 = pack_bf16(e[8 * ch + 2], e[8 * ch + 3]),
+                         q2 = pack_bf16(e[8 * ch + 4], e[8 * ch + 5]), q3 = pack_bf16(e[8 * ch + 6], e[8 * ch + 7]);
+          st_shared_v4(prow + ((ch ^ (r & 7)) << 4), q0, q1, q2, q3);
+          if (gpe != nullptr) st_global_v4(gpe + ((ch ^ (r & 7)) << 4), q0, q1, q2, q3);
+        }
         // ---- per-ray view-direction term of rgb0: b_rgb0[j] + sum_k W_dir[k][j] * dirPE[k]   (j = r)
         {
           float* db = reinterpret_cast<float*>(smem + kOffDirBias) + ((t * 2 + (int)(it & 1)) * kMaxRaysPerTile) * 128;
@@ -635,12 +462,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
             const uint32_t arow = sbase + kOffAct + t * kActBytes + (row >> 3) * 1024 + (row & 7) * 128 + hc * 2 * 16384;
             const uint32_t tcol = taddr + hc * 128;
             const uint32_t rx = (uint32_t)(row & 7) << 4;
+            uint8_t* grow = nullptr;
+            if (P.stash_h != nullptr && tile < P.ntiles)
+              grow = P.stash_h + ((size_t)tile * 9 + l) * 65536 + (row >> 3) * 1024 + (row & 7) * 128 + hc * 2 * 16384;
             if (P.dbg_flags & 2) {
             } else if (l == 7) {
-              const float sig = hidden_epilogue<true>(tcol, bl, wsig_s + hc * 128, arow, rx);
+              const float sig = hidden_epilogue<true>(tcol, bl, wsig_s + hc * 128, arow, rx, grow);
               if (hc == 1) sigpart_s[t * 128 + row] = sig; else sig_keep[t] = sig;
             } else {
-              hidden_epilogue<false>(tcol, bl, nullptr, arow, rx);
+              hidden_epilogue<false>(tcol, bl, nullptr, arow, rx, grow);
             }
             fence_proxy_async();
             tc_fence_before();
@@ -658,6 +488,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
               const int c0 = hc * 64 + b * 32;
               tmem_ld32(taddr + c0, v);
               tmem_ld_wait();
+              uint32_t fq[16];  // bf16 pairs of this block's 32 outputs (training stash)
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const int c = c0 + j;
@@ -672,6 +503,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
                 p0 = fmaf(f0, w0.x, p0); p0 = fmaf(f1, w0.y, p0); p0 = fmaf(f2, w0.z, p0); p0 = fmaf(f3, w0.w, p0);
                 p1 = fmaf(f0, w1.x, p1); p1 = fmaf(f1, w1.y, p1); p1 = fmaf(f2, w1.z, p1); p1 = fmaf(f3, w1.w, p1);
                 p2 = fmaf(f0, w2.x, p2); p2 = fmaf(f1, w2.y, p2); p2 = fmaf(f2, w2.z, p2); p2 = fmaf(f3, w2.w, p2);
+                fq[j / 2] = pack_bf16(f0, f1);
+                fq[j / 2 + 1] = pack_bf16(f2, f3);
+              }
+              if (P.stash_f != nullptr && tile < P.ntiles) {
+                // rgb0 output tile image: K block hc (64 columns), 16-byte chunks b*4 .. b*4+3 of this row
+                uint8_t* gf = P.stash_f + (size_t)tile * 32768 + hc * 16384 + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+                  st_global_v4(gf + (((b * 4 + ch) ^ (row & 7)) << 4), fq[4 * ch], fq[4 * ch + 1], fq[4 * ch + 2], fq[4 * ch + 3]);
               }
             }
             tc_fence_before();
@@ -726,7 +566,8 @@ static long long* g_dbg_trace = nullptr;
 extern "C" void tgtc_debug_tc_flags(int f) { g_dbg_flags = f; }
 extern "C" void tgtc_debug_tc_trace(long long* dev_buf) { g_dbg_trace = dev_buf; }
 
-static int launch_tc_common(tgtc_ctx* ctx, int net, const MlpIO& io, int dbg_layers, float* dbg_out, cudaStream_t st) {
+static int launch_tc_common(tgtc_ctx* ctx, int net, const MlpIO& io, int dbg_layers, float* dbg_out, const TcStash* stash,
+                            cudaStream_t st) {
   const NetImage& im = ctx->net[net];
   TcParams P;
   P.blob = im.tc_blob;
@@ -738,6 +579,9 @@ static int launch_tc_common(tgtc_ctx* ctx, int net, const MlpIO& io, int dbg_lay
   P.rays_per_tile = io.S < kTileM ? kTileM / io.S : 1;
   P.dbg_layers = dbg_layers;
   P.dbg_flags = g_dbg_flags;
+  P.stash_h = stash != nullptr ? stash->h : nullptr;
+  P.stash_f = stash != nullptr ? stash->f : nullptr;
+  P.stash_pe = stash != nullptr ? stash->pe : nullptr;
   P.dbg_trace = g_dbg_trace;
   P.dbg_out = dbg_out;
   static bool attr_set[64] = {};
@@ -753,8 +597,13 @@ static int launch_tc_common(tgtc_ctx* ctx, int net, const MlpIO& io, int dbg_lay
   return TGTC_OK;
 }
 
+// training forward: same kernel, additionally writing the activation stash the backward kernels read
+int launch_mlp_tc_train(tgtc_ctx* ctx, int net, const MlpIO& io, const TcStash& stash, cudaStream_t st) {
+  return launch_tc_common(ctx, net, io, 0, nullptr, &stash, st);
+}
+
 int launch_mlp_tc(tgtc_ctx* ctx, int net, const MlpIO& io, cudaStream_t st) {
-  return launch_tc_common(ctx, net, io, 0, nullptr, st);
+  return launch_tc_common(ctx, net, io, 0, nullptr, nullptr, st);
 }
 
 // test hook (not part of the public header): run the first `layers` GEMM layers of the bf16 kernel and dump
@@ -768,5 +617,5 @@ extern "C" int tgtc_debug_tc_layers(tgtc_ctx* ctx, int net, const float* rays_o,
   io.t_scale = (float)(far - near); io.t_near = (float)near;
   io.n_rays = n_rays; io.S = S;
   if (!mlp_tc_supports(io)) { tgtc_set_error("unsupported S"); return TGTC_ERR_UNSUPPORTED; }
-  return launch_tc_common(ctx, net, io, layers, acc_out, (cudaStream_t)stream);
+  return launch_tc_common(ctx, net, io, layers, acc_out, nullptr, (cudaStream_t)stream);
 }

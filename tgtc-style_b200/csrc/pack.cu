@@ -74,6 +74,35 @@ __global__ void pack_tc_kernel(Params24 P, __nv_bfloat16* __restrict__ out) {
   }
 }
 
+// transposed image for the activation-gradient chain (mlp_bwd.cu): GEMM g multiplies dz [128 x K=out features] by
+// B[n = input feature][k = output feature] = W[k][n]; chunks of [256 rows x 64 K], 128B-swizzled, in the order
+// rgb0 (remap columns; K=128), remap, L7, L6, L5 (hidden columns), L4, L3, L2, L1.
+__global__ void pack_tcT_kernel(Params24 P, __nv_bfloat16* __restrict__ out, size_t total) {
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t e0 = 2 * 256 * 64;                 // elements of GEMM 0 (two chunks)
+    int g;
+    size_t r;
+    if (idx < e0) { g = 0; r = idx; } else { g = 1 + (int)((idx - e0) / (4 * 256 * 64)); r = (idx - e0) % (4 * 256 * 64); }
+    const int chunk = (int)(r / (256 * 64));
+    const int byte = (int)(r % (256 * 64)) * 2;
+    const int grp = byte >> 10, rem = byte & 1023;
+    const int rr = rem >> 7, inrow = rem & 127;
+    const int c16 = (inrow >> 4) ^ rr, within = (inrow & 15) >> 1;
+    const int n = grp * 8 + rr;                     // input feature
+    const int k = chunk * 64 + c16 * 8 + within;    // output feature
+    float v;
+    switch (g) {
+      case 0: v = P.p[2 * 10][k * 283 + n]; break;          // rgb0 [128, 283]
+      case 1: v = P.p[2 * 9][k * 256 + n]; break;           // remap
+      case 2: v = P.p[2 * 7][k * 256 + n]; break;
+      case 3: v = P.p[2 * 6][k * 256 + n]; break;
+      case 4: v = P.p[2 * 5][k * 319 + 63 + n]; break;      // L5: hidden columns follow the 63 PE columns (models.py:100)
+      default: v = P.p[2 * (9 - g)][k * 256 + n]; break;    // g=5..8 -> L4..L1
+    }
+    out[idx] = __float2bfloat16_rn(v);
+  }
+}
+
 __global__ void pack_smalls_kernel(Params24 P, float* __restrict__ out) {
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < kSmallFloats; idx += gridDim.x * blockDim.x) {
     float v;
@@ -107,12 +136,15 @@ int pack_weights(tgtc_ctx* ctx, int net, const float* const* params, cudaStream_
     TGTC_CUDA(cudaMalloc(&im.f32_gemm, kF32GemmFloats * sizeof(float)));
     TGTC_CUDA(cudaMalloc(&im.smalls, kSmallFloats * sizeof(float)));
     TGTC_CUDA(cudaMalloc(&im.tc_blob, kTcBlobBytes));
+    TGTC_CUDA(cudaMalloc(&im.tc_blobT, bwd_blobT_bytes()));
   }
   Params24 P;
   for (int i = 0; i < TGTC_NUM_PARAMS; ++i) P.p[i] = params[i];
   pack_f32_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(P, im.f32_gemm);
   TGTC_LAUNCH_CHECK(ctx);
   pack_tc_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(P, reinterpret_cast<__nv_bfloat16*>(im.tc_blob));
+  TGTC_LAUNCH_CHECK(ctx);
+  pack_tcT_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(P, reinterpret_cast<__nv_bfloat16*>(im.tc_blobT), bwd_blobT_bytes() / 2);
   TGTC_LAUNCH_CHECK(ctx);
   pack_smalls_kernel<<<32, 256, 0, st>>>(P, im.smalls);
   TGTC_LAUNCH_CHECK(ctx);

@@ -344,6 +344,46 @@ class NerfRenderer:
                                               self._stream))
         return out
 
+    # ------------------------------------------------------------------ training step (a11)
+    def train_step(self, rays_o, rays_d, rgb_gt, n_total=None, near=0., far=1., n_samples=64, n_fine=64, grads=None,
+                   accumulate=False):
+        """Forward + backward of Origin_train's loss (train_tgtcs.py:228-255, perturb=0, noise=0) for one batch of rays:
+        loss = mse(rgb_gt, rgb_coarse) + mse(rgb_gt, rgb_fine), means taken over n_total rays (default: this batch).
+        Returns {"loss" (device scalar), "grads" (flat fp32 [2*P]: coarse net then fine net, tgtc_set_weights order),
+        "rgb_coarse", "rgb_fine"}.  Pass the same `grads` with accumulate=True for the later ray chunks of one step."""
+        self.refresh_weights()
+        ro, rd, gt = self._dev(rays_o), self._dev(rays_d), self._dev(rgb_gt)
+        n = ro.shape[0]
+        n_total = n if n_total is None else int(n_total)
+        P = int(self.lib.tgtc_num_params())
+        if grads is None:
+            grads = torch.empty(2 * P, dtype=torch.float32, device=self.device)
+            accumulate = False
+        sums = torch.zeros(2, dtype=torch.float32, device=self.device)
+        rgb_c = torch.empty(n, 3, dtype=torch.float32, device=self.device)
+        rgb_f = torch.empty(n, 3, dtype=torch.float32, device=self.device)
+        wsb = self.lib.tgtc_train_workspace_bytes(self._h, n, n_samples, n_fine)
+        ws = self._workspace(wsb + 1024)
+        off = (-ws.data_ptr()) % 1024
+        _lib.check(self.lib.tgtc_train_step(self._h, _ptr(ro), _ptr(rd), _ptr(gt), n, n_total, float(near), float(far), n_samples,
+                                            n_fine, _ptr(grads), int(accumulate), _ptr(sums), _ptr(rgb_c), _ptr(rgb_f),
+                                            ctypes.c_void_p(ws.data_ptr() + off), wsb, self._stream))
+        return {"loss": sums.sum() / (3.0 * n_total), "grads": grads, "rgb_coarse": rgb_c, "rgb_fine": rgb_f}
+
+    def grad_views(self, flat):
+        """Per-parameter views into a flat gradient buffer: (coarse dict, fine dict) keyed like the state_dict."""
+        P = int(self.lib.tgtc_num_params())
+        out = []
+        for net in range(2):
+            d, o = {}, net * P
+            for name, (no, ni) in zip(LAYER_NAMES, LAYER_SHAPES):
+                d[name + ".weight"] = flat[o:o + no * ni].view(no, ni)
+                o += no * ni
+                d[name + ".bias"] = flat[o:o + no]
+                o += no
+            out.append(d)
+        return tuple(out)
+
     # ------------------------------------------------------------------ test hook
     def debug_tc_layers(self, net, rays_o, rays_d, ts, n_samples, near, far, layers):
         ro, rd = self._dev(rays_o), self._dev(rays_d)
