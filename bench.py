@@ -166,6 +166,175 @@ def run_reference_arm(args):
     }))
 
 
+TRAIN_WORKLOAD = ("training step: 32768-ray batch (rays of one fern-shaped 1008x756 frame, seeded randperm), forward+backward "
+                  "through both fused MLPs and compositing, 64 coarse + 128 fine samples/ray, perturb=0, Adam, data-parallel with one "
+                  "gradient all-reduce")
+TRAIN_RAYS = 32768
+TRAIN_FLOP_PER_SAMPLE = 3489024.0    # fwd + wgrad + dgrad
+DGRAD_BYTES_PER_SAMPLE = 9 * 512 + 256 + 32 + 9 * 512 + 256 + 128   # stash read (h, f, d_rgbsigma, rgbsigma) + dz/dzf/dhead written
+
+
+def run_train_reference_arm(args):
+    """--impl reference --workload train: the reference's training step (train_tgtcs.py:228-255) through torch.autograd
+    on the host cores (oracle port), a bounded ray sample per step."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import torch
+    import render_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wc, wf = O.init_linear_like_reference(0)
+    ro, rd = O.make_rays(H, W, FOCAL, np.eye(4)[:3, :4])
+    per_step = 256
+    rng = np.random.RandomState(2)
+    t_steps = []
+    for i in range(args.warmup + args.steps):
+        sel = rng.permutation(H * W)[:per_step]
+        gt = rng.rand(per_step, 3).astype(np.float32)
+        t0 = time.perf_counter()
+        O.train_step_reference(wc, wf, ro[sel], rd[sel], gt)
+        if i >= args.warmup:
+            t_steps.append(time.perf_counter() - t0)
+    total = sum(t_steps)
+    value = per_step * args.steps / total
+    sample = "%d rays per step (forward + autograd backward, no optimizer), torch CPU fp32, %d threads" % (per_step, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "rays/s", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": TRAIN_WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_train(args):
+    """--workload train (BASELINE config 5): one optimisation step per bench step, strong scaling over --gpus."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    import tgtc_style_b200 as T
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import render_oracle as O   # synthetic weight set W0 only
+    wc, wf = O.init_linear_like_reference(0)
+    r = T.NerfRenderer(device=dev, mode="bf16")
+    tr = T.NerfTrainer(r, wc, wf, max_rays_per_pass=32768)
+    K = np.array([[FOCAL, 0, 0.5 * W], [0, FOCAL, 0.5 * H], [0, 0, 1]])
+    ro_all, rd_all = r.raygen(H, W, K, np.eye(4)[:3, :4])
+    n_local = TRAIN_RAYS // world
+    gen = torch.Generator(device="cpu").manual_seed(2)
+    batches = []
+    for i in range(4):   # a few distinct batches; rank r takes rays [r*n_local, (r+1)*n_local) of each
+        perm = torch.randperm(H * W, generator=gen)[:TRAIN_RAYS]
+        sel = perm[rank * n_local:(rank + 1) * n_local].to(dev)
+        gt = torch.rand(TRAIN_RAYS, 3, generator=gen)[rank * n_local:(rank + 1) * n_local].to(dev)
+        batches.append((ro_all[sel].contiguous(), rd_all[sel].contiguous(), gt.contiguous()))
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    for s in range(args.warmup):
+        tr.step(*batches[s % 4], sharded=True)
+    sync_all()
+    r.profile_enable(True)
+    l0 = r.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for s in range(args.steps):
+        tr.step(*batches[(args.warmup + s) % 4], sharded=True)
+    e1.record()
+    sync_all()
+    t_wall1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = r.launch_count() - l0
+    kinds = {name: r.profile_read_kind(k) for name, k in (("mlp_tc_kernel<train>", 1), ("mlp_dgrad_kernel", 2), ("mlp_wgrad_kernel", 3))}
+    r.profile_enable(False)
+
+    # end to end: rays + targets from pinned host memory every step, loss read back
+    h_batches = [tuple(t.cpu().pin_memory() for t in b) for b in batches[:2]]
+    loss_val = 0.0
+
+    def step_host(s):
+        nonlocal loss_val
+        ro, rd, gt = (t.to(dev, non_blocking=True) for t in h_batches[s % 2])
+        loss_val = float(tr.step(ro, rd, gt, sharded=True).item())
+
+    for s in range(args.warmup):
+        step_host(s)
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for s in range(args.steps):
+        step_host(s)
+    e3.record()
+    sync_all()
+    ms2 = torch.tensor([e2.elapsed_time(e3)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+
+    if rank == 0:
+        clocks.stop()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        ms_total = ms.item()
+        value = TRAIN_RAYS * args.steps / (ms_total * 1e-3)
+        n_d, ms_d, _ = kinds["mlp_dgrad_kernel"]
+        samples_local = n_local * SAMPLES_PER_RAY * args.steps
+        ach = samples_local * DGRAD_BYTES_PER_SAMPLE / (ms_d * 1e-3) / 1e9 if ms_d > 0 else None
+        res = {
+            "metric": "rays/s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": TRAIN_WORKLOAD, "global_batch_rays": TRAIN_RAYS, "rays_per_gpu": n_local, "samples_per_ray": SAMPLES_PER_RAY,
+                       "parallelism": "dp%d, one NCCL all-reduce of the flat 1 191 688-float gradient per step" % world if world > 1 else "1 GPU",
+                       "l2_policy": "per-step activation stash (%.1f GB) >> 126 MB L2; no flush needed" % (n_local * 1.25e6 / 1e9)},
+            "step_tflops": TRAIN_RAYS * SAMPLES_PER_RAY * TRAIN_FLOP_PER_SAMPLE * args.steps / (ms_total * 1e-3) / 1e12,
+            "e2e": {"value": TRAIN_RAYS * args.steps / (ms2.item() * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 36 * n_local,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms2.item() / args.steps, "api": "NerfTrainer.step (tgtc_train_step + all-reduce + Adam)",
+                    "loss": loss_val},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if ach else None, "traffic": None,
+                         "kernel": "mlp_dgrad_kernel", "launches_timed": int(n_d), "avg_launch_ms": ms_d / max(n_d, 1),
+                         "bytes_per_sample": DGRAD_BYTES_PER_SAMPLE, "peak_source": "MEASURED_PEAKS.json hbm_gbs"},
+            "kernels": {k: {"launches": int(v[0]), "ms_per_step": v[1] / args.steps,
+                            "tflops": (v[2] / (v[1] * 1e-3) / 1e12) if v[1] > 0 else None} for k, v in kinds.items()},
+            "clocks": clocks.window(t_wall0, t_wall1),
+        }
+        print(json.dumps(res))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -174,10 +343,18 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="render", choices=["render", "train"],
+                    help="render = BASELINE config 2 (the headline; default); train = config 5 (training step)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
-        run_reference_arm(args)
+        if args.workload == "train":
+            run_train_reference_arm(args)
+        else:
+            run_reference_arm(args)
+        return
+    if args.workload == "train":
+        run_train(args)
         return
 
     import numpy as np

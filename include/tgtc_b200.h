@@ -196,6 +196,9 @@ int tgtc_train_step(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, con
  * launches, their summed device time in ms, and their summed algorithmic FLOPs (1 186 816 per sample). */
 int tgtc_profile_enable(tgtc_ctx* ctx, int on);
 int tgtc_profile_read(tgtc_ctx* ctx, int64_t* launches, double* ms, double* flops);
+/* same per kernel kind, without resetting: 0 inference MLP forward, 1 training MLP forward (activation stash),
+ * 2 activation-gradient kernel, 3 weight-gradient kernel (+ partial reduction) */
+int tgtc_profile_read_kind(tgtc_ctx* ctx, int kind, int64_t* launches, double* ms, double* flops);
 
 /* number of kernel launches issued by this context so far (bench.py's
  * gpu_launches claim is counted here, not estimated) */

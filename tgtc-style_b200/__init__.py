@@ -3,6 +3,7 @@
 Public surface:
   NerfRenderer            render(rays_o, rays_d, near, far, chunk) -> {rgb, depth, acc, weights}
   make_callables / patch  the reference's four injected callables, B200-backed
+  NerfTrainer             data-parallel training step (forward + backward + Adam), one gradient all-reduce
   shard_range / gather_tiles / render_frame_sharded   multi-GPU ray sharding
 The directory name contains a hyphen; import it as `tgtc_style_b200` (root-level loader module).
 """
@@ -11,6 +12,7 @@ from ._lib import MLP_BF16, MLP_FP32, NET_COARSE, NET_FINE, TgtcError
 from .dist import gather_tiles, render_frame_sharded, shard_range, shard_sizes
 from .render import LAYER_NAMES, LAYER_SHAPES, NerfRenderer
 from .shims import make_callables, patch
+from .train import NerfTrainer
 
-__all__ = ["NerfRenderer", "make_callables", "patch", "shard_range", "shard_sizes", "gather_tiles", "render_frame_sharded",
+__all__ = ["NerfRenderer", "NerfTrainer", "make_callables", "patch", "shard_range", "shard_sizes", "gather_tiles", "render_frame_sharded",
            "TgtcError", "MLP_FP32", "MLP_BF16", "NET_COARSE", "NET_FINE", "LAYER_NAMES", "LAYER_SHAPES"]

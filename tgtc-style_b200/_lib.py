@@ -64,6 +64,7 @@ PROTOTYPES = {
                                        ctypes.c_size_t, c_void_p]),
     "tgtc_profile_enable": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "tgtc_profile_read": (ctypes.c_int, [c_void_p, ctypes.POINTER(c_i64), c_double_p, c_double_p]),
+    "tgtc_profile_read_kind": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.POINTER(c_i64), c_double_p, c_double_p]),
     "tgtc_launch_count": (c_i64, [c_void_p]),
 }
 

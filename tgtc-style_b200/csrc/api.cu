@@ -105,21 +105,31 @@ extern "C" int tgtc_sample_uniform(tgtc_ctx* ctx, const float* rays_o, const flo
   return launch_sample_uniform(ctx, rays_o, rays_d, n, n_samples, near, far, rnd, pts, ts, (cudaStream_t)stream);
 }
 
-static int run_mlp(tgtc_ctx* ctx, int net, int mode, const MlpIO& io, cudaStream_t st) {
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (ctx->profile) {
-    if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
-      for (int i = 0; i < 2; ++i) {
-        cudaEvent_t e;
-        TGTC_CUDA(cudaEventCreate(&e));
-        ctx->ev_pool.push_back(e);
-      }
+// per-launch device timing: a pair of events of kind `kind` around the next launch(es) on `st`
+static int prof_begin(tgtc_ctx* ctx, int kind, double flops, cudaStream_t st, cudaEvent_t* e1) {
+  *e1 = nullptr;
+  if (!ctx->profile) return TGTC_OK;
+  if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
+    for (int i = 0; i < 2; ++i) {
+      cudaEvent_t e;
+      TGTC_CUDA(cudaEventCreate(&e));
+      ctx->ev_pool.push_back(e);
     }
-    e0 = ctx->ev_pool[ctx->ev_used++];
-    e1 = ctx->ev_pool[ctx->ev_used++];
-    ctx->prof_flops += (double)io.n_rays * io.S * 1186816.0;
-    TGTC_CUDA(cudaEventRecord(e0, st));
   }
+  if (ctx->ev_kind.size() < ctx->ev_pool.size() / 2) ctx->ev_kind.resize(ctx->ev_pool.size() / 2, 0);
+  ctx->ev_kind[ctx->ev_used / 2] = kind;
+  cudaEvent_t e0 = ctx->ev_pool[ctx->ev_used++];
+  *e1 = ctx->ev_pool[ctx->ev_used++];
+  if (kind == 0) ctx->prof_flops += flops;
+  ctx->prof_work[kind & 3] += flops;
+  TGTC_CUDA(cudaEventRecord(e0, st));
+  return TGTC_OK;
+}
+
+static int run_mlp(tgtc_ctx* ctx, int net, int mode, const MlpIO& io, cudaStream_t st) {
+  cudaEvent_t e1 = nullptr;
+  int prc = prof_begin(ctx, 0, (double)io.n_rays * io.S * 1186816.0, st, &e1);
+  if (prc) return prc;
   int rc;
   if (mode == TGTC_MLP_BF16) {
     TGTC_REQUIRE(mlp_tc_supports(io), TGTC_ERR_UNSUPPORTED,
@@ -138,23 +148,49 @@ extern "C" int tgtc_profile_enable(tgtc_ctx* ctx, int on) {
   ctx->profile = on != 0;
   ctx->ev_used = 0;
   ctx->prof_flops = 0.0;
+  for (double& w : ctx->prof_work) w = 0.0;
+  return TGTC_OK;
+}
+
+// kind: 0 inference MLP forward, 1 training MLP forward (stash), 2 activation-gradient kernel, 3 weight-gradient kernel.
+// Does not reset (tgtc_profile_enable does).
+extern "C" int tgtc_profile_read_kind(tgtc_ctx* ctx, int kind, int64_t* launches, double* ms, double* flops) {
+  CHECK_CTX(ctx);
+  TGTC_REQUIRE(kind >= 0 && kind < 4, TGTC_ERR_ARG, "bad profile kind %d", kind);
+  double total = 0.0;
+  int64_t cnt = 0;
+  for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+    if (ctx->ev_kind[i / 2] != kind) continue;
+    TGTC_CUDA(cudaEventSynchronize(ctx->ev_pool[i + 1]));
+    float t = 0.f;
+    TGTC_CUDA(cudaEventElapsedTime(&t, ctx->ev_pool[i], ctx->ev_pool[i + 1]));
+    total += t;
+    ++cnt;
+  }
+  if (launches) *launches = cnt;
+  if (ms) *ms = total;
+  if (flops) *flops = ctx->prof_work[kind];
   return TGTC_OK;
 }
 
 extern "C" int tgtc_profile_read(tgtc_ctx* ctx, int64_t* launches, double* ms, double* flops) {
   CHECK_CTX(ctx);
   double total = 0.0;
+  int64_t cnt = 0;
   for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+    if (!ctx->ev_kind.empty() && ctx->ev_kind[i / 2] != 0) continue;
     TGTC_CUDA(cudaEventSynchronize(ctx->ev_pool[i + 1]));
     float t = 0.f;
     TGTC_CUDA(cudaEventElapsedTime(&t, ctx->ev_pool[i], ctx->ev_pool[i + 1]));
     total += t;
+    ++cnt;
   }
-  if (launches) *launches = (int64_t)(ctx->ev_used / 2);
+  if (launches) *launches = cnt;
   if (ms) *ms = total;
   if (flops) *flops = ctx->prof_flops;
   ctx->ev_used = 0;
   ctx->prof_flops = 0.0;
+  for (double& w : ctx->prof_work) w = 0.0;
   return TGTC_OK;
 }
 
@@ -507,17 +543,31 @@ static int train_pass(tgtc_ctx* ctx, int net, const float* rays_o, const float* 
   io.t_scale = (float)(far - near); io.t_near = (float)near;
   io.n_rays = n; io.S = S; io.rgbsigma = rs;
   TGTC_REQUIRE(mlp_tc_supports(io), TGTC_ERR_UNSUPPORTED, "training needs n_samples in {64,128} (tcgen05 path)");
-  int rc = launch_mlp_tc_train(ctx, net, io, stash, st);
+  const double samples = (double)n * S;
+  cudaEvent_t e1 = nullptr;
+  int rc = prof_begin(ctx, 1, samples * 1186816.0, st, &e1);
   if (rc) return rc;
+  rc = launch_mlp_tc_train(ctx, net, io, stash, st);
+  if (rc) return rc;
+  if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
   rc = launch_composite(ctx, nullptr, nullptr, rs, ts, ts_stride, nullptr, 0, n, S, rgb, nullptr, nullptr, weights_out, st);
   if (rc) return rc;
   rc = launch_mse_grad(ctx, rgb, rgb_gt, n, scale, g, sq_sum, st);
   if (rc) return rc;
   rc = launch_composite_backward(ctx, rs, ts, ts_stride, nullptr, 0, n, S, g, nullptr, nullptr, drs, st);
   if (rc) return rc;
+  // algorithmic FLOPs: dgrad skips the three slices into non-differentiable inputs (PE->L0, PE->L5, dirPE->rgb0)
+  rc = prof_begin(ctx, 2, samples * 2.0 * (593408.0 - 16128.0 - 16128.0 - 3456.0), st, &e1);
+  if (rc) return rc;
   rc = launch_mlp_dgrad(ctx, net, rs, drs, stash, dz, n * S, st);
   if (rc) return rc;
-  return launch_mlp_wgrad(ctx, stash, dz, rays_d, n * S, S, partial, grads, accumulate, st);
+  if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
+  rc = prof_begin(ctx, 3, samples * 1186816.0, st, &e1);
+  if (rc) return rc;
+  rc = launch_mlp_wgrad(ctx, stash, dz, rays_d, n * S, S, partial, grads, accumulate, st);
+  if (rc) return rc;
+  if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
+  return TGTC_OK;
 }
 
 extern "C" int tgtc_train_step(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, const float* rgb_gt, int64_t n_rays,

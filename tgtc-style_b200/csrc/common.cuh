@@ -78,7 +78,9 @@ struct tgtc_ctx {
   bool profile = false;
   std::vector<cudaEvent_t> ev_pool;   // pairs: [2i] start, [2i+1] stop
   size_t ev_used = 0;                 // events handed out since the last read
-  double prof_flops = 0.0;
+  std::vector<int> ev_kind;           // kind of pair i (TGTC_PROF_*)
+  double prof_flops = 0.0;            // forward MLP (kind 0) algorithmic FLOPs since the last read
+  double prof_work[4] = {0, 0, 0, 0}; // algorithmic FLOPs per kind
 };
 
 // ---------------------------------------------------------------------------

@@ -175,6 +175,8 @@ __device__ __forceinline__ int64_t my_tile(int64_t it, int t, uint32_t rank) {
 }
 
 // ---------------------------------------------------------------------------
+// kTrain: also write the activation stash (training forward); the inference instantiation carries none of that code
+template <bool kTrain>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -364,7 +366,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
           for (int a = 0; a < 3; ++a) fast_sincos(__fmul_rn(x[a], fr), &e[3 + 6 * f + a], &e[3 + 6 * f + 3 + a]);
         }
         e[63] = 0.f;
-        uint8_t* const gpe = (P.stash_pe != nullptr && tile < P.ntiles) ? P.stash_pe + (size_t)tile * 16384 + (r >> 3) * 1024 + (r & 7) * 128 : nullptr;
+        uint8_t* const gpe = (kTrain && tile < P.ntiles) ? P.stash_pe + (size_t)tile * 16384 + (r >> 3) * 1024 + (r & 7) * 128 : nullptr;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
           const uint32_t q0 = pack_bf16(e[8 * ch + 0], e[8 * ch + 1]), q1 = pack_bf16(e[8 * ch + 2], e[8 * ch + 3]),
@@ -463,7 +465,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
             const uint32_t tcol = taddr + hc * 128;
             const uint32_t rx = (uint32_t)(row & 7) << 4;
             uint8_t* grow = nullptr;
-            if (P.stash_h != nullptr && tile < P.ntiles)
+            if (kTrain && tile < P.ntiles)
               grow = P.stash_h + ((size_t)tile * 9 + l) * 65536 + (row >> 3) * 1024 + (row & 7) * 128 + hc * 2 * 16384;
             if (P.dbg_flags & 2) {
             } else if (l == 7) {
@@ -506,7 +508,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
                 fq[j / 2] = pack_bf16(f0, f1);
                 fq[j / 2 + 1] = pack_bf16(f2, f3);
               }
-              if (P.stash_f != nullptr && tile < P.ntiles) {
+              if (kTrain && tile < P.ntiles) {
                 // rgb0 output tile image: K block hc (64 columns), 16-byte chunks b*4 .. b*4+3 of this row
                 uint8_t* gf = P.stash_f + (size_t)tile * 32768 + hc * 16384 + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll
@@ -586,13 +588,15 @@ static int launch_tc_common(tgtc_ctx* ctx, int net, const MlpIO& io, int dbg_lay
   P.dbg_out = dbg_out;
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
-    TGTC_CUDA(cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    TGTC_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    TGTC_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set[ctx->device & 63] = true;
   }
   const int64_t nquads = (P.ntiles + 3) / 4;
   const int64_t max_pairs = ctx->num_sms / 2;
   const int grid = 2 * (int)(nquads < max_pairs ? nquads : max_pairs);   // CTA pairs (clusters of 2)
-  mlp_tc_kernel<<<grid, kNumThreads, kSmemBytes, st>>>(P);
+  if (stash != nullptr) mlp_tc_kernel<true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
+  else mlp_tc_kernel<false><<<grid, kNumThreads, kSmemBytes, st>>>(P);
   TGTC_LAUNCH_CHECK(ctx);
   return TGTC_OK;
 }

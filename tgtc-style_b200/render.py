@@ -94,6 +94,12 @@ class NerfRenderer:
         _lib.check(self.lib.tgtc_profile_read(self._h, ctypes.byref(n), ctypes.byref(ms), ctypes.byref(fl)))
         return n.value, ms.value, fl.value
 
+    def profile_read_kind(self, kind):
+        """-> (launches, summed device ms, algorithmic FLOPs) of kernel kind 0 fwd / 1 fwd-train / 2 dgrad / 3 wgrad."""
+        n, ms, fl = _lib.c_i64(0), ctypes.c_double(0), ctypes.c_double(0)
+        _lib.check(self.lib.tgtc_profile_read_kind(self._h, int(kind), ctypes.byref(n), ctypes.byref(ms), ctypes.byref(fl)))
+        return n.value, ms.value, fl.value
+
     # ------------------------------------------------------------------ weights
     def set_weights(self, coarse=None, fine=None):
         """coarse / fine: a models.StyleNerf (or any nn.Module / state_dict) whose parameters are named
