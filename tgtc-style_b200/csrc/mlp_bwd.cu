@@ -32,8 +32,8 @@ constexpr int kTileM = 128;
 // ===========================================================================================================
 constexpr int kStages = 3;
 constexpr int kStageBytes = 16384;   // this CTA's half (128 rows) of a [256 x 64] transposed-weight chunk
-constexpr int kNumThreads = 448;
-constexpr int kInWarp0 = 2, kEpiWarp0 = 6;
+constexpr int kNumThreads = 512;      // w0 weights, w1 MMA/forwarder, w2-5 input producers, w6-13 epilogue, w14-15 tile movers
+constexpr int kInWarp0 = 2, kEpiWarp0 = 6, kMoveWarp0 = 14;
 constexpr int kNumEpiThreads = 256, kNumInThreads = 128;
 constexpr int kNumGemm = 9;
 
@@ -45,7 +45,7 @@ constexpr int kOffWRgb1 = kOffW + kStages * kStageBytes;    // 3 x 128 fp32
 constexpr int kOffWSig = kOffWRgb1 + 384 * 4;               // 256 fp32
 constexpr int kOffBars = kOffWSig + 256 * 4;
 constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarInReady = 2 * kStages, kBarInFree = kBarInReady + 1,
-              kBarActReady = kBarInFree + 1, kBarAccFull = kBarActReady + 2, kNumBars = kBarAccFull + 2;
+              kBarActReady = kBarInFree + 1, kBarAccFull = kBarActReady + 2, kBarHFull = kBarAccFull + 2, kBarDzDone = kBarHFull + 2, kNumBars = kBarDzDone + 2;
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
@@ -62,7 +62,13 @@ struct DgradParams {
   uint8_t* dhead;             // [ntiles][16 KB]     columns 0..2 = d_rgb * rgb(1-rgb), column 3 = d_sigma
   int64_t M;
   int64_t ntiles;
+  long long* dbg_trace;       // timing experiments: [4 roles][4 iters][9 gemms][2 slots][3] clock64 stamps of CTA 0
 };
+#define BW_TRACE(role, it, g, t, k)                                                                        \
+  do {                                                                                                     \
+    if (P.dbg_trace != nullptr && blockIdx.x == 0 && (it) < 4)                                             \
+      P.dbg_trace[(((((role)*4 + (int)(it)) * 9 + (g)) * 2 + (t)) * 3) + (k)] = clock64();                 \
+  } while (0)
 
 __device__ __forceinline__ int64_t pair_tile(int64_t it, int t, uint32_t rank) {
   const int64_t quad = (int64_t)(blockIdx.x >> 1) + it * (int64_t)(gridDim.x >> 1);
@@ -73,6 +79,11 @@ __device__ __forceinline__ void st_global_v4(uint8_t* p, uint32_t a, uint32_t b,
 }
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 // two fp32 gradients -> bf16 pair, zeroed where the stashed post-ReLU activation (bf16 pair hw) is zero
 __device__ __forceinline__ uint32_t mask_pack(uint32_t hw, float lo, float hi) {
@@ -105,6 +116,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
     for (int t = 0; t < 2; ++t) {
       mbar_init(bar(kBarActReady + t), 2 * (kNumEpiThreads / 32));
       mbar_init(bar(kBarAccFull + t), 1);
+      mbar_init(bar(kBarHFull + t), 1);
+      mbar_init(bar(kBarDzDone + t), kNumEpiThreads / 32);
     }
     fence_barrier_init();
   }
@@ -196,6 +209,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
             mbar_wait_uniform(bar(kBarActReady + t), act_par); act_par ^= 1;
           }
           tc_fence_after();
+          BW_TRACE(0, it, g, t, 0);
           const uint32_t d_tmem = tmem_base + (uint32_t)(256 * t);
           const uint32_t act_lo = (((sbase + kOffAct + t * kActBytes) & 0x3FFFFu) >> 4) | (1u << 16);
           if (g == 0) {
@@ -210,6 +224,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
             umma_commit(bar(kBarAccFull + t));
           }
           __syncwarp();
+          BW_TRACE(0, it, g, t, 1);
         }
       }
     }
@@ -249,7 +264,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
 #pragma unroll
           for (int i = 0; i < 16; ++i) fm[i] = make_uint4(0u, 0u, 0u, 0u);
         }
+        if (r == 0) BW_TRACE(2, it, 0, t, 0);
         if (use > 0) mbar_wait_relaxed(bar(kBarInFree), (uint32_t)((use - 1) & 1), 64);
+        if (r == 0) BW_TRACE(2, it, 0, t, 1);
         uint8_t* gdst = tile_ok ? P.dzf + (size_t)tile * 32768 + rowoff : nullptr;
 #pragma unroll
         for (int kb = 0; kb < 2; ++kb) {
@@ -277,7 +294,49 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(leader_inready);
+        if (r == 0) BW_TRACE(2, it, 0, t, 2);
       }
+    }
+  } else if (warp >= kMoveWarp0) {
+    // ===================================================================== tile movers: one thread per slot
+    // Per GEMM: the moment the MMAs that read act[t] retire, stage the stashed activation tile (ReLU mask) of the layer into
+    // act[t] with one 64 KB bulk copy (per-thread 16-byte loads of a row-per-thread pattern touch 32 lines per instruction
+    // and saturate the L1 pipeline); when the epilogue has replaced it with the masked gradient, send that tile to HBM
+    // with one bulk store.  Both run while the epilogue warps work on the other slot.
+    if (lane == 0) {
+      const int t = warp - kMoveWarp0;
+      uint32_t acc_par = 0, dz_par = 0;
+      for (int64_t it = 0; it < iters; ++it) {
+        const int64_t tile = pair_tile(it, t, rank);
+        const bool tile_ok = tile < P.ntiles;
+        for (int g = 0; g < kNumGemm; ++g) {
+          const int ml = 8 - g;
+          mbar_wait(bar(kBarAccFull + t), acc_par); acc_par ^= 1;
+          bulk_wait_read0();   // my dz store of the previous GEMM has finished reading act[t]
+          if (tile_ok) {
+            mbar_arrive_expect_tx(bar(kBarHFull + t), 65536u);
+            bulk_g2s(sbase + kOffAct + t * kActBytes, P.stash_h + ((size_t)tile * 9 + ml) * 65536, 65536u, bar(kBarHFull + t));
+            // pull the NEXT mask image of this slot towards L2
+            if (g + 1 < kNumGemm) {
+              l2_prefetch_bulk(P.stash_h + ((size_t)tile * 9 + (ml - 1)) * 65536, 65536);
+            } else {
+              const int64_t nt = pair_tile(it + 1, t, rank);
+              if (it + 1 < iters && nt < P.ntiles) {
+                l2_prefetch_bulk(P.stash_h + ((size_t)nt * 9 + 8) * 65536, 65536);
+                l2_prefetch_bulk(P.stash_f + (size_t)nt * 32768, 32768);
+              }
+            }
+          } else {
+            mbar_arrive(bar(kBarHFull + t));
+          }
+          mbar_wait(bar(kBarDzDone + t), dz_par); dz_par ^= 1;
+          if (tile_ok) {
+            bulk_s2g(P.dz + ((size_t)tile * 9 + ml) * 65536, sbase + kOffAct + t * kActBytes, 65536u);
+            bulk_commit_group();
+          }
+        }
+      }
+      bulk_wait_all0();
     }
   } else {
     // ===================================================================== epilogue warps
@@ -288,7 +347,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
     const uint32_t leader_actready = mapa_cluster(bar(kBarActReady), 0);
     const uint32_t rowoff = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + hc * 2 * 16384);
     const uint32_t rx = (uint32_t)(row & 7);
-    uint32_t acc_par[2] = {0, 0};
+    uint32_t acc_par[2] = {0, 0}, h_par[2] = {0, 0};
     for (int64_t it = 0; it < iters; ++it) {
       for (int g = 0; g < kNumGemm; ++g) {
         const int ml = 8 - g;   // stash / dz index of the layer whose pre-activation gradient this GEMM produces
@@ -296,35 +355,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
           const int64_t tile = pair_tile(it, t, rank);
           const bool tile_ok = tile < P.ntiles;
           const int64_t m = tile * kTileM + row;
-          const uint8_t* hsrc = P.stash_h + ((size_t)tile * 9 + ml) * 65536 + rowoff;
-          uint8_t* gdst = P.dz + ((size_t)tile * 9 + ml) * 65536 + rowoff;
-          // pull the NEXT mask image of this slot towards L2 while this one is processed
-          if (warp == kEpiWarp0 && lane == 0) {
-            if (g + 1 < kNumGemm) {
-              if (tile_ok) l2_prefetch_bulk(P.stash_h + ((size_t)tile * 9 + (ml - 1)) * 65536, 65536);
-            } else {
-              const int64_t nt = pair_tile(it + 1, t, rank);
-              if (it + 1 < iters && nt < P.ntiles) {
-                l2_prefetch_bulk(P.stash_h + ((size_t)nt * 9 + 8) * 65536, 65536);
-                l2_prefetch_bulk(P.stash_f + (size_t)nt * 32768, 32768);
-              }
-            }
-          }
           float dsig = 0.f;
           if (g == 1 && tile_ok && m < P.M) dsig = P.d_rgbsigma[m].w;
           mbar_wait(bar(kBarAccFull + t), acc_par[t]); acc_par[t] ^= 1;
           tc_fence_after();
+          if (lane == 0 && q == 2 && hc == 0) BW_TRACE(1, it, g, t, 0);
+          // the slot's tile mover (warp 14/15) staged the stashed activation tile (the ReLU mask) into act[t] the moment the
+          // MMAs retired; every thread reads a mask chunk from exactly the address it overwrites with the masked gradient
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 * t) + (uint32_t)(hc * 128);
           const uint32_t sdst = sbase + kOffAct + t * kActBytes + rowoff;
+          mbar_wait(bar(kBarHFull + t), h_par[t]); h_par[t] ^= 1;
+          if (lane == 0 && q == 2 && hc == 0) BW_TRACE(1, it, g, t, 1);
 #pragma unroll 1
           for (int blk = 0; blk < 4; ++blk) {
             const uint32_t kboff = (uint32_t)(blk >> 1) * 16384u;
-            uint4 hm[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t coff = kboff + ((((uint32_t)(blk & 1) * 4u + (uint32_t)j) ^ rx) << 4);
-              hm[j] = tile_ok ? *reinterpret_cast<const uint4*>(hsrc + coff) : make_uint4(0u, 0u, 0u, 0u);
-            }
             uint32_t v[32];
             tmem_ld32(taddr + blk * 32, v);
             tmem_ld_wait_dep(v);
@@ -335,18 +379,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t coff = kboff + ((((uint32_t)(blk & 1) * 4u + (uint32_t)j) ^ rx) << 4);
-              const uint32_t q0 = mask_pack(hm[j].x, __uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-              const uint32_t q1 = mask_pack(hm[j].y, __uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-              const uint32_t q2 = mask_pack(hm[j].z, __uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-              const uint32_t q3 = mask_pack(hm[j].w, __uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-              if (g + 1 < kNumGemm) st_shared_v4(sdst + coff, q0, q1, q2, q3);   // A operand of the next GEMM (in place)
-              if (tile_ok) st_global_v4(gdst + coff, q0, q1, q2, q3);            // for the weight-gradient kernel
+              uint4 h = make_uint4(0u, 0u, 0u, 0u);
+              if (tile_ok) h = ld_shared_v4(sdst + coff);
+              const uint32_t q0 = mask_pack(h.x, __uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+              const uint32_t q1 = mask_pack(h.y, __uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+              const uint32_t q2 = mask_pack(h.z, __uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+              const uint32_t q3 = mask_pack(h.w, __uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+              st_shared_v4(sdst + coff, q0, q1, q2, q3);   // A operand of the next GEMM (in place) and source of the dz store
             }
           }
           fence_proxy_async();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(leader_actready + 8u * t);
+          if (lane == 0) {
+            mbar_arrive(bar(kBarDzDone + t));                      // local: the mover may store the dz tile
+            mbar_arrive_cluster(leader_actready + 8u * t);         // pair: the leader may issue the next GEMM
+          }
+          if (lane == 0 && q == 2 && hc == 0) BW_TRACE(1, it, g, t, 2);
         }
       }
     }
@@ -712,6 +761,9 @@ __global__ void mse_grad_kernel(const float* __restrict__ rgb, const float* __re
 
 }  // namespace
 
+static long long* g_bwd_trace = nullptr;
+extern "C" void tgtc_debug_bwd_trace(long long* dev_buf) { g_bwd_trace = dev_buf; }
+
 size_t bwd_partial_floats() { return kPartFloats; }
 size_t bwd_blobT_bytes() { return bwd_layer_off_bytes(kNumGemm); }
 size_t bwd_flat_floats() { return kFlatFloats; }
@@ -729,6 +781,7 @@ int launch_mlp_dgrad(tgtc_ctx* ctx, int net, const float* rgbsigma, const float*
   P.dz = dz.dz; P.dzf = dz.dzf; P.dhead = dz.dhead;
   P.M = M;
   P.ntiles = (M + kTileM - 1) / kTileM;
+  P.dbg_trace = g_bwd_trace;
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
     TGTC_CUDA(cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));

@@ -464,9 +464,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
             const uint32_t arow = sbase + kOffAct + t * kActBytes + (row >> 3) * 1024 + (row & 7) * 128 + hc * 2 * 16384;
             const uint32_t tcol = taddr + hc * 128;
             const uint32_t rx = (uint32_t)(row & 7) << 4;
-            uint8_t* grow = nullptr;
-            if (kTrain && tile < P.ntiles)
-              grow = P.stash_h + ((size_t)tile * 9 + l) * 65536 + (row >> 3) * 1024 + (row & 7) * 128 + hc * 2 * 16384;
+            uint8_t* grow = nullptr;   // (per-thread stash stores are not used: the tile goes out as one bulk store below)
             if (P.dbg_flags & 2) {
             } else if (l == 7) {
               const float sig = hidden_epilogue<true>(tcol, bl, wsig_s + hc * 128, arow, rx, grow);
@@ -475,6 +473,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
               hidden_epilogue<false>(tcol, bl, nullptr, arow, rx, grow);
             }
             fence_proxy_async();
+            if constexpr (kTrain) {
+              // activation stash: the finished tile image leaves as ONE 64 KB bulk store.  The issuer first waits until its
+              // previous store (the other slot, one epilogue ago) has finished reading shared memory -- that buffer is the one
+              // the NEXT epilogue overwrites, and every thread passes the named barrier after this wait.
+              const bool issuer = (warp == kEpiWarp0 && lane == 0);
+              if (issuer) bulk_wait_read0();
+              named_bar_sync(3, kNumEpiThreads);
+              if (issuer && tile < P.ntiles) {
+                bulk_s2g(P.stash_h + ((size_t)tile * 9 + l) * 65536, sbase + kOffAct + t * kActBytes, 65536u);
+                bulk_commit_group();
+              }
+            }
             tc_fence_before();
             act_arrive(t);
             if (lane == 0 && q == 2) TC_TRACE(1 + hc, it, l, t, 1);
@@ -543,6 +553,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
   }
 
   // ---- teardown
+  if constexpr (kTrain) {
+    if (warp == kEpiWarp0 && lane == 0) bulk_wait_all0();
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();   // neither CTA may exit (or free TMEM) while the other can still signal it / read its shared memory
