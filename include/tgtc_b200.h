@@ -182,13 +182,16 @@ int tgtc_render_frame(tgtc_ctx* ctx, int mode, int H, int W, const double* K, co
  * mean((rgb_coarse-gt)^2) + mean((rgb_fine-gt)^2) over n_rays_total*3 values (pass the whole step's ray count when
  * the step is split into chunks / ranks); loss_sums (device float[2], may be NULL) is incremented by the two
  * un-normalised squared-error sums.  rgb_coarse / rgb_fine [n,3] may be NULL.  bf16 tcgen05 path;
- * n_samples = n_fine = 64.  No gradient flows through the resampling (utils.py:576-579). */
+ * n_samples = n_fine = 64.  No gradient flows through the resampling (utils.py:576-579).
+ * Stochastic options of the reference replay caller-drawn tensors (so a torch generator stream can be reproduced):
+ * rand [n,64] uniforms = perturb=True (utils.py:518-524), noise_coarse [n,64] / noise_fine [n,128] =
+ * randn * sigma_noise_std (utils.py:372-374); each may be NULL (= off). */
 size_t tgtc_train_workspace_bytes(tgtc_ctx* ctx, int64_t n_rays, int n_samples, int n_fine);
 int64_t tgtc_num_params(void); /* 595 844 per net */
 int tgtc_train_step(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, const float* rgb_gt, int64_t n_rays,
-                    int64_t n_rays_total, double near, double far, int n_samples, int n_fine, float* grads, int accumulate,
-                    float* loss_sums, float* rgb_coarse, float* rgb_fine, void* workspace, size_t workspace_bytes,
-                    tgtc_stream stream);
+                    int64_t n_rays_total, double near, double far, int n_samples, int n_fine, const float* rand,
+                    const float* noise_coarse, const float* noise_fine, float* grads, int accumulate, float* loss_sums,
+                    float* rgb_coarse, float* rgb_fine, void* workspace, size_t workspace_bytes, tgtc_stream stream);
 
 /* Per-kernel device timing of the MLP launches (the dominant kernel), for the roofline line of bench.py:
  * while enabled, every MLP launch is bracketed by cudaEvents on its stream (no host sync).

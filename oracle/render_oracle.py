@@ -336,7 +336,8 @@ def render_chain(sd_coarse, sd_fine, rays_o, rays_d, near=0., far=1., n_samples=
     return out
 
 
-def train_step_reference(sd_coarse, sd_fine, rays_o, rays_d, rgb_gt, near=0., far=1., n_samples=64, n_fine=64):
+def train_step_reference(sd_coarse, sd_fine, rays_o, rays_d, rgb_gt, near=0., far=1., n_samples=64, n_fine=64, rand=None,
+                         noise_coarse=None, noise_fine=None):
     """train_tgtcs.py:228-255 (Origin_train's step) with perturb=0 and sigma_noise_std=0, through torch.autograd:
     loss = mse(rgb_gt, rgb_coarse) + mse(rgb_gt, rgb_fine)  (utils.py:460).  No gradient flows through the
     resampling (utils.py:576-579).  Returns (loss, grads_coarse, grads_fine, rgb_coarse, rgb_fine, ts_fine)."""
@@ -346,12 +347,12 @@ def train_step_reference(sd_coarse, sd_fine, rays_o, rays_d, rgb_gt, near=0., fa
     n = ro.shape[0]
     pc = {k: v.detach().clone().requires_grad_(True) for k, v in sd_coarse.items()}
     pf = {k: v.detach().clone().requires_grad_(True) for k, v in sd_fine.items()}
-    pts, ts = sample_uniform(ro, rd, n_samples, near, far)
+    pts, ts = sample_uniform(ro, rd, n_samples, near, far, rand=rand)
     ret = nerf_forward(pc, pts, rd.unsqueeze(1).expand(n, n_samples, 3))
-    rgb_c, _, w_c, _ = alpha_composition(ret["rgb"], ret["sigma"], ts)
+    rgb_c, _, w_c, _ = alpha_composition(ret["rgb"], ret["sigma"], ts, noise=noise_coarse)
     pts_f, ts_f = sample_fine(ro, rd, ts, w_c.detach(), n_fine)
     ret_f = nerf_forward(pf, pts_f.detach(), rd.unsqueeze(1).expand(n, n_samples + n_fine, 3))
-    rgb_f = alpha_composition(ret_f["rgb"], ret_f["sigma"], ts_f)[0]
+    rgb_f = alpha_composition(ret_f["rgb"], ret_f["sigma"], ts_f, noise=noise_fine)[0]
     loss = torch.mean((rgb_c - gt) ** 2) + torch.mean((rgb_f - gt) ** 2)
     loss.backward()
     return (loss.detach(), {k: v.grad for k, v in pc.items()}, {k: v.grad for k, v in pf.items()}, rgb_c.detach(), rgb_f.detach(),

@@ -111,3 +111,30 @@ def test_train_step_chunk_accumulation(renderer_bf16):
     torch.cuda.synchronize()
     rel = (b["grads"] - full).norm().item() / full.norm().item()
     assert rel <= 1e-5, rel
+
+
+def test_train_step_replays_perturb_and_noise(renderer_bf16):
+    """perturb=True (utils.py:518-524) and sigma_noise_std (utils.py:372-374) with caller-drawn tensors: same loss and
+    gradients as autograd through the oracle fed the same tensors."""
+    n = 128
+    wc, wf, ro, rd, gt = _train_inputs(n, seed=11)
+    g = torch.Generator().manual_seed(7)
+    rand = torch.rand(n, 64, generator=g)
+    nzc = torch.randn(n, 64, generator=g) * 1.0
+    nzf = torch.randn(n, 128, generator=g) * 1.0
+    loss_ref, gc, gf, rgbc_ref, rgbf_ref, _ = O.train_step_reference(wc, wf, ro, rd, gt, rand=rand, noise_coarse=nzc, noise_fine=nzf)
+    r = renderer_bf16
+    r.set_weights(wc, wf)
+    out = r.train_step(ro, rd, gt, rand=rand, noise_coarse=nzc, noise_fine=nzf)
+    torch.cuda.synchronize()
+    assert abs(out["loss"].item() - loss_ref.item()) <= 2e-3 * max(1.0, abs(loss_ref.item()))
+    assert (out["rgb_coarse"].cpu() - rgbc_ref).abs().max().item() <= 2e-2
+    vc, vf = r.grad_views(out["grads"])
+    for views, ref in ((vc, gc), (vf, gf)):
+        for k in ("net.rgb_layers.1.weight", "net.base_remap_layer.weight", "net.base_layers.7.weight", "net.base_layers.0.weight"):
+            a, b = views[k].cpu().flatten(), ref[k].flatten()
+            cos = torch.nn.functional.cosine_similarity(a, b, dim=0).item()
+            assert cos >= 0.99, (k, cos)
+    # and the unperturbed step is a different function of the same rays
+    plain = r.train_step(ro, rd, gt)
+    assert abs(plain["loss"].item() - out["loss"].item()) > 0

@@ -152,3 +152,20 @@ def test_reference_signature_shims(renderer_fp32):
     torch.manual_seed(0)
     noisy = fns["alpha_composition"](ret["rgb"], ret["sigma"], ts, 1.0)
     assert torch.isfinite(noisy[0]).all()
+
+
+def test_render_path_frames_match_single_frame_render(renderer_bf16):
+    """render_path_sharded (world 1) == render_frame per pose, rays generated on device, frames kept on device."""
+    import tgtc_style_b200 as T
+    H, W, f = 48, 64, 52.0
+    K = np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]])
+    poses = [np.eye(4)[:3, :4], np.array([[1, 0, 0, 0.1], [0, 1, 0, -0.05], [0, 0, 1, 0.02]], dtype=np.float64)]
+    wc, wf = weights("w1")
+    renderer_bf16.set_weights(wc, wf)
+    frames = dict(T.render_path_sharded(renderer_bf16, H, W, K, poses, split="rows"))
+    assert sorted(frames) == [0, 1]
+    for i, pose in enumerate(poses):
+        ref = renderer_bf16.render_frame(H, W, K, pose)
+        for k in ("rgb", "depth", "acc"):
+            assert torch.equal(frames[i][k], ref[k])
+    assert not torch.equal(frames[0]["rgb"], frames[1]["rgb"])

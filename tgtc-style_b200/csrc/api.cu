@@ -509,7 +509,7 @@ static TrainWs train_ws_layout(tgtc_ctx* ctx, int64_t n, int S, int F) {
   w.off_drs = o;      o = align_up(o + (size_t)Mmax * 16, 256);
   w.off_w_c = o;      o = align_up(o + (size_t)n * S * 4, 256);
   w.off_ts_f = o;     o = align_up(o + (size_t)n * (S + F) * 4, 256);
-  w.off_ts_c = o;     o = align_up(o + (size_t)S * 4, 256);
+  w.off_ts_c = o;     o = align_up(o + (size_t)n * S * 4, 256);
   w.off_rgb = o;      o = align_up(o + (size_t)n * 12, 256);
   w.off_g = o;        o = align_up(o + (size_t)n * 12, 256);
   w.off_partial = o;  o = align_up(o + (size_t)ctx->num_sms * bwd_partial_floats() * 4, 256);
@@ -527,8 +527,9 @@ extern "C" int64_t tgtc_num_params(void) { return (int64_t)bwd_flat_floats(); }
 // one network pass: forward (stash) -> compositing -> [caller hook: resampling] -> loss gradient -> compositing backward ->
 // activation gradients -> weight gradients
 static int train_pass(tgtc_ctx* ctx, int net, const float* rays_o, const float* rays_d, const float* ts, int64_t ts_stride, int64_t n,
-                      int S, double near, double far, const float* rgb_gt, float scale, const TrainWs& ws, uint8_t* base,
-                      float* grads, int accumulate, float* sq_sum, float* rgb_out, float* weights_out, cudaStream_t st) {
+                      int S, double near, double far, const float* noise, const float* rgb_gt, float scale, const TrainWs& ws,
+                      uint8_t* base, float* grads, int accumulate, float* sq_sum, float* rgb_out, float* weights_out,
+                      cudaStream_t st) {
   TcStash stash;
   stash.h = base + ws.off_stash_h; stash.f = base + ws.off_stash_f; stash.pe = base + ws.off_stash_pe;
   TcDz dz;
@@ -550,11 +551,11 @@ static int train_pass(tgtc_ctx* ctx, int net, const float* rays_o, const float* 
   rc = launch_mlp_tc_train(ctx, net, io, stash, st);
   if (rc) return rc;
   if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
-  rc = launch_composite(ctx, nullptr, nullptr, rs, ts, ts_stride, nullptr, 0, n, S, rgb, nullptr, nullptr, weights_out, st);
+  rc = launch_composite(ctx, nullptr, nullptr, rs, ts, ts_stride, noise, 0, n, S, rgb, nullptr, nullptr, weights_out, st);
   if (rc) return rc;
   rc = launch_mse_grad(ctx, rgb, rgb_gt, n, scale, g, sq_sum, st);
   if (rc) return rc;
-  rc = launch_composite_backward(ctx, rs, ts, ts_stride, nullptr, 0, n, S, g, nullptr, nullptr, drs, st);
+  rc = launch_composite_backward(ctx, rs, ts, ts_stride, noise, 0, n, S, g, nullptr, nullptr, drs, st);
   if (rc) return rc;
   // algorithmic FLOPs: dgrad skips the three slices into non-differentiable inputs (PE->L0, PE->L5, dirPE->rgb0)
   rc = prof_begin(ctx, 2, samples * 2.0 * (593408.0 - 16128.0 - 16128.0 - 3456.0), st, &e1);
@@ -571,9 +572,10 @@ static int train_pass(tgtc_ctx* ctx, int net, const float* rays_o, const float* 
 }
 
 extern "C" int tgtc_train_step(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, const float* rgb_gt, int64_t n_rays,
-                               int64_t n_rays_total, double near, double far, int n_samples, int n_fine, float* grads,
-                               int accumulate, float* loss_sums, float* rgb_coarse, float* rgb_fine, void* workspace,
-                               size_t workspace_bytes, tgtc_stream stream) {
+                               int64_t n_rays_total, double near, double far, int n_samples, int n_fine, const float* rand,
+                               const float* noise_coarse, const float* noise_fine, float* grads, int accumulate,
+                               float* loss_sums, float* rgb_coarse, float* rgb_fine, void* workspace, size_t workspace_bytes,
+                               tgtc_stream stream) {
   CHECK_CTX(ctx);
   CHECK_NET(ctx, TGTC_NET_COARSE);
   CHECK_NET(ctx, TGTC_NET_FINE);
@@ -596,15 +598,18 @@ extern "C" int tgtc_train_step(tgtc_ctx* ctx, const float* rays_o, const float* 
   const size_t np = bwd_flat_floats();
   // loss = mse(rgb_gt, rgb_coarse) + mse(rgb_gt, rgb_fine), each a mean over n_rays_total*3 values (train_tgtcs.py:238-251)
   const float scale = 2.0f / (3.0f * (float)n_rays_total);
-  int rc = launch_sample_uniform(ctx, nullptr, nullptr, 1, S, near, far, nullptr, nullptr, ts_c, st);
+  // coarse sample positions: one shared row (perturb=False, utils.py:512-516) or per-ray stratified positions replaying the
+  // caller's uniforms (perturb=True, utils.py:518-524)
+  const int64_t ts_c_stride = rand != nullptr ? S : 0;
+  int rc = launch_sample_uniform(ctx, nullptr, nullptr, rand != nullptr ? n_rays : 1, S, near, far, rand, nullptr, ts_c, st);
   if (rc) return rc;
-  rc = train_pass(ctx, TGTC_NET_COARSE, rays_o, rays_d, ts_c, 0, n_rays, S, near, far, rgb_gt, scale, ws, base, grads, accumulate,
-                  loss_sums, rgb_coarse, w_c, st);
+  rc = train_pass(ctx, TGTC_NET_COARSE, rays_o, rays_d, ts_c, ts_c_stride, n_rays, S, near, far, noise_coarse, rgb_gt, scale, ws, base,
+                  grads, accumulate, loss_sums, rgb_coarse, w_c, st);
   if (rc) return rc;
   // no gradient flows through the resampling (utils.py:576-579): the two nets' backward passes are independent
-  rc = launch_sample_fine(ctx, nullptr, nullptr, ts_c, 0, w_c, n_rays, S, F, nullptr, ts_f, nullptr, nullptr, st);
+  rc = launch_sample_fine(ctx, nullptr, nullptr, ts_c, ts_c_stride, w_c, n_rays, S, F, nullptr, ts_f, nullptr, nullptr, st);
   if (rc) return rc;
-  return train_pass(ctx, TGTC_NET_FINE, rays_o, rays_d, ts_f, S + F, n_rays, S + F, near, far, rgb_gt, scale, ws, base, grads + np,
-                    accumulate, loss_sums != nullptr ? loss_sums + 1 : nullptr, rgb_fine, nullptr, st);
+  return train_pass(ctx, TGTC_NET_FINE, rays_o, rays_d, ts_f, S + F, n_rays, S + F, near, far, noise_fine, rgb_gt, scale, ws, base,
+                    grads + np, accumulate, loss_sums != nullptr ? loss_sums + 1 : nullptr, rgb_fine, nullptr, st);
 }
 

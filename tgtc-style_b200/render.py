@@ -352,11 +352,13 @@ class NerfRenderer:
 
     # ------------------------------------------------------------------ training step (a11)
     def train_step(self, rays_o, rays_d, rgb_gt, n_total=None, near=0., far=1., n_samples=64, n_fine=64, grads=None,
-                   accumulate=False):
+                   accumulate=False, rand=None, noise_coarse=None, noise_fine=None):
         """Forward + backward of Origin_train's loss (train_tgtcs.py:228-255, perturb=0, noise=0) for one batch of rays:
         loss = mse(rgb_gt, rgb_coarse) + mse(rgb_gt, rgb_fine), means taken over n_total rays (default: this batch).
         Returns {"loss" (device scalar), "grads" (flat fp32 [2*P]: coarse net then fine net, tgtc_set_weights order),
-        "rgb_coarse", "rgb_fine"}.  Pass the same `grads` with accumulate=True for the later ray chunks of one step."""
+        "rgb_coarse", "rgb_fine"}.  Pass the same `grads` with accumulate=True for the later ray chunks of one step.
+        rand [n,S] (uniforms, perturb=True of utils.py:518-524) and noise_coarse [n,S] / noise_fine [n,S+F] (randn*std,
+        utils.py:372-374) replay the reference's stochastic options with caller-drawn tensors."""
         self.refresh_weights()
         ro, rd, gt = self._dev(rays_o), self._dev(rays_d), self._dev(rgb_gt)
         n = ro.shape[0]
@@ -371,8 +373,12 @@ class NerfRenderer:
         wsb = self.lib.tgtc_train_workspace_bytes(self._h, n, n_samples, n_fine)
         ws = self._workspace(wsb + 1024)
         off = (-ws.data_ptr()) % 1024
+        rnd = self._dev(rand) if rand is not None else None
+        nzc = self._dev(noise_coarse) if noise_coarse is not None else None
+        nzf = self._dev(noise_fine) if noise_fine is not None else None
         _lib.check(self.lib.tgtc_train_step(self._h, _ptr(ro), _ptr(rd), _ptr(gt), n, n_total, float(near), float(far), n_samples,
-                                            n_fine, _ptr(grads), int(accumulate), _ptr(sums), _ptr(rgb_c), _ptr(rgb_f),
+                                            n_fine, _ptr(rnd), _ptr(nzc), _ptr(nzf), _ptr(grads), int(accumulate), _ptr(sums),
+                                            _ptr(rgb_c), _ptr(rgb_f),
                                             ctypes.c_void_p(ws.data_ptr() + off), wsb, self._stream))
         return {"loss": sums.sum() / (3.0 * n_total), "grads": grads, "rgb_coarse": rgb_c, "rgb_fine": rgb_f}
 

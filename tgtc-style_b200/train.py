@@ -47,7 +47,7 @@ class NerfTrainer:
     def rank(self):
         return dist.get_rank(self.group) if dist.is_initialized() else 0
 
-    def forward_backward(self, rays_o, rays_d, rgb_gt, n_total=None):
+    def forward_backward(self, rays_o, rays_d, rgb_gt, n_total=None, perturb=False, sigma_noise_std=0.):
         """Gradients of this rank's rays into self.grads (ray chunks of max_rays_per_pass accumulate).  Returns the
         local loss contribution (device scalar; summing it over ranks gives the step's loss)."""
         n = rays_o.shape[0]
@@ -55,11 +55,19 @@ class NerfTrainer:
         loss = None
         for b in range(0, max(n, 1), self.max_rays):
             e = min(n, b + self.max_rays)
-            out = self.r.train_step(rays_o[b:e], rays_d[b:e], rgb_gt[b:e], n_total=n_total, grads=self.grads, accumulate=b > 0)
+            rand = nzc = nzf = None
+            if perturb:             # the generator call of utils.py:519-520
+                rand = torch.zeros([e - b, 64], device=rays_o.device)
+                torch.nn.init.uniform_(rand, 0, 1)
+            if sigma_noise_std > 0:  # the generator calls of utils.py:373-374 (coarse pass, then fine pass)
+                nzc = torch.randn([e - b, 64], device=rays_o.device) * sigma_noise_std
+                nzf = torch.randn([e - b, 128], device=rays_o.device) * sigma_noise_std
+            out = self.r.train_step(rays_o[b:e], rays_d[b:e], rgb_gt[b:e], n_total=n_total, grads=self.grads, accumulate=b > 0,
+                                    rand=rand, noise_coarse=nzc, noise_fine=nzf)
             loss = out["loss"] if loss is None else loss + out["loss"]
         return loss
 
-    def step(self, rays_o, rays_d, rgb_gt, sharded=False):
+    def step(self, rays_o, rays_d, rgb_gt, sharded=False, perturb=False, sigma_noise_std=0.):
         """One optimisation step.  rays: this step's global batch (every rank passes the same tensors and takes its
         shard_range) or, with sharded=True, this rank's own shard of a global batch of world * n rays."""
         world = self.world()
@@ -70,7 +78,7 @@ class NerfTrainer:
             b, e = shard_range(rays_o.shape[0], self.rank(), world)
             ro, rd, gt = rays_o[b:e], rays_d[b:e], rgb_gt[b:e]
             n_total = rays_o.shape[0]
-        loss = self.forward_backward(ro, rd, gt, n_total)
+        loss = self.forward_backward(ro, rd, gt, n_total, perturb=perturb, sigma_noise_std=sigma_noise_std)
         if world > 1:
             dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.group)   # the path's only collective
         self.opt.step()
