@@ -79,3 +79,5 @@ class RefArgs:
     netwidth = 256
     netwidth_fine = 256
     siren_sigma_mul = 0.0
+    style_D = 8          # configs/fern.txt:26
+    vae_latent = 32      # config.py:86

@@ -357,3 +357,90 @@ def train_step_reference(sd_coarse, sd_fine, rays_o, rays_d, rgb_gt, near=0., fa
     loss.backward()
     return (loss.detach(), {k: v.grad for k, v in pc.items()}, {k: v.grad for k, v in pf.items()}, rgb_c.detach(), rgb_f.detach(),
             ts_f.detach())
+
+
+# ----------------------------------------------------------------------------
+# per-ray style head: models.StyleMLP_before_concat (models.py:120-147),
+# models.StyleMLP_Wild_multilayers (models.py:149-180), called as in render_style (rendering.py:118-178)
+
+STYLE_C_SHAPES = [(256, 95), (256, 288), (256, 288), (256, 288), (256, 351)]                      # "layers.{i}" of the concat module
+STYLE_W_SHAPES = [(256, 607), (256, 288), (256, 288), (256, 288), (256, 351), (256, 288), (256, 288), (3, 288)]
+
+
+def init_style_like_reference(seed=1):
+    """torch.manual_seed(seed); StyleMLP_before_concat(args); StyleMLP_Wild_multilayers(args) with style_D=8, vae_latent=32,
+    netwidth=256, embed_freq_coor=10 (train_tgtcs.py:41-52 order): the same nn.Linear sequence, so bit-identical tensors
+    (checked against the imported reference in tests/test_oracle_golden.py)."""
+    torch.manual_seed(seed)
+    nets = []
+    for shapes in (STYLE_C_SHAPES, STYLE_W_SHAPES):
+        sd = OrderedDict()
+        for i, (out_f, in_f) in enumerate(shapes):
+            lin = torch.nn.Linear(in_f, out_f)
+            sd["layers.%d.weight" % i] = lin.weight.detach().clone()
+            sd["layers.%d.bias" % i] = lin.bias.detach().clone()
+        nets.append(sd)
+    return nets[0], nets[1]
+
+
+def style_concat_forward(sd, x, latent):
+    """StyleMLP_before_concat.forward (models.py:137-147): x = embedded pts [...,63], latent [...,32]."""
+    lin = torch.nn.functional.linear
+    h = x
+    for i in range(5):
+        h = torch.cat([h, latent], dim=-1)
+        if i == 4:
+            h = torch.cat([h, x], dim=-1)
+        h = torch.relu(lin(h, sd["layers.%d.weight" % i], sd["layers.%d.bias" % i]))
+    return h
+
+
+def style_wild_forward(sd, x, concated, latent):
+    """StyleMLP_Wild_multilayers.forward (models.py:165-180): concated = cat(base_remap, concat_features) [...,512]."""
+    lin = torch.nn.functional.linear
+    h = torch.cat([concated, x], dim=-1)
+    for i in range(7):
+        h = torch.cat([h, latent], dim=-1)
+        if i == 4:
+            h = torch.cat([h, x], dim=-1)
+        h = torch.relu(lin(h, sd["layers.%d.weight" % i], sd["layers.%d.bias" % i]))
+    h = torch.cat([h, latent], dim=-1)
+    return torch.sigmoid(lin(h, sd["layers.7.weight"], sd["layers.7.bias"]))
+
+
+@torch.no_grad()
+def render_style_chain(sd_coarse, sd_fine, sd_concat, sd_wild, rays_o, rays_d, latents, near=0., far=1., n_samples=64, n_fine=64,
+                       keep_intermediates=False):
+    """The loop body of render_style (rendering.py:118-178) for one batch of rays with perturb=False: NeRF trunk ->
+    base_remap, sigma, embedded pts; style module 1 on (pts_embed, latents); style module 2 on (pts_embed,
+    cat(base_remap, concat_features), mean-over-latent-dim broadcast) -> stylised rgb; compositing with the NeRF sigma;
+    resampling; the same on the fine net.  latents: [N,32] (what latents_model_1 returns, rendering.py:125)."""
+    ro = torch.as_tensor(rays_o, dtype=torch.float32)
+    rd = torch.as_tensor(rays_d, dtype=torch.float32)
+    lat = torch.as_tensor(latents, dtype=torch.float32)
+    n = ro.shape[0]
+    lat2 = torch.mean(lat, dim=1, keepdim=True)          # rendering.py:126 (mean over the LATENT dim, SURVEY App. D)
+    out = {}
+
+    def one_pass(sd_nerf, pts, S):
+        ret = nerf_forward(sd_nerf, pts, rd.unsqueeze(1).expand(n, S, 3))
+        l1 = lat.unsqueeze(1).expand(n, S, lat.shape[-1])
+        cf = style_concat_forward(sd_concat, ret["pts"], l1)
+        concated = torch.cat((ret["base_remap"], cf), dim=-1)
+        l2 = lat2.unsqueeze(2).expand(n, S, lat.shape[-1])
+        rgb_s = style_wild_forward(sd_wild, ret["pts"], concated, l2)
+        return ret, cf, rgb_s
+
+    pts, ts = sample_uniform(ro, rd, n_samples, near, far)
+    ret, cf, rgb_s = one_pass(sd_coarse, pts, n_samples)
+    rgb_c, t_c, w_c, acc_c = alpha_composition(rgb_s, ret["sigma"], ts)
+    out.update(rgb_coarse=rgb_c, depth_coarse=t_c, acc_coarse=acc_c, weights_coarse=w_c)
+    if keep_intermediates:
+        out.update(concat_features_coarse=cf, rgb_pts_coarse=rgb_s, sigma_coarse=ret["sigma"])
+    pts_f, ts_f = sample_fine(ro, rd, ts, w_c, n_fine)
+    ret_f, cf_f, rgb_sf = one_pass(sd_fine, pts_f, n_samples + n_fine)
+    rgb_f, t_f, w_f, acc_f = alpha_composition(rgb_sf, ret_f["sigma"], ts_f)
+    out.update(rgb=rgb_f, depth=t_f, acc=acc_f, weights=w_f, ts_fine=ts_f)
+    if keep_intermediates:
+        out.update(concat_features_fine=cf_f, rgb_pts_fine=rgb_sf, sigma_fine=ret_f["sigma"])
+    return out

@@ -137,3 +137,31 @@ def test_oracle_vs_live_reference():
     noise = torch.randn(ret["sigma"].shape) * 1.0
     ora_noisy = O.alpha_composition(ret["rgb"], ret["sigma"], ts, noise=noise)
     assert torch.equal(ref_noisy[0], ora_noisy[0]) and torch.equal(ref_noisy[2], ora_noisy[2])
+
+
+# ------------------------------------------------------------------ per-ray style head
+def test_style_weights_identical_to_reference():
+    """oracle.init_style_like_reference(1) == torch.manual_seed(1); StyleMLP_before_concat; StyleMLP_Wild_multilayers."""
+    import hashlib
+    g = golden("style_chain")
+    cs, ws = O.init_style_like_reference(1)
+    for tag, sd in (("concat", cs), ("wild", ws)):
+        for k, v in sd.items():
+            assert hashlib.sha256(np.ascontiguousarray(v.numpy()).tobytes()).hexdigest() == str(g["sha_%s/%s" % (tag, k)]), (tag, k)
+
+
+def test_style_chain_vs_golden():
+    """oracle.render_style_chain against the imported reference's render_style loop body (rendering.py:118-178)."""
+    g = golden("style_chain")
+    ro, rd = small_rays()
+    w0c, w0f = O.init_linear_like_reference(0)
+    probe = g["probe_index"]
+    wc, wf = O.recalibrate_sigma(w0c, ro[probe], rd[probe]), O.recalibrate_sigma(w0f, ro[probe], rd[probe])
+    cs, ws = O.init_style_like_reference(1)
+    sel = g["ray_index"]
+    out = O.render_style_chain(wc, wf, cs, ws, ro[sel], rd[sel], g["latents"], keep_intermediates=True)
+    assert np.array_equal(out["ts_fine"].numpy(), g["ts_fine"])
+    for k, tol in (("rgb_coarse", 2e-6), ("weights_coarse", 1e-6), ("rgb", 2e-6), ("depth", 2e-6), ("weights", 1e-6), ("rgb_pts_coarse", 2e-6)):
+        np.testing.assert_allclose(out[k].numpy(), g[k], atol=tol, rtol=0, err_msg=k)
+    np.testing.assert_allclose(out["concat_features_coarse"][:8].numpy(), g["concat_features_coarse"], atol=2e-5, rtol=1e-5)
+    np.testing.assert_allclose(out["rgb_pts_fine"][:16].numpy(), g["rgb_pts_fine"], atol=2e-6, rtol=0)
