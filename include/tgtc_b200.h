@@ -193,6 +193,24 @@ int tgtc_train_step(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, con
                     const float* noise_coarse, const float* noise_fine, float* grads, int accumulate, float* loss_sums,
                     float* rgb_coarse, float* rgb_fine, void* workspace, size_t workspace_bytes, tgtc_stream stream);
 
+/* Per-ray style head.  Replaces models.StyleMLP_before_concat (models.py:120-147) and
+ * models.StyleMLP_Wild_multilayers (models.py:149-180) as called by render_style / render_train_style
+ * (rendering.py:118-178, :280-327).  params: 26 device pointers = module 1 layers.{0..4} (weight [out,in] row-major, bias),
+ * then module 2 layers.{0..7}; shapes 256x95, 3x 256x288, 256x351 and 256x607, 3x 256x288, 256x351, 2x 256x288, 3x288
+ * (style_D = 8, vae_latent = 32).  The caller keeps the tensors alive (latent columns are re-read per call). */
+int tgtc_set_style_weights(tgtc_ctx* ctx, const float* const* params, tgtc_stream stream);
+
+/* The loop body of render_style for one batch of rays with perturb=False: NeRF trunk (base_remap, sigma) -> style
+ * module 1 (concat_features) -> style module 2 (stylised rgb) -> compositing with the NeRF sigma -> resampling -> the
+ * same on the fine net.  latent1 / latent2: device pointers to the 32 latent values of module 1 / module 2 for this
+ * batch (one (style, frame) per call: latent1 = latents_model_1(...) row, rendering.py:125; latent2 = its mean over the
+ * latent dim broadcast to 32, rendering.py:126,:139).  Outputs as tgtc_render.  bf16 tcgen05 path; 64 + 64 samples;
+ * chunk <= 0 means passes of 32768 rays (128 KB of feature tiles per 128 samples live in the workspace). */
+size_t tgtc_render_style_workspace_bytes(int64_t n_rays, int n_samples, int n_fine, int64_t chunk);
+int tgtc_render_style(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n_rays, double near, double far,
+                      int n_samples, int n_fine, int64_t chunk, const float* latent1, const float* latent2,
+                      const tgtc_render_out* out, void* workspace, size_t workspace_bytes, tgtc_stream stream);
+
 /* Per-kernel device timing of the MLP launches (the dominant kernel), for the roofline line of bench.py:
  * while enabled, every MLP launch is bracketed by cudaEvents on its stream (no host sync).
  * tgtc_profile_read synchronises those events and returns, since the last read/enable: the number of MLP

@@ -64,6 +64,11 @@ extern "C" int tgtc_destroy(tgtc_ctx* ctx) {
     if (ctx->net[i].tc_blob) cudaFree(ctx->net[i].tc_blob);
     if (ctx->net[i].tc_blobT) cudaFree(ctx->net[i].tc_blobT);
   }
+  {
+    StyleImage& si = ctx->style;
+    void* bufs[] = {si.blob_c, si.blob_w, si.head_w, si.bias_c, si.bias_w, si.head_b, si.latents, si.tables};
+    for (void* b : bufs) if (b) cudaFree(b);
+  }
   if (ctx->arena) cudaFree(ctx->arena);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   delete ctx;
@@ -613,3 +618,115 @@ extern "C" int tgtc_train_step(tgtc_ctx* ctx, const float* rays_o, const float* 
                     grads + np, accumulate, loss_sums != nullptr ? loss_sums + 1 : nullptr, rgb_fine, nullptr, st);
 }
 
+// ---------------------------------------------------------------------------
+// stylised render: the loop body of render_style (rendering.py:118-178) for one batch of rays
+
+extern "C" int tgtc_set_style_weights(tgtc_ctx* ctx, const float* const* params, tgtc_stream stream) {
+  CHECK_CTX(ctx);
+  TGTC_REQUIRE(params != nullptr, TGTC_ERR_ARG, "params is null");
+  for (int i = 0; i < 26; ++i) TGTC_REQUIRE(params[i] != nullptr && aligned4(params[i]), TGTC_ERR_ARG, "style param %d null or misaligned", i);
+  DeviceGuard g(ctx->device);
+  return style_set_weights(ctx, params, (cudaStream_t)stream);
+}
+
+struct StyleWs {
+  size_t off_remap, off_cf, off_rs_c, off_rs_f, off_w_c, off_ts_f, off_ts_c, total;
+};
+static StyleWs style_ws_layout(int64_t pass, int S, int F) {
+  StyleWs w;
+  const size_t tiles = (size_t)((pass * (S + F) + 127) / 128);
+  size_t o = 0;
+  w.off_remap = o; o = align_up(o + tiles * 65536, 1024);
+  w.off_cf = o;    o = align_up(o + tiles * 65536, 1024);
+  w.off_rs_c = o;  o = align_up(o + (size_t)pass * S * 16, 256);
+  w.off_rs_f = o;  o = align_up(o + (size_t)pass * (S + F) * 16, 256);
+  w.off_w_c = o;   o = align_up(o + (size_t)pass * S * 4, 256);
+  w.off_ts_f = o;  o = align_up(o + (size_t)pass * (S + F) * 4, 256);
+  w.off_ts_c = o;  o = align_up(o + (size_t)S * 4, 256);
+  w.total = o;
+  return w;
+}
+static inline int64_t style_pass(int64_t n, int64_t chunk) { return pass_size(n, chunk <= 0 ? 32768 : chunk); }
+
+extern "C" size_t tgtc_render_style_workspace_bytes(int64_t n_rays, int n_samples, int n_fine, int64_t chunk) {
+  if (n_rays <= 0 || n_samples <= 0 || n_fine < 0) return 0;
+  return style_ws_layout(style_pass(n_rays, chunk), n_samples, n_fine).total;
+}
+
+extern "C" int tgtc_render_style(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n_rays, double near, double far,
+                                 int n_samples, int n_fine, int64_t chunk, const float* latent1, const float* latent2,
+                                 const tgtc_render_out* out_p, void* workspace, size_t workspace_bytes, tgtc_stream stream) {
+  CHECK_CTX(ctx);
+  CHECK_NET(ctx, TGTC_NET_COARSE);
+  CHECK_NET(ctx, TGTC_NET_FINE);
+  TGTC_REQUIRE(ctx->style.set, TGTC_ERR_STATE, "style weights not set (tgtc_set_style_weights)");
+  TGTC_REQUIRE(n_rays >= 0, TGTC_ERR_ARG, "bad n_rays=%lld", (long long)n_rays);
+  if (n_rays == 0) return TGTC_OK;
+  const int S = n_samples, F = n_fine;
+  TGTC_REQUIRE(S == 64 && S + F == 128, TGTC_ERR_UNSUPPORTED, "stylised render supports n_samples=64, n_fine=64; got %d+%d", S, F);
+  CHECK_PTR(rays_o, "rays_o"); CHECK_PTR(rays_d, "rays_d"); CHECK_PTR(latent1, "latent1"); CHECK_PTR(latent2, "latent2");
+  TGTC_REQUIRE(out_p != nullptr, TGTC_ERR_ARG, "out is null");
+  const tgtc_render_out& out = *out_p;
+  const int64_t pass = style_pass(n_rays, chunk);
+  const StyleWs ws = style_ws_layout(pass, S, F);
+  TGTC_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0 && workspace_bytes >= ws.total,
+               TGTC_ERR_STATE, "style workspace too small or not 1024-byte aligned: need %zu bytes, got %zu", ws.total, workspace_bytes);
+  DeviceGuard g(ctx->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* base = static_cast<uint8_t*>(workspace);
+  uint8_t* remap = base + ws.off_remap;
+  uint8_t* cf = base + ws.off_cf;
+  float* rs_c = reinterpret_cast<float*>(base + ws.off_rs_c);
+  float* rs_f = reinterpret_cast<float*>(base + ws.off_rs_f);
+  float* ts_c = reinterpret_cast<float*>(base + ws.off_ts_c);
+  const int T = S + F;
+  int rc = style_set_latents(ctx, latent1, latent2, st);   // effective biases of both modules for this (style, frame)
+  if (rc) return rc;
+  rc = launch_sample_uniform(ctx, nullptr, nullptr, 1, S, near, far, nullptr, nullptr, ts_c, st);
+  if (rc) return rc;
+  for (int64_t r0 = 0; r0 < n_rays; r0 += pass) {
+    const int64_t m = (n_rays - r0 < pass) ? (n_rays - r0) : pass;
+    float* w_c = out.weights_coarse ? out.weights_coarse + r0 * S : reinterpret_cast<float*>(base + ws.off_w_c);
+    float* ts_f = out.ts_fine ? out.ts_fine + r0 * T : reinterpret_cast<float*>(base + ws.off_ts_f);
+    for (int which = 0; which < 2; ++which) {
+      MlpIO io;
+      io.rays_o = rays_o + r0 * 3; io.rays_d = rays_d + r0 * 3;
+      io.ts = which == 0 ? nullptr : ts_f;
+      io.t_scale = (float)(far - near); io.t_near = (float)near;
+      io.n_rays = m; io.S = which == 0 ? S : T;
+      io.rgbsigma = which == 0 ? rs_c : rs_f;
+      // NeRF trunk -> base_remap tile images + sigma (rendering.py:122-123 / :158-159)
+      cudaEvent_t e1 = nullptr;
+      rc = prof_begin(ctx, 0, (double)m * io.S * 2.0 * (593408.0 - 36224.0 - 384.0), st, &e1);
+      if (rc) return rc;
+      rc = launch_mlp_tc_trunk(ctx, which, io, remap, st);
+      if (rc) return rc;
+      if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
+      // style module 1 -> concat_features tile images (rendering.py:129-130)
+      rc = prof_begin(ctx, 1, (double)m * io.S * 2.0 * 335360.0, st, &e1);
+      if (rc) return rc;
+      rc = launch_style_concat(ctx, io, cf, st);
+      if (rc) return rc;
+      if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
+      // style module 2 -> stylised rgb (rendering.py:132-142)
+      rc = prof_begin(ctx, 2, (double)m * io.S * 2.0 * 614752.0, st, &e1);
+      if (rc) return rc;
+      rc = launch_style_wild(ctx, io, remap, cf, st);
+      if (rc) return rc;
+      if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
+      if (which == 0) {
+        rc = launch_composite(ctx, nullptr, nullptr, rs_c, ts_c, 0, nullptr, 0, m, S, out.rgb_coarse ? out.rgb_coarse + r0 * 3 : nullptr,
+                              out.depth_coarse ? out.depth_coarse + r0 : nullptr, out.acc_coarse ? out.acc_coarse + r0 : nullptr, w_c, st);
+        if (rc) return rc;
+        rc = launch_sample_fine(ctx, nullptr, nullptr, ts_c, 0, w_c, m, S, F, nullptr, ts_f, nullptr, nullptr, st);
+        if (rc) return rc;
+      } else {
+        rc = launch_composite(ctx, nullptr, nullptr, rs_f, ts_f, T, nullptr, 0, m, T, out.rgb ? out.rgb + r0 * 3 : nullptr,
+                              out.depth ? out.depth + r0 : nullptr, out.acc ? out.acc + r0 : nullptr,
+                              out.weights ? out.weights + r0 * T : nullptr, st);
+        if (rc) return rc;
+      }
+    }
+  }
+  return TGTC_OK;
+}

@@ -66,10 +66,25 @@ struct NetImage {
   bool set = false;
 };
 
+// per-ray style head (style_tc.cu): packed images of models.StyleMLP_before_concat / StyleMLP_Wild_multilayers
+struct StyleImage {
+  uint8_t* blob_c = nullptr;   // module 1: 18 chunks [256 x 64] bf16
+  uint8_t* blob_w = nullptr;   // module 2: 34 chunks
+  float* head_w = nullptr;     // [3][256] output layer of module 2
+  float* bias_c = nullptr;     // [5][256] effective biases for the current latents
+  float* bias_w = nullptr;     // [7][256]
+  float* head_b = nullptr;     // [3]
+  float* latents = nullptr;    // [2][32]
+  uint8_t* tables = nullptr;   // device scratch for the packing / bias tables
+  const float* params[26] = {};  // caller's fp32 tensors: module 1 (W,b) x 5, module 2 (W,b) x 8
+  bool set = false;
+};
+
 struct tgtc_ctx {
   int device = 0;
   int num_sms = 0;
   NetImage net[2];
+  StyleImage style;
   int64_t launches = 0;
   // staging arena for the *_host entry points
   void* arena = nullptr;
@@ -189,6 +204,12 @@ struct TcDz {
   uint8_t* dhead = nullptr;  // [ntiles][16 KB]     columns 0..2 = dz of rgb1, column 3 = d_sigma
 };
 
+// style_tc.cu
+int style_set_weights(tgtc_ctx* ctx, const float* const* params, cudaStream_t st);
+int style_set_latents(tgtc_ctx* ctx, const float* latent1, const float* latent2, cudaStream_t st);
+int launch_style_concat(tgtc_ctx* ctx, const MlpIO& io, uint8_t* cf_img, cudaStream_t st);
+int launch_style_wild(tgtc_ctx* ctx, const MlpIO& io, const uint8_t* remap_img, const uint8_t* cf_img, cudaStream_t st);
+
 // mlp_bwd.cu
 size_t bwd_partial_floats();
 size_t bwd_blobT_bytes();
@@ -203,6 +224,7 @@ int launch_mse_grad(tgtc_ctx* ctx, const float* rgb, const float* gt, int64_t n,
 int launch_mlp_fp32(tgtc_ctx* ctx, int net, const MlpIO& io, cudaStream_t st);
 int launch_mlp_tc(tgtc_ctx* ctx, int net, const MlpIO& io, cudaStream_t st);
 int launch_mlp_tc_train(tgtc_ctx* ctx, int net, const MlpIO& io, const TcStash& stash, cudaStream_t st);
+int launch_mlp_tc_trunk(tgtc_ctx* ctx, int net, const MlpIO& io, uint8_t* remap_img, cudaStream_t st);
 bool mlp_tc_supports(const MlpIO& io);
 
 // ---------------------------------------------------------------------------

@@ -156,6 +156,7 @@ struct TcParams {
   uint8_t* stash_h;   // [ntiles][9][128 x 256 bf16]  post-ReLU outputs of L0..L7 and remap
   uint8_t* stash_f;   // [ntiles][128 x 128 bf16]      post-ReLU output of rgb0
   uint8_t* stash_pe;  // [ntiles][128 x 64 bf16]       positional encoding tile
+  int trunk;          // style path: run L0..L7 + sigma + remap only; stash ONLY the remap tile ([ntiles][64 KB]) and write sigma
   int dbg_flags;      // timing experiments (results garbage): 2 = skip the hidden-layer epilogue work, 16 = no weight ring at all
   int dbg_layers;     // >0: stop after this many GEMM layers and dump the fp32 accumulator (tests)
   float* dbg_out;     // [ntiles*128, 256]
@@ -189,7 +190,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
   const int64_t nquads = (P.ntiles + 3) / 4;
   const int64_t ncl = gridDim.x >> 1, cid = blockIdx.x >> 1;
   const int64_t iters = nquads > cid ? (nquads - cid + ncl - 1) / ncl : 0;   // identical in both CTAs of the pair
-  const int nlayers = P.dbg_layers > 0 ? P.dbg_layers : kTcNumGemm;
+  const int nlayers = P.dbg_layers > 0 ? P.dbg_layers : (P.trunk ? 9 : kTcNumGemm);
 
   // ---- one-time setup
   if (threadIdx.x == 0) {
@@ -366,7 +367,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
           for (int a = 0; a < 3; ++a) fast_sincos(__fmul_rn(x[a], fr), &e[3 + 6 * f + a], &e[3 + 6 * f + 3 + a]);
         }
         e[63] = 0.f;
-        uint8_t* const gpe = (kTrain && tile < P.ntiles) ? P.stash_pe + (size_t)tile * 16384 + (r >> 3) * 1024 + (r & 7) * 128 : nullptr;
+        uint8_t* const gpe = (kTrain && !P.trunk && tile < P.ntiles) ? P.stash_pe + (size_t)tile * 16384 + (r >> 3) * 1024 + (r & 7) * 128 : nullptr;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
           const uint32_t q0 = pack_bf16(e[8 * ch + 0], e[8 * ch + 1]), q1 = pack_bf16(e[8 * ch + 2], e[8 * ch + 3]),
@@ -480,9 +481,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
               const bool issuer = (warp == kEpiWarp0 && lane == 0);
               if (issuer) bulk_wait_read0();
               named_bar_sync(3, kNumEpiThreads);
-              if (issuer && tile < P.ntiles) {
-                bulk_s2g(P.stash_h + ((size_t)tile * 9 + l) * 65536, sbase + kOffAct + t * kActBytes, 65536u);
+              if (issuer && tile < P.ntiles && (!P.trunk || l == 8)) {
+                uint8_t* gimg = P.trunk ? P.stash_h + (size_t)tile * 65536 : P.stash_h + ((size_t)tile * 9 + l) * 65536;
+                bulk_s2g(gimg, sbase + kOffAct + t * kActBytes, 65536u);
                 bulk_commit_group();
+              }
+              if (P.trunk && l == 8 && hc == 0 && m < P.M) {
+                // trunk mode ends here: sigma (fp32 head, models.py:103) goes to the .w lane of the per-sample float4; the style
+                // head kernels fill in (r,g,b).  sigpart_s was written by the hc==1 threads one layer ago (ordered through the
+                // ActReady -> MMA -> AccFull chain).
+                reinterpret_cast<float*>(P.io.rgbsigma)[m * 4 + 3] = sig_keep[t] + sigpart_s[t * 128 + row] + b_sigma;
               }
             }
             tc_fence_before();
@@ -582,7 +590,7 @@ extern "C" void tgtc_debug_tc_flags(int f) { g_dbg_flags = f; }
 extern "C" void tgtc_debug_tc_trace(long long* dev_buf) { g_dbg_trace = dev_buf; }
 
 static int launch_tc_common(tgtc_ctx* ctx, int net, const MlpIO& io, int dbg_layers, float* dbg_out, const TcStash* stash,
-                            cudaStream_t st) {
+                            cudaStream_t st, int trunk = 0) {
   const NetImage& im = ctx->net[net];
   TcParams P;
   P.blob = im.tc_blob;
@@ -593,6 +601,7 @@ static int launch_tc_common(tgtc_ctx* ctx, int net, const MlpIO& io, int dbg_lay
   P.ntiles = (P.M + kTileM - 1) / kTileM;
   P.rays_per_tile = io.S < kTileM ? kTileM / io.S : 1;
   P.dbg_layers = dbg_layers;
+  P.trunk = trunk;
   P.dbg_flags = g_dbg_flags;
   P.stash_h = stash != nullptr ? stash->h : nullptr;
   P.stash_f = stash != nullptr ? stash->f : nullptr;
@@ -612,6 +621,13 @@ static int launch_tc_common(tgtc_ctx* ctx, int net, const MlpIO& io, int dbg_lay
   else mlp_tc_kernel<false><<<grid, kNumThreads, kSmemBytes, st>>>(P);
   TGTC_LAUNCH_CHECK(ctx);
   return TGTC_OK;
+}
+
+// style path: NeRF trunk only (L0..L7, sigma head, remap); remap tile images -> remap_img [ntiles][64 KB], sigma -> rgbsigma[.].w
+int launch_mlp_tc_trunk(tgtc_ctx* ctx, int net, const MlpIO& io, uint8_t* remap_img, cudaStream_t st) {
+  TcStash stash;
+  stash.h = remap_img;
+  return launch_tc_common(ctx, net, io, 0, nullptr, &stash, st, 1);
 }
 
 // training forward: same kernel, additionally writing the activation stash the backward kernels read

@@ -1,0 +1,572 @@
+// Per-ray style head -- models.StyleMLP_before_concat (models.py:120-147) and
+// models.StyleMLP_Wild_multilayers (models.py:149-180) as called by render_style (rendering.py:118-178),
+// bf16 operands on tcgen05 (CTA pairs), fp32 accumulation in TMEM.
+//
+// One table-driven chain kernel runs either module on 128-sample tiles (two slots per CTA, weight ring, epilogue warps:
+// the structure of mlp_tc.cu).  A layer is a sequence of K segments:
+//     PE    one 64-column chunk: the positional-encoding tile (recomputed from the rays, never stored)
+//     ACT   four chunks: the activation tile of the previous layer (in place, shared memory)
+//     IMGk  four chunks: a tile image from HBM (base_remap written by the NeRF trunk kernel, concat_features written by the
+//           first module) staged into the activation buffer by the slot's tile-mover thread with one 64 KB bulk copy
+// and an output kind: ACT (bias + ReLU -> next A operand), ACT+IMG (also one 64 KB bulk store of the tile image), HEAD
+// (bias + ReLU, then the 3-row fp32 output layer + sigmoid on CUDA cores -> rgb).
+//     module 1: [PE] [ACT] [ACT] [ACT] [PE,ACT]->concat_features image
+//     module 2: [PE,IMG0=base_remap,IMG1=concat_features] [ACT] [ACT] [ACT] [PE,ACT] [ACT] [ACT]->HEAD
+// The 32-d latent inputs of every layer are constant per (style, frame): their products with the latent columns of the
+// weights are folded into per-call effective biases by style_bias_kernel (fp32).
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+using namespace tcptx;
+
+constexpr int kTileM = 128;
+constexpr int kStages = 3;
+constexpr int kStageBytes = 16384;
+constexpr int kNumThreads = 512;   // w0 weights, w1 MMA / forwarder, w2-5 PE producers, w6-13 epilogue, w14-15 tile movers
+constexpr int kPeWarp0 = 2, kEpiWarp0 = 6, kMoveWarp0 = 14;
+constexpr int kNumEpiThreads = 256, kNumPeThreads = 128;
+constexpr int kMaxLayers = 8;
+
+enum { SEG_PE = 1, SEG_ACT = 2, SEG_IMG0 = 3, SEG_IMG1 = 4 };
+enum { OUT_ACT = 0, OUT_ACT_IMG = 1, OUT_HEAD = 2 };
+
+struct ChainLayer {
+  uint8_t seg[3];
+  uint8_t nseg;
+  uint8_t out;
+  uint8_t pe_last;   // this layer's PE segment is the tile's last use of the PE buffer
+};
+struct ChainParams {
+  ChainLayer layer[kMaxLayers];
+  int nlayers;
+  const uint8_t* blob;       // chunks [256 x 64] bf16 SW128 in consumption order (first half = rows 0..127)
+  const float* bias;         // [nlayers][256] effective biases (bias + latent columns . latent)
+  const float* head_w;       // [3][256] output layer (HEAD), fp32
+  const float* head_b;       // [3] effective
+  const float* rays_o;
+  const float* rays_d;
+  const float* ts;           // [n_rays,S] or nullptr -> uniform coarse positions
+  float t_scale, t_near;
+  int S;
+  int64_t M;
+  int64_t ntiles;
+  const uint8_t* img0;       // [ntiles][64 KB]
+  const uint8_t* img1;
+  uint8_t* img_out;          // [ntiles][64 KB]
+  float* rgbsigma;           // [M][4]: HEAD writes .xyz
+};
+
+constexpr int kOffAct = 0;
+constexpr int kActBytes = 65536;
+constexpr int kOffPe = kOffAct + 2 * kActBytes;
+constexpr int kPeBytes = 16384;
+constexpr int kOffW = kOffPe + 2 * kPeBytes;
+constexpr int kOffBias = kOffW + kStages * kStageBytes;     // 8 x 256 fp32
+constexpr int kOffHeadW = kOffBias + kMaxLayers * 256 * 4;  // 3 x 256 fp32
+constexpr int kOffHeadPart = kOffHeadW + 3 * 256 * 4;       // [128][4] fp32
+constexpr int kOffBars = kOffHeadPart + 128 * 4 * 4;
+constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarPeReady = 2 * kStages /*leader, count 8*/, kBarPeFree = kBarPeReady + 2,
+              kBarActReady = kBarPeFree + 2, kBarAccFull = kBarActReady + 2, kBarAFull = kBarAccFull + 2 /*leader: both CTAs staged*/,
+              kBarAFree = kBarAFull + 2, kBarOutDone = kBarAFree + 2, kBarOutFree = kBarOutDone + 2 /*leader*/,
+              kBarLoad = kBarOutFree + 2 /*mover's own bulk loads*/, kNumBars = kBarLoad + 2;
+constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
+constexpr int kSmemBytes = kOffTmemPtr + 16;
+static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
+
+__device__ __forceinline__ int64_t pair_tile(int64_t it, int t, uint32_t rank) {
+  const int64_t quad = (int64_t)(blockIdx.x >> 1) + it * (int64_t)(gridDim.x >> 1);
+  return quad * 4 + 2 * (int64_t)rank + t;
+}
+__device__ __forceinline__ int seg_chunks(int s) { return s == SEG_PE ? 1 : 4; }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_chain_kernel(const __grid_constant__ ChainParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t bars = sbase + kOffBars;
+  auto bar = [&](int i) { return bars + 8u * i; };
+  const uint32_t rank = cluster_ctarank();
+  const int64_t nquads = (P.ntiles + 3) / 4;
+  const int64_t ncl = gridDim.x >> 1, cid = blockIdx.x >> 1;
+  const int64_t iters = nquads > cid ? (nquads - cid + ncl - 1) / ncl : 0;
+  const int nl = P.nlayers;
+  int chunks_per_tile = 0, imgs_per_tile = 0;
+  for (int l = 0; l < nl; ++l)
+    for (int s = 0; s < P.layer[l].nseg; ++s) {
+      chunks_per_tile += seg_chunks(P.layer[l].seg[s]);
+      imgs_per_tile += P.layer[l].seg[s] >= SEG_IMG0 ? 1 : 0;
+    }
+  const bool has_out_img = P.layer[nl - 1].out == OUT_ACT_IMG;
+
+  if (threadIdx.x == 0) {
+    if ((sbase & 1023u) != 0) { printf("tgtc mlp_chain: shared memory base not 1024-aligned\n"); __trap(); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(bar(kBarWFull + s), rank == 0 ? 2 : 1); mbar_init(bar(kBarWEmpty + s), 1); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(bar(kBarPeReady + t), 2 * (kNumPeThreads / 32));
+      mbar_init(bar(kBarPeFree + t), 1);
+      mbar_init(bar(kBarActReady + t), 2 * (kNumEpiThreads / 32));
+      mbar_init(bar(kBarAccFull + t), 1);
+      mbar_init(bar(kBarAFull + t), 2);                         // one remote arrive per CTA's mover after its copy landed
+      mbar_init(bar(kBarAFree + t), 1);
+      mbar_init(bar(kBarOutDone + t), kNumEpiThreads / 32);
+      mbar_init(bar(kBarOutFree + t), 2);
+      mbar_init(bar(kBarLoad + t), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(sbase + kOffTmemPtr), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::);
+  }
+  {
+    float* dst = reinterpret_cast<float*>(smem + kOffBias);
+    for (int i = threadIdx.x; i < nl * 256; i += kNumThreads) dst[i] = P.bias[i];
+    if (P.head_w != nullptr) {
+      float* hw = reinterpret_cast<float*>(smem + kOffHeadW);
+      for (int i = threadIdx.x; i < 3 * 256; i += kNumThreads) hw[i] = P.head_w[i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  if (*reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr) != 0u) {
+    if (threadIdx.x == 0) printf("tgtc mlp_chain: unexpected TMEM base\n");
+    __trap();
+  }
+  constexpr uint32_t tmem_base = 0u;
+
+  if (warp == 0) {
+    // ===================================================================== weight producer
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t it = 0; it < iters; ++it) {
+      int c0 = 0;
+      for (int l = 0; l < nl; ++l) {
+        int nch = 0;
+        for (int s = 0; s < P.layer[l].nseg; ++s) nch += seg_chunks(P.layer[l].seg[s]);
+        for (int t = 0; t < 2; ++t) {
+          for (int c = 0; c < nch; ++c) {
+            mbar_wait(bar(kBarWEmpty + stage), phase ^ 1);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(bar(kBarWFull + stage), kStageBytes);
+              bulk_g2s(sbase + kOffW + stage * kStageBytes, P.blob + (size_t)(c0 + c) * 2 * kStageBytes + (size_t)rank * kStageBytes,
+                       kStageBytes, bar(kBarWFull + stage));
+            }
+            __syncwarp();
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+        c0 += nch;
+      }
+    }
+  } else if (warp == 1 && rank != 0) {
+    // ===================================================================== peer: forward "my half of the stage landed"
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t leader_wfull = mapa_cluster(bar(kBarWFull), 0);
+    for (int64_t it = 0; it < iters; ++it) {
+      for (int c = 0; c < 2 * chunks_per_tile; ++c) {
+        mbar_wait(bar(kBarWFull + stage), phase);
+        if (elect_one()) mbar_arrive_cluster(leader_wfull + 8u * stage);
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== leader: MMA issuer for the pair
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t act_par[2] = {0, 0}, pe_par[2] = {0, 0}, af_par[2] = {0, 0}, of_par[2] = {0, 0};
+    const uint32_t w_lo0 = (((sbase + kOffW) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t idesc = make_idesc(2 * kTileM, 256);
+    auto issue_chunk = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t accumulate) {
+      mbar_wait_uniform(bar(kBarWFull + stage), phase);
+      tc_fence_after();
+      const uint32_t b_lo = w_lo0 + (uint32_t)stage * (kStageBytes >> 4);
+      if (elect_one()) {
+        umma_bf16_lohi(d_tmem, a_lo, kDescHiSW128, b_lo, kDescHiSW128, idesc, accumulate);
+        umma_bf16_lohi(d_tmem, a_lo + 2u, kDescHiSW128, b_lo + 2u, kDescHiSW128, idesc, 1u);
+        umma_bf16_lohi(d_tmem, a_lo + 4u, kDescHiSW128, b_lo + 4u, kDescHiSW128, idesc, 1u);
+        umma_bf16_lohi(d_tmem, a_lo + 6u, kDescHiSW128, b_lo + 6u, kDescHiSW128, idesc, 1u);
+        umma_commit(bar(kBarWEmpty + stage));
+      }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    };
+    for (int64_t it = 0; it < iters; ++it) {
+      for (int l = 0; l < nl; ++l) {
+        const ChainLayer L = P.layer[l];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(256 * t);
+          const uint32_t pe_lo = (((sbase + kOffPe + t * kPeBytes) & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t act_lo = (((sbase + kOffAct + t * kActBytes) & 0x3FFFFu) >> 4) | (1u << 16);
+          // the accumulator of this slot is drained / the activation tile is written (epilogue of the previous layer)
+          if (l > 0 || it > 0) { mbar_wait_uniform(bar(kBarActReady + t), act_par[t]); act_par[t] ^= 1; }
+          // first layer of a tile: the previous tile's image store out of act[t] must have finished reading it before this
+          // tile's first epilogue overwrites it
+          if (l == 0 && it > 0 && has_out_img) { mbar_wait_uniform(bar(kBarOutFree + t), of_par[t]); of_par[t] ^= 1; }
+          tc_fence_after();
+          uint32_t acc = 0u;
+          for (int s = 0; s < L.nseg; ++s) {
+            const int sg = L.seg[s];
+            if (sg == SEG_PE) {
+              mbar_wait_uniform(bar(kBarPeReady + t), pe_par[t]);   // completes once per tile; the parity advances at its last use
+              tc_fence_after();
+              issue_chunk(d_tmem, pe_lo, acc);
+              acc = 1u;
+              if (L.pe_last) {
+                pe_par[t] ^= 1;
+                if (elect_one()) umma_commit(bar(kBarPeFree + t));
+                __syncwarp();
+              }
+            } else {
+              if (sg >= SEG_IMG0) { mbar_wait_uniform(bar(kBarAFull + t), af_par[t]); af_par[t] ^= 1; tc_fence_after(); }
+#pragma unroll
+              for (int c = 0; c < 4; ++c) { issue_chunk(d_tmem, act_lo + 1024u * (uint32_t)c, acc); acc = 1u; }
+              // the image just consumed may be replaced by the next staged image (or, at the end of the tile, by the next tile's)
+              const bool next_is_img = (s + 1 < L.nseg && L.seg[s + 1] >= SEG_IMG0);
+              if (next_is_img || (imgs_per_tile > 0 && l == nl - 1 && s == L.nseg - 1)) {
+                if (elect_one()) umma_commit(bar(kBarAFree + t));
+                __syncwarp();
+              }
+            }
+          }
+          if (elect_one()) umma_commit(bar(kBarAccFull + t));
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp < kEpiWarp0) {
+    // ===================================================================== PE producers (one thread per tile row)
+    const int r = (warp - kPeWarp0) * 32 + lane;
+    const int S = P.S;
+    const uint32_t leader_peready = mapa_cluster(bar(kBarPeReady), 0);
+    for (int64_t it = 0; it < iters; ++it) {
+      for (int t = 0; t < 2; ++t) {
+        const int64_t tile = pair_tile(it, t, rank);
+        if (it > 0) mbar_wait_relaxed(bar(kBarPeFree + t), (uint32_t)((it - 1) & 1), 128);
+        int64_t m = tile * kTileM + r;
+        if (m >= P.M) m = P.M - 1;
+        const int64_t ray = m / S;
+        const int k = (int)(m - ray * S);
+        const float tt = P.ts != nullptr ? P.ts[m] : coarse_t(k, S, P.t_scale, P.t_near);
+        float x[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(P.rays_o[ray * 3 + c], __fmul_rn(tt, P.rays_d[ray * 3 + c]));
+        const uint32_t prow = sbase + kOffPe + t * kPeBytes + (r >> 3) * 1024 + (r & 7) * 128;
+        float e[64];
+        e[0] = x[0]; e[1] = x[1]; e[2] = x[2];
+#pragma unroll
+        for (int f = 0; f < 10; ++f) {
+          const float fr = (float)(1 << f);
+#pragma unroll
+          for (int a = 0; a < 3; ++a) fast_sincos(__fmul_rn(x[a], fr), &e[3 + 6 * f + a], &e[3 + 6 * f + 3 + a]);
+        }
+        e[63] = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+          st_shared_v4(prow + ((ch ^ (r & 7)) << 4), pack_bf16(e[8 * ch + 0], e[8 * ch + 1]), pack_bf16(e[8 * ch + 2], e[8 * ch + 3]),
+                       pack_bf16(e[8 * ch + 4], e[8 * ch + 5]), pack_bf16(e[8 * ch + 6], e[8 * ch + 7]));
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(leader_peready + 8u * t);
+      }
+    }
+  } else if (warp >= kMoveWarp0) {
+    // ===================================================================== tile movers: one thread per slot
+    if (lane == 0) {
+      const int t = warp - kMoveWarp0;
+      const uint32_t leader_afull = mapa_cluster(bar(kBarAFull), 0) + 8u * t;
+      const uint32_t leader_outfree = mapa_cluster(bar(kBarOutFree), 0) + 8u * t;
+      uint32_t afree_par = 0, od_par = 0, ld_par = 0;
+      bool first_stage = true;
+      for (int64_t it = 0; it < iters; ++it) {
+        const int64_t tile = pair_tile(it, t, rank);
+        const bool tile_ok = tile < P.ntiles;
+        for (int l = 0; l < nl; ++l) {
+          const ChainLayer L = P.layer[l];
+          for (int s = 0; s < L.nseg; ++s) {
+            if (L.seg[s] < SEG_IMG0) continue;
+            if (!first_stage) { mbar_wait(bar(kBarAFree + t), afree_par); afree_par ^= 1; }
+            first_stage = false;
+            const uint8_t* src = (L.seg[s] == SEG_IMG0 ? P.img0 : P.img1) + (size_t)(tile_ok ? tile : 0) * 65536;
+            // one 64 KB bulk copy into act[t]; when it has landed here, tell the leader's MMA warp (it needs both CTAs' tiles)
+            mbar_arrive_expect_tx(bar(kBarLoad + t), 65536u);
+            bulk_g2s(sbase + kOffAct + t * kActBytes, src, 65536u, bar(kBarLoad + t));
+            mbar_wait(bar(kBarLoad + t), ld_par); ld_par ^= 1;
+            mbar_arrive_cluster(leader_afull);
+          }
+          if (L.out == OUT_ACT_IMG) {
+            mbar_wait(bar(kBarOutDone + t), od_par); od_par ^= 1;
+            if (tile_ok) {
+              bulk_s2g(P.img_out + (size_t)tile * 65536, sbase + kOffAct + t * kActBytes, 65536u);
+              bulk_commit_group();
+            }
+            bulk_wait_read0();
+            mbar_arrive_cluster(leader_outfree);
+          }
+        }
+      }
+      bulk_wait_all0();
+    }
+  } else {
+    // ===================================================================== epilogue warps
+    const int q = warp & 3;
+    const int hc = (warp - kEpiWarp0) >> 2;
+    const int row = q * 32 + lane;
+    const float* bias_s = reinterpret_cast<const float*>(smem + kOffBias);
+    const float* headw_s = reinterpret_cast<const float*>(smem + kOffHeadW);
+    float* part_s = reinterpret_cast<float*>(smem + kOffHeadPart);
+    const uint32_t leader_actready = mapa_cluster(bar(kBarActReady), 0);
+    const uint32_t rx = (uint32_t)(row & 7) << 4;
+    uint32_t acc_par[2] = {0, 0};
+    float hb[3] = {0.f, 0.f, 0.f};
+    if (P.head_b != nullptr) { hb[0] = P.head_b[0]; hb[1] = P.head_b[1]; hb[2] = P.head_b[2]; }
+    for (int64_t it = 0; it < iters; ++it) {
+      for (int l = 0; l < nl; ++l) {
+        const int okind = P.layer[l].out;
+        for (int t = 0; t < 2; ++t) {
+          const int64_t tile = pair_tile(it, t, rank);
+          const int64_t m = tile * kTileM + row;
+          mbar_wait(bar(kBarAccFull + t), acc_par[t]); acc_par[t] ^= 1;
+          tc_fence_after();
+          const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 * t) + (uint32_t)(hc * 128);
+          const float* bl = bias_s + l * 256 + hc * 128;
+          const uint32_t arow = sbase + kOffAct + t * kActBytes + (row >> 3) * 1024 + (row & 7) * 128 + hc * 2 * 16384;
+          float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#pragma unroll 1
+          for (int blk = 0; blk < 4; ++blk) {
+            uint32_t v[32];
+            tmem_ld32(tcol + blk * 32, v);
+            tmem_ld_wait_dep(v);
+            const uint32_t kb = arow + (uint32_t)(blk >> 1) * 16384u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int c = blk * 32 + 8 * j;
+              const float4 b0 = *reinterpret_cast<const float4*>(bl + c);
+              const float4 b1 = *reinterpret_cast<const float4*>(bl + c + 4);
+              float h[8];
+              h[0] = fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x, 0.f); h[1] = fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y, 0.f);
+              h[2] = fmaxf(__uint_as_float(v[8 * j + 2]) + b0.z, 0.f); h[3] = fmaxf(__uint_as_float(v[8 * j + 3]) + b0.w, 0.f);
+              h[4] = fmaxf(__uint_as_float(v[8 * j + 4]) + b1.x, 0.f); h[5] = fmaxf(__uint_as_float(v[8 * j + 5]) + b1.y, 0.f);
+              h[6] = fmaxf(__uint_as_float(v[8 * j + 6]) + b1.z, 0.f); h[7] = fmaxf(__uint_as_float(v[8 * j + 7]) + b1.w, 0.f);
+              if (okind == OUT_HEAD) {
+                const float* w = headw_s + hc * 128 + c;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  p0 = fmaf(h[e], w[e], p0);
+                  p1 = fmaf(h[e], w[256 + e], p1);
+                  p2 = fmaf(h[e], w[512 + e], p2);
+                }
+              } else {
+                const uint32_t dst = kb + ((uint32_t)((((blk & 1) * 4) + j) << 4) ^ rx);
+                st_shared_v4(dst, pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+              }
+            }
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (okind == OUT_ACT_IMG) mbar_arrive(bar(kBarOutDone + t));   // local: the mover may store the tile image
+            mbar_arrive_cluster(leader_actready + 8u * t);
+          }
+          if (okind == OUT_HEAD) {
+            // models.py:177-179: sigmoid(W_out . [h, latent] + b); the latent columns live in the effective bias
+            if (hc == 1) *reinterpret_cast<float4*>(part_s + row * 4) = make_float4(p0, p1, p2, 0.f);
+            named_bar_sync(1, kNumEpiThreads);
+            if (hc == 0 && m < P.M) {
+              const float4 o = *reinterpret_cast<const float4*>(part_s + row * 4);
+              const float z0 = p0 + o.x + hb[0], z1 = p1 + o.y + hb[1], z2 = p2 + o.z + hb[2];
+              float* dst = P.rgbsigma + m * 4;
+              dst[0] = 1.0f / (1.0f + expf(-z0));
+              dst[1] = 1.0f / (1.0f + expf(-z1));
+              dst[2] = 1.0f / (1.0f + expf(-z2));
+            }
+            named_bar_sync(2, kNumEpiThreads);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    __syncwarp();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// packing: one chunk = [256 rows x 64 K] bf16 SW128; value = W[n][col0 + k] for k < ncols else 0
+struct ChunkSrc { const float* W; int ld; int col0; int ncols; };
+
+__global__ void pack_chunks_kernel(const ChunkSrc* __restrict__ table, int nchunks, __nv_bfloat16* __restrict__ out) {
+  const size_t total = (size_t)nchunks * 256 * 64;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int chunk = (int)(idx / (256 * 64));
+    const int byte = (int)(idx % (256 * 64)) * 2;
+    const int grp = byte >> 10, rem = byte & 1023;
+    const int rr = rem >> 7, inrow = rem & 127;
+    const int c16 = (inrow >> 4) ^ rr, within = (inrow & 15) >> 1;
+    const int n = grp * 8 + rr;
+    const int k = c16 * 8 + within;
+    const ChunkSrc s = table[chunk];
+    out[idx] = __float2bfloat16_rn(k < s.ncols ? s.W[(size_t)n * s.ld + s.col0 + k] : 0.f);
+  }
+}
+
+// effective biases: out[j] = b[j] + sum_k W[j][lat0 + k] * latent[k]   (32 latent columns)
+struct BiasSrc { const float* W; const float* b; int ld; int lat0; int nout; const float* latent; float* out; };
+__global__ void style_bias_kernel(const BiasSrc* __restrict__ table, int n) {
+  const BiasSrc s = table[blockIdx.x];
+  for (int j = threadIdx.x; j < s.nout; j += blockDim.x) {
+    float acc = s.b[j];
+    for (int k = 0; k < 32; ++k) acc = fmaf(s.W[(size_t)j * s.ld + s.lat0 + k], s.latent[k], acc);
+    s.out[j] = acc;
+  }
+}
+
+__global__ void head_copy_kernel(const float* __restrict__ W, int ld, float* __restrict__ out) {   // [3][256] <- W[3][ld][:256]
+  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) out[i] = W[(size_t)(i / 256) * ld + (i % 256)];
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// host side
+
+static const int kCIn[5] = {95, 288, 288, 288, 351};
+static const int kWIn[8] = {607, 288, 288, 288, 351, 288, 288, 288};
+constexpr int kCChunks = 1 + 4 + 4 + 4 + 5;            // 18
+constexpr int kWChunks = 9 + 4 + 4 + 4 + 5 + 4 + 4;    // 34
+
+int style_set_weights(tgtc_ctx* ctx, const float* const* params, cudaStream_t st) {
+  StyleImage& im = ctx->style;
+  if (im.blob_c == nullptr) {
+    TGTC_CUDA(cudaMalloc(&im.blob_c, (size_t)kCChunks * 32768));
+    TGTC_CUDA(cudaMalloc(&im.blob_w, (size_t)kWChunks * 32768));
+    TGTC_CUDA(cudaMalloc(&im.head_w, 3 * 256 * sizeof(float)));
+    TGTC_CUDA(cudaMalloc(&im.bias_c, 5 * 256 * sizeof(float)));
+    TGTC_CUDA(cudaMalloc(&im.bias_w, 7 * 256 * sizeof(float)));
+    TGTC_CUDA(cudaMalloc(&im.head_b, 4 * sizeof(float)));
+    TGTC_CUDA(cudaMalloc(&im.latents, 64 * sizeof(float)));
+    TGTC_CUDA(cudaMalloc(&im.tables, 4096));
+  }
+  for (int i = 0; i < 26; ++i) im.params[i] = params[i];
+  // chunk tables (consumption order, see the header comment)
+  std::vector<ChunkSrc> tc, tw;
+  auto act4 = [](std::vector<ChunkSrc>& v, const float* W, int ld, int col0) { for (int k = 0; k < 4; ++k) v.push_back({W, ld, col0 + 64 * k, 64}); };
+  const float* const* C = params;        // concat module: (W,b) x 5
+  const float* const* Wp = params + 10;  // wild module: (W,b) x 8
+  tc.push_back({C[0], 95, 0, 63});
+  for (int l = 1; l <= 3; ++l) act4(tc, C[2 * l], 288, 0);
+  tc.push_back({C[8], 351, 288, 63});                 // skip layer: [h(256), latent(32), x(63)] (models.py:141-144)
+  act4(tc, C[8], 351, 0);
+  tw.push_back({Wp[0], 607, 512, 63});                // layer 0: [base_remap(256), concat_features(256), x(63), latent(32)]
+  act4(tw, Wp[0], 607, 0);
+  act4(tw, Wp[0], 607, 256);
+  for (int l = 1; l <= 3; ++l) act4(tw, Wp[2 * l], 288, 0);
+  tw.push_back({Wp[8], 351, 288, 63});
+  act4(tw, Wp[8], 351, 0);
+  act4(tw, Wp[10], 288, 0);
+  act4(tw, Wp[12], 288, 0);
+  TGTC_REQUIRE((int)tc.size() == kCChunks && (int)tw.size() == kWChunks, TGTC_ERR_STATE, "style chunk tables inconsistent");
+  ChunkSrc* dtab = reinterpret_cast<ChunkSrc*>(im.tables);
+  TGTC_CUDA(cudaMemcpyAsync(dtab, tc.data(), tc.size() * sizeof(ChunkSrc), cudaMemcpyHostToDevice, st));
+  TGTC_CUDA(cudaMemcpyAsync(dtab + 64, tw.data(), tw.size() * sizeof(ChunkSrc), cudaMemcpyHostToDevice, st));
+  TGTC_CUDA(cudaStreamSynchronize(st));   // the host vectors go out of scope
+  pack_chunks_kernel<<<ctx->num_sms * 2, 256, 0, st>>>(dtab, kCChunks, reinterpret_cast<__nv_bfloat16*>(im.blob_c));
+  TGTC_LAUNCH_CHECK(ctx);
+  pack_chunks_kernel<<<ctx->num_sms * 2, 256, 0, st>>>(dtab + 64, kWChunks, reinterpret_cast<__nv_bfloat16*>(im.blob_w));
+  TGTC_LAUNCH_CHECK(ctx);
+  head_copy_kernel<<<1, 256, 0, st>>>(Wp[14], 288, im.head_w);
+  TGTC_LAUNCH_CHECK(ctx);
+  im.set = true;
+  return TGTC_OK;
+}
+
+// latent1 / latent2: device pointers to 32 floats (module 1 / module 2 latents of this call)
+int style_set_latents(tgtc_ctx* ctx, const float* latent1, const float* latent2, cudaStream_t st) {
+  StyleImage& im = ctx->style;
+  TGTC_CUDA(cudaMemcpyAsync(im.latents, latent1, 32 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  TGTC_CUDA(cudaMemcpyAsync(im.latents + 32, latent2, 32 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const float* const* C = im.params;
+  const float* const* Wp = im.params + 10;
+  std::vector<BiasSrc> tb;
+  static const int clat[5] = {63, 256, 256, 256, 256};
+  for (int l = 0; l < 5; ++l) tb.push_back({C[2 * l], C[2 * l + 1], kCIn[l], clat[l], 256, im.latents, im.bias_c + l * 256});
+  static const int wlat[8] = {575, 256, 256, 256, 256, 256, 256, 256};
+  for (int l = 0; l < 7; ++l) tb.push_back({Wp[2 * l], Wp[2 * l + 1], kWIn[l], wlat[l], 256, im.latents + 32, im.bias_w + l * 256});
+  tb.push_back({Wp[14], Wp[15], 288, 256, 3, im.latents + 32, im.head_b});
+  static_assert(sizeof(ChunkSrc) == 24 && 128 * sizeof(ChunkSrc) + 13 * sizeof(BiasSrc) <= 4096, "style tables do not fit");
+  BiasSrc* dtab = reinterpret_cast<BiasSrc*>(im.tables + 128 * sizeof(ChunkSrc));
+  TGTC_CUDA(cudaMemcpyAsync(dtab, tb.data(), tb.size() * sizeof(BiasSrc), cudaMemcpyHostToDevice, st));
+  TGTC_CUDA(cudaStreamSynchronize(st));
+  style_bias_kernel<<<(unsigned)tb.size(), 256, 0, st>>>(dtab, (int)tb.size());
+  TGTC_LAUNCH_CHECK(ctx);
+  return TGTC_OK;
+}
+
+static void fill_common(ChainParams& P, const MlpIO& io) {
+  P.rays_o = io.rays_o; P.rays_d = io.rays_d; P.ts = io.ts;
+  P.t_scale = io.t_scale; P.t_near = io.t_near; P.S = io.S;
+  P.M = io.n_rays * io.S;
+  P.ntiles = (P.M + kTileM - 1) / kTileM;
+}
+
+static int launch_chain(tgtc_ctx* ctx, const ChainParams& P, cudaStream_t st) {
+  static bool attr_set[64] = {};
+  if (!attr_set[ctx->device & 63]) {
+    TGTC_CUDA(cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set[ctx->device & 63] = true;
+  }
+  const int64_t nquads = (P.ntiles + 3) / 4;
+  const int64_t max_pairs = ctx->num_sms / 2;
+  const int grid = 2 * (int)(nquads < max_pairs ? nquads : max_pairs);
+  mlp_chain_kernel<<<grid, kNumThreads, kSmemBytes, st>>>(P);
+  TGTC_LAUNCH_CHECK(ctx);
+  return TGTC_OK;
+}
+
+// module 1: concat_features tile images for the samples of io -> cf_img [ntiles][64 KB]
+int launch_style_concat(tgtc_ctx* ctx, const MlpIO& io, uint8_t* cf_img, cudaStream_t st) {
+  if (io.n_rays == 0) return TGTC_OK;
+  ChainParams P = {};
+  fill_common(P, io);
+  P.nlayers = 5;
+  P.layer[0] = {{SEG_PE, 0, 0}, 1, OUT_ACT, 0};
+  for (int l = 1; l <= 3; ++l) P.layer[l] = {{SEG_ACT, 0, 0}, 1, OUT_ACT, 0};
+  P.layer[4] = {{SEG_PE, SEG_ACT, 0}, 2, OUT_ACT_IMG, 1};
+  P.blob = ctx->style.blob_c;
+  P.bias = ctx->style.bias_c;
+  P.img_out = cf_img;
+  return launch_chain(ctx, P, st);
+}
+
+// module 2: stylised rgb -> rgbsigma[.].xyz from base_remap images (NeRF trunk) and concat_features images (module 1)
+int launch_style_wild(tgtc_ctx* ctx, const MlpIO& io, const uint8_t* remap_img, const uint8_t* cf_img, cudaStream_t st) {
+  if (io.n_rays == 0) return TGTC_OK;
+  ChainParams P = {};
+  fill_common(P, io);
+  P.nlayers = 7;
+  P.layer[0] = {{SEG_PE, SEG_IMG0, SEG_IMG1}, 3, OUT_ACT, 0};
+  for (int l = 1; l <= 3; ++l) P.layer[l] = {{SEG_ACT, 0, 0}, 1, OUT_ACT, 0};
+  P.layer[4] = {{SEG_PE, SEG_ACT, 0}, 2, OUT_ACT, 1};
+  P.layer[5] = {{SEG_ACT, 0, 0}, 1, OUT_ACT, 0};
+  P.layer[6] = {{SEG_ACT, 0, 0}, 1, OUT_HEAD, 0};
+  P.blob = ctx->style.blob_w;
+  P.bias = ctx->style.bias_w;
+  P.head_w = ctx->style.head_w;
+  P.head_b = ctx->style.head_b;
+  P.img0 = remap_img;
+  P.img1 = cf_img;
+  P.rgbsigma = io.rgbsigma;
+  return launch_chain(ctx, P, st);
+}

@@ -350,6 +350,54 @@ class NerfRenderer:
                                               self._stream))
         return out
 
+    # ------------------------------------------------------------------ per-ray style head (f1)
+    STYLE_C_SHAPES = [(256, 95), (256, 288), (256, 288), (256, 288), (256, 351)]
+    STYLE_W_SHAPES = [(256, 607), (256, 288), (256, 288), (256, 288), (256, 351), (256, 288), (256, 288), (3, 288)]
+
+    def set_style_weights(self, concat_style, style):
+        """concat_style: models.StyleMLP_before_concat, style: models.StyleMLP_Wild_multilayers (nn.Modules or state_dicts with
+        keys layers.{i}.weight / layers.{i}.bias; models.py:120-180)."""
+        tensors = []
+        for src, shapes in ((concat_style, self.STYLE_C_SHAPES), (style, self.STYLE_W_SHAPES)):
+            sd = src.state_dict() if hasattr(src, "state_dict") else src
+            for i, (o, k) in enumerate(shapes):
+                w, b = sd["layers.%d.weight" % i], sd["layers.%d.bias" % i]
+                if tuple(w.shape) != (o, k) or tuple(b.shape) != (o,):
+                    raise ValueError("style layers.%d has shape %s/%s, expected %s/%s" % (i, tuple(w.shape), tuple(b.shape), (o, k), (o,)))
+                tensors += [self._dev(w.detach()), self._dev(b.detach())]
+        arr = (ctypes.c_void_p * 26)(*[t.data_ptr() for t in tensors])
+        _lib.check(self.lib.tgtc_set_style_weights(self._h, arr, self._stream))
+        self._style_keep = tensors
+
+    def render_style(self, rays_o, rays_d, latents, near=0., far=1., chunk=None, n_samples=64, n_fine=64, extras=False,
+                     want_weights=False, out=None):
+        """The loop body of render_style (rendering.py:118-178, perturb=False) for one batch of rays that share one (style,
+        frame): latents = the [32] (or [N,32] with identical rows) output of latents_model_1 (rendering.py:125).
+        -> {rgb, depth, acc} (+ weights / coarse outputs / ts_fine like render())."""
+        self.refresh_weights()
+        ro, rd = self._dev(rays_o), self._dev(rays_d)
+        n = ro.shape[0]
+        lat = self._dev(latents)
+        if lat.dim() == 2:
+            if n > 1 and not bool((lat == lat[:1]).all()):
+                raise ValueError("render_style takes one (style, frame) per call: split the batch where the latents change")
+            lat = lat[0]
+        lat1 = lat.reshape(32).contiguous()
+        lat2 = lat1.mean().expand(32).contiguous()          # rendering.py:126: mean over the latent dim, broadcast (:139)
+        if out is None:
+            out = self._alloc_out(n, n_samples, n_fine, extras, self.device)
+            if not want_weights:
+                out.pop("weights")
+        ck = int(chunk) if chunk else 0
+        wsb = self.lib.tgtc_render_style_workspace_bytes(n, n_samples, n_fine, ck)
+        ws = self._workspace(wsb + 1024)
+        off = (-ws.data_ptr()) % 1024
+        s = self._out_struct(out)
+        _lib.check(self.lib.tgtc_render_style(self._h, _ptr(ro), _ptr(rd), n, float(near), float(far), n_samples, n_fine, ck,
+                                              _ptr(lat1), _ptr(lat2), ctypes.byref(s), ctypes.c_void_p(ws.data_ptr() + off), wsb,
+                                              self._stream))
+        return out
+
     # ------------------------------------------------------------------ training step (a11)
     def train_step(self, rays_o, rays_d, rgb_gt, n_total=None, near=0., far=1., n_samples=64, n_fine=64, grads=None,
                    accumulate=False, rand=None, noise_coarse=None, noise_fine=None):
