@@ -174,6 +174,182 @@ TRAIN_FLOP_PER_SAMPLE = 3489024.0    # fwd + wgrad + dgrad
 DGRAD_BYTES_PER_SAMPLE = 9 * 512 + 256 + 32 + 9 * 512 + 256 + 128   # stash read (h, f, d_rgbsigma, rgbsigma) + dz/dzf/dhead written
 
 
+STYLE_WORKLOAD = ("stylised render (render_style loop body, rendering.py:118-178): fern-shaped 1008x756 frame in 4096-ray batches, NeRF "
+                  "trunk features fed to the per-ray style head (StyleMLP_before_concat + StyleMLP_Wild_multilayers, 32-d latent), "
+                  "64 coarse + 128 fine samples/ray, perturb=0, random-init weights")
+STYLE_FLOP_PER_SAMPLE = 2.0 * (593408 - 36224 - 384 + 335360 + 614752)   # trunk (no rgb head) + module 1 + module 2, un-padded
+STYLE_M2_FLOP_PER_SAMPLE = 2.0 * 614752
+
+
+def run_style_reference_arm(args):
+    """--impl reference --workload style: oracle port of the reference's stylised chain on the host cores, bounded sample."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import torch
+    import render_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wc, wf = O.init_linear_like_reference(0)
+    cs, ws = O.init_style_like_reference(1)
+    ro, rd = O.make_rays(H, W, FOCAL, np.eye(4)[:3, :4])
+    per_step = 1024
+    lat = torch.randn(1, 32, generator=torch.Generator().manual_seed(3)).expand(per_step, 32)
+    sel = np.linspace(0, H * W - 1, per_step * (args.steps + args.warmup)).astype(np.int64)
+    t_steps = []
+    for i in range(args.warmup + args.steps):
+        s = sel[i * per_step:(i + 1) * per_step]
+        t0 = time.perf_counter()
+        O.render_style_chain(wc, wf, cs, ws, ro[s], rd[s], lat)
+        if i >= args.warmup:
+            t_steps.append(time.perf_counter() - t0)
+    total = sum(t_steps)
+    value = per_step * args.steps / total
+    sample = "%d rays per step spread over the 1008x756 frame, torch CPU fp32, %d threads" % (per_step, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "rays/s", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": STYLE_WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_style(args):
+    """--workload style (BASELINE config 4): one stylised 1008x756 frame per step and per GPU, 4096-ray batches."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    import tgtc_style_b200 as T
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import render_oracle as O   # synthetic weight sets only
+    wc, wf = O.init_linear_like_reference(0)
+    cs, ws = O.init_style_like_reference(1)
+    r = T.NerfRenderer(device=dev, mode="bf16")
+    r.set_weights(wc, wf)
+    r.set_style_weights(cs, ws)
+    K = np.array([[FOCAL, 0, 0.5 * W], [0, FOCAL, 0.5 * H], [0, 0, 1]])
+    poses = spiral_poses(120)
+    n = H * W
+    lat = torch.randn(32, generator=torch.Generator().manual_seed(3)).to(dev)
+    rays = [r.raygen(H, W, K, np.eye(4)[:3, :4] if world == 1 else poses[(s * world + rank) % 120]) for s in range(2)]
+    out = r._alloc_out(n, N_SAMPLES, N_FINE, False, dev)
+    out.pop("weights")
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_dev(s):
+        ro, rd = rays[s % 2]
+        r.render_style(ro, rd, lat, chunk=4096, out=out)
+        if world > 1:
+            T.gather_tiles({"rgb": out["rgb"], "depth": out["depth"], "acc": out["acc"]}, n * world)
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    for s in range(args.warmup):
+        step_dev(s)
+    sync_all()
+    r.profile_enable(True)
+    l0 = r.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for s in range(args.steps):
+        step_dev(args.warmup + s)
+    e1.record()
+    sync_all()
+    t_wall1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = r.launch_count() - l0
+    kinds = {name: r.profile_read_kind(k) for name, k in (("mlp_tc_kernel<trunk>", 0), ("mlp_chain_kernel<module 1>", 1),
+                                                            ("mlp_chain_kernel<module 2>", 2))}
+    r.profile_enable(False)
+
+    # end to end: pinned host rays in, rgb/depth/acc out to pinned host memory, every step
+    h_rays = [(a.cpu().pin_memory(), b.cpu().pin_memory()) for a, b in rays]
+    h_out = {k: torch.empty_like(v, device="cpu").pin_memory() for k, v in out.items()}
+
+    def step_host(s):
+        ro, rd = (t.to(dev, non_blocking=True) for t in h_rays[s % 2])
+        r.render_style(ro, rd, lat, chunk=4096, out=out)
+        for k in h_out:
+            h_out[k].copy_(out[k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for s in range(args.warmup):
+        step_host(s)
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for s in range(args.steps):
+        step_host(s)
+    e3.record()
+    sync_all()
+    ms2 = torch.tensor([e2.elapsed_time(e3)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    checksum = float(h_out["rgb"].double().sum())
+
+    if rank == 0:
+        clocks.stop()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        ms_total = ms.item()
+        rays_total = n * world * args.steps
+        n2, ms2k, fl2 = kinds["mlp_chain_kernel<module 2>"]
+        ach = fl2 / (ms2k * 1e-3) / 1e12 if ms2k > 0 else None
+        res = {
+            "metric": "rays/s", "value": rays_total / (ms_total * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": STYLE_WORKLOAD, "rays_per_step_per_gpu": n, "batch_rays": 4096, "samples_per_ray": SAMPLES_PER_RAY,
+                       "parallelism": "one frame per GPU per step, NCCL all-gather of rgb/depth/acc tiles" if world > 1 else "1 GPU",
+                       "l2_policy": "frame working set (rays, outputs, per-batch feature tiles) cycles through HBM; weights stay L2-resident"},
+            "step_tflops": rays_total * SAMPLES_PER_RAY * STYLE_FLOP_PER_SAMPLE / (ms_total * 1e-3) / 1e12,
+            "e2e": {"value": rays_total / (ms2.item() * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 20 * n,
+                    "ms_per_step": ms2.item() / args.steps, "api": "NerfRenderer.render_style -> tgtc_render_style", "checksum": checksum},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
+                         "traffic": None, "kernel": "mlp_chain_kernel (style module 2)", "launches_timed": int(n2),
+                         "avg_launch_ms": ms2k / max(n2, 1), "flop_per_sample": STYLE_M2_FLOP_PER_SAMPLE,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"},
+            "kernels": {k: {"launches": int(v[0]), "ms_per_step": v[1] / args.steps,
+                            "tflops": (v[2] / (v[1] * 1e-3) / 1e12) if v[1] > 0 else None} for k, v in kinds.items()},
+            "clocks": clocks.window(t_wall0, t_wall1),
+        }
+        print(json.dumps(res))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_train_reference_arm(args):
     """--impl reference --workload train: the reference's training step (train_tgtcs.py:228-255) through torch.autograd
     on the host cores (oracle port), a bounded ray sample per step."""
@@ -343,18 +519,24 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="render", choices=["render", "train"],
-                    help="render = BASELINE config 2 (the headline; default); train = config 5 (training step)")
+    ap.add_argument("--workload", default="render", choices=["render", "train", "style"],
+                    help="render = BASELINE config 2 (the headline; default); train = config 5 (training step); "
+                         "style = config 4 (stylised render, 4096-ray batches)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         if args.workload == "train":
             run_train_reference_arm(args)
+        elif args.workload == "style":
+            run_style_reference_arm(args)
         else:
             run_reference_arm(args)
         return
     if args.workload == "train":
         run_train(args)
+        return
+    if args.workload == "style":
+        run_style(args)
         return
 
     import numpy as np
