@@ -128,6 +128,75 @@ def cpu_chain_rays_per_s(n_rays, chunk=1024, min_seconds=8.0, max_chunks=16):
     return done * chunk / dt, cores, "%d chunks of %d rays of the 1008x756 frame, chunk=%d, %.1f s" % (done, chunk, chunk, dt)
 
 
+def run_eager_gpu_arm(args):
+    """--impl eager-gpu (extra comparator): the reference chain's own torch ops (rendering.py:27-51) in eager
+    fp32 on the B200 -- what a user of the reference actually runs.  Not the driver's reference arm."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import torch
+    import render_oracle as O
+    dev = torch.device("cuda", 0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    wc, wf = O.init_linear_like_reference(0)
+    wc = {k: v.to(dev) for k, v in wc.items()}
+    wf = {k: v.to(dev) for k, v in wf.items()}
+    ro_np, rd_np = O.make_rays(H, W, FOCAL, np.eye(4)[:3, :4])
+    chunk = 1024 * 8          # rays per batch (the reference default --chunk is 32768 samples-agnostic rays; README uses 1024)
+    per_step = chunk * 8
+    ro = torch.from_numpy(ro_np[:per_step]).to(dev)
+    rd = torch.from_numpy(rd_np[:per_step]).to(dev)
+
+    def sample_pdf(bins, weights, n):            # utils.py:583-609, det=True, torch ops only
+        weights = weights + 1e-5
+        pdf = weights / torch.sum(weights, -1, keepdim=True)
+        cdf = torch.cat([torch.zeros_like(pdf[..., :1]), torch.cumsum(pdf, -1)], -1)
+        u = torch.linspace(0., 1., n, device=dev).expand(list(cdf.shape[:-1]) + [n]).contiguous()
+        inds = torch.searchsorted(cdf, u, right=True)
+        below = torch.max(torch.zeros_like(inds), inds - 1)
+        above = torch.min((cdf.shape[-1] - 1) * torch.ones_like(inds), inds)
+        cg = torch.stack([torch.gather(cdf, -1, below), torch.gather(cdf, -1, above)], -1)
+        bg = torch.stack([torch.gather(bins, -1, below), torch.gather(bins, -1, above)], -1)
+        denom = cg[..., 1] - cg[..., 0]
+        denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
+        return bg[..., 0] + (u - cg[..., 0]) / denom * (bg[..., 1] - bg[..., 0])
+
+    @torch.no_grad()
+    def chain(o, d):
+        n = o.shape[0]
+        ts = torch.linspace(0., 1., N_SAMPLES, device=dev).unsqueeze(0).expand(n, N_SAMPLES)
+        pts = o.unsqueeze(1) + ts.unsqueeze(-1) * d.unsqueeze(1)
+        ret = O.nerf_forward(wc, pts, d.unsqueeze(1).expand(n, N_SAMPLES, 3))
+        _, _, w_c, _ = O.alpha_composition(ret["rgb"], ret["sigma"], ts)
+        mid = 0.5 * (ts[..., 1:] + ts[..., :-1])
+        t_s = sample_pdf(mid, w_c[..., 1:-1], N_FINE)
+        ts_f = torch.sort(torch.cat([ts, t_s], -1), -1)[0]
+        pts_f = o.unsqueeze(1) + ts_f.unsqueeze(-1) * d.unsqueeze(1)
+        ret_f = O.nerf_forward(wf, pts_f, d.unsqueeze(1).expand(n, N_SAMPLES + N_FINE, 3))
+        return O.alpha_composition(ret_f["rgb"], ret_f["sigma"], ts_f)[0]
+
+    def step():
+        for b in range(0, per_step, chunk):
+            chain(ro[b:b + chunk], rd[b:b + chunk])
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    value = per_step * args.steps / (ms * 1e-3)
+    print(json.dumps({"impl": "eager-gpu", "metric": "rays/s", "value": value, "unit": "rays/s", "n_gpus": 1, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": WORKLOAD, "sample": "%d rays per step in batches of %d, eager torch fp32 (TF32 off) on one B200" % (per_step, chunk)},
+                      "mlp_samples_per_s": value * SAMPLES_PER_RAY}))
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's own CPU implementation of the path (its arithmetic restated in
     oracle/render_oracle.py, pinned bit-for-bit to /root/reference in the build container; the reference tree
@@ -516,7 +585,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "eager-gpu"])
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="render", choices=["render", "train", "style"],
@@ -524,6 +593,9 @@ def main():
                          "style = config 4 (stylised render, 4096-ray batches)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "eager-gpu":
+        run_eager_gpu_arm(args)
+        return
     if args.impl == "reference":
         if args.workload == "train":
             run_train_reference_arm(args)

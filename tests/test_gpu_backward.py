@@ -138,3 +138,29 @@ def test_train_step_replays_perturb_and_noise(renderer_bf16):
     # and the unperturbed step is a different function of the same rays
     plain = r.train_step(ro, rd, gt)
     assert abs(plain["loss"].item() - out["loss"].item()) > 0
+
+
+def test_train_step_ragged_batch(renderer_bf16):
+    """an odd ray count: the last coarse tile is half empty and the tile quads of both kernels end in padding tiles;
+    gradients still match autograd (padding rows must contribute exactly nothing)."""
+    n = 193
+    wc, wf, ro, rd, gt = _train_inputs(n, seed=13)
+    loss_ref, gc, gf, _, _, _ = O.train_step_reference(wc, wf, ro, rd, gt)
+    r = renderer_bf16
+    r.set_weights(wc, wf)
+    out = r.train_step(ro, rd, gt)
+    torch.cuda.synchronize()
+    assert abs(out["loss"].item() - loss_ref.item()) <= 2e-3 * max(1.0, abs(loss_ref.item()))
+    vc, vf = r.grad_views(out["grads"])
+    for views, ref in ((vc, gc), (vf, gf)):
+        for k, g_ref in ref.items():
+            g = views[k].cpu()
+            rel = (g - g_ref).norm().item() / max(g_ref.norm().item(), 1e-12)
+            assert torch.isfinite(g).all() and rel <= 0.12, (k, rel)
+
+
+def test_train_step_rejects_unsupported_sizes(renderer_bf16):
+    import tgtc_style_b200 as T
+    ro, rd = small_rays()
+    with pytest.raises(T.TgtcError):
+        renderer_bf16.train_step(ro[:8], rd[:8], torch.rand(8, 3), n_samples=32, n_fine=32)
