@@ -465,6 +465,7 @@ struct WgradParams {
   const float* rays_d;     // [n_rays,3]
   float* partial;          // [gridDim.x][kPartFloats]
   int64_t ntiles;
+  int64_t n_rays;
   int S;
 };
 
@@ -651,7 +652,8 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WgradPara
             // all 64 samples of a stage belong to one ray (S is a multiple of 64): view-direction columns of rgb0
             // (models.py:108) get  sum_s dz_f[s,o] * dirPE_k(ray)  =  colsum * dirPE_k
             const int64_t tile = (int64_t)blockIdx.x + (s >> 1) * gridDim.x;
-            const int64_t ray = (tile * kTileM + (s & 1) * 64) / P.S;
+            int64_t ray = (tile * kTileM + (s & 1) * 64) / P.S;
+            if (ray >= P.n_rays) ray = P.n_rays - 1;   // padding half of the last tile: its dz rows are zero
             const float v[3] = {P.rays_d[ray * 3 + 0], P.rays_d[ray * 3 + 1], P.rays_d[ray * 3 + 2]};
 #pragma unroll
             for (int a = 0; a < 3; ++a) dir_acc[a] = fmaf(acc, v[a], dir_acc[a]);
@@ -804,6 +806,7 @@ int launch_mlp_wgrad(tgtc_ctx* ctx, const TcStash& stash, const TcDz& dz, const 
   P.rays_d = rays_d;
   P.partial = partial;
   P.ntiles = (M + kTileM - 1) / kTileM;
+  P.n_rays = M / S;
   P.S = S;
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
