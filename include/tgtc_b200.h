@@ -193,6 +193,13 @@ int tgtc_train_step(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, con
                     const float* noise_coarse, const float* noise_fine, float* grads, int accumulate, float* loss_sums,
                     float* rgb_coarse, float* rgb_fine, void* workspace, size_t workspace_bytes, tgtc_stream stream);
 
+/* The reference's optimizer step (torch.optim.Adam, betas (0.9, 0.999), eps 1e-8; train_tgtcs.py:39, :255) on flat fp32
+ * device buffers of n values -- e.g. the 2 * tgtc_num_params() masters laid out like the gradient buffer of
+ * tgtc_train_step.  step is the 1-based step count (bias corrections); the lr schedule (train_tgtcs.py:272-276) is the
+ * caller's.  One kernel, 28 B per parameter. */
+int tgtc_adam_step(tgtc_ctx* ctx, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                   double beta1, double beta2, double eps, int64_t step, tgtc_stream stream);
+
 /* Per-ray style head.  Replaces models.StyleMLP_before_concat (models.py:120-147) and
  * models.StyleMLP_Wild_multilayers (models.py:149-180) as called by render_style / render_train_style
  * (rendering.py:118-178, :280-327).  params: 26 device pointers = module 1 layers.{0..4} (weight [out,in] row-major, bias),

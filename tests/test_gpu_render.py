@@ -169,3 +169,24 @@ def test_render_path_frames_match_single_frame_render(renderer_bf16):
         for k in ("rgb", "depth", "acc"):
             assert torch.equal(frames[i][k], ref[k])
     assert not torch.equal(frames[0]["rgb"], frames[1]["rgb"])
+
+
+def test_cal_geometry_outputs(renderer_fp32, tmp_path):
+    """rendering.py:54,:66-81: coor_map = t*d + o and the per-frame npz the 2-D temporal trainer reads."""
+    import tgtc_style_b200 as T
+    H, W, f = 24, 32, 26.0
+    K = np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]])
+    poses = [np.eye(4)[:3, :4], np.array([[1, 0, 0, 0.1], [0, 1, 0, 0.0], [0, 0, 1, 0.05]], dtype=np.float64)]
+    wc, wf = weights("w1")
+    renderer_fp32.set_weights(wc, wf)
+    rgb_map, t_map = T.cal_geometry(renderer_fp32, H, W, K, poses, hwf=[H, W, f], sv_path=str(tmp_path))
+    assert rgb_map.shape == (2, H, W, 3) and t_map.shape == (2, H, W, 1)
+    ro, rd = O.make_rays(H, W, f, poses[1])
+    ref = O.render_chain(wc, wf, ro, rd, 0., 1., 64, 64, 1024)
+    np.testing.assert_allclose(t_map[1].reshape(-1), ref["depth"].numpy(), atol=1e-3)
+    g = np.load(str(tmp_path / "geometry_00001.npz"))
+    assert set(g.files) == {"coor_map", "cps", "hwf", "near", "far"} and g["coor_map"].shape == (H, W, 3)
+    coor_ref = ref["depth"].numpy()[:, None] * rd + ro
+    np.testing.assert_allclose(g["coor_map"].reshape(-1, 3), coor_ref, atol=2e-3)
+    full = np.load(str(tmp_path / "geometry.npz"))
+    assert full["coor_map"].shape == (2, H, W, 3) and (tmp_path / "rgb_00000.png").exists() and (tmp_path / "depth_00001.png").exists()

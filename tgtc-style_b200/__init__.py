@@ -10,9 +10,10 @@ The directory name contains a hyphen; import it as `tgtc_style_b200` (root-level
 from . import _lib
 from ._lib import MLP_BF16, MLP_FP32, NET_COARSE, NET_FINE, TgtcError
 from .dist import gather_tiles, render_frame_sharded, render_path_sharded, shard_range, shard_sizes
+from .geometry import cal_geometry, frame_geometry, save_frame
 from .render import LAYER_NAMES, LAYER_SHAPES, NerfRenderer
 from .shims import make_callables, patch
 from .train import NerfTrainer
 
 __all__ = ["NerfRenderer", "NerfTrainer", "make_callables", "patch", "shard_range", "shard_sizes", "gather_tiles", "render_frame_sharded", "render_path_sharded",
-           "TgtcError", "MLP_FP32", "MLP_BF16", "NET_COARSE", "NET_FINE", "LAYER_NAMES", "LAYER_SHAPES"]
+           "cal_geometry", "frame_geometry", "save_frame", "TgtcError", "MLP_FP32", "MLP_BF16", "NET_COARSE", "NET_FINE", "LAYER_NAMES", "LAYER_SHAPES"]

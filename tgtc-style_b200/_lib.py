@@ -62,6 +62,8 @@ PROTOTYPES = {
     "tgtc_train_step": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, ctypes.c_double, ctypes.c_double,
                                        ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int, c_void_p,
                                        c_void_p, c_void_p, c_void_p, ctypes.c_size_t, c_void_p]),
+    "tgtc_adam_step": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, ctypes.c_double, ctypes.c_double,
+                                      ctypes.c_double, ctypes.c_double, c_i64, c_void_p]),
     "tgtc_set_style_weights": (ctypes.c_int, [c_void_p, ctypes.POINTER(c_void_p), c_void_p]),
     "tgtc_render_style_workspace_bytes": (ctypes.c_size_t, [c_i64, ctypes.c_int, ctypes.c_int, c_i64]),
     "tgtc_render_style": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_int,

@@ -730,3 +730,14 @@ extern "C" int tgtc_render_style(tgtc_ctx* ctx, const float* rays_o, const float
   }
   return TGTC_OK;
 }
+
+// torch.optim.Adam on flat fp32 buffers (the optimizer of train_tgtcs.py:39)
+extern "C" int tgtc_adam_step(tgtc_ctx* ctx, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                              double beta1, double beta2, double eps, int64_t step, tgtc_stream stream) {
+  CHECK_CTX(ctx);
+  TGTC_REQUIRE(n >= 0 && step >= 1, TGTC_ERR_ARG, "bad n=%lld / step=%lld", (long long)n, (long long)step);
+  if (n == 0) return TGTC_OK;
+  CHECK_PTR(params, "params"); CHECK_PTR(grads, "grads"); CHECK_PTR(exp_avg, "exp_avg"); CHECK_PTR(exp_avg_sq, "exp_avg_sq");
+  DeviceGuard g(ctx->device);
+  return launch_adam(ctx, params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, (cudaStream_t)stream);
+}

@@ -21,6 +21,7 @@
 // HBM-bound by the stash traffic (about 25 KB per sample for forward + backward); see DESIGN.md.
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include <math.h>
 
 namespace {
 using namespace tcptx;
@@ -747,6 +748,21 @@ __global__ void grad_reduce_kernel(const float* __restrict__ partial, int nparts
   }
 }
 
+// torch.optim.Adam (the reference's optimizer, train_tgtcs.py:39: betas (0.9, 0.999), eps 1e-8, no weight decay, no amsgrad)
+// on the flat fp32 parameter buffer of both nets: one pass, 28 B per parameter.  step = 1-based step count.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                            float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;            // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;       // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;           // (exp_avg_sq.sqrt() / sqrt(bias_correction2)).add_(eps)
+    p[i] = p[i] - (lr / bc1) * (mi / denom);                  // param.addcdiv_(exp_avg, denom, value=-lr / bias_correction1)
+  }
+}
+
 // g = scale * (rgb - gt); block-summed squared error atomically added to *sq_sum (the loss value, for logging only)
 __global__ void mse_grad_kernel(const float* __restrict__ rgb, const float* __restrict__ gt, int64_t n3, float scale,
                                 float* __restrict__ g, float* __restrict__ sq_sum) {
@@ -817,6 +833,15 @@ int launch_mlp_wgrad(tgtc_ctx* ctx, const TcStash& stash, const TcDz& dz, const 
   mlp_wgrad_kernel<<<grid, kWThreads, kWSmemBytes, st>>>(P);
   TGTC_LAUNCH_CHECK(ctx);
   grad_reduce_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(partial, grid, grads, accumulate);
+  TGTC_LAUNCH_CHECK(ctx);
+  return TGTC_OK;
+}
+
+int launch_adam(tgtc_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n, double lr, double b1, double b2, double eps,
+                int64_t step, cudaStream_t st) {
+  if (n == 0) return TGTC_OK;
+  const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
+  adam_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(p, g, m, v, n, (float)lr, (float)b1, (float)b2, (float)eps, (float)bc1, (float)sqrt(bc2));
   TGTC_LAUNCH_CHECK(ctx);
   return TGTC_OK;
 }

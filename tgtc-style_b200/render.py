@@ -430,6 +430,12 @@ class NerfRenderer:
                                             ctypes.c_void_p(ws.data_ptr() + off), wsb, self._stream))
         return {"loss": sums.sum() / (3.0 * n_total), "grads": grads, "rgb_coarse": rgb_c, "rgb_fine": rgb_f}
 
+    def adam_step(self, params, grads, exp_avg, exp_avg_sq, step, lr=5e-4, betas=(0.9, 0.999), eps=1e-8):
+        """torch.optim.Adam's update (train_tgtcs.py:39) on flat fp32 device buffers, one kernel (tgtc_adam_step)."""
+        n = params.numel()
+        _lib.check(self.lib.tgtc_adam_step(self._h, _ptr(params), _ptr(grads), _ptr(exp_avg), _ptr(exp_avg_sq), n, float(lr),
+                                           float(betas[0]), float(betas[1]), float(eps), int(step), self._stream))
+
     def grad_views(self, flat):
         """Per-parameter views into a flat gradient buffer: (coarse dict, fine dict) keyed like the state_dict."""
         P = int(self.lib.tgtc_num_params())

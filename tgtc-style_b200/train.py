@@ -4,7 +4,7 @@ Replaces the body of Origin_train's loop (train_tgtcs.py:222-276) for perturb=0 
     forward coarse+fine -> loss = mse(coarse)+mse(fine) -> backward -> Adam step -> lr decay
 The forward/backward arithmetic is one C-ABI call (tgtc_train_step); this module owns only the plumbing the
 reference leaves to torch: the fp32 master parameters (nn.Linear layout, the reference's own state_dict names), the
-optimizer (torch.optim.Adam, as train_tgtcs.py:39) and -- with more than one rank -- the single gradient
+optimizer (Adam as train_tgtcs.py:39 -- one fused kernel over the flat buffers, tgtc_adam_step) and -- with more than one rank -- the single gradient
 all-reduce (NCCL sum over the flat 2 x 595 844-float buffer; the 1/N of the mean is already folded into the loss
 through n_total).  Rays shard across ranks with dist.shard_range; nothing else is exchanged.
 """
@@ -23,22 +23,33 @@ class NerfTrainer:
         self.group = group
         self.max_rays = int(max_rays_per_pass)
         dev = renderer.device
+        # fp32 masters of both nets live in ONE flat buffer laid out like the gradient buffer; the per-parameter tensors are
+        # views into it (state_dict export, re-packing) and the optimizer is one fused kernel over the flat buffers
+        self.flat = torch.zeros(2 * 595844, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        pviews = renderer.grad_views(self.flat)
         self.params = []
-        for src in (coarse, fine):
+        for src, views in zip((coarse, fine), pviews):
             sd = src.state_dict() if hasattr(src, "state_dict") else src
-            d = {}
-            for name, (o, i) in zip(LAYER_NAMES, LAYER_SHAPES):
-                d[name + ".weight"] = torch.nn.Parameter(sd[name + ".weight"].detach().to(dev, torch.float32).clone().contiguous())
-                d[name + ".bias"] = torch.nn.Parameter(sd[name + ".bias"].detach().to(dev, torch.float32).clone().contiguous())
-            self.params.append(d)
-        self.opt = torch.optim.Adam([p for d in self.params for p in d.values()], lr=lr, betas=(0.9, 0.999))
+            for name in LAYER_NAMES:
+                for suffix in (".weight", ".bias"):
+                    views[name + suffix].copy_(sd[name + suffix].detach().to(dev, torch.float32))
+            self.params.append(views)
+        self.fused = hasattr(renderer, "adam_step")
+        if not self.fused:                      # host-logic tests with a stand-in renderer: torch's own Adam on the same views
+            gviews = renderer.grad_views(self.grads)
+            plist = []
+            for d, gv in zip(self.params, gviews):
+                for k in d:
+                    d[k] = torch.nn.Parameter(d[k])
+                    d[k].grad = gv[k]
+                    plist.append(d[k])
+            self.opt = torch.optim.Adam(plist, lr=lr, betas=(0.9, 0.999))
         self.lr0, self.decay_steps, self.decay_rate = lr, lr_decay_steps, lr_decay_rate
+        self.lr = lr
         self.step_count = 0
-        self.grads = torch.zeros(2 * 595844, dtype=torch.float32, device=dev)
-        views = renderer.grad_views(self.grads)
-        for d, v in zip(self.params, views):
-            for k, p in d.items():
-                p.grad = v[k]                      # zero-copy: the optimizer reads the flat buffer
         self.r.set_weights(self.params[0], self.params[1])
 
     def world(self):
@@ -81,11 +92,15 @@ class NerfTrainer:
         loss = self.forward_backward(ro, rd, gt, n_total, perturb=perturb, sigma_noise_std=sigma_noise_std)
         if world > 1:
             dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.group)   # the path's only collective
-        self.opt.step()
         self.step_count += 1
-        lr = self.lr0 * (self.decay_rate ** (self.step_count / self.decay_steps))  # train_tgtcs.py:272-276
-        for g in self.opt.param_groups:
-            g["lr"] = lr
+        if self.fused:
+            self.r.adam_step(self.flat, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count, lr=self.lr)
+        else:
+            self.opt.step()
+        self.lr = self.lr0 * (self.decay_rate ** (self.step_count / self.decay_steps))  # train_tgtcs.py:272-276
+        if not self.fused:
+            for g in self.opt.param_groups:
+                g["lr"] = self.lr
         self.r.set_weights(self.params[0], self.params[1])    # re-pack the bf16 / transposed images from the fp32 masters
         return loss
 
