@@ -67,7 +67,20 @@ def test_style_requires_weights_and_single_latent(renderer_bf16):
     r2.set_weights(w0c, w0f)
     with pytest.raises(T.TgtcError):
         r2.render_style(ro[:64], rd[:64], torch.zeros(32))
-    g, _, _, _ = _setup(renderer_bf16)
-    with pytest.raises(ValueError):
-        renderer_bf16.render_style(ro[:4], rd[:4], torch.randn(4, 32))
     r2.close()
+
+
+def test_style_per_ray_latents_run_segmentation(renderer_bf16):
+    """[N,32] latents that change along the batch (two frames in one loader batch) == the two runs rendered separately."""
+    r = renderer_bf16
+    g, ro, rd, _ = _setup(r)
+    sel = np.linspace(0, ro.shape[0] - 1, 96).astype(np.int64)
+    gen = torch.Generator().manual_seed(2)
+    la, lb = torch.randn(32, generator=gen), torch.randn(32, generator=gen)
+    lat = torch.cat([la.expand(40, 32), lb.expand(56, 32)], 0)
+    both = r.render_style(ro[sel], rd[sel], lat)
+    a = r.render_style(ro[sel[:40]], rd[sel[:40]], la)
+    b = r.render_style(ro[sel[40:]], rd[sel[40:]], lb)
+    torch.cuda.synchronize()
+    for k in ("rgb", "depth", "acc"):
+        assert torch.equal(both[k][:40], a[k]) and torch.equal(both[k][40:], b[k]), k

@@ -186,13 +186,10 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(uint32_t lo, uint32_t hi) {
   return r;
 }
 
-// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): K-major, swizzled.
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): K-major, swizzled; built as (lo, hi) words by the kernels:
+//   lo = (addr & 0x3FFFF) >> 4 | LBO field, hi = kDescHiSW128
 //   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major; 1 as CUTLASS) | [32,46) SBO>>4 |
 //   [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t hi) {
-  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
-  return ((uint64_t)hi << 32) | lo;
-}
 constexpr uint32_t kDescHiSW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major

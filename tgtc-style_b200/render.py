@@ -371,23 +371,32 @@ class NerfRenderer:
 
     def render_style(self, rays_o, rays_d, latents, near=0., far=1., chunk=None, n_samples=64, n_fine=64, extras=False,
                      want_weights=False, out=None):
-        """The loop body of render_style (rendering.py:118-178, perturb=False) for one batch of rays that share one (style,
-        frame): latents = the [32] (or [N,32] with identical rows) output of latents_model_1 (rendering.py:125).
+        """The loop body of render_style (rendering.py:118-178, perturb=False) for one batch of rays.
+        latents = the output of latents_model_1 (rendering.py:125): [32] for a batch that shares one (style, frame), or [N,32];
+        per-ray latents are handled as runs of consecutive rays with equal latents (the reference's loaders walk frames in
+        order, train_tgtcs.py:170), one library call per run.
         -> {rgb, depth, acc} (+ weights / coarse outputs / ts_fine like render())."""
         self.refresh_weights()
         ro, rd = self._dev(rays_o), self._dev(rays_d)
         n = ro.shape[0]
         lat = self._dev(latents)
-        if lat.dim() == 2:
-            if n > 1 and not bool((lat == lat[:1]).all()):
-                raise ValueError("render_style takes one (style, frame) per call: split the batch where the latents change")
-            lat = lat[0]
-        lat1 = lat.reshape(32).contiguous()
-        lat2 = lat1.mean().expand(32).contiguous()          # rendering.py:126: mean over the latent dim, broadcast (:139)
         if out is None:
             out = self._alloc_out(n, n_samples, n_fine, extras, self.device)
             if not want_weights:
                 out.pop("weights")
+        if lat.dim() == 2 and n > 1 and not bool((lat == lat[:1]).all()):
+            if lat.shape[0] != n:
+                raise ValueError("latents must be [32] or [N,32]")
+            change = (lat[1:] != lat[:-1]).any(dim=1).nonzero().flatten().add(1).tolist()
+            bounds = [0] + change + [n]
+            for b, e in zip(bounds[:-1], bounds[1:]):
+                self.render_style(ro[b:e], rd[b:e], lat[b], near, far, chunk, n_samples, n_fine, extras, want_weights,
+                                  out={k: v[b:e] for k, v in out.items()})
+            return out
+        if lat.dim() == 2:
+            lat = lat[0]
+        lat1 = lat.reshape(32).contiguous()
+        lat2 = lat1.mean().expand(32).contiguous()          # rendering.py:126: mean over the latent dim, broadcast (:139)
         ck = int(chunk) if chunk else 0
         wsb = self.lib.tgtc_render_style_workspace_bytes(n, n_samples, n_fine, ck)
         ws = self._workspace(wsb + 1024)

@@ -10,7 +10,7 @@ from quick_bench import timeit
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1008 * 128
-    flags = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 1, 2, 3, 4, 8, 6, 7, 15]
+    flags = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 2, 16, 18]
     lib = _lib.load()
     lib.tgtc_debug_tc_flags.argtypes = [ctypes.c_int]
     H, W, f = 756, 1008, 815.13
@@ -25,7 +25,7 @@ def main():
         ms = timeit(lambda: r.nerf_forward_rays(T.NET_COARSE, ro, rd, None, 64, 0., 1.), iters=5, warm=2)
         cyc = ms * 1e-3 * 1.9e9 / (tiles / 148)
         print("flags=%2d (%s): %.3f ms  %.1f TFLOP/s-equiv  ~%.0f cycles/tile @1.9GHz" % (
-            fl, "+".join(nm for b, nm in ((1, "noMMA"), (2, "noEPI"), (4, "noW"), (8, "noPE"), (16, "noRing")) if fl & b) or "full", ms,
+            fl, "+".join(nm for b, nm in ((2, "noEPI"), (16, "noRing")) if fl & b) or "full", ms,
             n * 64 * 1186816 / ms / 1e9, cyc))
     lib.tgtc_debug_tc_flags(0)
 
