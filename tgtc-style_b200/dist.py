@@ -60,21 +60,31 @@ def render_frame_sharded(render_fn, n_total, group=None, gather=True):
     return gather_tiles(local, n_total, group)
 
 
-def render_path_sharded(renderer, H, W, K, poses, group=None, split="rows", **render_kw):
+def render_path_sharded(renderer, H, W, K, poses, group=None, split="rows", latents=None, **render_kw):
     """The spiral / validation path of the reference (render_style's frame loop, rendering.py:109-217, over the
     load_llff.render_path_spiral poses) on one or more GPUs.  Rays are generated on the device per pose
     (NerfRenderer.render_frame), frames stay on the device.
       split="rows"   every frame is split into contiguous ray ranges, one per rank, and all-gathered (lowest latency per frame)
       split="frames" whole frames go round-robin to ranks; the tiles of `world` frames are exchanged with ONE all-gather
+    latents: None = plain NeRF frames (cal_geometry); a [32] tensor or a per-frame sequence of [32] tensors = stylised frames
+    (render_valid_style: NerfRenderer.render_style with the frame's latent, rendering.py:118-178).
     Yields (frame_index, {"rgb": [H*W,3], "depth": [H*W], "acc": [H*W]}) on every rank."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     n = H * W
     keys = ("rgb", "depth", "acc")
+
+    def frame(i, b, cnt):
+        if latents is None:
+            return renderer.render_frame(H, W, K, poses[i], pix_begin=b, n=cnt, **render_kw)
+        lat = latents if (torch.is_tensor(latents) and latents.dim() == 1) else latents[i]
+        ro, rd = renderer.raygen(H, W, K, poses[i], pix_begin=b, n=cnt)
+        return renderer.render_style(ro, rd, lat, **render_kw)
+
     if split == "rows" or world == 1:
         b, e = shard_range(n, rank, world)
-        for i, pose in enumerate(poses):
-            out = renderer.render_frame(H, W, K, pose, pix_begin=b, n=e - b, **render_kw)
+        for i in range(len(poses)):
+            out = frame(i, b, e - b)
             yield i, gather_tiles({k: out[k] for k in keys}, n, group)
         return
     if split != "frames":
@@ -82,7 +92,7 @@ def render_path_sharded(renderer, H, W, K, poses, group=None, split="rows", **re
     for base in range(0, len(poses), world):
         mine = base + rank
         idx = min(mine, len(poses) - 1)          # ranks past the end re-render the last frame (dropped below)
-        out = renderer.render_frame(H, W, K, poses[idx], **render_kw)
+        out = frame(idx, 0, n)
         full = gather_tiles({k: out[k] for k in keys}, n * world, group)   # equal shards: one all_gather_into_tensor per key
         for r in range(world):
             if base + r < len(poses):
