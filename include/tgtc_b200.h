@@ -204,7 +204,7 @@ int tgtc_adam_step(tgtc_ctx* ctx, float* params, const float* grads, float* exp_
  * models.StyleMLP_Wild_multilayers (models.py:149-180) as called by render_style / render_train_style
  * (rendering.py:118-178, :280-327).  params: 26 device pointers = module 1 layers.{0..4} (weight [out,in] row-major, bias),
  * then module 2 layers.{0..7}; shapes 256x95, 3x 256x288, 256x351 and 256x607, 3x 256x288, 256x351, 2x 256x288, 3x288
- * (style_D = 8, vae_latent = 32).  The caller keeps the tensors alive (latent columns are re-read per call). */
+ * (style_D = 8, vae_latent = 32).  Everything needed later is packed / copied here; the tensors may be freed afterwards. */
 int tgtc_set_style_weights(tgtc_ctx* ctx, const float* const* params, tgtc_stream stream);
 
 /* The loop body of render_style for one batch of rays with perturb=False: NeRF trunk (base_remap, sigma) -> style

@@ -76,7 +76,8 @@ struct StyleImage {
   float* head_b = nullptr;     // [3]
   float* latents = nullptr;    // [2][32]
   uint8_t* tables = nullptr;   // device scratch for the packing / bias tables
-  const float* params[26] = {};  // caller's fp32 tensors: module 1 (W,b) x 5, module 2 (W,b) x 8
+  float* wlat = nullptr;       // per layer: the 32 latent columns [256][32] and the bias [256] (owned copies)
+  const void* bias_table = nullptr;  // device table the per-call effective-bias kernel walks
   bool set = false;
 };
 

@@ -422,15 +422,22 @@ __global__ void pack_chunks_kernel(const ChunkSrc* __restrict__ table, int nchun
   }
 }
 
-// effective biases: out[j] = b[j] + sum_k W[j][lat0 + k] * latent[k]   (32 latent columns)
-struct BiasSrc { const float* W; const float* b; int ld; int lat0; int nout; const float* latent; float* out; };
+// effective biases: out[j] = b[j] + sum_k Wlat[j][k] * latent[k]   (the 32 latent columns of a layer, copied at set time)
+struct BiasSrc { const float* wlat; const float* b; int nout; const float* latent; float* out; };
 __global__ void style_bias_kernel(const BiasSrc* __restrict__ table, int n) {
   const BiasSrc s = table[blockIdx.x];
   for (int j = threadIdx.x; j < s.nout; j += blockDim.x) {
     float acc = s.b[j];
-    for (int k = 0; k < 32; ++k) acc = fmaf(s.W[(size_t)j * s.ld + s.lat0 + k], s.latent[k], acc);
+    for (int k = 0; k < 32; ++k) acc = fmaf(s.wlat[j * 32 + k], s.latent[k], acc);
     s.out[j] = acc;
   }
+}
+// own copies of what the per-call bias kernel needs, so nothing of the caller's tensors is referenced after set_weights
+struct LatSrc { const float* W; const float* b; int ld; int lat0; int nout; float* wlat; float* bout; };
+__global__ void style_latcopy_kernel(const LatSrc* __restrict__ table) {
+  const LatSrc s = table[blockIdx.x];
+  for (int i = threadIdx.x; i < s.nout * 32; i += blockDim.x) s.wlat[i] = s.W[(size_t)(i / 32) * s.ld + s.lat0 + (i % 32)];
+  for (int j = threadIdx.x; j < s.nout; j += blockDim.x) s.bout[j] = s.b[j];
 }
 
 __global__ void head_copy_kernel(const float* __restrict__ W, int ld, float* __restrict__ out) {   // [3][256] <- W[3][ld][:256]
@@ -457,9 +464,9 @@ int style_set_weights(tgtc_ctx* ctx, const float* const* params, cudaStream_t st
     TGTC_CUDA(cudaMalloc(&im.bias_w, 7 * 256 * sizeof(float)));
     TGTC_CUDA(cudaMalloc(&im.head_b, 4 * sizeof(float)));
     TGTC_CUDA(cudaMalloc(&im.latents, 64 * sizeof(float)));
-    TGTC_CUDA(cudaMalloc(&im.tables, 4096));
+    TGTC_CUDA(cudaMalloc(&im.tables, 8192));
+    TGTC_CUDA(cudaMalloc(&im.wlat, 13 * 256 * 33 * sizeof(float)));   // per layer: [256][32] latent columns, then [256] bias
   }
-  for (int i = 0; i < 26; ++i) im.params[i] = params[i];
   // chunk tables (consumption order, see the header comment)
   std::vector<ChunkSrc> tc, tw;
   auto act4 = [](std::vector<ChunkSrc>& v, const float* W, int ld, int col0) { for (int k = 0; k < 4; ++k) v.push_back({W, ld, col0 + 64 * k, 64}); };
@@ -488,28 +495,40 @@ int style_set_weights(tgtc_ctx* ctx, const float* const* params, cudaStream_t st
   TGTC_LAUNCH_CHECK(ctx);
   head_copy_kernel<<<1, 256, 0, st>>>(Wp[14], 288, im.head_w);
   TGTC_LAUNCH_CHECK(ctx);
+  // latent columns + biases -> owned buffers; the per-call bias table (device) is built once here
+  static const int clat[5] = {63, 256, 256, 256, 256};
+  static const int wlat0[8] = {575, 256, 256, 256, 256, 256, 256, 256};
+  std::vector<LatSrc> tl;
+  std::vector<BiasSrc> tb;
+  auto slot = [&](int i) { return im.wlat + (size_t)i * 256 * 33; };
+  for (int l = 0; l < 5; ++l) {
+    tl.push_back({C[2 * l], C[2 * l + 1], kCIn[l], clat[l], 256, slot(l), slot(l) + 256 * 32});
+    tb.push_back({slot(l), slot(l) + 256 * 32, 256, im.latents, im.bias_c + l * 256});
+  }
+  for (int l = 0; l < 8; ++l) {
+    const int nout = l < 7 ? 256 : 3;
+    tl.push_back({Wp[2 * l], Wp[2 * l + 1], kWIn[l], wlat0[l], nout, slot(5 + l), slot(5 + l) + 256 * 32});
+    tb.push_back({slot(5 + l), slot(5 + l) + 256 * 32, nout, im.latents + 32, l < 7 ? im.bias_w + l * 256 : im.head_b});
+  }
+  static_assert(sizeof(ChunkSrc) == 24 && 128 * sizeof(ChunkSrc) + 13 * (sizeof(BiasSrc) + sizeof(LatSrc)) <= 8192, "style tables do not fit");
+  LatSrc* dlat = reinterpret_cast<LatSrc*>(im.tables + 128 * sizeof(ChunkSrc));
+  BiasSrc* dbias = reinterpret_cast<BiasSrc*>(im.tables + 128 * sizeof(ChunkSrc) + 13 * sizeof(LatSrc));
+  TGTC_CUDA(cudaMemcpyAsync(dlat, tl.data(), tl.size() * sizeof(LatSrc), cudaMemcpyHostToDevice, st));
+  TGTC_CUDA(cudaMemcpyAsync(dbias, tb.data(), tb.size() * sizeof(BiasSrc), cudaMemcpyHostToDevice, st));
+  style_latcopy_kernel<<<13, 256, 0, st>>>(dlat);
+  TGTC_LAUNCH_CHECK(ctx);
+  TGTC_CUDA(cudaStreamSynchronize(st));   // the host tables go out of scope; the caller's tensors are no longer referenced
+  im.bias_table = dbias;
   im.set = true;
   return TGTC_OK;
 }
 
-// latent1 / latent2: device pointers to 32 floats (module 1 / module 2 latents of this call)
+// latent1 / latent2: device pointers to 32 floats (module 1 / module 2 latents of this call).  Fully stream-ordered.
 int style_set_latents(tgtc_ctx* ctx, const float* latent1, const float* latent2, cudaStream_t st) {
   StyleImage& im = ctx->style;
   TGTC_CUDA(cudaMemcpyAsync(im.latents, latent1, 32 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   TGTC_CUDA(cudaMemcpyAsync(im.latents + 32, latent2, 32 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  const float* const* C = im.params;
-  const float* const* Wp = im.params + 10;
-  std::vector<BiasSrc> tb;
-  static const int clat[5] = {63, 256, 256, 256, 256};
-  for (int l = 0; l < 5; ++l) tb.push_back({C[2 * l], C[2 * l + 1], kCIn[l], clat[l], 256, im.latents, im.bias_c + l * 256});
-  static const int wlat[8] = {575, 256, 256, 256, 256, 256, 256, 256};
-  for (int l = 0; l < 7; ++l) tb.push_back({Wp[2 * l], Wp[2 * l + 1], kWIn[l], wlat[l], 256, im.latents + 32, im.bias_w + l * 256});
-  tb.push_back({Wp[14], Wp[15], 288, 256, 3, im.latents + 32, im.head_b});
-  static_assert(sizeof(ChunkSrc) == 24 && 128 * sizeof(ChunkSrc) + 13 * sizeof(BiasSrc) <= 4096, "style tables do not fit");
-  BiasSrc* dtab = reinterpret_cast<BiasSrc*>(im.tables + 128 * sizeof(ChunkSrc));
-  TGTC_CUDA(cudaMemcpyAsync(dtab, tb.data(), tb.size() * sizeof(BiasSrc), cudaMemcpyHostToDevice, st));
-  TGTC_CUDA(cudaStreamSynchronize(st));
-  style_bias_kernel<<<(unsigned)tb.size(), 256, 0, st>>>(dtab, (int)tb.size());
+  style_bias_kernel<<<13, 256, 0, st>>>(reinterpret_cast<const BiasSrc*>(im.bias_table), 13);
   TGTC_LAUNCH_CHECK(ctx);
   return TGTC_OK;
 }
