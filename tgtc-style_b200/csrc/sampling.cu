@@ -99,15 +99,15 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_fine_kernel(
     // Every partial sum of these <=126 non-negative fp32 values in [~1e-7, 1] is exactly
     // representable in fp64 (span < 53 bits), so the warp-parallel scan is bit-identical to
     // torch's sequential fp64 accumulation.
-    const int per = (nw + 31) >> 5;            // contiguous elements per lane
+    const int per = (nw + 31) >> 5;            // contiguous elements per lane (<= 4: S <= 128)
     const int j0 = lane * per;
+    float pdfv[4];
     double run = 0.0;
-    for (int q = 0; q < per; ++q) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
       const int j = j0 + q;
-      if (j < nw) {
-        const float pdf = __fdiv_rn(sm.w[j], fin);
-        run += (double)pdf;
-      }
+      pdfv[q] = (q < per && j < nw) ? __fdiv_rn(sm.w[j], fin) : 0.f;
+      run += (double)pdfv[q];
     }
     double incl = run;
 #pragma unroll
@@ -117,10 +117,11 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_fine_kernel(
     }
     double pre = incl - run;                   // exclusive prefix of this lane (exact)
     if (lane == 0) sm.cdf[0] = 0.f;
-    for (int q = 0; q < per; ++q) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
       const int j = j0 + q;
-      if (j < nw) {
-        pre += (double)__fdiv_rn(sm.w[j], fin);
+      if (q < per && j < nw) {
+        pre += (double)pdfv[q];
         sm.cdf[j + 1] = (float)pre;
       }
     }
@@ -151,32 +152,45 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_fine_kernel(
     }
     __syncwarp();
     // ---- torch.sort(cat(ts, t_samples)) (utils.py:577), values only.  ts is ascending by construction; the new
-    // samples are non-decreasing except in rare fp32 corner cases.  When they are (warp vote) and S+F is a power of
-    // two, asc(ts) ++ reversed(samples) is a bitonic sequence and ONE bitonic merge (log2 n steps) sorts it;
+    // samples are non-decreasing except in rare fp32 corner cases.  When they are (warp vote) the union is a rank merge;
     // otherwise fall back to the full bitonic network (log2^2 n steps).
     bool mono = true;
     for (int k = lane; k + 1 < F; k += 32) mono = mono && (sm.smp[k] <= sm.smp[k + 1]);
     for (int i = lane; i + 1 < S; i += 32) mono = mono && (sm.ts[i] <= sm.ts[i + 1]);
-    const bool merge_only = __all_sync(0xffffffffu, mono) && (total == sort_n);
-    for (int i = lane; i < S; i += 32) sm.out[i] = sm.ts[i];
-    if (merge_only) {
-      for (int k = lane; k < F; k += 32) sm.out[S + (F - 1 - k)] = sm.smp[k];
+    const bool sorted_inputs = __all_sync(0xffffffffu, mono);
+    if (sorted_inputs) {
+      // both lists ascending: every element's place in the union is its own index plus the number of elements of the OTHER
+      // list that precede it (ties: ts first) -- two binary searches per element instead of a sorting network
+      for (int i = lane; i < S; i += 32) {
+        const float v = sm.ts[i];
+        int lo = 0, hi = F;                      // #{samples < v}
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.smp[mid] < v) lo = mid + 1; else hi = mid; }
+        sm.out[i + lo] = v;
+      }
+      for (int k = lane; k < F; k += 32) {
+        const float v = sm.smp[k];
+        int lo = 0, hi = S;                      // #{ts <= v}
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (sm.ts[mid] <= v) lo = mid + 1; else hi = mid; }
+        sm.out[k + lo] = v;
+      }
+      __syncwarp();
     } else {
+      for (int i = lane; i < S; i += 32) sm.out[i] = sm.ts[i];
       for (int k = lane; k < F; k += 32) sm.out[S + k] = sm.smp[k];
       for (int i = total + lane; i < sort_n; i += 32) sm.out[i] = __int_as_float(0x7f800000);  // +inf padding
-    }
-    __syncwarp();
-    for (int k = merge_only ? sort_n : 2; k <= sort_n; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = lane; i < sort_n; i += 32) {
-          const int ixj = i ^ j;
-          if (ixj > i) {
-            const float a = sm.out[i], b = sm.out[ixj];
-            const bool up = ((i & k) == 0);
-            if ((a > b) == up) { sm.out[i] = b; sm.out[ixj] = a; }
+      __syncwarp();
+      for (int k = 2; k <= sort_n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = lane; i < sort_n; i += 32) {
+            const int ixj = i ^ j;
+            if (ixj > i) {
+              const float a = sm.out[i], b = sm.out[ixj];
+              const bool up = ((i & k) == 0);
+              if ((a > b) == up) { sm.out[i] = b; sm.out[ixj] = a; }
+            }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
 
