@@ -10,8 +10,8 @@ meaning and return structure; `patch(renderer, modules)` rebinds them in the
 reference's module globals (star-imports copy names, so each module's copy is
 patched) so train_tgtcs.py / rendering.py run unchanged.
 
-Forward only: the autograd path of Origin_train (train_tgtcs.py:236-255) is not
-provided in this round; tensors returned here do not carry grad.
+These stage shims are forward-only (their tensors carry no grad): training goes through the fused step
+(NerfTrainer / tgtc_train_step, train.py), stylised rendering through NerfRenderer.render_style.
 """
 import torch
 
