@@ -33,6 +33,27 @@ SAMPLES_PER_RAY = N_SAMPLES + (N_SAMPLES + N_FINE)
 WORKLOAD = "fern-shaped 1008x756 single-view render, 64 coarse + 128 fine samples/ray, NDC rays, perturb=0, random-init (seed 0) NeRF MLPs"
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line (the contract): library chatter on fd 1 (NCCL prints its version banner there)
+    is sent to stderr for the whole run and the result line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    if _REAL_STDOUT is None:
+        print(line, flush=True)
+    else:
+        _REAL_STDOUT.write(line + "\n")
+        _REAL_STDOUT.flush()
+
+
 def spiral_poses(n=120):
     """load_llff.render_path_spiral (load_llff.py:145-154) for the synthetic camera of SURVEY 8d: c2w = I,
     up=[0,1,0], rads=[0.3,0.3,0.05], focal=3.9, zrate=.5, rots=2 (restated: viewmatrix/normalize are 10 lines)."""
@@ -191,7 +212,7 @@ def run_eager_gpu_arm(args):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     value = per_step * args.steps / (ms * 1e-3)
-    print(json.dumps({"impl": "eager-gpu", "metric": "rays/s", "value": value, "unit": "rays/s", "n_gpus": 1, "steps": args.steps,
+    emit(json.dumps({"impl": "eager-gpu", "metric": "rays/s", "value": value, "unit": "rays/s", "n_gpus": 1, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
                       "config": {"workload": WORKLOAD, "sample": "%d rays per step in batches of %d, eager torch fp32 (TF32 off) on one B200" % (per_step, chunk)},
                       "mlp_samples_per_s": value * SAMPLES_PER_RAY}))
@@ -224,7 +245,7 @@ def run_reference_arm(args):
     total = sum(t_steps)
     value = per_step * args.steps / total
     sample = "%d rays per step spread over the 1008x756 frame, chunk 1024, torch CPU fp32, %d threads" % (per_step, cores)
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "rays/s", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -276,7 +297,7 @@ def run_style_reference_arm(args):
     total = sum(t_steps)
     value = per_step * args.steps / total
     sample = "%d rays per step spread over the 1008x756 frame, torch CPU fp32, %d threads" % (per_step, cores)
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "rays/s", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": STYLE_WORKLOAD, "sample": sample},
@@ -413,7 +434,7 @@ def run_style(args):
                             "tflops": (v[2] / (v[1] * 1e-3) / 1e12) if v[1] > 0 else None} for k, v in kinds.items()},
             "clocks": clocks.window(t_wall0, t_wall1),
         }
-        print(json.dumps(res))
+        emit(json.dumps(res))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -445,7 +466,7 @@ def run_train_reference_arm(args):
     total = sum(t_steps)
     value = per_step * args.steps / total
     sample = "%d rays per step (forward + autograd backward, no optimizer), torch CPU fp32, %d threads" % (per_step, cores)
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "rays/s", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": TRAIN_WORKLOAD, "sample": sample},
@@ -574,7 +595,7 @@ def run_train(args):
                             "tflops": (v[2] / (v[1] * 1e-3) / 1e12) if v[1] > 0 else None} for k, v in kinds.items()},
             "clocks": clocks.window(t_wall0, t_wall1),
         }
-        print(json.dumps(res))
+        emit(json.dumps(res))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -592,6 +613,7 @@ def main():
                     help="render = BASELINE config 2 (the headline; default); train = config 5 (training step); "
                          "style = config 4 (stylised render, 4096-ray batches)")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "eager-gpu":
         run_eager_gpu_arm(args)
@@ -753,7 +775,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample = cpu_chain_rays_per_s(16 * 1024)
             res["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(res))
+        emit(json.dumps(res))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
