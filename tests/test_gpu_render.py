@@ -190,3 +190,18 @@ def test_cal_geometry_outputs(renderer_fp32, tmp_path):
     np.testing.assert_allclose(g["coor_map"].reshape(-1, 3), coor_ref, atol=2e-3)
     full = np.load(str(tmp_path / "geometry.npz"))
     assert full["coor_map"].shape == (2, H, W, 3) and (tmp_path / "rgb_00000.png").exists() and (tmp_path / "depth_00001.png").exists()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 127, 129, 1000, 4097])
+def test_render_bf16_ragged_sizes_match_prefix_of_larger_batch(renderer_bf16, n):
+    """tile quads with padding tiles / half-filled last tiles (CTA pairs work on 4 tiles at a time): rendering the first n
+    rays alone gives bit-identical results to rendering them inside a larger batch."""
+    wc, wf = weights("w1")
+    renderer_bf16.set_weights(wc, wf)
+    ro, rd = small_rays()
+    sel = np.linspace(0, ro.shape[0] - 1, 5000).astype(np.int64)
+    big = renderer_bf16.render(ro[sel], rd[sel], 0., 1., extras=True)
+    small = renderer_bf16.render(ro[sel[:n]], rd[sel[:n]], 0., 1., extras=True)
+    for k in ("rgb", "depth", "acc", "weights", "rgb_coarse", "ts_fine"):
+        assert torch.equal(small[k], big[k][:n]), k
+    assert torch.isfinite(small["rgb"]).all()
