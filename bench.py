@@ -33,6 +33,42 @@ SAMPLES_PER_RAY = N_SAMPLES + (N_SAMPLES + N_FINE)
 WORKLOAD = "fern-shaped 1008x756 single-view render, 64 coarse + 128 fine samples/ray, NDC rays, perturb=0, random-init (seed 0) NeRF MLPs"
 
 
+NERF_LAYERS = (["net.base_layers.%d" % i for i in range(8)] + ["net.sigma_layer", "net.base_remap_layer", "net.rgb_layers.0", "net.rgb_layers.1"],
+               [(256, 63)] + [(256, 256)] * 4 + [(256, 319)] + [(256, 256)] * 2 + [(1, 256), (256, 256), (128, 283), (3, 128)])
+STYLE_C_SHAPES = [(256, 95), (256, 288), (256, 288), (256, 288), (256, 351)]
+STYLE_W_SHAPES = [(256, 607), (256, 288), (256, 288), (256, 288), (256, 351), (256, 288), (256, 288), (3, 288)]
+
+
+def synth_nerf_weights(seed=0):
+    """Random-init weights of the reference architecture for the measured arms (input synthesis only; the product arms do not
+    import oracle/): torch.manual_seed(seed), then nn.Linear default init in the constructor order of models.StyleNerf
+    (coarse, then fine) -- the same tensors as the reference's own random init."""
+    import torch
+    torch.manual_seed(seed)
+    nets = []
+    for _ in range(2):
+        sd = {}
+        for name, (o, i) in zip(*NERF_LAYERS):
+            lin = torch.nn.Linear(i, o)
+            sd[name + ".weight"], sd[name + ".bias"] = lin.weight.detach().clone(), lin.bias.detach().clone()
+        nets.append(sd)
+    return nets[0], nets[1]
+
+
+def synth_style_weights(seed=1):
+    """StyleMLP_before_concat / StyleMLP_Wild_multilayers random init (models.py:120-180), same scheme."""
+    import torch
+    torch.manual_seed(seed)
+    nets = []
+    for shapes in (STYLE_C_SHAPES, STYLE_W_SHAPES):
+        sd = {}
+        for i, (o, k) in enumerate(shapes):
+            lin = torch.nn.Linear(k, o)
+            sd["layers.%d.weight" % i], sd["layers.%d.bias" % i] = lin.weight.detach().clone(), lin.bias.detach().clone()
+        nets.append(sd)
+    return nets[0], nets[1]
+
+
 _REAL_STDOUT = None
 
 
@@ -327,10 +363,8 @@ def run_style(args):
         entry.build()
     if world > 1:
         dist.barrier()
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import render_oracle as O   # synthetic weight sets only
-    wc, wf = O.init_linear_like_reference(0)
-    cs, ws = O.init_style_like_reference(1)
+    wc, wf = synth_nerf_weights(0)
+    cs, ws = synth_style_weights(1)
     r = T.NerfRenderer(device=dev, mode="bf16")
     r.set_weights(wc, wf)
     r.set_style_weights(cs, ws)
@@ -496,9 +530,7 @@ def run_train(args):
         entry.build()
     if world > 1:
         dist.barrier()
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import render_oracle as O   # synthetic weight set W0 only
-    wc, wf = O.init_linear_like_reference(0)
+    wc, wf = synth_nerf_weights(0)
     r = T.NerfRenderer(device=dev, mode="bf16")
     tr = T.NerfTrainer(r, wc, wf, max_rays_per_pass=32768)
     K = np.array([[FOCAL, 0, 0.5 * W], [0, FOCAL, 0.5 * H], [0, 0, 1]])
@@ -653,9 +685,7 @@ def main():
     if world > 1:
         dist.barrier()
 
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import render_oracle as O   # only for the synthetic weight set W0 (input synthesis) and the cpu_baseline leg
-    wc, wf = O.init_linear_like_reference(0)
+    wc, wf = synth_nerf_weights(0)    # the oracle is imported only by the cpu_baseline leg (cpu_chain_rays_per_s) below
     r = T.NerfRenderer(device=dev, mode=args.mode)
     r.set_weights(wc, wf)
     K = np.array([[FOCAL, 0, 0.5 * W], [0, FOCAL, 0.5 * H], [0, 0, 1]])
