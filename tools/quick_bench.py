@@ -1,9 +1,9 @@
 """Quick device timing of the individual kernels (development aid; bench.py is the contract)."""
 import sys, os, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
 import numpy as np, torch
-import render_oracle as O
+import bench as B
 import tgtc_style_b200 as T
 
 def timeit(fn, iters=5, warm=2):
@@ -19,7 +19,7 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1008 * 64
     modes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["bf16", "fp32"]
     H, W, f = 756, 1008, 815.13
-    w0c, w0f = O.init_linear_like_reference(0)
+    w0c, w0f = B.synth_nerf_weights(0)
     K = np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]])
     for mode in modes:
         r = T.NerfRenderer("cuda:0", mode=mode)

@@ -5,9 +5,9 @@ round-robin over ranks, one NCCL tile all-gather per group of `world` frames.  P
 """
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
 import numpy as np, torch, torch.distributed as dist
-import render_oracle as O
+import bench as B
 import tgtc_style_b200 as T
 from bench import spiral_poses, H, W, FOCAL
 
@@ -19,8 +19,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    wc, wf = O.init_linear_like_reference(0)
-    cs, ws = O.init_style_like_reference(1)
+    wc, wf = B.synth_nerf_weights(0)
+    cs, ws = B.synth_style_weights(1)
     r = T.NerfRenderer(device=dev, mode="bf16")
     r.set_weights(wc, wf)
     r.set_style_weights(cs, ws)

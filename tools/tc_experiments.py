@@ -1,9 +1,9 @@
 """Timing experiments on the tcgen05 MLP kernel with parts of it switched off (results are garbage; timing only)."""
 import sys, os, ctypes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
 import numpy as np, torch
-import render_oracle as O
+import bench as B
 import tgtc_style_b200 as T
 from tgtc_style_b200 import _lib
 from quick_bench import timeit
@@ -14,7 +14,7 @@ def main():
     lib = _lib.load()
     lib.tgtc_debug_tc_flags.argtypes = [ctypes.c_int]
     H, W, f = 756, 1008, 815.13
-    w0c, w0f = O.init_linear_like_reference(0)
+    w0c, w0f = B.synth_nerf_weights(0)
     K = np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]])
     r = T.NerfRenderer("cuda:0", mode="bf16")
     r.set_weights(w0c, w0f)

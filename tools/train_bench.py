@@ -1,16 +1,16 @@
 """Device timing of the training step (forward with stash + backward, both nets).  Development aid."""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
 import numpy as np, torch
-import render_oracle as O
+import bench as B
 import tgtc_style_b200 as T
 from quick_bench import timeit
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
     H, W, f = 756, 1008, 815.13
-    w0c, w0f = O.init_linear_like_reference(0)
+    w0c, w0f = B.synth_nerf_weights(0)
     K = np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]])
     r = T.NerfRenderer("cuda:0", mode="bf16")
     r.set_weights(w0c, w0f)
