@@ -570,7 +570,7 @@ static int train_pass(tgtc_ctx* ctx, int net, const float* rays_o, const float* 
   if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
   rc = prof_begin(ctx, 3, samples * 1186816.0, st, &e1);
   if (rc) return rc;
-  rc = launch_mlp_wgrad(ctx, stash, dz, rays_d, n * S, S, partial, grads, accumulate, st);
+  rc = launch_mlp_wgrad(ctx, stash, dz, rays_d, drs, n * S, S, partial, grads, accumulate, st);
   if (rc) return rc;
   if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
   return TGTC_OK;

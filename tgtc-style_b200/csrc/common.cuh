@@ -217,8 +217,8 @@ size_t bwd_blobT_bytes();
 size_t bwd_flat_floats();
 int launch_mlp_dgrad(tgtc_ctx* ctx, int net, const float* rgbsigma, const float* d_rgbsigma, const TcStash& stash, const TcDz& dz,
                      int64_t M, cudaStream_t st);
-int launch_mlp_wgrad(tgtc_ctx* ctx, const TcStash& stash, const TcDz& dz, const float* rays_d, int64_t M, int S, float* partial,
-                     float* grads, int accumulate, cudaStream_t st);
+int launch_mlp_wgrad(tgtc_ctx* ctx, const TcStash& stash, const TcDz& dz, const float* rays_d, const float* d_rgbsigma, int64_t M, int S,
+                     float* partial, float* grads, int accumulate, cudaStream_t st);
 int launch_adam(tgtc_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t n, double lr, double b1, double b2, double eps,
                 int64_t step, cudaStream_t st);
 int launch_mse_grad(tgtc_ctx* ctx, const float* rgb, const float* gt, int64_t n, float scale, float* g, float* sq_sum, cudaStream_t st);

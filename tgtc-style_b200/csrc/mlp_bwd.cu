@@ -13,7 +13,7 @@
 //                      (layer 5 uses only the hidden columns of W_5; the positional encoding and the view
 //                      directions are not differentiable inputs).  Every dz tile is written to HBM as a tile image.
 //   mlp_wgrad_kernel   dW_l = dz_l^T . x_l summed over all samples: per CTA a 256x256 fp32 accumulator in TMEM, the
-//                      tile images of dz_l and x_l used directly as MN-major operands (K = samples), 13 jobs;
+//                      tile images of dz_l and x_l used directly as MN-major operands (K = samples), 12 jobs;
 //                      bias gradients and the view-direction columns of rgb0 as column sums on CUDA cores.
 //   grad_reduce_kernel sums the per-CTA partials into the flat fp32 gradient buffer in nn.Linear layout
 //                      (deterministic: no atomics anywhere).
@@ -414,12 +414,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
 // ===========================================================================================================
 // wgrad
 // ===========================================================================================================
-// One CTA per SM, cta_group::1.  13 jobs; per job the CTA walks its tiles in 64-sample stages:
+// One CTA per SM, cta_group::1.  12 jobs; per job the CTA walks its tiles in 64-sample stages:
 //   A = image blocks of dz (out features, MN-major, K = samples), B = image blocks of the layer input.
 constexpr int kWStages = 3;
 constexpr int kWStageBytes = 65536;      // A: up to 4 blocks x 8 KB, then B: up to 4 blocks x 8 KB
 constexpr int kWThreads = 448;           // w0 producer, w1 MMA, w2-5 drain, w6-13 column sums
-constexpr int kNumJobs = 13;
+constexpr int kNumJobs = 12;
 constexpr int kWOffBars = kWStages * kWStageBytes;
 constexpr int kWBarFull = 0, kWBarEmpty = kWStages, kWBarAccDone = 2 * kWStages, kWBarAccFree = kWBarAccDone + 1,
               kWNumBars = kWBarAccFree + 1;
@@ -440,9 +440,10 @@ __constant__ WJob c_jobs[kNumJobs] = {
     {SRC_DZ, 7, 4, SRC_H, 6, 4, 1},      // 8  L7
     {SRC_DZ, 8, 4, SRC_H, 7, 4, 1},      // 9  remap
     {SRC_DZF, 0, 2, SRC_H, 8, 4, 1},     // 10 rgb0 (remap columns) + view-direction columns from the column sums
-    {SRC_DHEAD, 0, 1, SRC_F, 0, 2, 1},   // 11 rgb1 (rows 0..2)
-    {SRC_DHEAD, 0, 1, SRC_H, 7, 4, 0},   // 12 sigma head (row 3)
+    {SRC_DHEAD, 0, 1, SRC_F, 0, 2, 1},   // 11 rgb1 (rows 0..2); column sums: rgb1 bias (0..2), sigma bias (3)
 };
+// The sigma head's weight gradient  dw_sigma[i] = sum_s d_sigma[s] * h7[s,i]  needs no job of its own: h7 is the B operand of
+// job 9, so the column-sum warps take it as a d_sigma-weighted column sum of the staged tile (fp32 d_sigma, no extra HBM read).
 // offsets (floats) of each job's [Mo x Ni] partial inside a CTA's partial block; Mo = 256 (4 A blocks) else 128
 __host__ __device__ constexpr int job_mo(int j) { return (j <= 9) ? 256 : 128; }
 __host__ __device__ constexpr int job_ni(int j) { return (j == 0 || j == 5) ? 64 : (j == 11 ? 128 : 256); }
@@ -452,9 +453,10 @@ __host__ __device__ constexpr size_t job_off(int j) {
   return o;
 }
 constexpr size_t kPartMat = job_off(kNumJobs);            // 638 976 floats
-constexpr size_t kPartColsum = kPartMat;                  // [13][256]
+constexpr size_t kPartColsum = kPartMat;                  // [12][256]
 constexpr size_t kPartDir = kPartColsum + kNumJobs * 256; // [128][32]
-constexpr size_t kPartFloats = kPartDir + 128 * 32;
+constexpr size_t kPartSig = kPartDir + 128 * 32;          // [256] sigma-head weight gradient
+constexpr size_t kPartFloats = kPartSig + 256;
 
 struct WgradParams {
   const uint8_t* stash_h;
@@ -464,6 +466,8 @@ struct WgradParams {
   const uint8_t* dzf;
   const uint8_t* dhead;
   const float* rays_d;     // [n_rays,3]
+  const float4* d_rgbsigma; // [M] (d_sigma in .w)
+  int64_t M;
   float* partial;          // [gridDim.x][kPartFloats]
   int64_t ntiles;
   int64_t n_rays;
@@ -632,13 +636,20 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WgradPara
     for (int j = 0; j < kNumJobs; ++j) {
       const WJob jb = c_jobs[j];
       const bool mine = jb.colsum && cb < jb.a_blocks;
-      float total = 0.f;
+      float total = 0.f, sig_total = 0.f;
       float dir_acc[27];
       if (j == 10) {
 #pragma unroll
         for (int k = 0; k < 27; ++k) dir_acc[k] = 0.f;
       }
       for (int64_t s = 0; s < nst; ++s) {
+        float ds_lo = 0.f, ds_hi = 0.f;
+        if (j == 9) {
+          // each lane fetches two of the stage's 64 d_sigma values (before the wait, so the latency hides behind it)
+          const int64_t m0 = ((int64_t)blockIdx.x + (s >> 1) * gridDim.x) * kTileM + (s & 1) * 64;
+          if (m0 + lane < P.M) ds_lo = __ldg(&P.d_rgbsigma[m0 + lane].w);
+          if (m0 + 32 + lane < P.M) ds_hi = __ldg(&P.d_rgbsigma[m0 + 32 + lane].w);
+        }
         mbar_wait(bar(kWBarFull + stage), phase);
         if (mine) {
           const uint8_t* blk = smem + stage * kWStageBytes + cb * 8192;
@@ -649,6 +660,18 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WgradPara
             acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(blk + off));
           }
           total += acc;
+          if (j == 9) {
+            // B operand of this job = h7: d_sigma-weighted column sum = the sigma head's weight gradient (models.py:103)
+            const uint8_t* hb = smem + stage * kWStageBytes + 32768 + cb * 8192;
+            float sacc = 0.f;   // d_sigma broadcast lane -> warp by shuffle
+#pragma unroll
+            for (int r = 0; r < 64; ++r) {
+              const uint32_t off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((cc >> 3) ^ (r & 7))) << 4) + (cc & 7) * 2);
+              const float ds = __shfl_sync(0xffffffffu, r < 32 ? ds_lo : ds_hi, r & 31);
+              sacc = fmaf(ds, __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(hb + off)), sacc);
+            }
+            sig_total += sacc;
+          }
           if (j == 10 && c < 128) {
             // all 64 samples of a stage belong to one ray (S is a multiple of 64): view-direction columns of rgb0
             // (models.py:108) get  sum_s dz_f[s,o] * dirPE_k(ray)  =  colsum * dirPE_k
@@ -676,6 +699,7 @@ __global__ void __launch_bounds__(kWThreads, 1) mlp_wgrad_kernel(const WgradPara
         if (++stage == kWStages) { stage = 0; phase ^= 1; }
       }
       part[kPartColsum + j * 256 + c] = total;
+      if (j == 9) part[kPartSig + c] = sig_total;
       if (j == 10 && c < 128) {
 #pragma unroll
         for (int k = 0; k < 27; ++k) part[kPartDir + c * 32 + k] = dir_acc[k];
@@ -732,7 +756,7 @@ __device__ __forceinline__ long long flat_to_partial(size_t idx) {
     case 5: return i < 63 ? job_off(5) + (size_t)o * 64 + i : job_off(6) + (size_t)o * 256 + (i - 63);
     case 6: return job_off(7) + (size_t)o * 256 + i;
     case 7: return job_off(8) + (size_t)o * 256 + i;
-    case 8: return job_off(12) + (size_t)3 * 256 + i;
+    case 8: return kPartSig + i;
     case 9: return job_off(9) + (size_t)o * 256 + i;
     case 10: return i < 256 ? job_off(10) + (size_t)o * 256 + i : kPartDir + (size_t)o * 32 + (i - 256);
     default: return job_off(11) + (size_t)o * 128 + i;
@@ -813,13 +837,15 @@ int launch_mlp_dgrad(tgtc_ctx* ctx, int net, const float* rgbsigma, const float*
   return TGTC_OK;
 }
 
-int launch_mlp_wgrad(tgtc_ctx* ctx, const TcStash& stash, const TcDz& dz, const float* rays_d, int64_t M, int S, float* partial,
-                     float* grads, int accumulate, cudaStream_t st) {
+int launch_mlp_wgrad(tgtc_ctx* ctx, const TcStash& stash, const TcDz& dz, const float* rays_d, const float* d_rgbsigma, int64_t M, int S,
+                     float* partial, float* grads, int accumulate, cudaStream_t st) {
   if (M == 0) return TGTC_OK;
   WgradParams P;
   P.stash_h = stash.h; P.stash_f = stash.f; P.stash_pe = stash.pe;
   P.dz = dz.dz; P.dzf = dz.dzf; P.dhead = dz.dhead;
   P.rays_d = rays_d;
+  P.d_rgbsigma = reinterpret_cast<const float4*>(d_rgbsigma);
+  P.M = M;
   P.partial = partial;
   P.ntiles = (M + kTileM - 1) / kTileM;
   P.n_rays = M / S;
