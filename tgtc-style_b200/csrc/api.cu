@@ -494,7 +494,7 @@ extern "C" int tgtc_render_frame(tgtc_ctx* ctx, int mode, int H, int W, const do
 // training step: forward with activation stash + backward, both nets
 
 struct TrainWs {
-  size_t off_stash_h, off_stash_f, off_stash_pe, off_dz, off_dzf, off_dhead, off_rs, off_drs, off_w_c, off_ts_f, off_ts_c,
+  size_t off_stash_h, off_stash_f, off_stash_pe, off_stash_mask, off_dz, off_dzf, off_dhead, off_rs, off_drs, off_w_c, off_ts_f, off_ts_c,
       off_rgb, off_g, off_partial, total;
 };
 
@@ -507,6 +507,7 @@ static TrainWs train_ws_layout(tgtc_ctx* ctx, int64_t n, int S, int F) {
   w.off_stash_h = o;  o = align_up(o + tiles * kStashHBytesPerTile, 1024);
   w.off_stash_f = o;  o = align_up(o + tiles * kStashFBytesPerTile, 1024);
   w.off_stash_pe = o; o = align_up(o + tiles * kStashPeBytesPerTile, 1024);
+  w.off_stash_mask = o; o = align_up(o + tiles * kStashMaskBytesPerTile, 1024);
   w.off_dz = o;       o = align_up(o + tiles * kStashHBytesPerTile, 1024);
   w.off_dzf = o;      o = align_up(o + tiles * kStashFBytesPerTile, 1024);
   w.off_dhead = o;    o = align_up(o + tiles * kStashPeBytesPerTile, 1024);
@@ -537,6 +538,7 @@ static int train_pass(tgtc_ctx* ctx, int net, const float* rays_o, const float* 
                       cudaStream_t st) {
   TcStash stash;
   stash.h = base + ws.off_stash_h; stash.f = base + ws.off_stash_f; stash.pe = base + ws.off_stash_pe;
+  stash.mask = reinterpret_cast<uint32_t*>(base + ws.off_stash_mask);
   TcDz dz;
   dz.dz = base + ws.off_dz; dz.dzf = base + ws.off_dzf; dz.dhead = base + ws.off_dhead;
   float* rs = reinterpret_cast<float*>(base + ws.off_rs);

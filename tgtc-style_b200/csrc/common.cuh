@@ -195,8 +195,13 @@ struct TcStash {
   uint8_t* h = nullptr;    // [ntiles][9][4 blocks][16 KB]  post-ReLU outputs of L0..L7 and remap
   uint8_t* f = nullptr;    // [ntiles][2 blocks][16 KB]     post-ReLU output of rgb0
   uint8_t* pe = nullptr;   // [ntiles][16 KB]               positional encoding (column 63 = 0)
+  // ReLU masks as bits: [ntiles][10 layers: L0..L7, remap, rgb0][8 column blocks of 32][128 rows] u32; bit (31-c) of a word =
+  // sign bit of the fp32 pre-activation of column 32*block+c (1 = the gradient is blocked).  The dgrad kernel reads these
+  // 40 KB per tile instead of the 608 KB of activation images (which only the wgrad kernel still needs).
+  uint32_t* mask = nullptr;
 };
-constexpr size_t kStashHBytesPerTile = 9 * 65536, kStashFBytesPerTile = 32768, kStashPeBytesPerTile = 16384;
+constexpr size_t kStashHBytesPerTile = 9 * 65536, kStashFBytesPerTile = 32768, kStashPeBytesPerTile = 16384,
+                 kStashMaskBytesPerTile = 10 * 8 * 128 * 4;
 
 // gradients of the pre-activations, written by the dgrad kernel and read by the wgrad kernel (tile images like TcStash)
 struct TcDz {

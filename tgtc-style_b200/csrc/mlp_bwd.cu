@@ -46,7 +46,7 @@ constexpr int kOffWRgb1 = kOffW + kStages * kStageBytes;    // 3 x 128 fp32
 constexpr int kOffWSig = kOffWRgb1 + 384 * 4;               // 256 fp32
 constexpr int kOffBars = kOffWSig + 256 * 4;
 constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarInReady = 2 * kStages, kBarInFree = kBarInReady + 1,
-              kBarActReady = kBarInFree + 1, kBarAccFull = kBarActReady + 2, kBarHFull = kBarAccFull + 2, kBarDzDone = kBarHFull + 2, kNumBars = kBarDzDone + 2;
+              kBarActReady = kBarInFree + 1, kBarAccFull = kBarActReady + 2, kBarSlotFree = kBarAccFull + 2, kBarDzDone = kBarSlotFree + 2, kNumBars = kBarDzDone + 2;
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
@@ -56,8 +56,7 @@ struct DgradParams {
   const float* smalls;
   const float4* rgbsigma;     // [M] forward outputs (r,g,b,sigma)
   const float4* d_rgbsigma;   // [M] dL/d(r,g,b,sigma) from the compositing backward
-  const uint8_t* stash_h;     // forward activation stash
-  const uint8_t* stash_f;
+  const uint32_t* mask;       // forward ReLU mask words (common.cuh: TcStash.mask)
   uint8_t* dz;                // [ntiles][9][64 KB]  dz_0..dz_7, dz_r
   uint8_t* dzf;               // [ntiles][32 KB]
   uint8_t* dhead;             // [ntiles][16 KB]     columns 0..2 = d_rgb * rgb(1-rgb), column 3 = d_sigma
@@ -78,18 +77,10 @@ __device__ __forceinline__ int64_t pair_tile(int64_t it, int t, uint32_t rank) {
 __device__ __forceinline__ void st_global_v4(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
 }
-__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-// two fp32 gradients -> bf16 pair, zeroed where the stashed post-ReLU activation (bf16 pair hw) is zero
-__device__ __forceinline__ uint32_t mask_pack(uint32_t hw, float lo, float hi) {
-  const float l = (hw & 0xFFFFu) != 0u ? lo : 0.f;
-  const float h = (hw >> 16) != 0u ? hi : 0.f;
+// two fp32 gradients -> bf16 pair, zeroed where the ReLU blocked them: bit 31 of mb belongs to lo, bit 30 to hi (1 = blocked)
+__device__ __forceinline__ uint32_t mask_pack(uint32_t mb, float lo, float hi) {
+  const float l = (int32_t)mb < 0 ? 0.f : lo;
+  const float h = (int32_t)(mb << 1) < 0 ? 0.f : hi;
   return pack_bf16(l, h);
 }
 
@@ -117,7 +108,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
     for (int t = 0; t < 2; ++t) {
       mbar_init(bar(kBarActReady + t), 2 * (kNumEpiThreads / 32));
       mbar_init(bar(kBarAccFull + t), 1);
-      mbar_init(bar(kBarHFull + t), 1);
+      mbar_init(bar(kBarSlotFree + t), 1);
       mbar_init(bar(kBarDzDone + t), kNumEpiThreads / 32);
     }
     fence_barrier_init();
@@ -253,17 +244,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
           dzc[2] = d.z * o.z * (1.0f - o.z);
           dsig = d.w;
         }
-        // the stashed rgb0 output row (mask); fetched before waiting for the staging buffer
-        uint4 fm[16];
+        // ReLU mask of the rgb0 output (4 words = 128 columns); fetched before waiting for the staging buffer
+        uint32_t fm[4] = {~0u, ~0u, ~0u, ~0u};
         if (tile_ok) {
-          const uint8_t* fsrc = P.stash_f + (size_t)tile * 32768 + rowoff;
+          const uint32_t* ms = P.mask + (((size_t)tile * 10 + 9) * 8) * 128 + r;
 #pragma unroll
-          for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch) fm[kb * 8 + ch] = *reinterpret_cast<const uint4*>(fsrc + kb * 16384 + ((ch ^ rx) << 4));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) fm[i] = make_uint4(0u, 0u, 0u, 0u);
+          for (int w = 0; w < 4; ++w) fm[w] = __ldg(ms + w * 128);
         }
         if (r == 0) BW_TRACE(2, it, 0, t, 0);
         if (use > 0) mbar_wait_relaxed(bar(kBarInFree), (uint32_t)((use - 1) & 1), 64);
@@ -278,9 +264,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
 #pragma unroll
             for (int e = 0; e < 8; ++e)
               df[e] = fmaf(dzc[2], wr[256 + j0 + e], fmaf(dzc[1], wr[128 + j0 + e], dzc[0] * wr[j0 + e]));
-            const uint4 h = fm[kb * 8 + ch];
-            const uint32_t q0 = mask_pack(h.x, df[0], df[1]), q1 = mask_pack(h.y, df[2], df[3]), q2 = mask_pack(h.z, df[4], df[5]),
-                           q3 = mask_pack(h.w, df[6], df[7]);
+            const uint32_t mb = fm[kb * 2 + (ch >> 2)] << ((ch & 3) * 8);   // bit 31 = first of these 8 columns
+            const uint32_t q0 = mask_pack(mb, df[0], df[1]), q1 = mask_pack(mb << 2, df[2], df[3]), q2 = mask_pack(mb << 4, df[4], df[5]),
+                           q3 = mask_pack(mb << 6, df[6], df[7]);
             const uint32_t off = (uint32_t)kb * 16384u + (((uint32_t)ch ^ rx) << 4);
             st_shared_v4(sbase + kOffIn + rowoff + off, q0, q1, q2, q3);
             if (gdst != nullptr) st_global_v4(gdst + off, q0, q1, q2, q3);
@@ -300,41 +286,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
     }
   } else if (warp >= kMoveWarp0) {
     // ===================================================================== tile movers: one thread per slot
-    // Per GEMM: the moment the MMAs that read act[t] retire, stage the stashed activation tile (ReLU mask) of the layer into
-    // act[t] with one 64 KB bulk copy (per-thread 16-byte loads of a row-per-thread pattern touch 32 lines per instruction
-    // and saturate the L1 pipeline); when the epilogue has replaced it with the masked gradient, send that tile to HBM
-    // with one bulk store.  Both run while the epilogue warps work on the other slot.
+    // When the epilogue has filled act[t] with the masked gradient of a layer, send that tile image to HBM with one bulk store
+    // and tell the epilogue warps when the store has finished reading shared memory (the next epilogue overwrites the slot).
     if (lane == 0) {
       const int t = warp - kMoveWarp0;
-      uint32_t acc_par = 0, dz_par = 0;
+      uint32_t dz_par = 0;
+      mbar_arrive(bar(kBarSlotFree + t));   // the slot starts out free
       for (int64_t it = 0; it < iters; ++it) {
         const int64_t tile = pair_tile(it, t, rank);
         const bool tile_ok = tile < P.ntiles;
         for (int g = 0; g < kNumGemm; ++g) {
           const int ml = 8 - g;
-          mbar_wait(bar(kBarAccFull + t), acc_par); acc_par ^= 1;
-          bulk_wait_read0();   // my dz store of the previous GEMM has finished reading act[t]
-          if (tile_ok) {
-            mbar_arrive_expect_tx(bar(kBarHFull + t), 65536u);
-            bulk_g2s(sbase + kOffAct + t * kActBytes, P.stash_h + ((size_t)tile * 9 + ml) * 65536, 65536u, bar(kBarHFull + t));
-            // pull the NEXT mask image of this slot towards L2
-            if (g + 1 < kNumGemm) {
-              l2_prefetch_bulk(P.stash_h + ((size_t)tile * 9 + (ml - 1)) * 65536, 65536);
-            } else {
-              const int64_t nt = pair_tile(it + 1, t, rank);
-              if (it + 1 < iters && nt < P.ntiles) {
-                l2_prefetch_bulk(P.stash_h + ((size_t)nt * 9 + 8) * 65536, 65536);
-                l2_prefetch_bulk(P.stash_f + (size_t)nt * 32768, 32768);
-              }
-            }
-          } else {
-            mbar_arrive(bar(kBarHFull + t));
-          }
           mbar_wait(bar(kBarDzDone + t), dz_par); dz_par ^= 1;
           if (tile_ok) {
             bulk_s2g(P.dz + ((size_t)tile * 9 + ml) * 65536, sbase + kOffAct + t * kActBytes, 65536u);
             bulk_commit_group();
+            bulk_wait_read0();
           }
+          mbar_arrive(bar(kBarSlotFree + t));
         }
       }
       bulk_wait_all0();
@@ -358,16 +327,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
           const int64_t m = tile * kTileM + row;
           float dsig = 0.f;
           if (g == 1 && tile_ok && m < P.M) dsig = P.d_rgbsigma[m].w;
+          // this thread's four ReLU mask words of the layer (fetched ahead of the accumulator wait)
+          uint32_t mw[4] = {~0u, ~0u, ~0u, ~0u};
+          if (tile_ok) {
+            const uint32_t* ms = P.mask + (((size_t)tile * 10 + ml) * 8 + hc * 4) * 128 + row;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) mw[w] = __ldg(ms + w * 128);
+          }
           mbar_wait(bar(kBarAccFull + t), acc_par[t]); acc_par[t] ^= 1;
           tc_fence_after();
           if (lane == 0 && q == 2 && hc == 0) BW_TRACE(1, it, g, t, 0);
-          // the slot's tile mover (warp 14/15) staged the stashed activation tile (the ReLU mask) into act[t] the moment the
-          // MMAs retired; every thread reads a mask chunk from exactly the address it overwrites with the masked gradient
+          // AccFull: the MMAs that read act[t] have retired; SlotFree: the slot's tile mover (warp 14/15) has finished reading the
+          // previous gradient tile out of act[t].  From here the slot is this epilogue's to overwrite.
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 * t) + (uint32_t)(hc * 128);
           const uint32_t sdst = sbase + kOffAct + t * kActBytes + rowoff;
-          mbar_wait(bar(kBarHFull + t), h_par[t]); h_par[t] ^= 1;
+          mbar_wait(bar(kBarSlotFree + t), h_par[t]); h_par[t] ^= 1;
           if (lane == 0 && q == 2 && hc == 0) BW_TRACE(1, it, g, t, 1);
-#pragma unroll 1
+#pragma unroll
           for (int blk = 0; blk < 4; ++blk) {
             const uint32_t kboff = (uint32_t)(blk >> 1) * 16384u;
             uint32_t v[32];
@@ -380,12 +356,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint32_t coff = kboff + ((((uint32_t)(blk & 1) * 4u + (uint32_t)j) ^ rx) << 4);
-              uint4 h = make_uint4(0u, 0u, 0u, 0u);
-              if (tile_ok) h = ld_shared_v4(sdst + coff);
-              const uint32_t q0 = mask_pack(h.x, __uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
-              const uint32_t q1 = mask_pack(h.y, __uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-              const uint32_t q2 = mask_pack(h.z, __uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
-              const uint32_t q3 = mask_pack(h.w, __uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+              const uint32_t mb = mw[blk] << (8 * j);   // bit 31 = column 8j of this block
+              const uint32_t q0 = mask_pack(mb, __uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+              const uint32_t q1 = mask_pack(mb << 2, __uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+              const uint32_t q2 = mask_pack(mb << 4, __uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+              const uint32_t q3 = mask_pack(mb << 6, __uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
               st_shared_v4(sdst + coff, q0, q1, q2, q3);   // A operand of the next GEMM (in place) and source of the dz store
             }
           }
@@ -819,7 +794,7 @@ int launch_mlp_dgrad(tgtc_ctx* ctx, int net, const float* rgbsigma, const float*
   P.smalls = im.smalls;
   P.rgbsigma = reinterpret_cast<const float4*>(rgbsigma);
   P.d_rgbsigma = reinterpret_cast<const float4*>(d_rgbsigma);
-  P.stash_h = stash.h; P.stash_f = stash.f;
+  P.mask = stash.mask;
   P.dz = dz.dz; P.dzf = dz.dzf; P.dhead = dz.dhead;
   P.M = M;
   P.ntiles = (M + kTileM - 1) / kTileM;

@@ -76,72 +76,103 @@ using namespace tcptx;
 
 // one 32-column block of a hidden-layer epilogue: +bias, ReLU, bf16, 4 x 16-byte swizzled stores.
 // blk = 32-column block index inside this thread's 128 columns; kb = row base of the 64-column K block.
-// gk: when training, the same 16-byte chunk also goes to the activation stash in HBM (tile image = the shared-memory
-// layout verbatim), at the address that corresponds to kb; nullptr otherwise.
+// mrow: when training, the block's ReLU mask word (bit 31-c = sign of pre-activation c, i.e. 1 = gradient blocked) goes to the
+// mask stash in HBM that mlp_dgrad_kernel reads instead of the 16x larger activation image; nullptr otherwise.
 __device__ __forceinline__ void st_global_v4(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
 }
-template <bool kSigma>
-__device__ __forceinline__ void epi_block(uint32_t (&v)[32], const float* bl, const float* wsig, uint32_t kb, uint32_t rx, int blk,
-                                          float& sig, uint8_t* gk) {
+__device__ __forceinline__ uint32_t sign_mask32(const uint32_t (&v)[32]) {
+  uint32_t m = 0u;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = blk * 32 + 8 * j;  // column inside the 128-column half
-    const float4 b0 = *reinterpret_cast<const float4*>(bl + c);
-    const float4 b1 = *reinterpret_cast<const float4*>(bl + c + 4);
-    const uint32_t coff = (uint32_t)((((blk & 1) * 4) + j) << 4) ^ rx;
-    const uint32_t dst = kb + coff;
-    if constexpr (kSigma) {
-      float h[8];
-      h[0] = fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x, 0.f);
-      h[1] = fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y, 0.f);
-      h[2] = fmaxf(__uint_as_float(v[8 * j + 2]) + b0.z, 0.f);
-      h[3] = fmaxf(__uint_as_float(v[8 * j + 3]) + b0.w, 0.f);
-      h[4] = fmaxf(__uint_as_float(v[8 * j + 4]) + b1.x, 0.f);
-      h[5] = fmaxf(__uint_as_float(v[8 * j + 5]) + b1.y, 0.f);
-      h[6] = fmaxf(__uint_as_float(v[8 * j + 6]) + b1.z, 0.f);
-      h[7] = fmaxf(__uint_as_float(v[8 * j + 7]) + b1.w, 0.f);
-      // fp32 sigma head on the un-rounded activations (models.py:103)
-      const float4 w0 = *reinterpret_cast<const float4*>(wsig + c);
-      const float4 w1 = *reinterpret_cast<const float4*>(wsig + c + 4);
-      sig = fmaf(h[0], w0.x, sig); sig = fmaf(h[1], w0.y, sig); sig = fmaf(h[2], w0.z, sig); sig = fmaf(h[3], w0.w, sig);
-      sig = fmaf(h[4], w1.x, sig); sig = fmaf(h[5], w1.y, sig); sig = fmaf(h[6], w1.z, sig); sig = fmaf(h[7], w1.w, sig);
-      const uint32_t q0 = pack_bf16(h[0], h[1]), q1 = pack_bf16(h[2], h[3]), q2 = pack_bf16(h[4], h[5]), q3 = pack_bf16(h[6], h[7]);
-      st_shared_v4(dst, q0, q1, q2, q3);
-      if (gk != nullptr) st_global_v4(gk + coff, q0, q1, q2, q3);
-    } else {
+  for (int c = 0; c < 32; ++c) m = __funnelshift_l(v[c], m, 1);
+  return m;
+}
+template <bool kSigma, bool kMask>
+__device__ __forceinline__ void epi_block(uint32_t (&v)[32], const float* bl, const float* wsig, uint32_t kb, uint32_t rx, int blk,
+                                          float& sig, uint32_t* mrow) {
+  if constexpr (kMask) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = blk * 32 + 8 * j;  // column inside the 128-column half
+      const float4 b0 = *reinterpret_cast<const float4*>(bl + c);
+      const float4 b1 = *reinterpret_cast<const float4*>(bl + c + 4);
       add2(v[8 * j + 0], v[8 * j + 1], b0.x, b0.y);
       add2(v[8 * j + 2], v[8 * j + 3], b0.z, b0.w);
       add2(v[8 * j + 4], v[8 * j + 5], b1.x, b1.y);
       add2(v[8 * j + 6], v[8 * j + 7], b1.z, b1.w);
+    }
+    if (mrow != nullptr) mrow[blk * 128] = sign_mask32(v);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = blk * 32 + 8 * j;
+    const uint32_t coff = (uint32_t)((((blk & 1) * 4) + j) << 4) ^ rx;
+    const uint32_t dst = kb + coff;
+    if constexpr (!kMask) {
+      const float4 b0 = *reinterpret_cast<const float4*>(bl + c);
+      const float4 b1 = *reinterpret_cast<const float4*>(bl + c + 4);
+      if constexpr (kSigma) {
+        float h[8];
+        h[0] = fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x, 0.f);
+        h[1] = fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y, 0.f);
+        h[2] = fmaxf(__uint_as_float(v[8 * j + 2]) + b0.z, 0.f);
+        h[3] = fmaxf(__uint_as_float(v[8 * j + 3]) + b0.w, 0.f);
+        h[4] = fmaxf(__uint_as_float(v[8 * j + 4]) + b1.x, 0.f);
+        h[5] = fmaxf(__uint_as_float(v[8 * j + 5]) + b1.y, 0.f);
+        h[6] = fmaxf(__uint_as_float(v[8 * j + 6]) + b1.z, 0.f);
+        h[7] = fmaxf(__uint_as_float(v[8 * j + 7]) + b1.w, 0.f);
+        // fp32 sigma head on the un-rounded activations (models.py:103)
+        const float4 w0 = *reinterpret_cast<const float4*>(wsig + c);
+        const float4 w1 = *reinterpret_cast<const float4*>(wsig + c + 4);
+        sig = fmaf(h[0], w0.x, sig); sig = fmaf(h[1], w0.y, sig); sig = fmaf(h[2], w0.z, sig); sig = fmaf(h[3], w0.w, sig);
+        sig = fmaf(h[4], w1.x, sig); sig = fmaf(h[5], w1.y, sig); sig = fmaf(h[6], w1.z, sig); sig = fmaf(h[7], w1.w, sig);
+        const uint32_t q0 = pack_bf16(h[0], h[1]), q1 = pack_bf16(h[2], h[3]), q2 = pack_bf16(h[4], h[5]), q3 = pack_bf16(h[6], h[7]);
+        st_shared_v4(dst, q0, q1, q2, q3);
+      } else {
+        add2(v[8 * j + 0], v[8 * j + 1], b0.x, b0.y);
+        add2(v[8 * j + 2], v[8 * j + 3], b0.z, b0.w);
+        add2(v[8 * j + 4], v[8 * j + 5], b1.x, b1.y);
+        add2(v[8 * j + 6], v[8 * j + 7], b1.z, b1.w);
+        const uint32_t q0 = pack_bf16_relu(v[8 * j + 0], v[8 * j + 1]), q1 = pack_bf16_relu(v[8 * j + 2], v[8 * j + 3]),
+                       q2 = pack_bf16_relu(v[8 * j + 4], v[8 * j + 5]), q3 = pack_bf16_relu(v[8 * j + 6], v[8 * j + 7]);
+        st_shared_v4(dst, q0, q1, q2, q3);
+      }
+    } else {
+      // bias already added above (the mask wants the pre-activations)
+      if constexpr (kSigma) {
+        // fp32 sigma head on the un-rounded activations (models.py:103)
+        const float4 w0 = *reinterpret_cast<const float4*>(wsig + c);
+        const float4 w1 = *reinterpret_cast<const float4*>(wsig + c + 4);
+        const float ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sig = fmaf(fmaxf(__uint_as_float(v[8 * j + e]), 0.f), ws[e], sig);
+      }
       const uint32_t q0 = pack_bf16_relu(v[8 * j + 0], v[8 * j + 1]), q1 = pack_bf16_relu(v[8 * j + 2], v[8 * j + 3]),
                      q2 = pack_bf16_relu(v[8 * j + 4], v[8 * j + 5]), q3 = pack_bf16_relu(v[8 * j + 6], v[8 * j + 7]);
       st_shared_v4(dst, q0, q1, q2, q3);
-      if (gk != nullptr) st_global_v4(gk + coff, q0, q1, q2, q3);
     }
   }
 }
 
 // this thread's 128 columns of one hidden layer: TMEM loads software-pipelined against the math
 // (the load of block b+1 is in flight while block b is converted and stored)
-template <bool kSigma>
+template <bool kSigma, bool kMask>
 __device__ __forceinline__ float hidden_epilogue(uint32_t tcol, const float* bl, const float* wsig, uint32_t arow, uint32_t rx,
-                                                 uint8_t* grow) {
-  uint8_t* const grow1 = grow != nullptr ? grow + 16384 : nullptr;
+                                                 uint32_t* mrow) {
   float sig = 0.f;
   uint32_t va[32], vb[32];
   tmem_ld32(tcol, va);
   tmem_ld_wait_dep(va);
   tmem_ld32(tcol + 32, vb);
-  epi_block<kSigma>(va, bl, wsig, arow, rx, 0, sig, grow);
+  epi_block<kSigma, kMask>(va, bl, wsig, arow, rx, 0, sig, mrow);
   tmem_ld_wait_dep(vb);
   tmem_ld32(tcol + 64, va);
-  epi_block<kSigma>(vb, bl, wsig, arow, rx, 1, sig, grow);
+  epi_block<kSigma, kMask>(vb, bl, wsig, arow, rx, 1, sig, mrow);
   tmem_ld_wait_dep(va);
   tmem_ld32(tcol + 96, vb);
-  epi_block<kSigma>(va, bl, wsig, arow + 16384, rx, 2, sig, grow1);
+  epi_block<kSigma, kMask>(va, bl, wsig, arow + 16384, rx, 2, sig, mrow);
   tmem_ld_wait_dep(vb);
-  epi_block<kSigma>(vb, bl, wsig, arow + 16384, rx, 3, sig, grow1);
+  epi_block<kSigma, kMask>(vb, bl, wsig, arow + 16384, rx, 3, sig, mrow);
   return sig;
 }
 
@@ -156,6 +187,7 @@ struct TcParams {
   uint8_t* stash_h;   // [ntiles][9][128 x 256 bf16]  post-ReLU outputs of L0..L7 and remap
   uint8_t* stash_f;   // [ntiles][128 x 128 bf16]      post-ReLU output of rgb0
   uint8_t* stash_pe;  // [ntiles][128 x 64 bf16]       positional encoding tile
+  uint32_t* stash_mask;  // [ntiles][10][8][128] ReLU mask words (sign bits of the pre-activations), see common.cuh: TcStash
   int trunk;          // style path: run L0..L7 + sigma + remap only; stash ONLY the remap tile ([ntiles][64 KB]) and write sigma
   int dbg_flags;      // timing experiments (results garbage): 2 = skip the hidden-layer epilogue work, 16 = no weight ring at all
   int dbg_layers;     // >0: stop after this many GEMM layers and dump the fp32 accumulator (tests)
@@ -465,13 +497,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
             const uint32_t arow = sbase + kOffAct + t * kActBytes + (row >> 3) * 1024 + (row & 7) * 128 + hc * 2 * 16384;
             const uint32_t tcol = taddr + hc * 128;
             const uint32_t rx = (uint32_t)(row & 7) << 4;
-            uint8_t* grow = nullptr;   // (per-thread stash stores are not used: the tile goes out as one bulk store below)
+            uint32_t* mrow = nullptr;   // training: this thread's first mask word of the layer (the image itself leaves by bulk store)
+            if constexpr (kTrain) {
+              if (P.stash_mask != nullptr && tile < P.ntiles) mrow = P.stash_mask + (((size_t)tile * 10 + l) * 8 + hc * 4) * 128 + row;
+            }
             if (P.dbg_flags & 2) {
             } else if (l == 7) {
-              const float sig = hidden_epilogue<true>(tcol, bl, wsig_s + hc * 128, arow, rx, grow);
+              const float sig = hidden_epilogue<true, kTrain>(tcol, bl, wsig_s + hc * 128, arow, rx, mrow);
               if (hc == 1) sigpart_s[t * 128 + row] = sig; else sig_keep[t] = sig;
             } else {
-              hidden_epilogue<false>(tcol, bl, nullptr, arow, rx, grow);
+              hidden_epilogue<false, kTrain>(tcol, bl, nullptr, arow, rx, mrow);
             }
             fence_proxy_async();
             if constexpr (kTrain) {
@@ -509,6 +544,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
               tmem_ld32(taddr + c0, v);
               tmem_ld_wait();
               uint32_t fq[16];  // bf16 pairs of this block's 32 outputs (training stash)
+              uint32_t fmask = 0u;
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const int c = c0 + j;
@@ -516,10 +552,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
                 const float4 w0 = *reinterpret_cast<const float4*>(wrgb_s + c);
                 const float4 w1 = *reinterpret_cast<const float4*>(wrgb_s + 128 + c);
                 const float4 w2 = *reinterpret_cast<const float4*>(wrgb_s + 256 + c);
-                const float f0 = fmaxf(__uint_as_float(v[j + 0]) + bb.x, 0.f);
-                const float f1 = fmaxf(__uint_as_float(v[j + 1]) + bb.y, 0.f);
-                const float f2 = fmaxf(__uint_as_float(v[j + 2]) + bb.z, 0.f);
-                const float f3 = fmaxf(__uint_as_float(v[j + 3]) + bb.w, 0.f);
+                const float z0 = __uint_as_float(v[j + 0]) + bb.x, z1 = __uint_as_float(v[j + 1]) + bb.y;
+                const float z2 = __uint_as_float(v[j + 2]) + bb.z, z3 = __uint_as_float(v[j + 3]) + bb.w;
+                if constexpr (kTrain) {
+                  fmask = __funnelshift_l(__float_as_uint(z0), fmask, 1);
+                  fmask = __funnelshift_l(__float_as_uint(z1), fmask, 1);
+                  fmask = __funnelshift_l(__float_as_uint(z2), fmask, 1);
+                  fmask = __funnelshift_l(__float_as_uint(z3), fmask, 1);
+                }
+                const float f0 = fmaxf(z0, 0.f), f1 = fmaxf(z1, 0.f), f2 = fmaxf(z2, 0.f), f3 = fmaxf(z3, 0.f);
                 p0 = fmaf(f0, w0.x, p0); p0 = fmaf(f1, w0.y, p0); p0 = fmaf(f2, w0.z, p0); p0 = fmaf(f3, w0.w, p0);
                 p1 = fmaf(f0, w1.x, p1); p1 = fmaf(f1, w1.y, p1); p1 = fmaf(f2, w1.z, p1); p1 = fmaf(f3, w1.w, p1);
                 p2 = fmaf(f0, w2.x, p2); p2 = fmaf(f1, w2.y, p2); p2 = fmaf(f2, w2.z, p2); p2 = fmaf(f3, w2.w, p2);
@@ -527,6 +568,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
                 fq[j / 2 + 1] = pack_bf16(f2, f3);
               }
               if (kTrain && tile < P.ntiles) {
+                if (P.stash_mask != nullptr) P.stash_mask[(((size_t)tile * 10 + 9) * 8 + hc * 2 + b) * 128 + row] = fmask;
                 // rgb0 output tile image: K block hc (64 columns), 16-byte chunks b*4 .. b*4+3 of this row
                 uint8_t* gf = P.stash_f + (size_t)tile * 32768 + hc * 16384 + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll
@@ -606,6 +648,7 @@ static int launch_tc_common(tgtc_ctx* ctx, int net, const MlpIO& io, int dbg_lay
   P.stash_h = stash != nullptr ? stash->h : nullptr;
   P.stash_f = stash != nullptr ? stash->f : nullptr;
   P.stash_pe = stash != nullptr ? stash->pe : nullptr;
+  P.stash_mask = stash != nullptr ? stash->mask : nullptr;
   P.dbg_trace = g_dbg_trace;
   P.dbg_out = dbg_out;
   static bool attr_set[64] = {};
