@@ -232,6 +232,28 @@ int tgtc_profile_read_kind(tgtc_ctx* ctx, int kind, int64_t* launches, double* m
  * gpu_launches claim is counted here, not estimated) */
 int64_t tgtc_launch_count(const tgtc_ctx* ctx);
 
+/* ---- Style_train: the second training phase (train_tgtcs.py:311-495) ------------------------------------
+ * The reference's step: perturbed coarse samples (train_tgtcs.py:362) -> frozen NeRF net -> style module 1 with the ray's
+ * latent (latents_model_1(style_id, frame_id), :409) -> style module 2 with mean(latent) (:410-421) -> compositing (:424) ->
+ * resampling -> the same on the fine net (:456-479) -> losses on the two rgb maps (:425, :480-483) -> backward into the two
+ * style modules (style_optimizer, :54) and the latents (latents_model_1.optimize, :495).
+ * tgtc_style_train_forward runs everything up to the rgb maps and leaves the activation stash of both passes in the
+ * workspace; the caller evaluates its loss on (rgb_coarse, rgb_fine) and passes dL/d rgb_coarse, dL/d rgb_fine [n,3] to
+ * tgtc_style_train_backward (same workspace, same n/lat1/noise arguments), which writes
+ *   grads  flat fp32 [tgtc_style_num_params()] in tgtc_set_style_weights order (module 1 (W,b) x 5, module 2 (W,b) x 8)
+ *   dlat1  [n,32]  dL/d lat1 (module 2 sees mean(lat1) broadcast to 32 dims; its share comes back as 1/32 per component)
+ * lat1 [n,32]: per-ray latents.  rand [n,S] uniforms or NULL (perturb=False).  noise_*: randn*sigma_noise_std or NULL.
+ * The NeRF nets are constants here (they are not in style_optimizer); no gradient flows through the resampling. */
+size_t tgtc_style_train_workspace_bytes(tgtc_ctx* ctx, int64_t n_rays, int n_samples, int n_fine);
+int64_t tgtc_style_num_params(void);
+int tgtc_style_train_forward(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n_rays, double near, double far,
+                             int n_samples, int n_fine, const float* lat1, const float* rand, const float* noise_coarse,
+                             const float* noise_fine, float* rgb_coarse, float* rgb_fine, void* workspace, size_t workspace_bytes,
+                             tgtc_stream stream);
+int tgtc_style_train_backward(tgtc_ctx* ctx, int64_t n_rays, int n_samples, int n_fine, const float* lat1, int has_rand,
+                              const float* noise_coarse, const float* noise_fine, const float* d_rgb_coarse, const float* d_rgb_fine,
+                              float* grads, int accumulate, float* dlat1, void* workspace, size_t workspace_bytes, tgtc_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

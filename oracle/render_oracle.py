@@ -444,3 +444,40 @@ def render_style_chain(sd_coarse, sd_fine, sd_concat, sd_wild, rays_o, rays_d, l
     if keep_intermediates:
         out.update(concat_features_fine=cf_f, rgb_pts_fine=rgb_sf, sigma_fine=ret_f["sigma"])
     return out
+
+
+def style_train_forward_backward(sd_coarse, sd_fine, sd_concat, sd_wild, rays_o, rays_d, latents, g_rgb_coarse, g_rgb_fine, near=0., far=1.,
+                                 n_samples=64, n_fine=64, rand=None):
+    """One batch of Style_train (train_tgtcs.py:354-483) through torch.autograd: the forward of render_style_chain with
+    per-ray latents [N,32] (latents_model_1 output, train_tgtcs.py:409) and stratified positions from `rand`
+    (perturb=True, train_tgtcs.py:362), then the vector-Jacobian product of (rgb_coarse, rgb_fine) with the given
+    upstream gradients -- i.e. what loss.backward() sends into the two style modules and the latents for any loss built
+    on the two rgb maps (train_tgtcs.py:425, :480-483).  The NeRF nets are constants (style_optimizer does not hold
+    them, train_tgtcs.py:54); no gradient flows through the resampling (utils.py:576-579).
+    Returns (rgb_coarse, rgb_fine, grads_concat, grads_wild, d_latents)."""
+    ro = torch.as_tensor(rays_o, dtype=torch.float32)
+    rd = torch.as_tensor(rays_d, dtype=torch.float32)
+    n = ro.shape[0]
+    pc = {k: v.detach().clone().requires_grad_(True) for k, v in sd_concat.items()}
+    pw = {k: v.detach().clone().requires_grad_(True) for k, v in sd_wild.items()}
+    lat = torch.as_tensor(latents, dtype=torch.float32).detach().clone().requires_grad_(True)
+    lat2 = torch.mean(lat, dim=1, keepdim=True)          # train_tgtcs.py:410
+
+    def one_pass(sd_nerf, pts, S):
+        with torch.no_grad():
+            ret = nerf_forward(sd_nerf, pts, rd.unsqueeze(1).expand(n, S, 3))
+        l1 = lat.unsqueeze(1).expand(n, S, lat.shape[-1])
+        cf = style_concat_forward(pc, ret["pts"], l1)
+        concated = torch.cat((ret["base_remap"], cf), dim=-1)
+        l2 = lat2.unsqueeze(2).expand(n, S, lat.shape[-1])
+        return ret, style_wild_forward(pw, ret["pts"], concated, l2)
+
+    pts, ts = sample_uniform(ro, rd, n_samples, near, far, rand=rand)
+    ret, rgb_s = one_pass(sd_coarse, pts, n_samples)
+    rgb_c, _, w_c, _ = alpha_composition(rgb_s, ret["sigma"], ts)
+    pts_f, ts_f = sample_fine(ro, rd, ts, w_c.detach(), n_fine)
+    ret_f, rgb_sf = one_pass(sd_fine, pts_f.detach(), n_samples + n_fine)
+    rgb_f = alpha_composition(rgb_sf, ret_f["sigma"], ts_f)[0]
+    obj = (rgb_c * torch.as_tensor(g_rgb_coarse, dtype=torch.float32)).sum() + (rgb_f * torch.as_tensor(g_rgb_fine, dtype=torch.float32)).sum()
+    obj.backward()
+    return (rgb_c.detach(), rgb_f.detach(), {k: v.grad for k, v in pc.items()}, {k: v.grad for k, v in pw.items()}, lat.grad)

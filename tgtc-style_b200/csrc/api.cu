@@ -66,7 +66,7 @@ extern "C" int tgtc_destroy(tgtc_ctx* ctx) {
   }
   {
     StyleImage& si = ctx->style;
-    void* bufs[] = {si.blob_c, si.blob_w, si.head_w, si.bias_c, si.bias_w, si.head_b, si.latents, si.tables, si.wlat};
+    void* bufs[] = {si.blob_c, si.blob_w, si.blob_T, si.head_w, si.bias_c, si.bias_w, si.head_b, si.latents, si.tables, si.wlat};
     for (void* b : bufs) if (b) cudaFree(b);
   }
   if (ctx->arena) cudaFree(ctx->arena);
@@ -729,6 +729,146 @@ extern "C" int tgtc_render_style(tgtc_ctx* ctx, const float* rays_o, const float
         if (rc) return rc;
       }
     }
+  }
+  return TGTC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Style_train (train_tgtcs.py:311-495): forward with per-ray latents + stash, then the backward into the
+// two style modules and the latents.  The loss lives between the two calls (it needs both rgb maps and, for the coherence
+// term, the previous batch), so the stash of both passes stays in the caller's workspace.
+
+struct StyleTrainWs {
+  size_t off_c[2], off_w[2], off_pe[2], off_mask[2], off_remap[2], off_rs[2], off_ts[2];
+  size_t off_w_c, off_bias, off_dz, off_dhead, off_drs, off_g, off_R, off_partial, total;
+};
+static StyleTrainWs style_train_ws_layout(tgtc_ctx* ctx, int64_t n, int S, int F) {
+  StyleTrainWs w;
+  size_t o = 0;
+  const int Sp[2] = {S, S + F};
+  for (int p = 0; p < 2; ++p) {
+    const size_t tiles = (size_t)((n * Sp[p] + 127) / 128);
+    w.off_c[p] = o;     o = align_up(o + tiles * 5 * 65536, 1024);
+    w.off_w[p] = o;     o = align_up(o + tiles * 7 * 65536, 1024);
+    w.off_pe[p] = o;    o = align_up(o + tiles * 16384, 1024);
+    w.off_mask[p] = o;  o = align_up(o + tiles * kStyleMaskLayers * 8 * 128 * 4, 1024);
+    w.off_remap[p] = o; o = align_up(o + tiles * 65536, 1024);
+    w.off_rs[p] = o;    o = align_up(o + (size_t)n * Sp[p] * 16, 256);
+    w.off_ts[p] = o;    o = align_up(o + (size_t)n * Sp[p] * 4, 256);
+  }
+  const size_t tiles = (size_t)((n * (S + F) + 127) / 128);
+  w.off_w_c = o;     o = align_up(o + (size_t)n * S * 4, 256);
+  w.off_bias = o;    o = align_up(o + (size_t)n * 13 * 256 * 4, 256);
+  w.off_dz = o;      o = align_up(o + tiles * 12 * 65536, 1024);
+  w.off_dhead = o;   o = align_up(o + tiles * 16384, 1024);
+  w.off_drs = o;     o = align_up(o + (size_t)n * (S + F) * 16, 256);
+  w.off_g = o;       o = align_up(o + (size_t)n * 12, 256);
+  w.off_R = o;       o = align_up(o + (size_t)13 * 2 * tiles * 256 * 4, 256);
+  w.off_partial = o; o = align_up(o + (size_t)ctx->num_sms * style_partial_floats() * 4, 256);
+  w.total = o;
+  return w;
+}
+
+extern "C" size_t tgtc_style_train_workspace_bytes(tgtc_ctx* ctx, int64_t n_rays, int n_samples, int n_fine) {
+  if (ctx == nullptr || n_rays <= 0 || n_samples <= 0 || n_fine < 0) return 0;
+  return style_train_ws_layout(ctx, n_rays, n_samples, n_fine).total;
+}
+extern "C" int64_t tgtc_style_num_params(void) { return (int64_t)style_flat_floats(); }
+
+static StyleStash style_stash_of(const StyleTrainWs& ws, uint8_t* base, int p) {
+  StyleStash s;
+  s.c = base + ws.off_c[p]; s.w = base + ws.off_w[p]; s.pe = base + ws.off_pe[p];
+  s.mask = reinterpret_cast<uint32_t*>(base + ws.off_mask[p]);
+  return s;
+}
+
+#define STYLE_TRAIN_PROLOGUE()                                                                                                   \
+  CHECK_CTX(ctx);                                                                                                               \
+  CHECK_NET(ctx, TGTC_NET_COARSE);                                                                                              \
+  CHECK_NET(ctx, TGTC_NET_FINE);                                                                                                \
+  TGTC_REQUIRE(ctx->style.set, TGTC_ERR_STATE, "style weights not set (tgtc_set_style_weights)");                               \
+  TGTC_REQUIRE(n_rays >= 0, TGTC_ERR_ARG, "bad n_rays=%lld", (long long)n_rays);                                                \
+  if (n_rays == 0) return TGTC_OK;                                                                                              \
+  const int S = n_samples, F = n_fine, T = n_samples + n_fine;                                                                  \
+  TGTC_REQUIRE(S == 64 && T == 128, TGTC_ERR_UNSUPPORTED, "style training supports n_samples=64, n_fine=64; got %d+%d", S, F);  \
+  const StyleTrainWs ws = style_train_ws_layout(ctx, n_rays, S, F);                                                             \
+  TGTC_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0 && workspace_bytes >= ws.total,     \
+               TGTC_ERR_STATE, "style training workspace too small or not 1024-byte aligned: need %zu bytes, got %zu", ws.total, \
+               workspace_bytes);                                                                                                \
+  DeviceGuard g(ctx->device);                                                                                                   \
+  cudaStream_t st = (cudaStream_t)stream;                                                                                       \
+  uint8_t* base = static_cast<uint8_t*>(workspace)
+
+extern "C" int tgtc_style_train_forward(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n_rays, double near, double far,
+                                        int n_samples, int n_fine, const float* lat1, const float* rand, const float* noise_coarse,
+                                        const float* noise_fine, float* rgb_coarse, float* rgb_fine, void* workspace,
+                                        size_t workspace_bytes, tgtc_stream stream) {
+  STYLE_TRAIN_PROLOGUE();
+  CHECK_PTR(rays_o, "rays_o"); CHECK_PTR(rays_d, "rays_d"); CHECK_PTR(lat1, "lat1");
+  CHECK_PTR(rgb_coarse, "rgb_coarse"); CHECK_PTR(rgb_fine, "rgb_fine");
+  float* bias_rays = reinterpret_cast<float*>(base + ws.off_bias);
+  float* w_c = reinterpret_cast<float*>(base + ws.off_w_c);
+  int rc = launch_style_bias_rays(ctx, lat1, n_rays, bias_rays, st);
+  if (rc) return rc;
+  float* ts_c = reinterpret_cast<float*>(base + ws.off_ts[0]);
+  float* ts_f = reinterpret_cast<float*>(base + ws.off_ts[1]);
+  const int64_t ts_c_stride = rand != nullptr ? S : 0;
+  rc = launch_sample_uniform(ctx, nullptr, nullptr, rand != nullptr ? n_rays : 1, S, near, far, rand, nullptr, ts_c, st);
+  if (rc) return rc;
+  for (int p = 0; p < 2; ++p) {
+    const StyleStash stash = style_stash_of(ws, base, p);
+    uint8_t* remap = base + ws.off_remap[p];
+    float* rs = reinterpret_cast<float*>(base + ws.off_rs[p]);
+    MlpIO io;
+    io.rays_o = rays_o; io.rays_d = rays_d;
+    io.ts = p == 0 ? (ts_c_stride ? ts_c : nullptr) : ts_f;
+    io.t_scale = (float)(far - near); io.t_near = (float)near;
+    io.n_rays = n_rays; io.S = p == 0 ? S : T;
+    io.rgbsigma = rs;
+    rc = launch_mlp_tc_trunk(ctx, p, io, remap, st);                       // frozen NeRF net: base_remap images + sigma
+    if (rc) return rc;
+    rc = launch_style_concat_train(ctx, io, bias_rays, stash, st);
+    if (rc) return rc;
+    rc = launch_style_wild_train(ctx, io, bias_rays, remap, stash, st);
+    if (rc) return rc;
+    if (p == 0) {
+      rc = launch_composite(ctx, nullptr, nullptr, rs, ts_c, ts_c_stride, noise_coarse, 0, n_rays, S, rgb_coarse, nullptr, nullptr, w_c, st);
+      if (rc) return rc;
+      rc = launch_sample_fine(ctx, nullptr, nullptr, ts_c, ts_c_stride, w_c, n_rays, S, F, nullptr, ts_f, nullptr, nullptr, st);
+      if (rc) return rc;
+    } else {
+      rc = launch_composite(ctx, nullptr, nullptr, rs, ts_f, T, noise_fine, 0, n_rays, T, rgb_fine, nullptr, nullptr, nullptr, st);
+      if (rc) return rc;
+    }
+  }
+  return TGTC_OK;
+}
+
+extern "C" int tgtc_style_train_backward(tgtc_ctx* ctx, int64_t n_rays, int n_samples, int n_fine, const float* lat1, int has_rand,
+                                         const float* noise_coarse, const float* noise_fine, const float* d_rgb_coarse,
+                                         const float* d_rgb_fine, float* grads, int accumulate, float* dlat1, void* workspace,
+                                         size_t workspace_bytes, tgtc_stream stream) {
+  STYLE_TRAIN_PROLOGUE();
+  CHECK_PTR(lat1, "lat1"); CHECK_PTR(d_rgb_coarse, "d_rgb_coarse"); CHECK_PTR(d_rgb_fine, "d_rgb_fine"); CHECK_PTR(grads, "grads");
+  StyleDz dz;
+  dz.dz = base + ws.off_dz; dz.dhead = base + ws.off_dhead;
+  float* drs = reinterpret_cast<float*>(base + ws.off_drs);
+  float* R = reinterpret_cast<float*>(base + ws.off_R);
+  float* partial = reinterpret_cast<float*>(base + ws.off_partial);
+  for (int p = 0; p < 2; ++p) {
+    const StyleStash stash = style_stash_of(ws, base, p);
+    const float* rs = reinterpret_cast<const float*>(base + ws.off_rs[p]);
+    const float* ts = reinterpret_cast<const float*>(base + ws.off_ts[p]);
+    const int Sp = p == 0 ? S : T;
+    const int64_t ts_stride = p == 0 ? (has_rand ? S : 0) : T;
+    int rc = launch_composite_backward(ctx, rs, ts, ts_stride, p == 0 ? noise_coarse : noise_fine, 0, n_rays, Sp,
+                                       p == 0 ? d_rgb_coarse : d_rgb_fine, nullptr, nullptr, drs, st);
+    if (rc) return rc;
+    rc = launch_style_dgrad(ctx, rs, drs, stash, dz, n_rays * Sp, st);
+    if (rc) return rc;
+    rc = launch_style_wgrad(ctx, stash, base + ws.off_remap[p], dz, lat1, n_rays, Sp, partial, R, grads, (p == 0) ? accumulate : 1, dlat1,
+                            p == 0 ? 0 : 1, st);
+    if (rc) return rc;
   }
   return TGTC_OK;
 }

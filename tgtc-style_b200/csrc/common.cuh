@@ -70,6 +70,7 @@ struct NetImage {
 struct StyleImage {
   uint8_t* blob_c = nullptr;   // module 1: 18 chunks [256 x 64] bf16
   uint8_t* blob_w = nullptr;   // module 2: 34 chunks
+  uint8_t* blob_T = nullptr;   // 45 transposed chunks for the style dgrad (style_bwd.cu)
   float* head_w = nullptr;     // [3][256] output layer of module 2
   float* bias_c = nullptr;     // [5][256] effective biases for the current latents
   float* bias_w = nullptr;     // [7][256]
@@ -209,6 +210,30 @@ struct TcDz {
   uint8_t* dzf = nullptr;    // [ntiles][32 KB]     dz of rgb0
   uint8_t* dhead = nullptr;  // [ntiles][16 KB]     columns 0..2 = dz of rgb1, column 3 = d_sigma
 };
+
+// Style_train stash (tile images / mask words written by the training forward of the style head, read by style_bwd.cu)
+constexpr int kStyleMaskLayers = 12;   // module 2 layers 0..6, then module 1 layers 0..4
+struct StyleStash {
+  uint8_t* c = nullptr;      // [ntiles][5][64 KB]  module 1 (StyleMLP_before_concat) outputs; image 4 = concat_features
+  uint8_t* w = nullptr;      // [ntiles][7][64 KB]  module 2 (StyleMLP_Wild_multilayers) hidden outputs h0..h6
+  uint8_t* pe = nullptr;     // [ntiles][16 KB]
+  uint32_t* mask = nullptr;  // [ntiles][12][8][128]
+};
+struct StyleDz {
+  uint8_t* dz = nullptr;     // [ntiles][12][64 KB]
+  uint8_t* dhead = nullptr;  // [ntiles][16 KB]
+};
+size_t style_flat_floats();
+size_t style_partial_floats();
+int launch_style_dgrad(tgtc_ctx* ctx, const float* rgbsigma, const float* d_rgbsigma, const StyleStash& stash, const StyleDz& dz, int64_t M,
+                       cudaStream_t st);
+int launch_style_wgrad(tgtc_ctx* ctx, const StyleStash& stash, const uint8_t* remap_img, const StyleDz& dz, const float* lat1,
+                       int64_t n_rays, int S, float* partial, float* R, float* grads, int accumulate, float* dlat, int dlat_accumulate,
+                       cudaStream_t st);
+int launch_style_bias_rays(tgtc_ctx* ctx, const float* lat1, int64_t n_rays, float* bias_rays, cudaStream_t st);
+int launch_style_concat_train(tgtc_ctx* ctx, const MlpIO& io, const float* bias_rays, const StyleStash& stash, cudaStream_t st);
+int launch_style_wild_train(tgtc_ctx* ctx, const MlpIO& io, const float* bias_rays, const uint8_t* remap_img, const StyleStash& stash,
+                            cudaStream_t st);
 
 // style_tc.cu
 int style_set_weights(tgtc_ctx* ctx, const float* const* params, cudaStream_t st);

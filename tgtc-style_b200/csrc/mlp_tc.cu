@@ -78,15 +78,6 @@ using namespace tcptx;
 // blk = 32-column block index inside this thread's 128 columns; kb = row base of the 64-column K block.
 // mrow: when training, the block's ReLU mask word (bit 31-c = sign of pre-activation c, i.e. 1 = gradient blocked) goes to the
 // mask stash in HBM that mlp_dgrad_kernel reads instead of the 16x larger activation image; nullptr otherwise.
-__device__ __forceinline__ void st_global_v4(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
-}
-__device__ __forceinline__ uint32_t sign_mask32(const uint32_t (&v)[32]) {
-  uint32_t m = 0u;
-#pragma unroll
-  for (int c = 0; c < 32; ++c) m = __funnelshift_l(v[c], m, 1);
-  return m;
-}
 template <bool kSigma, bool kMask>
 __device__ __forceinline__ void epi_block(uint32_t (&v)[32], const float* bl, const float* wsig, uint32_t kb, uint32_t rx, int blk,
                                           float& sig, uint32_t* mrow) {
@@ -189,7 +180,8 @@ struct TcParams {
   uint8_t* stash_pe;  // [ntiles][128 x 64 bf16]       positional encoding tile
   uint32_t* stash_mask;  // [ntiles][10][8][128] ReLU mask words (sign bits of the pre-activations), see common.cuh: TcStash
   int trunk;          // style path: run L0..L7 + sigma + remap only; stash ONLY the remap tile ([ntiles][64 KB]) and write sigma
-  int dbg_flags;      // timing experiments (results garbage): 2 = skip the hidden-layer epilogue work, 16 = no weight ring at all
+  int dbg_flags;      // timing experiments (results garbage): 2 = skip the hidden-layer epilogue work, 16 = no weight ring at all,
+                      // training: 32 = no activation-image store, 64 = no store-drain wait/barrier, 128 = no mask words
   int dbg_layers;     // >0: stop after this many GEMM layers and dump the fp32 accumulator (tests)
   float* dbg_out;     // [ntiles*128, 256]
   long long* dbg_trace;  // timing experiments: clock64 stamps of CTA 0's roles, [4 roles][4 iters][10 layers][2 slots][2]
@@ -499,7 +491,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
             const uint32_t rx = (uint32_t)(row & 7) << 4;
             uint32_t* mrow = nullptr;   // training: this thread's first mask word of the layer (the image itself leaves by bulk store)
             if constexpr (kTrain) {
-              if (P.stash_mask != nullptr && tile < P.ntiles) mrow = P.stash_mask + (((size_t)tile * 10 + l) * 8 + hc * 4) * 128 + row;
+              if (P.stash_mask != nullptr && tile < P.ntiles && !(P.dbg_flags & 128)) mrow = P.stash_mask + (((size_t)tile * 10 + l) * 8 + hc * 4) * 128 + row;
             }
             if (P.dbg_flags & 2) {
             } else if (l == 7) {
@@ -514,9 +506,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
               // previous store (the other slot, one epilogue ago) has finished reading shared memory -- that buffer is the one
               // the NEXT epilogue overwrites, and every thread passes the named barrier after this wait.
               const bool issuer = (warp == kEpiWarp0 && lane == 0);
-              if (issuer) bulk_wait_read0();
-              named_bar_sync(3, kNumEpiThreads);
-              if (issuer && tile < P.ntiles && (!P.trunk || l == 8)) {
+              if (!(P.dbg_flags & 64)) {
+                if (issuer) bulk_wait_read0();
+                named_bar_sync(3, kNumEpiThreads);
+              }
+              if (issuer && tile < P.ntiles && (!P.trunk || l == 8) && !(P.dbg_flags & 32)) {
                 uint8_t* gimg = P.trunk ? P.stash_h + (size_t)tile * 65536 : P.stash_h + ((size_t)tile * 9 + l) * 65536;
                 bulk_s2g(gimg, sbase + kOffAct + t * kActBytes, 65536u);
                 bulk_commit_group();

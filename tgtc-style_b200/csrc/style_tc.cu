@@ -55,6 +55,15 @@ struct ChainParams {
   const uint8_t* img1;
   uint8_t* img_out;          // [ntiles][64 KB]
   float* rgbsigma;           // [M][4]: HEAD writes .xyz
+  int64_t img0_stride, img1_stride;   // bytes between consecutive tiles of img0 / img1
+  // training forward (kTrain): per-ray latents and the activation stash the style backward reads
+  const float* bias_rays;    // [n_rays][bias_ray_stride] effective biases of this module's layers (then the head's 3), per ray
+  int64_t bias_ray_stride;   // floats
+  uint8_t* stash;            // [ntiles][stash_layers][64 KB]: the post-ReLU output image of every layer
+  int stash_layers;
+  uint32_t* mask;            // [ntiles][mask_layers][8][128] ReLU mask words (common.cuh: TcStash.mask), this module at mask_slot0
+  int mask_layers, mask_slot0;
+  uint8_t* stash_pe;         // [ntiles][16 KB] positional-encoding tile image, or nullptr
 };
 
 constexpr int kOffAct = 0;
@@ -69,7 +78,8 @@ constexpr int kOffBars = kOffHeadPart + 128 * 4 * 4;
 constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarPeReady = 2 * kStages /*leader, count 8*/, kBarPeFree = kBarPeReady + 2,
               kBarActReady = kBarPeFree + 2, kBarAccFull = kBarActReady + 2, kBarAFull = kBarAccFull + 2 /*leader: both CTAs staged*/,
               kBarAFree = kBarAFull + 2, kBarOutDone = kBarAFree + 2, kBarOutFree = kBarOutDone + 2 /*leader*/,
-              kBarLoad = kBarOutFree + 2 /*mover's own bulk loads*/, kNumBars = kBarLoad + 2;
+              kBarLoad = kBarOutFree + 2 /*mover's own bulk loads*/, kBarSlotFree = kBarLoad + 2 /*training: store drained*/,
+              kNumBars = kBarSlotFree + 2;
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
@@ -80,6 +90,10 @@ __device__ __forceinline__ int64_t pair_tile(int64_t it, int t, uint32_t rank) {
 }
 __device__ __forceinline__ int seg_chunks(int s) { return s == SEG_PE ? 1 : 4; }
 
+
+// kTrain: the training forward of Style_train (train_tgtcs.py:311-483) -- per-ray latents (effective biases per ray from
+// global memory), every layer's output image and ReLU mask words stashed for the backward, the PE tile stashed once.
+template <bool kTrain>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_chain_kernel(const __grid_constant__ ChainParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -98,7 +112,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
       chunks_per_tile += seg_chunks(P.layer[l].seg[s]);
       imgs_per_tile += P.layer[l].seg[s] >= SEG_IMG0 ? 1 : 0;
     }
-  const bool has_out_img = P.layer[nl - 1].out == OUT_ACT_IMG;
+  const bool has_out_img = !kTrain && P.layer[nl - 1].out == OUT_ACT_IMG;
 
   if (threadIdx.x == 0) {
     if ((sbase & 1023u) != 0) { printf("tgtc mlp_chain: shared memory base not 1024-aligned\n"); __trap(); }
@@ -113,6 +127,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
       mbar_init(bar(kBarOutDone + t), kNumEpiThreads / 32);
       mbar_init(bar(kBarOutFree + t), 2);
       mbar_init(bar(kBarLoad + t), 1);
+      mbar_init(bar(kBarSlotFree + t), 1);
     }
     fence_barrier_init();
   }
@@ -122,7 +137,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
   }
   {
     float* dst = reinterpret_cast<float*>(smem + kOffBias);
-    for (int i = threadIdx.x; i < nl * 256; i += kNumThreads) dst[i] = P.bias[i];
+    if (!kTrain)
+      for (int i = threadIdx.x; i < nl * 256; i += kNumThreads) dst[i] = P.bias[i];
     if (P.head_w != nullptr) {
       float* hw = reinterpret_cast<float*>(smem + kOffHeadW);
       for (int i = threadIdx.x; i < 3 * 256; i += kNumThreads) hw[i] = P.head_w[i];
@@ -267,10 +283,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
           for (int a = 0; a < 3; ++a) fast_sincos(__fmul_rn(x[a], fr), &e[3 + 6 * f + a], &e[3 + 6 * f + 3 + a]);
         }
         e[63] = 0.f;
+        uint8_t* gpe = nullptr;
+        if constexpr (kTrain) {
+          if (P.stash_pe != nullptr && tile < P.ntiles) gpe = P.stash_pe + (size_t)tile * 16384 + (r >> 3) * 1024 + (r & 7) * 128;
+        }
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch)
-          st_shared_v4(prow + ((ch ^ (r & 7)) << 4), pack_bf16(e[8 * ch + 0], e[8 * ch + 1]), pack_bf16(e[8 * ch + 2], e[8 * ch + 3]),
-                       pack_bf16(e[8 * ch + 4], e[8 * ch + 5]), pack_bf16(e[8 * ch + 6], e[8 * ch + 7]));
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint32_t q0 = pack_bf16(e[8 * ch + 0], e[8 * ch + 1]), q1 = pack_bf16(e[8 * ch + 2], e[8 * ch + 3]),
+                         q2 = pack_bf16(e[8 * ch + 4], e[8 * ch + 5]), q3 = pack_bf16(e[8 * ch + 6], e[8 * ch + 7]);
+          st_shared_v4(prow + ((ch ^ (r & 7)) << 4), q0, q1, q2, q3);
+          if (gpe != nullptr) *reinterpret_cast<uint4*>(gpe + ((ch ^ (r & 7)) << 4)) = make_uint4(q0, q1, q2, q3);
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(leader_peready + 8u * t);
@@ -284,6 +307,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
       const uint32_t leader_outfree = mapa_cluster(bar(kBarOutFree), 0) + 8u * t;
       uint32_t afree_par = 0, od_par = 0, ld_par = 0;
       bool first_stage = true;
+      if (kTrain) mbar_arrive(bar(kBarSlotFree + t));   // the slot starts out free
       for (int64_t it = 0; it < iters; ++it) {
         const int64_t tile = pair_tile(it, t, rank);
         const bool tile_ok = tile < P.ntiles;
@@ -293,14 +317,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
             if (L.seg[s] < SEG_IMG0) continue;
             if (!first_stage) { mbar_wait(bar(kBarAFree + t), afree_par); afree_par ^= 1; }
             first_stage = false;
-            const uint8_t* src = (L.seg[s] == SEG_IMG0 ? P.img0 : P.img1) + (size_t)(tile_ok ? tile : 0) * 65536;
+            const uint8_t* src = L.seg[s] == SEG_IMG0 ? P.img0 + (size_t)(tile_ok ? tile : 0) * P.img0_stride
+                                                      : P.img1 + (size_t)(tile_ok ? tile : 0) * P.img1_stride;
             // one 64 KB bulk copy into act[t]; when it has landed here, tell the leader's MMA warp (it needs both CTAs' tiles)
             mbar_arrive_expect_tx(bar(kBarLoad + t), 65536u);
             bulk_g2s(sbase + kOffAct + t * kActBytes, src, 65536u, bar(kBarLoad + t));
             mbar_wait(bar(kBarLoad + t), ld_par); ld_par ^= 1;
             mbar_arrive_cluster(leader_afull);
           }
-          if (L.out == OUT_ACT_IMG) {
+          if constexpr (kTrain) {
+            // every layer's output image goes to the stash; the epilogue of the next layer waits for the store to have drained
+            mbar_wait(bar(kBarOutDone + t), od_par); od_par ^= 1;
+            if (tile_ok) {
+              bulk_s2g(P.stash + ((size_t)tile * P.stash_layers + l) * 65536, sbase + kOffAct + t * kActBytes, 65536u);
+              bulk_commit_group();
+            }
+            bulk_wait_read0();
+            mbar_arrive(bar(kBarSlotFree + t));
+          } else if (L.out == OUT_ACT_IMG) {
             mbar_wait(bar(kBarOutDone + t), od_par); od_par ^= 1;
             if (tile_ok) {
               bulk_s2g(P.img_out + (size_t)tile * 65536, sbase + kOffAct + t * kActBytes, 65536u);
@@ -323,7 +357,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
     float* part_s = reinterpret_cast<float*>(smem + kOffHeadPart);
     const uint32_t leader_actready = mapa_cluster(bar(kBarActReady), 0);
     const uint32_t rx = (uint32_t)(row & 7) << 4;
-    uint32_t acc_par[2] = {0, 0};
+    uint32_t acc_par[2] = {0, 0}, sf_par[2] = {0, 0};
     float hb[3] = {0.f, 0.f, 0.f};
     if (P.head_b != nullptr) { hb[0] = P.head_b[0]; hb[1] = P.head_b[1]; hb[2] = P.head_b[2]; }
     for (int64_t it = 0; it < iters; ++it) {
@@ -335,9 +369,46 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
           mbar_wait(bar(kBarAccFull + t), acc_par[t]); acc_par[t] ^= 1;
           tc_fence_after();
           const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 * t) + (uint32_t)(hc * 128);
-          const float* bl = bias_s + l * 256 + hc * 128;
           const uint32_t arow = sbase + kOffAct + t * kActBytes + (row >> 3) * 1024 + (row & 7) * 128 + hc * 2 * 16384;
           float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+          if constexpr (kTrain) {
+            // per-ray effective biases (the latent columns folded per ray); all 32 rows of a warp belong to one ray
+            const int64_t mc = m < P.M ? m : P.M - 1;
+            const float* bl = P.bias_rays + (mc / P.S) * P.bias_ray_stride + l * 256 + hc * 128;
+            uint32_t* mrow = tile < P.ntiles ? P.mask + (((size_t)tile * P.mask_layers + P.mask_slot0 + l) * 8 + hc * 4) * 128 + row : nullptr;
+            mbar_wait(bar(kBarSlotFree + t), sf_par[t]); sf_par[t] ^= 1;   // the previous image store has drained act[t]
+#pragma unroll 1
+            for (int blk = 0; blk < 4; ++blk) {
+              uint32_t v[32];
+              tmem_ld32(tcol + blk * 32, v);
+              tmem_ld_wait_dep(v);
+              const uint32_t kb = arow + (uint32_t)(blk >> 1) * 16384u;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(bl + blk * 32 + 4 * j));
+                add2(v[4 * j + 0], v[4 * j + 1], b.x, b.y);
+                add2(v[4 * j + 2], v[4 * j + 3], b.z, b.w);
+              }
+              if (mrow != nullptr) mrow[blk * 128] = sign_mask32(v);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (okind == OUT_HEAD) {
+                  const float* w = headw_s + hc * 128 + blk * 32 + 8 * j;
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const float h = fmaxf(__uint_as_float(v[8 * j + e]), 0.f);
+                    p0 = fmaf(h, w[e], p0);
+                    p1 = fmaf(h, w[256 + e], p1);
+                    p2 = fmaf(h, w[512 + e], p2);
+                  }
+                }
+                const uint32_t dst = kb + ((uint32_t)((((blk & 1) * 4) + j) << 4) ^ rx);
+                st_shared_v4(dst, pack_bf16_relu(v[8 * j + 0], v[8 * j + 1]), pack_bf16_relu(v[8 * j + 2], v[8 * j + 3]),
+                             pack_bf16_relu(v[8 * j + 4], v[8 * j + 5]), pack_bf16_relu(v[8 * j + 6], v[8 * j + 7]));
+              }
+            }
+          } else {
+          const float* bl = bias_s + l * 256 + hc * 128;
 #pragma unroll 1
           for (int blk = 0; blk < 4; ++blk) {
             uint32_t v[32];
@@ -368,11 +439,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
               }
             }
           }
+          }
           fence_proxy_async();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (okind == OUT_ACT_IMG) mbar_arrive(bar(kBarOutDone + t));   // local: the mover may store the tile image
+            if (kTrain || okind == OUT_ACT_IMG) mbar_arrive(bar(kBarOutDone + t));   // local: the mover may store the tile image
             mbar_arrive_cluster(leader_actready + 8u * t);
           }
           if (okind == OUT_HEAD) {
@@ -381,6 +453,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
             named_bar_sync(1, kNumEpiThreads);
             if (hc == 0 && m < P.M) {
               const float4 o = *reinterpret_cast<const float4*>(part_s + row * 4);
+              if constexpr (kTrain) {
+                const float* hbr = P.bias_rays + (m / P.S) * P.bias_ray_stride + nl * 256;
+                hb[0] = hbr[0]; hb[1] = hbr[1]; hb[2] = hbr[2];
+              }
               const float z0 = p0 + o.x + hb[0], z1 = p1 + o.y + hb[1], z2 = p2 + o.z + hb[2];
               float* dst = P.rgbsigma + m * 4;
               dst[0] = 1.0f / (1.0f + expf(-z0));
@@ -405,7 +481,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
 
 // ---------------------------------------------------------------------------
 // packing: one chunk = [256 rows x 64 K] bf16 SW128; value = W[n][col0 + k] for k < ncols else 0
-struct ChunkSrc { const float* W; int ld; int col0; int ncols; };
+// transposed chunks (the dgrad of style_bwd.cu): row n = input feature col0 + n, value = W[k0 + k][col0 + n] for k < ncols else 0
+struct ChunkSrc { const float* W; int ld; int col0; int ncols; int k0; int trans; };
 
 __global__ void pack_chunks_kernel(const ChunkSrc* __restrict__ table, int nchunks, __nv_bfloat16* __restrict__ out) {
   const size_t total = (size_t)nchunks * 256 * 64;
@@ -418,7 +495,9 @@ __global__ void pack_chunks_kernel(const ChunkSrc* __restrict__ table, int nchun
     const int n = grp * 8 + rr;
     const int k = c16 * 8 + within;
     const ChunkSrc s = table[chunk];
-    out[idx] = __float2bfloat16_rn(k < s.ncols ? s.W[(size_t)n * s.ld + s.col0 + k] : 0.f);
+    float v = 0.f;
+    if (k < s.ncols) v = s.trans ? s.W[(size_t)(s.k0 + k) * s.ld + s.col0 + n] : s.W[(size_t)n * s.ld + s.col0 + k];
+    out[idx] = __float2bfloat16_rn(v);
   }
 }
 
@@ -440,6 +519,38 @@ __global__ void style_latcopy_kernel(const LatSrc* __restrict__ table) {
   for (int j = threadIdx.x; j < s.nout; j += blockDim.x) s.bout[j] = s.b[j];
 }
 
+// training: effective biases per RAY.  lat1 [n_rays][32] = the module-1 latent of each ray (latents_model_1(style_id, frame_id));
+// module 2 sees mean(lat1) broadcast to 32 dims (train_tgtcs.py:376, :410).  out [n_rays][13][256]: module 1 layers 0..4,
+// module 2 layers 0..6, head (3 used).  wlat: 13 slots of [256][32] latent columns followed by [256] biases.
+__global__ void style_bias_rays_kernel(const float* __restrict__ wlat, const float* __restrict__ lat1, int64_t n_rays, float* __restrict__ out) {
+  __shared__ float lat[33];
+  const int64_t ray = blockIdx.x;
+  if (threadIdx.x < 32) lat[threadIdx.x] = lat1[ray * 32 + threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int k = 0; k < 32; ++k) s += lat[k];
+    lat[32] = s * (1.0f / 32.0f);
+  }
+  __syncthreads();
+  const int j = threadIdx.x;
+  for (int l = 0; l < 13; ++l) {
+    const float* w = wlat + (size_t)l * 256 * 33;
+    float acc = 0.f;
+    if (l < 12 || j < 3) {
+      acc = w[256 * 32 + j];
+      if (l < 5) {
+        for (int k = 0; k < 32; ++k) acc = fmaf(w[j * 32 + k], lat[k], acc);
+      } else {
+        float rs = 0.f;
+        for (int k = 0; k < 32; ++k) rs += w[j * 32 + k];
+        acc = fmaf(rs, lat[32], acc);
+      }
+    }
+    out[(ray * 13 + l) * 256 + j] = acc;
+  }
+}
+
 __global__ void head_copy_kernel(const float* __restrict__ W, int ld, float* __restrict__ out) {   // [3][256] <- W[3][ld][:256]
   for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) out[i] = W[(size_t)(i / 256) * ld + (i % 256)];
 }
@@ -453,6 +564,7 @@ static const int kCIn[5] = {95, 288, 288, 288, 351};
 static const int kWIn[8] = {607, 288, 288, 288, 351, 288, 288, 288};
 constexpr int kCChunks = 1 + 4 + 4 + 4 + 5;            // 18
 constexpr int kWChunks = 9 + 4 + 4 + 4 + 5 + 4 + 4;    // 34
+constexpr int kTChunks = 1 + 11 * 4;                    // 45: transposed chunks of the 12 dgrad GEMMs (style_bwd.cu)
 
 int style_set_weights(tgtc_ctx* ctx, const float* const* params, cudaStream_t st) {
   StyleImage& im = ctx->style;
@@ -464,34 +576,46 @@ int style_set_weights(tgtc_ctx* ctx, const float* const* params, cudaStream_t st
     TGTC_CUDA(cudaMalloc(&im.bias_w, 7 * 256 * sizeof(float)));
     TGTC_CUDA(cudaMalloc(&im.head_b, 4 * sizeof(float)));
     TGTC_CUDA(cudaMalloc(&im.latents, 64 * sizeof(float)));
-    TGTC_CUDA(cudaMalloc(&im.tables, 8192));
+    TGTC_CUDA(cudaMalloc(&im.blob_T, (size_t)kTChunks * 32768));
+    TGTC_CUDA(cudaMalloc(&im.tables, 16384));
     TGTC_CUDA(cudaMalloc(&im.wlat, 13 * 256 * 33 * sizeof(float)));   // per layer: [256][32] latent columns, then [256] bias
   }
   // chunk tables (consumption order, see the header comment)
   std::vector<ChunkSrc> tc, tw;
-  auto act4 = [](std::vector<ChunkSrc>& v, const float* W, int ld, int col0) { for (int k = 0; k < 4; ++k) v.push_back({W, ld, col0 + 64 * k, 64}); };
+  auto act4 = [](std::vector<ChunkSrc>& v, const float* W, int ld, int col0) { for (int k = 0; k < 4; ++k) v.push_back({W, ld, col0 + 64 * k, 64, 0, 0}); };
+  auto actT = [](std::vector<ChunkSrc>& v, const float* W, int ld, int col0) { for (int k = 0; k < 4; ++k) v.push_back({W, ld, col0, 64, 64 * k, 1}); };
   const float* const* C = params;        // concat module: (W,b) x 5
   const float* const* Wp = params + 10;  // wild module: (W,b) x 8
-  tc.push_back({C[0], 95, 0, 63});
+  tc.push_back({C[0], 95, 0, 63, 0, 0});
   for (int l = 1; l <= 3; ++l) act4(tc, C[2 * l], 288, 0);
-  tc.push_back({C[8], 351, 288, 63});                 // skip layer: [h(256), latent(32), x(63)] (models.py:141-144)
+  tc.push_back({C[8], 351, 288, 63, 0, 0});                 // skip layer: [h(256), latent(32), x(63)] (models.py:141-144)
   act4(tc, C[8], 351, 0);
-  tw.push_back({Wp[0], 607, 512, 63});                // layer 0: [base_remap(256), concat_features(256), x(63), latent(32)]
+  tw.push_back({Wp[0], 607, 512, 63, 0, 0});                // layer 0: [base_remap(256), concat_features(256), x(63), latent(32)]
   act4(tw, Wp[0], 607, 0);
   act4(tw, Wp[0], 607, 256);
   for (int l = 1; l <= 3; ++l) act4(tw, Wp[2 * l], 288, 0);
-  tw.push_back({Wp[8], 351, 288, 63});
+  tw.push_back({Wp[8], 351, 288, 63, 0, 0});
   act4(tw, Wp[8], 351, 0);
   act4(tw, Wp[10], 288, 0);
   act4(tw, Wp[12], 288, 0);
-  TGTC_REQUIRE((int)tc.size() == kCChunks && (int)tw.size() == kWChunks, TGTC_ERR_STATE, "style chunk tables inconsistent");
+  // transposed chunks, in the order the style dgrad consumes them: head, W6..W1, W0 (concat_features columns), C4..C1
+  std::vector<ChunkSrc> tt;
+  tt.push_back({Wp[14], 288, 0, 3, 0, 1});
+  for (int l = 6; l >= 1; --l) actT(tt, Wp[2 * l], kWIn[l], 0);
+  actT(tt, Wp[0], 607, 256);
+  for (int l = 4; l >= 1; --l) actT(tt, C[2 * l], kCIn[l], 0);
+  TGTC_REQUIRE((int)tc.size() == kCChunks && (int)tw.size() == kWChunks && (int)tt.size() == kTChunks, TGTC_ERR_STATE,
+               "style chunk tables inconsistent");
   ChunkSrc* dtab = reinterpret_cast<ChunkSrc*>(im.tables);
   TGTC_CUDA(cudaMemcpyAsync(dtab, tc.data(), tc.size() * sizeof(ChunkSrc), cudaMemcpyHostToDevice, st));
   TGTC_CUDA(cudaMemcpyAsync(dtab + 64, tw.data(), tw.size() * sizeof(ChunkSrc), cudaMemcpyHostToDevice, st));
+  TGTC_CUDA(cudaMemcpyAsync(dtab + 128, tt.data(), tt.size() * sizeof(ChunkSrc), cudaMemcpyHostToDevice, st));
   TGTC_CUDA(cudaStreamSynchronize(st));   // the host vectors go out of scope
   pack_chunks_kernel<<<ctx->num_sms * 2, 256, 0, st>>>(dtab, kCChunks, reinterpret_cast<__nv_bfloat16*>(im.blob_c));
   TGTC_LAUNCH_CHECK(ctx);
   pack_chunks_kernel<<<ctx->num_sms * 2, 256, 0, st>>>(dtab + 64, kWChunks, reinterpret_cast<__nv_bfloat16*>(im.blob_w));
+  TGTC_LAUNCH_CHECK(ctx);
+  pack_chunks_kernel<<<ctx->num_sms * 2, 256, 0, st>>>(dtab + 128, kTChunks, reinterpret_cast<__nv_bfloat16*>(im.blob_T));
   TGTC_LAUNCH_CHECK(ctx);
   head_copy_kernel<<<1, 256, 0, st>>>(Wp[14], 288, im.head_w);
   TGTC_LAUNCH_CHECK(ctx);
@@ -510,9 +634,9 @@ int style_set_weights(tgtc_ctx* ctx, const float* const* params, cudaStream_t st
     tl.push_back({Wp[2 * l], Wp[2 * l + 1], kWIn[l], wlat0[l], nout, slot(5 + l), slot(5 + l) + 256 * 32});
     tb.push_back({slot(5 + l), slot(5 + l) + 256 * 32, nout, im.latents + 32, l < 7 ? im.bias_w + l * 256 : im.head_b});
   }
-  static_assert(sizeof(ChunkSrc) == 24 && 128 * sizeof(ChunkSrc) + 13 * (sizeof(BiasSrc) + sizeof(LatSrc)) <= 8192, "style tables do not fit");
-  LatSrc* dlat = reinterpret_cast<LatSrc*>(im.tables + 128 * sizeof(ChunkSrc));
-  BiasSrc* dbias = reinterpret_cast<BiasSrc*>(im.tables + 128 * sizeof(ChunkSrc) + 13 * sizeof(LatSrc));
+  static_assert(sizeof(ChunkSrc) == 32 && 192 * sizeof(ChunkSrc) + 13 * (sizeof(BiasSrc) + sizeof(LatSrc)) <= 16384, "style tables do not fit");
+  LatSrc* dlat = reinterpret_cast<LatSrc*>(im.tables + 192 * sizeof(ChunkSrc));
+  BiasSrc* dbias = reinterpret_cast<BiasSrc*>(im.tables + 192 * sizeof(ChunkSrc) + 13 * sizeof(LatSrc));
   TGTC_CUDA(cudaMemcpyAsync(dlat, tl.data(), tl.size() * sizeof(LatSrc), cudaMemcpyHostToDevice, st));
   TGTC_CUDA(cudaMemcpyAsync(dbias, tb.data(), tb.size() * sizeof(BiasSrc), cudaMemcpyHostToDevice, st));
   style_latcopy_kernel<<<13, 256, 0, st>>>(dlat);
@@ -538,18 +662,21 @@ static void fill_common(ChainParams& P, const MlpIO& io) {
   P.t_scale = io.t_scale; P.t_near = io.t_near; P.S = io.S;
   P.M = io.n_rays * io.S;
   P.ntiles = (P.M + kTileM - 1) / kTileM;
+  P.img0_stride = P.img1_stride = 65536;
 }
 
-static int launch_chain(tgtc_ctx* ctx, const ChainParams& P, cudaStream_t st) {
+static int launch_chain(tgtc_ctx* ctx, const ChainParams& P, cudaStream_t st, bool train = false) {
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
-    TGTC_CUDA(cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    TGTC_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    TGTC_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set[ctx->device & 63] = true;
   }
   const int64_t nquads = (P.ntiles + 3) / 4;
   const int64_t max_pairs = ctx->num_sms / 2;
   const int grid = 2 * (int)(nquads < max_pairs ? nquads : max_pairs);
-  mlp_chain_kernel<<<grid, kNumThreads, kSmemBytes, st>>>(P);
+  if (train) mlp_chain_kernel<true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
+  else mlp_chain_kernel<false><<<grid, kNumThreads, kSmemBytes, st>>>(P);
   TGTC_LAUNCH_CHECK(ctx);
   return TGTC_OK;
 }
@@ -588,4 +715,52 @@ int launch_style_wild(tgtc_ctx* ctx, const MlpIO& io, const uint8_t* remap_img, 
   P.img1 = cf_img;
   P.rgbsigma = io.rgbsigma;
   return launch_chain(ctx, P, st);
+}
+
+// ---------------------------------------------------------------------------
+// training forward (Style_train): per-ray latents, stash for the backward
+int launch_style_bias_rays(tgtc_ctx* ctx, const float* lat1, int64_t n_rays, float* bias_rays, cudaStream_t st) {
+  if (n_rays == 0) return TGTC_OK;
+  style_bias_rays_kernel<<<(unsigned)n_rays, 256, 0, st>>>(ctx->style.wlat, lat1, n_rays, bias_rays);
+  TGTC_LAUNCH_CHECK(ctx);
+  return TGTC_OK;
+}
+
+int launch_style_concat_train(tgtc_ctx* ctx, const MlpIO& io, const float* bias_rays, const StyleStash& stash, cudaStream_t st) {
+  if (io.n_rays == 0) return TGTC_OK;
+  ChainParams P = {};
+  fill_common(P, io);
+  P.nlayers = 5;
+  P.layer[0] = {{SEG_PE, 0, 0}, 1, OUT_ACT, 0};
+  for (int l = 1; l <= 3; ++l) P.layer[l] = {{SEG_ACT, 0, 0}, 1, OUT_ACT, 0};
+  P.layer[4] = {{SEG_PE, SEG_ACT, 0}, 2, OUT_ACT_IMG, 1};
+  P.blob = ctx->style.blob_c;
+  P.bias_rays = bias_rays; P.bias_ray_stride = 13 * 256;
+  P.stash = stash.c; P.stash_layers = 5;
+  P.mask = stash.mask; P.mask_layers = kStyleMaskLayers; P.mask_slot0 = 7;
+  P.stash_pe = stash.pe;
+  return launch_chain(ctx, P, st, true);
+}
+
+int launch_style_wild_train(tgtc_ctx* ctx, const MlpIO& io, const float* bias_rays, const uint8_t* remap_img, const StyleStash& stash,
+                            cudaStream_t st) {
+  if (io.n_rays == 0) return TGTC_OK;
+  ChainParams P = {};
+  fill_common(P, io);
+  P.nlayers = 7;
+  P.layer[0] = {{SEG_PE, SEG_IMG0, SEG_IMG1}, 3, OUT_ACT, 0};
+  for (int l = 1; l <= 3; ++l) P.layer[l] = {{SEG_ACT, 0, 0}, 1, OUT_ACT, 0};
+  P.layer[4] = {{SEG_PE, SEG_ACT, 0}, 2, OUT_ACT, 1};
+  P.layer[5] = {{SEG_ACT, 0, 0}, 1, OUT_ACT, 0};
+  P.layer[6] = {{SEG_ACT, 0, 0}, 1, OUT_HEAD, 0};
+  P.blob = ctx->style.blob_w;
+  P.head_w = ctx->style.head_w;
+  P.bias_rays = bias_rays + 5 * 256; P.bias_ray_stride = 13 * 256;
+  P.img0 = remap_img;
+  P.img1 = stash.c + 4 * 65536;            // concat_features = the last image of module 1's stash
+  P.img1_stride = 5 * 65536;
+  P.stash = stash.w; P.stash_layers = 7;
+  P.mask = stash.mask; P.mask_layers = kStyleMaskLayers; P.mask_slot0 = 0;
+  P.rgbsigma = io.rgbsigma;
+  return launch_chain(ctx, P, st, true);
 }

@@ -207,5 +207,48 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 }
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
 
+__device__ __forceinline__ void st_global_v4(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
+}
+// ReLU mask word of 32 fp32 pre-activations: bit (31-c) = sign bit of v[c] (1 = the gradient is blocked)
+__device__ __forceinline__ uint32_t sign_mask32(const uint32_t (&v)[32]) {
+  uint32_t m = 0u;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) m = __funnelshift_l(v[c], m, 1);
+  return m;
+}
+// two fp32 gradients -> bf16 pair, zeroed where the ReLU blocked them: bit 31 of mb belongs to lo, bit 30 to hi (1 = blocked)
+__device__ __forceinline__ uint32_t mask_pack(uint32_t mb, float lo, float hi) {
+  const float l = (int32_t)mb < 0 ? 0.f : lo;
+  const float h = (int32_t)(mb << 1) < 0 ? 0.f : hi;
+  return pack_bf16(l, h);
+}
+
+// ---- cta_group::1 MMAs with MN-major operands (weight-gradient kernels: K = samples)
+// MN-major, 128B-swizzled operand descriptor: 64-feature atoms 8 KB apart (LBO), 8-sample row groups 1 KB apart (SBO)
+__device__ __forceinline__ uint32_t mn_desc_hi() { return (1024u >> 4) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ uint32_t mn_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+__host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {   // both operands MN-major (bits 15, 16)
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma1_bf16(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma1_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
 
 }  // namespace tcptx

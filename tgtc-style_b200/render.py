@@ -439,6 +439,63 @@ class NerfRenderer:
                                             ctypes.c_void_p(ws.data_ptr() + off), wsb, self._stream))
         return {"loss": sums.sum() / (3.0 * n_total), "grads": grads, "rgb_coarse": rgb_c, "rgb_fine": rgb_f}
 
+    # ------------------------------------------------------------------ Style_train (train_tgtcs.py:311-495)
+    def style_train_forward(self, rays_o, rays_d, latents, near=0., far=1., n_samples=64, n_fine=64, rand=None, noise_coarse=None,
+                            noise_fine=None, workspace=None):
+        """Forward of one Style_train batch (train_tgtcs.py:404-479): frozen NeRF nets, both style modules with per-ray
+        latents [N,32], stratified positions replaying `rand` [N,S] (perturb=True) -> {"rgb_coarse", "rgb_fine"} plus an
+        opaque "state" for style_train_backward (the activation stash lives in `workspace`, a uint8 device tensor; by default
+        one owned by this call's state -- use separate workspaces for batches whose backward passes are both pending)."""
+        self.refresh_weights()
+        ro, rd = self._dev(rays_o), self._dev(rays_d)
+        lat = self._dev(latents).contiguous()
+        n = ro.shape[0]
+        if tuple(lat.shape) != (n, 32):
+            raise ValueError("latents must be [N,32]")
+        wsb = self.lib.tgtc_style_train_workspace_bytes(self._h, n, n_samples, n_fine)
+        ws = workspace if workspace is not None else torch.empty(int(wsb) + 1024, dtype=torch.uint8, device=self.device)
+        if ws.numel() < wsb + 1024:
+            raise ValueError("workspace needs %d bytes" % (wsb + 1024))
+        off = (-ws.data_ptr()) % 1024
+        rnd = self._dev(rand) if rand is not None else None
+        nzc = self._dev(noise_coarse) if noise_coarse is not None else None
+        nzf = self._dev(noise_fine) if noise_fine is not None else None
+        rgb_c = torch.empty(n, 3, dtype=torch.float32, device=self.device)
+        rgb_f = torch.empty(n, 3, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.tgtc_style_train_forward(self._h, _ptr(ro), _ptr(rd), n, float(near), float(far), n_samples, n_fine, _ptr(lat),
+                                                     _ptr(rnd), _ptr(nzc), _ptr(nzf), _ptr(rgb_c), _ptr(rgb_f),
+                                                     ctypes.c_void_p(ws.data_ptr() + off), wsb, self._stream))
+        state = dict(n=n, S=n_samples, F=n_fine, lat=lat, rand=rnd, nzc=nzc, nzf=nzf, ws=ws, off=off, wsb=wsb)
+        return {"rgb_coarse": rgb_c, "rgb_fine": rgb_f, "state": state}
+
+    def style_train_backward(self, state, d_rgb_coarse, d_rgb_fine, grads=None, accumulate=False):
+        """Backward of the batch `state` came from: dL/d rgb_coarse, dL/d rgb_fine [N,3] -> {"grads": flat fp32
+        [tgtc_style_num_params()] in set_style_weights order, "d_latents": [N,32]}."""
+        gc, gf = self._dev(d_rgb_coarse).contiguous(), self._dev(d_rgb_fine).contiguous()
+        P = int(self.lib.tgtc_style_num_params())
+        if grads is None:
+            grads = torch.empty(P, dtype=torch.float32, device=self.device)
+            accumulate = False
+        dlat = torch.empty(state["n"], 32, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.tgtc_style_train_backward(self._h, state["n"], state["S"], state["F"], _ptr(state["lat"]),
+                                                      int(state["rand"] is not None), _ptr(state["nzc"]), _ptr(state["nzf"]), _ptr(gc),
+                                                      _ptr(gf), _ptr(grads), int(accumulate), _ptr(dlat),
+                                                      ctypes.c_void_p(state["ws"].data_ptr() + state["off"]), state["wsb"], self._stream))
+        return {"grads": grads, "d_latents": dlat}
+
+    def style_grad_views(self, flat):
+        """Per-parameter views into a flat style gradient buffer: (concat-module dict, wild-module dict), state_dict keys."""
+        out, o = [], 0
+        for shapes in (self.STYLE_C_SHAPES, self.STYLE_W_SHAPES):
+            d = {}
+            for i, (no, ni) in enumerate(shapes):
+                d["layers.%d.weight" % i] = flat[o:o + no * ni].view(no, ni)
+                o += no * ni
+                d["layers.%d.bias" % i] = flat[o:o + no]
+                o += no
+            out.append(d)
+        return tuple(out)
+
     def adam_step(self, params, grads, exp_avg, exp_avg_sq, step, lr=5e-4, betas=(0.9, 0.999), eps=1e-8):
         """torch.optim.Adam's update (train_tgtcs.py:39) on flat fp32 device buffers, one kernel (tgtc_adam_step)."""
         n = params.numel()
