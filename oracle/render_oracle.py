@@ -446,21 +446,9 @@ def render_style_chain(sd_coarse, sd_fine, sd_concat, sd_wild, rays_o, rays_d, l
     return out
 
 
-def style_train_forward_backward(sd_coarse, sd_fine, sd_concat, sd_wild, rays_o, rays_d, latents, g_rgb_coarse, g_rgb_fine, near=0., far=1.,
-                                 n_samples=64, n_fine=64, rand=None):
-    """One batch of Style_train (train_tgtcs.py:354-483) through torch.autograd: the forward of render_style_chain with
-    per-ray latents [N,32] (latents_model_1 output, train_tgtcs.py:409) and stratified positions from `rand`
-    (perturb=True, train_tgtcs.py:362), then the vector-Jacobian product of (rgb_coarse, rgb_fine) with the given
-    upstream gradients -- i.e. what loss.backward() sends into the two style modules and the latents for any loss built
-    on the two rgb maps (train_tgtcs.py:425, :480-483).  The NeRF nets are constants (style_optimizer does not hold
-    them, train_tgtcs.py:54); no gradient flows through the resampling (utils.py:576-579).
-    Returns (rgb_coarse, rgb_fine, grads_concat, grads_wild, d_latents)."""
-    ro = torch.as_tensor(rays_o, dtype=torch.float32)
-    rd = torch.as_tensor(rays_d, dtype=torch.float32)
+def _style_forward_diff(sd_coarse, sd_fine, pc, pw, ro, rd, lat, near, far, n_samples, n_fine, rand):
+    """Differentiable (w.r.t. pc, pw, lat) forward of one Style_train batch; NeRF nets constant, resampling detached."""
     n = ro.shape[0]
-    pc = {k: v.detach().clone().requires_grad_(True) for k, v in sd_concat.items()}
-    pw = {k: v.detach().clone().requires_grad_(True) for k, v in sd_wild.items()}
-    lat = torch.as_tensor(latents, dtype=torch.float32).detach().clone().requires_grad_(True)
     lat2 = torch.mean(lat, dim=1, keepdim=True)          # train_tgtcs.py:410
 
     def one_pass(sd_nerf, pts, S):
@@ -478,6 +466,73 @@ def style_train_forward_backward(sd_coarse, sd_fine, sd_concat, sd_wild, rays_o,
     pts_f, ts_f = sample_fine(ro, rd, ts, w_c.detach(), n_fine)
     ret_f, rgb_sf = one_pass(sd_fine, pts_f.detach(), n_samples + n_fine)
     rgb_f = alpha_composition(rgb_sf, ret_f["sigma"], ts_f)[0]
+    return rgb_c, rgb_f
+
+
+def style_train_forward_backward(sd_coarse, sd_fine, sd_concat, sd_wild, rays_o, rays_d, latents, g_rgb_coarse, g_rgb_fine, near=0., far=1.,
+                                 n_samples=64, n_fine=64, rand=None):
+    """One batch of Style_train (train_tgtcs.py:354-483) through torch.autograd: the forward of render_style_chain with
+    per-ray latents [N,32] (latents_model_1 output, train_tgtcs.py:409) and stratified positions from `rand`
+    (perturb=True, train_tgtcs.py:362), then the vector-Jacobian product of (rgb_coarse, rgb_fine) with the given
+    upstream gradients -- i.e. what loss.backward() sends into the two style modules and the latents for any loss built
+    on the two rgb maps (train_tgtcs.py:425, :480-483).  The NeRF nets are constants (style_optimizer does not hold
+    them, train_tgtcs.py:54); no gradient flows through the resampling (utils.py:576-579).
+    Returns (rgb_coarse, rgb_fine, grads_concat, grads_wild, d_latents)."""
+    ro = torch.as_tensor(rays_o, dtype=torch.float32)
+    rd = torch.as_tensor(rays_d, dtype=torch.float32)
+    pc = {k: v.detach().clone().requires_grad_(True) for k, v in sd_concat.items()}
+    pw = {k: v.detach().clone().requires_grad_(True) for k, v in sd_wild.items()}
+    lat = torch.as_tensor(latents, dtype=torch.float32).detach().clone().requires_grad_(True)
+    rgb_c, rgb_f = _style_forward_diff(sd_coarse, sd_fine, pc, pw, ro, rd, lat, near, far, n_samples, n_fine, rand)
     obj = (rgb_c * torch.as_tensor(g_rgb_coarse, dtype=torch.float32)).sum() + (rgb_f * torch.as_tensor(g_rgb_fine, dtype=torch.float32)).sum()
     obj.backward()
     return (rgb_c.detach(), rgb_f.detach(), {k: v.grad for k, v in pc.items()}, {k: v.grad for k, v in pw.items()}, lat.grad)
+
+
+def _cos_rows(a, b):
+    """VGGNet.cosine_similarity (VGGNet.py:204-210)."""
+    an = a / (torch.norm(a, dim=1, keepdim=True) + 1e-8)
+    bn = b / (torch.norm(b, dim=1, keepdim=True) + 1e-8)
+    return torch.sum(an * bn, dim=1)
+
+
+def style_train_step_reference(sd_coarse, sd_fine, sd_concat, sd_wild, lat_table, mu, logvar, batch, coh_batch, prev, frame_num,
+                               rgb_loss_lambda=1.0, logp_lambda=0.1, loss_coh_lambda=1e2, dataset_type="llff", near=0., far=1.):
+    """Loss and gradients of one Style_train iteration (train_tgtcs.py:354-495) with the previous loss_coh batch's maps
+    `prev` = (x, y, x_origin) as constants (or None: no coherence term).  batch / coh_batch: dicts with rays_o, rays_d,
+    rgb_gt, style_id, frame_id, rand (+ rgb_origin).  lat_table [style_num, frame_num, 32]; forward and minus_logp of
+    models.StyleLatents_variational (models.py:490-506, :531-537) with sigma_scale = 1.
+    Returns (losses dict, grads_concat, grads_wild, d lat_table)."""
+    pc = {k: v.detach().clone().requires_grad_(True) for k, v in sd_concat.items()}
+    pw = {k: v.detach().clone().requires_grad_(True) for k, v in sd_wild.items()}
+    tab = torch.as_tensor(lat_table, dtype=torch.float32).detach().clone().requires_grad_(True)
+
+    def lat_of(sid, fid):
+        t = tab.reshape(-1, tab.shape[-1])
+        if dataset_type == "llff":
+            t = t.repeat((7, 1))
+        m = mu[sid]
+        return m + 1.0 * (t[sid * frame_num + fid] - m)
+
+    def fwd(b):
+        ro = torch.as_tensor(b["rays_o"], dtype=torch.float32)
+        rd = torch.as_tensor(b["rays_d"], dtype=torch.float32)
+        return _style_forward_diff(sd_coarse, sd_fine, pc, pw, ro, rd, lat_of(b["style_id"], b["frame_id"]), near, far, 64, 64, b["rand"])
+
+    rgb_c, rgb_f = fwd(batch)
+    gt = batch["rgb_gt"]
+    loss_rgb = rgb_loss_lambda * (torch.mean((rgb_c - gt) ** 2) + torch.mean((rgb_f - gt) ** 2))
+    lat = lat_of(batch["style_id"], batch["frame_id"])
+    loss_logp = logp_lambda * torch.sum((lat - mu[batch["style_id"]]) ** 2 / (torch.exp(0.5 * logvar[batch["style_id"]]) + 1e-3), -1).mean()
+    loss_coh = torch.zeros(())
+    if coh_batch is not None and prev is not None:
+        c2, f2 = fwd(coh_batch)
+        x, y, x_org = prev
+        org2 = coh_batch["rgb_origin"]
+        l2 = lambda v: torch.sqrt(torch.sum(v ** 2) + 1e-8)          # utils.py:459
+        # train_tgtcs.py:401 / :456 -- the fine term compares with x_origin AFTER line 403 replaced it by this batch's originals
+        loss_coh = l2(_cos_rows(c2, x) - _cos_rows(org2, x_org)) + l2(_cos_rows(f2, y) - _cos_rows(org2, org2))
+    loss = loss_rgb + loss_logp + loss_coh_lambda * loss_coh
+    loss.backward()
+    losses = {"loss": loss.detach(), "loss_rgb": loss_rgb.detach(), "loss_logp": loss_logp.detach(), "loss_coh": loss_coh.detach()}
+    return losses, {k: v.grad for k, v in pc.items()}, {k: v.grad for k, v in pw.items()}, tab.grad

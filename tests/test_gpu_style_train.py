@@ -102,3 +102,63 @@ def test_style_train_rejects_bad_arguments(renderer_bf16):
         r.style_train_forward(ro, rd, lat[:10])
     with pytest.raises(Exception):
         r.style_train_forward(ro, rd, lat, n_samples=32)
+
+
+def _batch(ro, rd, idx, style_num, frame_num, g, origin=False):
+    n = len(idx)
+    idx = idx.numpy()
+    b = {"rays_o": torch.from_numpy(ro[idx]), "rays_d": torch.from_numpy(rd[idx]), "rgb_gt": torch.rand(n, 3, generator=g),
+         "style_id": torch.randint(0, style_num, (n,), generator=g), "frame_id": torch.randint(0, frame_num, (n,), generator=g),
+         "rand": torch.rand(n, 64, generator=g)}
+    if origin:
+        b["rgb_origin"] = torch.rand(n, 3, generator=g)
+    return b
+
+
+def test_style_trainer_step_vs_oracle(renderer_bf16):
+    """Two StyleTrainer iterations (train_tgtcs.py:354-495): the second one carries the coherence term against the first one's
+    maps.  Losses, style-module gradients and the gradient of the latent table against torch.autograd through the oracle."""
+    import tgtc_style_b200 as T
+    r = renderer_bf16
+    (wc, wf, cs, ws), ro, rd, _, _, _, _ = _inputs(8)
+    ro_all, rd_all = small_rays()
+    r.set_weights(wc, wf)
+    g = torch.Generator().manual_seed(21)
+    style_num, frame_num, n = 2, 5, 128
+    table = torch.randn(style_num, frame_num, 32, generator=g) * 0.5
+    mu, logvar = torch.randn(style_num, 32, generator=g) * 0.3, torch.randn(style_num, 32, generator=g) * 0.2
+    dev = r.device
+    lat = T.StyleLatents(table.to(dev), mu.to(dev), logvar.to(dev), dataset_type="llff")
+    tr = T.StyleTrainer(r, cs, ws, lat, lr=5e-4, loss_coh_lambda=1e2, frame_num=frame_num)
+    to_dev = lambda b: {k: v.to(dev) for k, v in b.items()}
+    perm = torch.randperm(ro_all.shape[0], generator=g)
+    b1, c1 = _batch(ro_all, rd_all, perm[:n], style_num, frame_num, g), _batch(ro_all, rd_all, perm[n:2 * n], style_num, frame_num, g, True)
+    out1 = tr.step(to_dev(b1), to_dev(c1))
+    assert out1["loss_coh"].item() == 0.0 and tr.prev is not None          # cnt == 0: no coherence term yet (train_tgtcs.py:400)
+    # second iteration: oracle on the trainer's current parameters / latent table / previous maps
+    sdc, sdw = (dict((k, v.cpu().clone()) for k, v in d.items()) for d in tr.state_dicts())
+    tab = lat.latents.detach().cpu().clone()
+    prev = tuple(t.cpu() for t in tr.prev)
+    b2, c2 = _batch(ro_all, rd_all, perm[2 * n:3 * n], style_num, frame_num, g), _batch(ro_all, rd_all, perm[3 * n:4 * n], style_num, frame_num, g, True)
+    losses, gcs, gws, gtab = O.style_train_step_reference(wc, wf, sdc, sdw, tab, mu, logvar, b2, c2, prev, frame_num, loss_coh_lambda=1e2)
+    out2 = tr.step(to_dev(b2), to_dev(c2))
+    torch.cuda.synchronize()
+    for k in ("loss_rgb", "loss_logp", "loss_coh", "loss"):
+        a, b = out2[k].item(), losses[k].item()
+        print("%-9s ours %.6f oracle %.6f" % (k, a, b))
+        assert abs(a - b) <= 2e-2 * max(abs(b), 1e-3), (k, a, b)
+    assert out2["loss_coh"].item() > 0.0
+    ours_c, ours_w = r.style_grad_views(tr.grads)
+    for ref, ours, tag in ((gcs, ours_c, "concat"), (gws, ours_w, "wild")):
+        for k, gr in ref.items():
+            a, b = ours[k].cpu().double().flatten(), gr.double().flatten()
+            rel = ((a - b).norm() / (b.norm() + 1e-30)).item()
+            cos = (torch.dot(a, b) / (a.norm() * b.norm() + 1e-30)).item()
+            assert rel <= 0.15 and cos >= 0.99, (tag, k, rel, cos)
+    a, b = lat.latents.grad.cpu().double().flatten(), gtab.double().flatten()
+    rel, cos = ((a - b).norm() / b.norm()).item(), (torch.dot(a, b) / (a.norm() * b.norm())).item()
+    print("latent table grad rel %.3e cos %.5f" % (rel, cos))
+    assert rel <= 0.1 and cos >= 0.995
+    # the step moved the parameters and the table
+    assert not torch.equal(lat.latents.detach().cpu(), tab)
+    assert not torch.equal(tr.state_dicts()[1]["layers.7.weight"].cpu(), sdw["layers.7.weight"])

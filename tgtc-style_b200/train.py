@@ -106,3 +106,155 @@ class NerfTrainer:
 
     def state_dicts(self):
         return tuple({k: p.detach() for k, p in d.items()} for d in self.params)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Style_train (train_tgtcs.py:311-495): second training phase -- the two style modules and the per-(style, frame) latents
+# learn on frozen NeRF nets.
+
+def cosine_similarity_rows(a, b):
+    """VGGNet.cosine_similarity (VGGNet.py:204-210): per-row cosine of two [N,3] maps."""
+    an = a / (torch.norm(a, dim=1, keepdim=True) + 1e-8)
+    bn = b / (torch.norm(b, dim=1, keepdim=True) + 1e-8)
+    return torch.sum(an * bn, dim=1)
+
+
+def l2_norm(x):
+    """utils.L2_norm (utils.py:459)."""
+    return torch.sqrt(torch.sum(x ** 2) + 1e-8)
+
+
+class StyleLatents:
+    """Host mirror of models.StyleLatents_variational (models.py:475-549): a [style_num, frame_num, 32] table of latents, per-style
+    mu / logvar, `forward` = mu + sigma_scale * (latents[id] - mu), `minus_logp`, Adam(lr=1e-3) on the table.  Tiny tensors:
+    plain torch on the device (plumbing); the per-ray latents it returns feed tgtc_style_train_forward."""
+
+    def __init__(self, latents, mu, logvar, dataset_type="llff", sigma_scale=1.0, lr=1e-3):
+        self.latents = latents.detach().clone().requires_grad_(True)
+        self.mu, self.logvar = mu.detach(), logvar.detach()
+        self.frame_num = latents.shape[1]
+        self.dataset_type = dataset_type
+        self.sigma_scale = sigma_scale
+        self.opt = torch.optim.Adam([self.latents], lr=lr)          # models.py:541-542
+
+    def __call__(self, style_ids, frame_ids):
+        flat = style_ids * self.frame_num + frame_ids
+        tab = self.latents.reshape(-1, self.latents.shape[-1])
+        if self.dataset_type == "llff":
+            tab = tab.repeat((7, 1))                                 # models.py:496 (SURVEY App. D)
+        mu = self.mu[style_ids]
+        return mu + self.sigma_scale * (tab[flat] - mu)              # models.py:506
+
+    def minus_logp(self, style_ids, frame_ids):
+        lat = self(style_ids, frame_ids)
+        mu, logvar = self.mu[style_ids], self.logvar[style_ids]
+        return torch.sum((lat - mu) ** 2 / (torch.exp(0.5 * logvar) + 1e-3), -1).mean()   # models.py:531-537
+
+
+class StyleTrainer:
+    """One Style_train iteration (train_tgtcs.py:354-495) per `step`:
+         batch 2 (the loss_coh batch, unshuffled) and batch 1 (shuffled): forward of the frozen NeRF nets + both style modules
+         with per-ray latents and perturbed samples (tgtc_style_train_forward), compositing, resampling, fine pass;
+         loss = lambda_rgb (mse(coarse) + mse(fine)) + lambda_logp(step) * minus_logp  [+ lambda_coh * loss_coh];
+         backward into the style modules (tgtc_style_train_backward) and the latents; Adam on both.
+    The per-ray losses on the [N,3] maps are evaluated with torch on the device and differentiated there; everything
+    per-sample runs in the CUDA library.  Two deviations from the reference loop, both forced by it not running as written on
+    torch >= 1.5 (it backpropagates twice through a graph whose weights the first optimizer step modified in place, and
+    through the previous iteration's graph via `x` / `y`): the previous batch's maps enter loss_coh as constants, and one
+    backward serves both optimizers."""
+
+    def __init__(self, renderer, concat_style, style, latents, lr=5e-4, rgb_loss_lambda=1.0, logp_loss_lambda=0.1, logp_loss_decay=1.0,
+                 loss_coh_lambda=1e2, origin_step=0, frame_num=None, sigma_noise_std=0.0, group=None):
+        self.r = renderer
+        self.group = group
+        self.lat = latents
+        dev = renderer.device
+        P = int(renderer.lib.tgtc_style_num_params())
+        self.flat = torch.zeros(P, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.params = renderer.style_grad_views(self.flat)
+        for src, views in zip((concat_style, style), self.params):
+            sd = src.state_dict() if hasattr(src, "state_dict") else src
+            for k in views:
+                views[k].copy_(sd[k].detach().to(dev, torch.float32))
+        self.lr = lr
+        self.lam_rgb, self.lam_logp, self.logp_decay, self.lam_coh = rgb_loss_lambda, logp_loss_lambda, logp_loss_decay, loss_coh_lambda
+        self.origin_step = origin_step
+        self.frame_num = frame_num if frame_num is not None else latents.frame_num
+        self.noise_std = sigma_noise_std
+        self.step_count = 0
+        self.cnt = 0                       # the reference's `cnt` (train_tgtcs.py:347)
+        self.prev = None                   # (x, y, x_origin): previous loss_coh batch's coarse / fine maps and its originals
+        self.r.set_style_weights(*self.params)
+
+    def _forward(self, rays_o, rays_d, lat, rand=None):
+        n = rays_o.shape[0]
+        if rand is None:
+            rand = torch.rand(n, 64, device=rays_o.device)           # perturb=True (train_tgtcs.py:362)
+        nzc = nzf = None
+        if self.noise_std > 0:
+            nzc = torch.randn(n, 64, device=rays_o.device) * self.noise_std
+            nzf = torch.randn(n, 128, device=rays_o.device) * self.noise_std
+        return self.r.style_train_forward(rays_o, rays_d, lat.detach(), rand=rand, noise_coarse=nzc, noise_fine=nzf)
+
+    def step(self, batch, coh_batch=None, global_step=None):
+        """batch / coh_batch: dicts with rays_o, rays_d [N,3], rgb_gt [N,3], style_id, frame_id [N] (+ rgb_origin [N,3] in
+        coh_batch), as LightDataLoader.get_batch / loss_coh_get_batch return them (train_tgtcs.py:356-370); an optional
+        "rand" [N,64] replays the stratified-sampling uniforms (tests).
+        Returns {"loss", "loss_rgb", "loss_logp", "loss_coh"} (device scalars)."""
+        gstep = self.step_count if global_step is None else global_step
+        dev = self.r.device
+        sid, fid = batch["style_id"].long().to(dev), batch["frame_id"].long().to(dev)
+        lat1 = self.lat(sid, fid)                                    # [N,32], differentiable w.r.t. the table
+        fw = self._forward(batch["rays_o"], batch["rays_d"], lat1, batch.get("rand"))
+        rgb_c = fw["rgb_coarse"].requires_grad_(True)
+        rgb_f = fw["rgb_fine"].requires_grad_(True)
+        gt = batch["rgb_gt"]
+        loss_rgb = self.lam_rgb * (torch.mean((rgb_c - gt) ** 2) + torch.mean((rgb_f - gt) ** 2))      # train_tgtcs.py:425, :480-481
+        lam = self.lam_logp * (self.logp_decay ** int((gstep - self.origin_step) / 1000))             # train_tgtcs.py:426
+        loss_logp = lam * self.lat.minus_logp(sid, fid)
+        loss_coh = torch.zeros((), device=dev)
+        fw2 = None
+        if coh_batch is not None:
+            sid2, fid2 = coh_batch["style_id"].long().to(dev), coh_batch["frame_id"].long().to(dev)
+            lat2 = self.lat(sid2, fid2)
+            fw2 = self._forward(coh_batch["rays_o"], coh_batch["rays_d"], lat2, coh_batch.get("rand"))
+            c2 = fw2["rgb_coarse"].requires_grad_(True)
+            f2 = fw2["rgb_fine"].requires_grad_(True)
+            org2 = coh_batch["rgb_origin"]
+            # train_tgtcs.py:397-404, :449-459: compare with the previous batch unless a new pass over the frames starts
+            if self.cnt == self.frame_num:
+                self.cnt = 1
+            else:
+                if self.cnt != 0 and self.prev is not None:
+                    x, y, x_org = self.prev
+                    # :401 compares with the previous originals; :456 runs after :403 replaced x_origin by THIS batch's originals
+                    loss_coh = (l2_norm(cosine_similarity_rows(c2, x) - cosine_similarity_rows(org2, x_org)) +
+                                l2_norm(cosine_similarity_rows(f2, y) - cosine_similarity_rows(org2, org2)))
+                self.cnt += 1
+            self.prev = (c2.detach(), f2.detach(), org2)
+        use_coh = gstep <= 122000                                    # train_tgtcs.py:486-493
+        loss = loss_rgb + loss_logp + (self.lam_coh * loss_coh if use_coh else 0.0)
+        # d loss / d (rgb maps) and the direct latent term (minus_logp) by torch on the tiny tensors
+        self.lat.opt.zero_grad()
+        leaves = [rgb_c, rgb_f] + ([c2, f2] if (fw2 is not None and loss_coh.requires_grad and use_coh) else [])
+        gr = torch.autograd.grad(loss, leaves, retain_graph=True)
+        loss_logp.backward()                                         # -> latents table (direct term)
+        bw = self.r.style_train_backward(fw["state"], gr[0], gr[1], grads=self.grads, accumulate=False)
+        lat1.backward(bw["d_latents"])                               # -> latents table (through the style modules)
+        if len(gr) == 4:
+            bw2 = self.r.style_train_backward(fw2["state"], gr[2], gr[3], grads=self.grads, accumulate=True)
+            lat2.backward(bw2["d_latents"])
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(self.lat.latents.grad, op=dist.ReduceOp.SUM, group=self.group)
+        self.step_count += 1
+        self.r.adam_step(self.flat, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count, lr=self.lr)   # style_optimizer (:54)
+        self.lat.opt.step()                                          # latents_model_1.optimize (:495)
+        self.r.set_style_weights(*self.params)
+        return {"loss": loss.detach(), "loss_rgb": loss_rgb.detach(), "loss_logp": loss_logp.detach(), "loss_coh": loss_coh.detach()}
+
+    def state_dicts(self):
+        return tuple({k: p.detach() for k, p in d.items()} for d in self.params)
