@@ -633,6 +633,205 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+STYLE_TRAIN_WORKLOAD = ("Style_train iteration (train_tgtcs.py:354-495): a shuffled 4096-ray batch plus the 4096-ray coherence batch, "
+                        "per-ray latents, perturbed samples, frozen NeRF nets -> style module 1 -> style module 2 -> compositing -> "
+                        "resampling -> fine pass; rgb + logp + coherence losses; backward into both style modules and the latent "
+                        "table; Adam on both")
+STYLE_TRAIN_RAYS = 4096          # per batch; an iteration runs two batches
+STYLE_TRAIN_FLOP_PER_SAMPLE = 2.0 * (593408 - 36224 - 384) + 2.0 * (335360 + 614752) * 2 + 2.0 * (11 * 65536 + 768)
+
+
+def _style_train_batches(ro_all, rd_all, n, style_num, frame_num, gen, dev, count=4):
+    import torch
+    out = []
+    for _ in range(count):
+        pair = []
+        for origin in (False, True):
+            sel = torch.randperm(H * W, generator=gen)[:n].to(dev)
+            b = {"rays_o": ro_all[sel].contiguous(), "rays_d": rd_all[sel].contiguous(), "rgb_gt": torch.rand(n, 3, generator=gen).to(dev),
+                 "style_id": torch.randint(0, style_num, (n,), generator=gen).to(dev),
+                 "frame_id": torch.randint(0, frame_num, (n,), generator=gen).to(dev)}
+            if origin:
+                b["rgb_origin"] = torch.rand(n, 3, generator=gen).to(dev)
+            pair.append(b)
+        out.append(tuple(pair))
+    return out
+
+
+def run_style_train_reference_arm(args):
+    """--impl reference --workload style-train: the oracle port of one Style_train iteration (torch.autograd on the host
+    cores), bounded sample."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import torch
+    import render_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wc, wf = O.init_linear_like_reference(0)
+    cs, ws = O.init_style_like_reference(1)
+    ro, rd = O.make_rays(H, W, FOCAL, np.eye(4)[:3, :4])
+    ro, rd = torch.from_numpy(np.ascontiguousarray(ro)), torch.from_numpy(np.ascontiguousarray(rd))
+    per_batch, style_num, frame_num = 128, 4, 20
+    gen = torch.Generator().manual_seed(4)
+    table = torch.randn(style_num, frame_num, 32, generator=gen) * 0.5
+    mu, logvar = torch.randn(style_num, 32, generator=gen) * 0.3, torch.randn(style_num, 32, generator=gen) * 0.2
+    batches = _style_train_batches(ro, rd, per_batch, style_num, frame_num, gen, "cpu", count=2)
+    for b, c in batches:
+        b["rand"], c["rand"] = torch.rand(per_batch, 64, generator=gen), torch.rand(per_batch, 64, generator=gen)
+    prev = (torch.rand(per_batch, 3, generator=gen), torch.rand(per_batch, 3, generator=gen), torch.rand(per_batch, 3, generator=gen))
+    t_steps = []
+    for i in range(args.warmup + args.steps):
+        b, c = batches[i % 2]
+        t0 = time.perf_counter()
+        O.style_train_step_reference(wc, wf, cs, ws, table, mu, logvar, b, c, prev, frame_num)
+        if i >= args.warmup:
+            t_steps.append(time.perf_counter() - t0)
+    total = sum(t_steps)
+    value = 2 * per_batch * args.steps / total
+    sample = "2 x %d rays per iteration, torch CPU fp32 autograd, %d threads" % (per_batch, cores)
+    emit(json.dumps({
+        "impl": "reference", "metric": "rays/s", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": STYLE_TRAIN_WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_style_train(args):
+    """--workload style-train (BASELINE config 4's batch, training side): one Style_train iteration per bench step."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    import tgtc_style_b200 as T
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        dist.barrier()
+    wc, wf = synth_nerf_weights(0)
+    cs, ws = synth_style_weights(1)
+    r = T.NerfRenderer(device=dev, mode="bf16")
+    r.set_weights(wc, wf)
+    style_num, frame_num = 4, 20
+    gen = torch.Generator(device="cpu").manual_seed(4)
+    table = torch.randn(style_num, frame_num, 32, generator=gen) * 0.5
+    mu, logvar = torch.randn(style_num, 32, generator=gen) * 0.3, torch.randn(style_num, 32, generator=gen) * 0.2
+    lat = T.StyleLatents(table.to(dev), mu.to(dev), logvar.to(dev), dataset_type="llff")
+    tr = T.StyleTrainer(r, cs, ws, lat, frame_num=frame_num)
+    K = np.array([[FOCAL, 0, 0.5 * W], [0, FOCAL, 0.5 * H], [0, 0, 1]])
+    ro_all, rd_all = r.raygen(H, W, K, np.eye(4)[:3, :4])
+    n_local = STYLE_TRAIN_RAYS // world          # strong scaling: the two 4096-ray batches split over the ranks
+    gen_r = torch.Generator(device="cpu").manual_seed(100 + rank)
+    batches = _style_train_batches(ro_all, rd_all, n_local, style_num, frame_num, gen_r, dev)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    for s in range(args.warmup):
+        tr.step(*batches[s % 4])
+    sync_all()
+    r.profile_enable(True)
+    l0 = r.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for s in range(args.steps):
+        tr.step(*batches[(args.warmup + s) % 4])
+    e1.record()
+    sync_all()
+    t_wall1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = r.launch_count() - l0
+    kinds = {name: r.profile_read_kind(k) for name, k in (("mlp_tc_kernel<trunk>", 0), ("mlp_chain_kernel<train> (modules 1+2)", 1),
+                                                            ("style_dgrad_kernel", 2), ("style_wgrad_kernel (+reduce, latents)", 3))}
+    r.profile_enable(False)
+
+    # end to end: both batches from pinned host memory every iteration, the loss read back
+    h_batches = [tuple({k: v.cpu().pin_memory() for k, v in b.items()} for b in pair) for pair in batches[:2]]
+    loss_val = 0.0
+
+    def step_host(s):
+        nonlocal loss_val
+        b, c = ({k: v.to(dev, non_blocking=True) for k, v in d.items()} for d in h_batches[s % 2])
+        loss_val = float(tr.step(b, c)["loss"].item())
+
+    for s in range(args.warmup):
+        step_host(s)
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for s in range(args.steps):
+        step_host(s)
+    e3.record()
+    sync_all()
+    ms2 = torch.tensor([e2.elapsed_time(e3)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+
+    if rank == 0:
+        clocks.stop()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        ms_total = ms.item()
+        rays_step = 2 * STYLE_TRAIN_RAYS
+        n_w, ms_w, _ = kinds["style_wgrad_kernel (+reduce, latents)"]
+        # wgrad reads per sample: 17 jobs' A and B blocks = (1 + 4*16 + 4*12 + 5) blocks of 128 B rows
+        wbytes = (1 + 16 * 4 + 12 * 4 + 5) * 128
+        samples_local = 2 * n_local * SAMPLES_PER_RAY * args.steps
+        ach = samples_local * wbytes / (ms_w * 1e-3) / 1e9 if ms_w > 0 else None
+        bytes_in = sum(v.numel() * v.element_size() for pair in h_batches[:1] for b in pair for v in b.values())
+        res = {
+            "metric": "rays/s", "value": rays_step * args.steps / (ms_total * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": STYLE_TRAIN_WORKLOAD, "rays_per_batch": STYLE_TRAIN_RAYS, "batches_per_iteration": 2,
+                       "rays_per_gpu_per_batch": n_local, "samples_per_ray": SAMPLES_PER_RAY,
+                       "parallelism": "dp%d, all-reduce of the style gradients and the latent-table gradient" % world if world > 1 else "1 GPU",
+                       "l2_policy": "per-iteration activation stash (%.1f GB) >> 126 MB L2; no flush needed" % (2 * n_local * 192 / 128 * 1.7e6 / 1e9)},
+            "step_tflops": rays_step * SAMPLES_PER_RAY * STYLE_TRAIN_FLOP_PER_SAMPLE * args.steps / (ms_total * 1e-3) / 1e12,
+            "e2e": {"value": rays_step * args.steps / (ms2.item() * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": int(bytes_in),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms2.item() / args.steps,
+                    "api": "StyleTrainer.step (tgtc_style_train_forward/backward x 2 batches + losses + Adam)", "loss": loss_val},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if ach else None, "traffic": None,
+                         "kernel": "style_wgrad_kernel", "launches_timed": int(n_w), "avg_launch_ms": ms_w / max(n_w, 1),
+                         "bytes_per_sample": wbytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs",
+                         "note": "timed interval includes the partial reduction and the two latent kernels"},
+            "kernels": {k: {"launches": int(v[0]), "ms_per_step": v[1] / args.steps,
+                            "tflops": (v[2] / (v[1] * 1e-3) / 1e12) if v[1] > 0 else None} for k, v in kinds.items()},
+            "clocks": clocks.window(t_wall0, t_wall1),
+        }
+        emit(json.dumps(res))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -641,9 +840,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "eager-gpu"])
     ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="render", choices=["render", "train", "style"],
+    ap.add_argument("--workload", default="render", choices=["render", "train", "style", "style-train"],
                     help="render = BASELINE config 2 (the headline; default); train = config 5 (training step); "
-                         "style = config 4 (stylised render, 4096-ray batches)")
+                         "style = config 4 (stylised render, 4096-ray batches); style-train = one Style_train iteration "
+                         "(two 4096-ray batches)")
     args = ap.parse_args()
     claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -655,6 +855,8 @@ def main():
             run_train_reference_arm(args)
         elif args.workload == "style":
             run_style_reference_arm(args)
+        elif args.workload == "style-train":
+            run_style_train_reference_arm(args)
         else:
             run_reference_arm(args)
         return
@@ -663,6 +865,9 @@ def main():
         return
     if args.workload == "style":
         run_style(args)
+        return
+    if args.workload == "style-train":
+        run_style_train(args)
         return
 
     import numpy as np

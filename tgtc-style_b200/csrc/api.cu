@@ -740,7 +740,7 @@ extern "C" int tgtc_render_style(tgtc_ctx* ctx, const float* rays_o, const float
 
 struct StyleTrainWs {
   size_t off_c[2], off_w[2], off_pe[2], off_mask[2], off_remap[2], off_rs[2], off_ts[2];
-  size_t off_w_c, off_bias, off_dz, off_dhead, off_drs, off_g, off_R, off_partial, total;
+  size_t off_w_c, off_bias, off_dz, off_dhead, off_drs, off_g, off_R, off_wlat, off_partial, total;
 };
 static StyleTrainWs style_train_ws_layout(tgtc_ctx* ctx, int64_t n, int S, int F) {
   StyleTrainWs w;
@@ -764,6 +764,7 @@ static StyleTrainWs style_train_ws_layout(tgtc_ctx* ctx, int64_t n, int S, int F
   w.off_drs = o;     o = align_up(o + (size_t)n * (S + F) * 16, 256);
   w.off_g = o;       o = align_up(o + (size_t)n * 12, 256);
   w.off_R = o;       o = align_up(o + (size_t)13 * 2 * tiles * 256 * 4, 256);
+  w.off_wlat = o;    o = align_up(o + style_wlat_part_floats() * 4, 256);
   w.off_partial = o; o = align_up(o + (size_t)ctx->num_sms * style_partial_floats() * 4, 256);
   w.total = o;
   return w;
@@ -825,12 +826,20 @@ extern "C" int tgtc_style_train_forward(tgtc_ctx* ctx, const float* rays_o, cons
     io.t_scale = (float)(far - near); io.t_near = (float)near;
     io.n_rays = n_rays; io.S = p == 0 ? S : T;
     io.rgbsigma = rs;
+    const double samples = (double)n_rays * io.S;
+    cudaEvent_t e1 = nullptr;
+    rc = prof_begin(ctx, 0, samples * 2.0 * (593408.0 - 36224.0 - 384.0), st, &e1);
+    if (rc) return rc;
     rc = launch_mlp_tc_trunk(ctx, p, io, remap, st);                       // frozen NeRF net: base_remap images + sigma
+    if (rc) return rc;
+    if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
+    rc = prof_begin(ctx, 1, samples * 2.0 * (335360.0 + 614752.0), st, &e1);
     if (rc) return rc;
     rc = launch_style_concat_train(ctx, io, bias_rays, stash, st);
     if (rc) return rc;
     rc = launch_style_wild_train(ctx, io, bias_rays, remap, stash, st);
     if (rc) return rc;
+    if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
     if (p == 0) {
       rc = launch_composite(ctx, nullptr, nullptr, rs, ts_c, ts_c_stride, noise_coarse, 0, n_rays, S, rgb_coarse, nullptr, nullptr, w_c, st);
       if (rc) return rc;
@@ -864,11 +873,20 @@ extern "C" int tgtc_style_train_backward(tgtc_ctx* ctx, int64_t n_rays, int n_sa
     int rc = launch_composite_backward(ctx, rs, ts, ts_stride, p == 0 ? noise_coarse : noise_fine, 0, n_rays, Sp,
                                        p == 0 ? d_rgb_coarse : d_rgb_fine, nullptr, nullptr, drs, st);
     if (rc) return rc;
+    const double samples = (double)n_rays * Sp;
+    cudaEvent_t e1 = nullptr;
+    rc = prof_begin(ctx, 2, samples * 2.0 * (11.0 * 65536.0 + 768.0), st, &e1);   // hidden-to-hidden slices + the head
+    if (rc) return rc;
     rc = launch_style_dgrad(ctx, rs, drs, stash, dz, n_rays * Sp, st);
     if (rc) return rc;
-    rc = launch_style_wgrad(ctx, stash, base + ws.off_remap[p], dz, lat1, n_rays, Sp, partial, R, grads, (p == 0) ? accumulate : 1, dlat1,
+    if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
+    rc = prof_begin(ctx, 3, samples * 2.0 * (335360.0 + 614752.0), st, &e1);
+    if (rc) return rc;
+    rc = launch_style_wgrad(ctx, stash, base + ws.off_remap[p], dz, lat1, n_rays, Sp, partial, R,
+                            reinterpret_cast<float*>(base + ws.off_wlat), grads, (p == 0) ? accumulate : 1, dlat1,
                             p == 0 ? 0 : 1, st);
     if (rc) return rc;
+    if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
   }
   return TGTC_OK;
 }

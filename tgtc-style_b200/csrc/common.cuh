@@ -79,6 +79,7 @@ struct StyleImage {
   uint8_t* tables = nullptr;   // device scratch for the packing / bias tables
   float* wlat = nullptr;       // per layer: the 32 latent columns [256][32] and the bias [256] (owned copies)
   const void* bias_table = nullptr;  // device table the per-call effective-bias kernel walks
+  const float* src[26] = {};         // the caller's parameter pointers the device tables were built for
   bool set = false;
 };
 
@@ -228,8 +229,9 @@ size_t style_partial_floats();
 int launch_style_dgrad(tgtc_ctx* ctx, const float* rgbsigma, const float* d_rgbsigma, const StyleStash& stash, const StyleDz& dz, int64_t M,
                        cudaStream_t st);
 int launch_style_wgrad(tgtc_ctx* ctx, const StyleStash& stash, const uint8_t* remap_img, const StyleDz& dz, const float* lat1,
-                       int64_t n_rays, int S, float* partial, float* R, float* grads, int accumulate, float* dlat, int dlat_accumulate,
-                       cudaStream_t st);
+                       int64_t n_rays, int S, float* partial, float* R, float* wlat_part, float* grads, int accumulate, float* dlat,
+                       int dlat_accumulate, cudaStream_t st);
+size_t style_wlat_part_floats();
 int launch_style_bias_rays(tgtc_ctx* ctx, const float* lat1, int64_t n_rays, float* bias_rays, cudaStream_t st);
 int launch_style_concat_train(tgtc_ctx* ctx, const MlpIO& io, const float* bias_rays, const StyleStash& stash, cudaStream_t st);
 int launch_style_wild_train(tgtc_ctx* ctx, const MlpIO& io, const float* bias_rays, const uint8_t* remap_img, const StyleStash& stash,

@@ -14,7 +14,7 @@
 //      accumulators in TMEM; the column-sum warps also leave the per-64-sample column sums of every dz ("R" rows): biases,
 //      latent columns and latent gradients are all linear in those.
 //   style_reduce_kernel  per-CTA partials -> flat gradient buffer (nn.Linear layout, deterministic)
-//   style_latgrad_kernel / style_wlat_kernel   d latent[ray] and the latent columns of every weight from the R rows.
+//   style_latgrad_kernel / style_wlat_partial+reduce kernels   d latent[ray] and the latent columns of every weight from the R rows.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -528,63 +528,117 @@ __global__ void style_reduce_kernel(const __grid_constant__ SReduceParams P) {
 // latents.  R [13][nstages][256]: slot l = column sums of dz of layer l over each 64-sample stage; a ray owns S/64 consecutive
 // stages.  Slots 0..4 = module 1 (latent = lat1[ray]), 5..11 = module 2 layers 0..6, 12 = head (3 rows) (latent = mean(lat1[ray])).
 //   d lat1[ray][k] = sum_{l<5} sum_j Rray_l[j] Wlat_l[j][k]  +  (1/32) sum_{l>=5} sum_j Rray_l[j] rowsum(Wlat_l[j][:])
-__global__ void style_latgrad_kernel(const float* __restrict__ R, int64_t nstages, int spr, const float* __restrict__ wlat, int64_t n_rays,
-                                     float* __restrict__ dlat, int accumulate) {
-  __shared__ float rr[13][256];
-  __shared__ float red[8][33];
-  const int64_t ray = blockIdx.x;
-  const int j = threadIdx.x;
-  for (int l = 0; l < 13; ++l) {
-    float a = 0.f;
-    for (int s = 0; s < spr; ++s) a += R[((size_t)l * nstages + ray * spr + s) * 256 + j];
-    rr[l][j] = (l == 12 && j >= 3) ? 0.f : a;
-  }
-  __syncthreads();
+constexpr int kLatRays = 8;   // rays per block
+__global__ void __launch_bounds__(256) style_latgrad_kernel(const float* __restrict__ R, int64_t nstages, int spr, const float* __restrict__ wlat,
+                                                            int64_t n_rays, float* __restrict__ dlat, int accumulate) {
+  __shared__ float rr[kLatRays][256];
+  __shared__ float red[kLatRays][8][33];
+  const int64_t ray0 = (int64_t)blockIdx.x * kLatRays;
   const int k = threadIdx.x & 31, jg = threadIdx.x >> 5;
-  float a1 = 0.f, a2 = 0.f;
-  for (int l = 0; l < 13; ++l) {
-    const float* w = wlat + (size_t)l * 256 * 33;
-    float a = 0.f;
-    for (int jj = jg; jj < 256; jj += 8) a = fmaf(rr[l][jj], w[jj * 32 + k], a);
-    if (l < 5) a1 += a; else a2 += a;
-  }
-  // a2 summed over k gives the gradient of the scalar mean
+  float a1[kLatRays], a2[kLatRays];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-  red[jg][k] = a1;
-  if (k == 0) red[jg][32] = a2;
+  for (int q = 0; q < kLatRays; ++q) a1[q] = a2[q] = 0.f;
+  for (int l = 0; l < 13; ++l) {
+    __syncthreads();
+    for (int q = 0; q < kLatRays; ++q) {
+      const int64_t ray = ray0 + q;
+      float a = 0.f;
+      if (ray < n_rays && !(l == 12 && threadIdx.x >= 3))
+        for (int s = 0; s < spr; ++s) a += R[((size_t)l * nstages + ray * spr + s) * 256 + threadIdx.x];
+      rr[q][threadIdx.x] = a;
+    }
+    __syncthreads();
+    const float* w = wlat + (size_t)l * 256 * 33;
+    float acc[kLatRays];
+#pragma unroll
+    for (int q = 0; q < kLatRays; ++q) acc[q] = 0.f;
+    for (int jj = jg; jj < 256; jj += 8) {
+      const float wv = w[jj * 32 + k];
+#pragma unroll
+      for (int q = 0; q < kLatRays; ++q) acc[q] = fmaf(rr[q][jj], wv, acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < kLatRays; ++q) {
+      if (l < 5) a1[q] += acc[q]; else a2[q] += acc[q];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kLatRays; ++q) {
+    float m = a2[q];   // summed over k: the gradient of the scalar mean
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+    red[q][jg][k] = a1[q];
+    if (k == 0) red[q][jg][32] = m;
+  }
   __syncthreads();
-  if (threadIdx.x < 32) {
-    float g = 0.f, gm = 0.f;
-    for (int q = 0; q < 8; ++q) { g += red[q][threadIdx.x]; gm += red[q][32]; }
-    g += gm * (1.0f / 32.0f);
-    float* d = dlat + ray * 32 + threadIdx.x;
-    *d = accumulate ? *d + g : g;
+  {
+    const int q = threadIdx.x >> 5;   // 8 warps = 8 rays
+    const int64_t ray = ray0 + q;
+    if (ray < n_rays) {
+      float g = 0.f, gm = 0.f;
+      for (int i = 0; i < 8; ++i) { g += red[q][i][k]; gm += red[q][i][32]; }
+      g += gm * (1.0f / 32.0f);
+      float* d = dlat + ray * 32 + k;
+      *d = accumulate ? *d + g : g;
+    }
   }
 }
 
-// latent columns of every weight:  dW_l[j][lat0 + k] = sum_ray Rray_l[j] * lat_l(ray)[k]
-struct SLatDst { int64_t dst_off; int ld; int lat0; int nout; };
-struct SWlatParams { SLatDst d[13]; const float* R; int64_t nstages; int spr; const float* lat1; int64_t n_rays; float* grads; int accumulate; };
-__global__ void style_wlat_kernel(const __grid_constant__ SWlatParams P) {
+// latent columns of every weight:  dW_l[j][lat0 + k] = sum_ray Rray_l[j] * lat_l(ray)[k]  -- a [256 x stages] x [stages x 32] product
+// per layer, split over stage chunks (partials), then summed in chunk order (deterministic).
+constexpr int kWlatChunks = 64;
+__global__ void __launch_bounds__(256) style_wlat_partial_kernel(const float* __restrict__ R, int64_t nstages, int spr, const float* __restrict__ lat1,
+                                                                 int64_t n_rays, float* __restrict__ part) {
+  __shared__ float lat_s[8][32];
   const int l = blockIdx.y;
-  const SLatDst& d = P.d[l];
-  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int k = threadIdx.x & 31;
-  if (j >= d.nout) return;
-  const float* Rl = P.R + (size_t)l * P.nstages * 256 + j;
-  float acc = 0.f;
-  for (int64_t ray = 0; ray < P.n_rays; ++ray) {
-    float r = 0.f;
-    for (int s = 0; s < P.spr; ++s) r += Rl[(ray * P.spr + s) * 256];
-    float lv = P.lat1[ray * 32 + k];
-    if (l >= 5) {   // module 2: every latent input is mean(lat1[ray])
+  const int j = threadIdx.x;
+  const int64_t nvalid = n_rays * spr;
+  const int64_t per = (nvalid + gridDim.x - 1) / gridDim.x;
+  const int64_t s0 = (int64_t)blockIdx.x * per;
+  const int64_t s1 = s0 + per < nvalid ? s0 + per : nvalid;
+  float acc[32];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) lv += __shfl_xor_sync(0xffffffffu, lv, o);
-      lv *= (1.0f / 32.0f);
+  for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+  const float* Rl = R + (size_t)l * nstages * 256 + j;
+  for (int64_t s = s0; s < s1; s += 8) {
+    __syncthreads();
+    {
+      const int q = threadIdx.x >> 5, k = threadIdx.x & 31;
+      float v = 0.f;
+      if (s + q < s1) {
+        v = lat1[((s + q) / spr) * 32 + k];
+        if (l >= 5) {   // module 2: every latent input is mean(lat1[ray])
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          v *= (1.0f / 32.0f);
+        }
+      }
+      lat_s[q][k] = v;
     }
-    acc = fmaf(r, lv, acc);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (s + q < s1) {
+        const float r = Rl[(s + q) * 256];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) acc[k] = fmaf(r, lat_s[q][k], acc[k]);
+      }
+    }
   }
+  float* dst = part + (((size_t)blockIdx.x * 13 + l) * 256 + j) * 32;
+#pragma unroll
+  for (int k = 0; k < 32; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]);
+}
+struct SLatDst { int64_t dst_off; int ld; int lat0; int nout; };
+struct SWlatParams { SLatDst d[13]; const float* part; int nchunks; float* grads; int accumulate; };
+__global__ void style_wlat_reduce_kernel(const __grid_constant__ SWlatParams P) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over 13 * 256 * 32
+  if (idx >= 13 * 256 * 32) return;
+  const int l = idx / (256 * 32), j = (idx / 32) % 256, k = idx % 32;
+  const SLatDst& d = P.d[l];
+  if (j >= d.nout) return;
+  float acc = 0.f;
+  for (int c = 0; c < P.nchunks; ++c) acc += P.part[(size_t)c * 13 * 256 * 32 + idx];
   float* dst = P.grads + d.dst_off + (int64_t)j * d.ld + d.lat0 + k;
   *dst = P.accumulate ? *dst + acc : acc;
 }
@@ -634,6 +688,7 @@ static StyleJobPlan style_plan() {
   return p;
 }
 size_t style_partial_floats() { return (size_t)style_plan().part_floats; }
+size_t style_wlat_part_floats() { return (size_t)kWlatChunks * 13 * 256 * 32; }
 
 int launch_style_dgrad(tgtc_ctx* ctx, const float* rgbsigma, const float* d_rgbsigma, const StyleStash& stash, const StyleDz& dz, int64_t M,
                        cudaStream_t st) {
@@ -662,8 +717,8 @@ int launch_style_dgrad(tgtc_ctx* ctx, const float* rgbsigma, const float* d_rgbs
 
 // dW of both style modules into grads (flat, style_flat layout) and d lat1 [n_rays][32]
 int launch_style_wgrad(tgtc_ctx* ctx, const StyleStash& stash, const uint8_t* remap_img, const StyleDz& dz, const float* lat1,
-                       int64_t n_rays, int S, float* partial, float* R, float* grads, int accumulate, float* dlat, int dlat_accumulate,
-                       cudaStream_t st) {
+                       int64_t n_rays, int S, float* partial, float* R, float* wlat_part, float* grads, int accumulate, float* dlat,
+                       int dlat_accumulate, cudaStream_t st) {
   const int64_t M = n_rays * S;
   if (M == 0) return TGTC_OK;
   TGTC_REQUIRE(S % 64 == 0, TGTC_ERR_UNSUPPORTED, "style wgrad needs n_samples a multiple of 64");
@@ -744,14 +799,17 @@ int launch_style_wgrad(tgtc_ctx* ctx, const StyleStash& stash, const uint8_t* re
   // latent columns and latent gradients from the R rows
   static const int clat[5] = {63, 256, 256, 256, 256};
   static const int wlat0[8] = {575, 256, 256, 256, 256, 256, 256, 256};
+  style_wlat_partial_kernel<<<dim3(kWlatChunks, 13), 256, 0, st>>>(R, 2 * ntiles, S / 64, lat1, n_rays, wlat_part);
+  TGTC_LAUNCH_CHECK(ctx);
   SWlatParams L = {};
   for (int l = 0; l < 5; ++l) L.d[l] = {flat.w[l], kCIn[l], clat[l], 256};
   for (int l = 0; l < 8; ++l) L.d[5 + l] = {flat.w[5 + l], kWIn[l], wlat0[l], l < 7 ? 256 : 3};
-  L.R = R; L.nstages = 2 * ntiles; L.spr = S / 64; L.lat1 = lat1; L.n_rays = n_rays; L.grads = grads; L.accumulate = accumulate;
-  style_wlat_kernel<<<dim3(32, 13), 256, 0, st>>>(L);
+  L.part = wlat_part; L.nchunks = kWlatChunks; L.grads = grads; L.accumulate = accumulate;
+  style_wlat_reduce_kernel<<<(13 * 256 * 32 + 255) / 256, 256, 0, st>>>(L);
   TGTC_LAUNCH_CHECK(ctx);
   if (dlat != nullptr) {
-    style_latgrad_kernel<<<(unsigned)n_rays, 256, 0, st>>>(R, 2 * ntiles, S / 64, ctx->style.wlat, n_rays, dlat, dlat_accumulate);
+    style_latgrad_kernel<<<(unsigned)((n_rays + kLatRays - 1) / kLatRays), 256, 0, st>>>(R, 2 * ntiles, S / 64, ctx->style.wlat, n_rays, dlat,
+                                                                                        dlat_accumulate);
     TGTC_LAUNCH_CHECK(ctx);
   }
   return TGTC_OK;

@@ -187,17 +187,23 @@ class StyleTrainer:
         self.step_count = 0
         self.cnt = 0                       # the reference's `cnt` (train_tgtcs.py:347)
         self.prev = None                   # (x, y, x_origin): previous loss_coh batch's coarse / fine maps and its originals
+        self._ws = [None, None]
         self.r.set_style_weights(*self.params)
 
-    def _forward(self, rays_o, rays_d, lat, rand=None):
+    def _forward(self, rays_o, rays_d, lat, rand=None, slot=0):
         n = rays_o.shape[0]
+        need = int(self.r.lib.tgtc_style_train_workspace_bytes(self.r._h, n, 64, 64)) + 1024
+        if self._ws[slot] is None or self._ws[slot].numel() < need:      # one persistent stash per pending batch
+            self._ws[slot] = None
+            self._ws[slot] = torch.empty(need, dtype=torch.uint8, device=self.r.device)
         if rand is None:
             rand = torch.rand(n, 64, device=rays_o.device)           # perturb=True (train_tgtcs.py:362)
         nzc = nzf = None
         if self.noise_std > 0:
             nzc = torch.randn(n, 64, device=rays_o.device) * self.noise_std
             nzf = torch.randn(n, 128, device=rays_o.device) * self.noise_std
-        return self.r.style_train_forward(rays_o, rays_d, lat.detach(), rand=rand, noise_coarse=nzc, noise_fine=nzf)
+        return self.r.style_train_forward(rays_o, rays_d, lat.detach(), rand=rand, noise_coarse=nzc, noise_fine=nzf,
+                                          workspace=self._ws[slot])
 
     def step(self, batch, coh_batch=None, global_step=None):
         """batch / coh_batch: dicts with rays_o, rays_d [N,3], rgb_gt [N,3], style_id, frame_id [N] (+ rgb_origin [N,3] in
@@ -220,7 +226,7 @@ class StyleTrainer:
         if coh_batch is not None:
             sid2, fid2 = coh_batch["style_id"].long().to(dev), coh_batch["frame_id"].long().to(dev)
             lat2 = self.lat(sid2, fid2)
-            fw2 = self._forward(coh_batch["rays_o"], coh_batch["rays_d"], lat2, coh_batch.get("rand"))
+            fw2 = self._forward(coh_batch["rays_o"], coh_batch["rays_d"], lat2, coh_batch.get("rand"), slot=1)
             c2 = fw2["rgb_coarse"].requires_grad_(True)
             f2 = fw2["rgb_fine"].requires_grad_(True)
             org2 = coh_batch["rgb_origin"]
