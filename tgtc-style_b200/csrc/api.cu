@@ -66,7 +66,7 @@ extern "C" int tgtc_destroy(tgtc_ctx* ctx) {
   }
   {
     StyleImage& si = ctx->style;
-    void* bufs[] = {si.blob_c, si.blob_w, si.blob_T, si.head_w, si.bias_c, si.bias_w, si.head_b, si.latents, si.tables, si.wlat};
+    void* bufs[] = {si.blob_c, si.blob_w, si.blob_T, si.head_w, si.bias_c, si.bias_w, si.head_b, si.latents, si.tables, si.wlat, si.wlatT};
     for (void* b : bufs) if (b) cudaFree(b);
   }
   if (ctx->arena) cudaFree(ctx->arena);

@@ -78,6 +78,7 @@ struct StyleImage {
   float* latents = nullptr;    // [2][32]
   uint8_t* tables = nullptr;   // device scratch for the packing / bias tables
   float* wlat = nullptr;       // per layer: the 32 latent columns [256][32] and the bias [256] (owned copies)
+  float* wlatT = nullptr;      // per layer: the latent columns transposed [32][256] and their row sums [256]
   const void* bias_table = nullptr;  // device table the per-call effective-bias kernel walks
   const float* src[26] = {};         // the caller's parameter pointers the device tables were built for
   bool set = false;

@@ -512,17 +512,32 @@ __global__ void style_bias_kernel(const BiasSrc* __restrict__ table, int n) {
   }
 }
 // own copies of what the per-call bias kernel needs, so nothing of the caller's tensors is referenced after set_weights
+// wlatT: per layer the same latent columns transposed [32][256] followed by their row sums [256] (the per-ray bias kernel of the
+// training forward reads them coalesced over the output feature)
 struct LatSrc { const float* W; const float* b; int ld; int lat0; int nout; float* wlat; float* bout; };
-__global__ void style_latcopy_kernel(const LatSrc* __restrict__ table) {
+__global__ void style_latcopy_kernel(const LatSrc* __restrict__ table, float* __restrict__ wlatT) {
   const LatSrc s = table[blockIdx.x];
-  for (int i = threadIdx.x; i < s.nout * 32; i += blockDim.x) s.wlat[i] = s.W[(size_t)(i / 32) * s.ld + s.lat0 + (i % 32)];
-  for (int j = threadIdx.x; j < s.nout; j += blockDim.x) s.bout[j] = s.b[j];
+  float* T = wlatT + (size_t)blockIdx.x * 256 * 33;
+  for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) {
+    const int j = i / 32, k = i % 32;
+    const float v = j < s.nout ? s.W[(size_t)j * s.ld + s.lat0 + k] : 0.f;
+    s.wlat[i] = v;
+    T[k * 256 + j] = v;
+  }
+  for (int j = threadIdx.x; j < 256; j += blockDim.x) {
+    s.bout[j] = j < s.nout ? s.b[j] : 0.f;
+    float rs = 0.f;
+    if (j < s.nout)
+      for (int k = 0; k < 32; ++k) rs += s.W[(size_t)j * s.ld + s.lat0 + k];
+    T[32 * 256 + j] = rs;
+  }
 }
 
 // training: effective biases per RAY.  lat1 [n_rays][32] = the module-1 latent of each ray (latents_model_1(style_id, frame_id));
 // module 2 sees mean(lat1) broadcast to 32 dims (train_tgtcs.py:376, :410).  out [n_rays][13][256]: module 1 layers 0..4,
 // module 2 layers 0..6, head (3 used).  wlat: 13 slots of [256][32] latent columns followed by [256] biases.
-__global__ void style_bias_rays_kernel(const float* __restrict__ wlat, const float* __restrict__ lat1, int64_t n_rays, float* __restrict__ out) {
+__global__ void style_bias_rays_kernel(const float* __restrict__ wlat, const float* __restrict__ wlatT, const float* __restrict__ lat1,
+                                       int64_t n_rays, float* __restrict__ out) {
   __shared__ float lat[33];
   const int64_t ray = blockIdx.x;
   if (threadIdx.x < 32) lat[threadIdx.x] = lat1[ray * 32 + threadIdx.x];
@@ -535,17 +550,13 @@ __global__ void style_bias_rays_kernel(const float* __restrict__ wlat, const flo
   __syncthreads();
   const int j = threadIdx.x;
   for (int l = 0; l < 13; ++l) {
-    const float* w = wlat + (size_t)l * 256 * 33;
-    float acc = 0.f;
-    if (l < 12 || j < 3) {
-      acc = w[256 * 32 + j];
-      if (l < 5) {
-        for (int k = 0; k < 32; ++k) acc = fmaf(w[j * 32 + k], lat[k], acc);
-      } else {
-        float rs = 0.f;
-        for (int k = 0; k < 32; ++k) rs += w[j * 32 + k];
-        acc = fmaf(rs, lat[32], acc);
-      }
+    const float* T = wlatT + (size_t)l * 256 * 33;
+    float acc = wlat[(size_t)l * 256 * 33 + 256 * 32 + j];   // bias (0 beyond the layer's outputs)
+    if (l < 5) {
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) acc = fmaf(T[k * 256 + j], lat[k], acc);
+    } else {
+      acc = fmaf(T[32 * 256 + j], lat[32], acc);
     }
     out[(ray * 13 + l) * 256 + j] = acc;
   }
@@ -579,6 +590,7 @@ int style_set_weights(tgtc_ctx* ctx, const float* const* params, cudaStream_t st
     TGTC_CUDA(cudaMalloc(&im.blob_T, (size_t)kTChunks * 32768));
     TGTC_CUDA(cudaMalloc(&im.tables, 16384));
     TGTC_CUDA(cudaMalloc(&im.wlat, 13 * 256 * 33 * sizeof(float)));   // per layer: [256][32] latent columns, then [256] bias
+    TGTC_CUDA(cudaMalloc(&im.wlatT, 13 * 256 * 33 * sizeof(float)));  // per layer: the same transposed [32][256], then row sums [256]
   }
   // The device tables hold the caller's parameter pointers; they are rebuilt only when those change (a trainer re-packs the
   // same 26 tensors after every optimizer step: then this call is five kernel launches, fully stream-ordered).
@@ -646,7 +658,7 @@ int style_set_weights(tgtc_ctx* ctx, const float* const* params, cudaStream_t st
   TGTC_LAUNCH_CHECK(ctx);
   head_copy_kernel<<<1, 256, 0, st>>>(Wp[14], 288, im.head_w);
   TGTC_LAUNCH_CHECK(ctx);
-  style_latcopy_kernel<<<13, 256, 0, st>>>(dlat);
+  style_latcopy_kernel<<<13, 256, 0, st>>>(dlat, im.wlatT);
   TGTC_LAUNCH_CHECK(ctx);
   im.bias_table = dbias;
   im.set = true;
@@ -727,7 +739,7 @@ int launch_style_wild(tgtc_ctx* ctx, const MlpIO& io, const uint8_t* remap_img, 
 // training forward (Style_train): per-ray latents, stash for the backward
 int launch_style_bias_rays(tgtc_ctx* ctx, const float* lat1, int64_t n_rays, float* bias_rays, cudaStream_t st) {
   if (n_rays == 0) return TGTC_OK;
-  style_bias_rays_kernel<<<(unsigned)n_rays, 256, 0, st>>>(ctx->style.wlat, lat1, n_rays, bias_rays);
+  style_bias_rays_kernel<<<(unsigned)n_rays, 256, 0, st>>>(ctx->style.wlat, ctx->style.wlatT, lat1, n_rays, bias_rays);
   TGTC_LAUNCH_CHECK(ctx);
   return TGTC_OK;
 }
