@@ -162,3 +162,31 @@ def test_style_trainer_step_vs_oracle(renderer_bf16):
     # the step moved the parameters and the table
     assert not torch.equal(lat.latents.detach().cpu(), tab)
     assert not torch.equal(tr.state_dicts()[1]["layers.7.weight"].cpu(), sdw["layers.7.weight"])
+
+
+def test_style_train_forward_vs_reference_golden(renderer_bf16):
+    """The training forward on the golden batch of oracle/make_golden_style_train.py (the imported reference's own modules,
+    perturb=True replayed through the stored uniforms, per-ray latents from StyleLatents_variational)."""
+    import tgtc_style_b200 as T
+    from helpers import golden
+    g = golden("style_train")
+    r = renderer_bf16
+    (wc, wf, cs, ws), _, _, _, _, _, _ = _inputs(8)
+    ro, rd = small_rays()
+    r.set_weights(wc, wf)
+    r.set_style_weights(cs, ws)
+    dev = r.device
+    lat = T.StyleLatents(torch.from_numpy(g["table"]).to(dev), torch.from_numpy(g["mu"]).to(dev), torch.from_numpy(g["logvar"]).to(dev))
+    for tag, kc, kf in (("b1", "rgb_coarse", "rgb_fine"), ("b2", "coh_rgb_coarse", "coh_rgb_fine")):
+        idx = g[tag + "/ray_index"]
+        l1 = lat(torch.from_numpy(g[tag + "/style_id"]).to(dev), torch.from_numpy(g[tag + "/frame_id"]).to(dev)).detach()
+        out = r.style_train_forward(ro[idx], rd[idx], l1, rand=torch.from_numpy(g[tag + "/rand"]))
+        torch.cuda.synchronize()
+        ec = np.abs(out["rgb_coarse"].cpu().numpy() - g[kc])
+        ef = np.abs(out["rgb_fine"].cpu().numpy() - g[kf])
+        print("%s: coarse max %.3e mean %.3e, fine max %.3e mean %.3e" % (tag, ec.max(), ec.mean(), ef.max(), ef.mean()))
+        assert ec.mean() <= 3e-3 and ec.max() <= 3e-2
+        assert ef.mean() <= 5e-3
+    # minus_logp of the host latent model against the reference's (models.py:531-537)
+    lp = 0.1 * lat.minus_logp(torch.from_numpy(g["b1/style_id"]).to(dev), torch.from_numpy(g["b1/frame_id"]).to(dev))
+    assert abs(lp.item() - float(g["loss_logp"])) <= 1e-5 * max(1.0, float(g["loss_logp"]))

@@ -165,3 +165,38 @@ def test_style_chain_vs_golden():
         np.testing.assert_allclose(out[k].numpy(), g[k], atol=tol, rtol=0, err_msg=k)
     np.testing.assert_allclose(out["concat_features_coarse"][:8].numpy(), g["concat_features_coarse"], atol=2e-5, rtol=1e-5)
     np.testing.assert_allclose(out["rgb_pts_fine"][:16].numpy(), g["rgb_pts_fine"], atol=2e-6, rtol=0)
+
+
+# ------------------------------------------------------------------ Style_train iteration
+def test_style_train_step_vs_golden():
+    """oracle.style_train_step_reference against the imported reference's own modules and loss functions wired as
+    train_tgtcs.py:354-495 (oracle/make_golden_style_train.py): loss terms, style-module gradients, latent-table gradient."""
+    g = golden("style_train")
+    ro, rd = small_rays()
+    w0c, w0f = weights("w0")
+    probe = np.arange(0, ro.shape[0], 743)
+    wc = O.recalibrate_sigma(w0c, ro[probe], rd[probe], gain=4.0, shift=10.0)
+    wf = O.recalibrate_sigma(w0f, ro[probe], rd[probe], gain=4.0, shift=10.0)
+    cs, ws = O.init_style_like_reference(1)
+    t = torch.from_numpy
+
+    def batch(tag):
+        idx = g[tag + "/ray_index"]
+        b = {"rays_o": ro[idx], "rays_d": rd[idx], "rgb_gt": t(g[tag + "/rgb_gt"]), "style_id": t(g[tag + "/style_id"]),
+             "frame_id": t(g[tag + "/frame_id"]), "rand": t(g[tag + "/rand"])}
+        if tag + "/rgb_origin" in g:
+            b["rgb_origin"] = t(g[tag + "/rgb_origin"])
+        return b
+
+    prev = (t(g["prev_x"]), t(g["prev_y"]), t(g["prev_x_origin"]))
+    losses, gcs, gws, gtab = O.style_train_step_reference(wc, wf, cs, ws, t(g["table"]), t(g["mu"]), t(g["logvar"]), batch("b1"), batch("b2"),
+                                                          prev, int(g["frame_num"]), rgb_loss_lambda=1.0, logp_lambda=0.1, loss_coh_lambda=1e2)
+    for k in ("loss", "loss_rgb", "loss_logp", "loss_coh"):
+        assert abs(losses[k].item() - float(g[k])) <= 2e-6 * max(1.0, abs(float(g[k]))), (k, losses[k].item(), float(g[k]))
+    np.testing.assert_allclose(gtab.numpy(), g["grad_table"], rtol=2e-4, atol=1e-7)
+    for tag, grads in (("concat", gcs), ("wild", gws)):
+        for k, gr in grads.items():
+            ref_norm = float(g["gnorm_%s/%s" % (tag, k)])
+            sl = gr.numpy().reshape(-1)[::97]
+            assert abs(np.linalg.norm(gr.numpy().astype(np.float64)) - ref_norm) <= 1e-3 * ref_norm + 1e-9, (tag, k)
+            np.testing.assert_allclose(sl, g["gslice_%s/%s" % (tag, k)], rtol=5e-3, atol=1e-5 * ref_norm + 1e-9, err_msg="%s %s" % (tag, k))
