@@ -151,3 +151,117 @@ def test_trainer_data_parallel_matches_single_process(world, n):
     for rank, p_s, g_s in res:
         np.testing.assert_allclose(g_s, ref_g, rtol=2e-5, atol=1e-7)      # summed shard gradients == full-batch gradients
         np.testing.assert_allclose(p_s, ref_p, rtol=1e-5, atol=1e-6)      # identical Adam step on every rank
+
+
+# ------------------------------------------------------------------ Style_train data parallelism (host logic, gloo)
+class _FakeStyleRenderer:
+    """CPU stand-in for NerfRenderer in StyleTrainer: forward and backward are per-ray separable and linear in the upstream
+    gradients, so equal shards + the trainer's all-reduces must reproduce the single-process iteration."""
+    STYLE_C_SHAPES = T.NerfRenderer.STYLE_C_SHAPES
+    STYLE_W_SHAPES = T.NerfRenderer.STYLE_W_SHAPES
+    style_grad_views = T.NerfRenderer.style_grad_views
+
+    def __init__(self):
+        self.device = torch.device("cpu")
+        self.P = sum(o * i + o for o, i in list(self.STYLE_C_SHAPES) + list(self.STYLE_W_SHAPES))
+        self.basis = torch.linspace(-1, 1, self.P, dtype=torch.float64)
+
+    def style_num_params(self):
+        return self.P
+
+    def style_train_workspace_bytes(self, n, n_samples=64, n_fine=64):
+        return 16
+
+    def set_style_weights(self, concat_style, style):
+        pass
+
+    def style_train_forward(self, ro, rd, lat, rand=None, noise_coarse=None, noise_fine=None, workspace=None, **kw):
+        return {"rgb_coarse": torch.sigmoid(0.3 * ro + lat[:, :3]), "rgb_fine": torch.sigmoid(0.2 * rd + lat[:, 3:6]),
+                "state": {"ro": ro, "rd": rd, "n": ro.shape[0]}}
+
+    def style_train_backward(self, state, gc, gf, grads=None, accumulate=False):
+        s = (gc.double() * state["ro"].double()).sum() + 2.0 * (gf.double() * state["rd"].double()).sum()
+        g = (self.basis * s).float()
+        if accumulate:
+            grads += g
+        else:
+            grads.copy_(g)
+        dl = torch.zeros(state["n"], 32)
+        dl[:, :3], dl[:, 3:6] = gc, gf
+        return {"grads": grads, "d_latents": dl}
+
+    def adam_step(self, params, grads, exp_avg, exp_avg_sq, step, lr=5e-4, betas=(0.9, 0.999), eps=1e-8):
+        exp_avg.mul_(betas[0]).add_(grads, alpha=1 - betas[0])
+        exp_avg_sq.mul_(betas[1]).addcmul_(grads, grads, value=1 - betas[1])
+        denom = (exp_avg_sq.sqrt() / (1 - betas[1] ** step) ** 0.5).add_(eps)
+        params.addcdiv_(exp_avg, denom, value=-lr / (1 - betas[0] ** step))
+
+
+def _style_sd(shapes, seed):
+    g = torch.Generator().manual_seed(seed)
+    d = {}
+    for i, (o, k) in enumerate(shapes):
+        d["layers.%d.weight" % i] = torch.randn(o, k, generator=g) * 0.05
+        d["layers.%d.bias" % i] = torch.randn(o, generator=g) * 0.05
+    return d
+
+
+def _style_iteration_inputs(n):
+    g = torch.Generator().manual_seed(3)
+    out = []
+    for it in range(2):
+        pair = []
+        for origin in (False, True):
+            b = {"rays_o": torch.randn(n, 3, generator=g), "rays_d": torch.randn(n, 3, generator=g), "rgb_gt": torch.rand(n, 3, generator=g),
+                 "style_id": torch.randint(0, 2, (n,), generator=g), "frame_id": torch.randint(0, 4, (n,), generator=g)}
+            if origin:
+                b["rgb_origin"] = torch.rand(n, 3, generator=g)
+            pair.append(b)
+        out.append(pair)
+    table = torch.randn(2, 4, 32, generator=g) * 0.5
+    mu, logvar = torch.randn(2, 32, generator=g) * 0.3, torch.randn(2, 32, generator=g) * 0.2
+    return out, table, mu, logvar
+
+
+def _style_run(n, rank=0, world=1):
+    its, table, mu, logvar = _style_iteration_inputs(n)
+    r = _FakeStyleRenderer()
+    lat = T.StyleLatents(table, mu, logvar, dataset_type="llff")
+    tr = T.StyleTrainer(r, _style_sd(r.STYLE_C_SHAPES, 1), _style_sd(r.STYLE_W_SHAPES, 2), lat, frame_num=4)
+    b, e = rank * n // world, (rank + 1) * n // world
+    losses = None
+    for pair in its:
+        losses = tr.step(*({k: v[b:e] for k, v in d.items()} for d in pair))
+    return (tr.grads[::991].clone().numpy(), tr.flat[::991].clone().numpy(), lat.latents.detach().clone().numpy(),
+            {k: float(v) for k, v in losses.items()})
+
+
+def _style_worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        q.put((rank,) + _style_run(n, rank, world))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_style_trainer_data_parallel_matches_single_process():
+    n, world = 64, 2
+    g_ref, p_ref, tab_ref, l_ref = _style_run(n)
+    assert l_ref["loss_coh"] > 0.0                      # the second iteration carries the coherence term
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_style_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+    for rank, g_s, p_s, tab, losses in res:
+        np.testing.assert_allclose(g_s, g_ref, rtol=2e-4, atol=1e-7)
+        np.testing.assert_allclose(p_s, p_ref, rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(tab, tab_ref, rtol=1e-4, atol=2e-6)
+        for k in ("loss", "loss_rgb", "loss_logp", "loss_coh"):
+            assert abs(losses[k] - l_ref[k]) <= 1e-4 * max(1.0, abs(l_ref[k])), (k, losses[k], l_ref[k])

@@ -468,6 +468,12 @@ class NerfRenderer:
         state = dict(n=n, S=n_samples, F=n_fine, lat=lat, rand=rnd, nzc=nzc, nzf=nzf, ws=ws, off=off, wsb=wsb)
         return {"rgb_coarse": rgb_c, "rgb_fine": rgb_f, "state": state}
 
+    def style_train_workspace_bytes(self, n, n_samples=64, n_fine=64):
+        return int(self.lib.tgtc_style_train_workspace_bytes(self._h, int(n), n_samples, n_fine)) + 1024
+
+    def style_num_params(self):
+        return int(self.lib.tgtc_style_num_params())
+
     def style_train_backward(self, state, d_rgb_coarse, d_rgb_fine, grads=None, accumulate=False):
         """Backward of the batch `state` came from: dL/d rgb_coarse, dL/d rgb_fine [N,3] -> {"grads": flat fp32
         [tgtc_style_num_params()] in set_style_weights order, "d_latents": [N,32]}."""

@@ -169,7 +169,7 @@ class StyleTrainer:
         self.group = group
         self.lat = latents
         dev = renderer.device
-        P = int(renderer.lib.tgtc_style_num_params())
+        P = renderer.style_num_params()
         self.flat = torch.zeros(P, dtype=torch.float32, device=dev)
         self.grads = torch.zeros_like(self.flat)
         self.exp_avg = torch.zeros_like(self.flat)
@@ -192,7 +192,7 @@ class StyleTrainer:
 
     def _forward(self, rays_o, rays_d, lat, rand=None, slot=0):
         n = rays_o.shape[0]
-        need = int(self.r.lib.tgtc_style_train_workspace_bytes(self.r._h, n, 64, 64)) + 1024
+        need = self.r.style_train_workspace_bytes(n)
         if self._ws[slot] is None or self._ws[slot].numel() < need:      # one persistent stash per pending batch
             self._ws[slot] = None
             self._ws[slot] = torch.empty(need, dtype=torch.uint8, device=self.r.device)
@@ -212,16 +212,21 @@ class StyleTrainer:
         Returns {"loss", "loss_rgb", "loss_logp", "loss_coh"} (device scalars)."""
         gstep = self.step_count if global_step is None else global_step
         dev = self.r.device
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         sid, fid = batch["style_id"].long().to(dev), batch["frame_id"].long().to(dev)
         lat1 = self.lat(sid, fid)                                    # [N,32], differentiable w.r.t. the table
         fw = self._forward(batch["rays_o"], batch["rays_d"], lat1, batch.get("rand"))
         rgb_c = fw["rgb_coarse"].requires_grad_(True)
         rgb_f = fw["rgb_fine"].requires_grad_(True)
         gt = batch["rgb_gt"]
-        loss_rgb = self.lam_rgb * (torch.mean((rgb_c - gt) ** 2) + torch.mean((rgb_f - gt) ** 2))      # train_tgtcs.py:425, :480-481
+        # every rank holds an equal shard of the iteration's two batches: batch means become (local mean) / world, and the
+        # coherence norm is taken over all ranks' rows (one scalar all-reduce per term), so the summed gradients equal the
+        # single-process ones
+        loss_rgb = self.lam_rgb * (torch.mean((rgb_c - gt) ** 2) + torch.mean((rgb_f - gt) ** 2)) / world   # train_tgtcs.py:425, :480-481
         lam = self.lam_logp * (self.logp_decay ** int((gstep - self.origin_step) / 1000))             # train_tgtcs.py:426
-        loss_logp = lam * self.lat.minus_logp(sid, fid)
-        loss_coh = torch.zeros((), device=dev)
+        loss_logp = lam * self.lat.minus_logp(sid, fid) / world
+        loss_coh = torch.zeros((), device=dev)       # value of the term (global)
+        coh_local = None                             # this rank's differentiable share: its gradient is d(term)/d(local rows)
         fw2 = None
         if coh_batch is not None:
             sid2, fid2 = coh_batch["style_id"].long().to(dev), coh_batch["frame_id"].long().to(dev)
@@ -237,25 +242,39 @@ class StyleTrainer:
                 if self.cnt != 0 and self.prev is not None:
                     x, y, x_org = self.prev
                     # :401 compares with the previous originals; :456 runs after :403 replaced x_origin by THIS batch's originals
-                    loss_coh = (l2_norm(cosine_similarity_rows(c2, x) - cosine_similarity_rows(org2, x_org)) +
-                                l2_norm(cosine_similarity_rows(f2, y) - cosine_similarity_rows(org2, org2)))
+                    terms = (cosine_similarity_rows(c2, x) - cosine_similarity_rows(org2, x_org),
+                             cosine_similarity_rows(f2, y) - cosine_similarity_rows(org2, org2))
+                    coh_local = 0.0
+                    for v in terms:
+                        ss = torch.sum(v ** 2)
+                        ss_all = ss.detach().clone()
+                        if world > 1:
+                            dist.all_reduce(ss_all, op=dist.ReduceOp.SUM, group=self.group)
+                        norm = torch.sqrt(ss_all + 1e-8)                # utils.L2_norm over all ranks' rows
+                        loss_coh = loss_coh + norm
+                        coh_local = coh_local + ss / (2.0 * norm)        # d/dv = v / norm = d L2_norm / dv
                 self.cnt += 1
             self.prev = (c2.detach(), f2.detach(), org2)
         use_coh = gstep <= 122000                                    # train_tgtcs.py:486-493
-        loss = loss_rgb + loss_logp + (self.lam_coh * loss_coh if use_coh else 0.0)
+        loss = loss_rgb + loss_logp + ((self.lam_coh * loss_coh) if use_coh else 0.0)
+        objective = loss_rgb + loss_logp + ((self.lam_coh * coh_local) if (use_coh and coh_local is not None) else 0.0)
         # d loss / d (rgb maps) and the direct latent term (minus_logp) by torch on the tiny tensors
         self.lat.opt.zero_grad()
-        leaves = [rgb_c, rgb_f] + ([c2, f2] if (fw2 is not None and loss_coh.requires_grad and use_coh) else [])
-        gr = torch.autograd.grad(loss, leaves, retain_graph=True)
+        with_coh = use_coh and coh_local is not None
+        leaves = [rgb_c, rgb_f] + ([c2, f2] if with_coh else [])
+        gr = torch.autograd.grad(objective, leaves, retain_graph=True)
         loss_logp.backward()                                         # -> latents table (direct term)
         bw = self.r.style_train_backward(fw["state"], gr[0], gr[1], grads=self.grads, accumulate=False)
         lat1.backward(bw["d_latents"])                               # -> latents table (through the style modules)
-        if len(gr) == 4:
+        if with_coh:
             bw2 = self.r.style_train_backward(fw2["state"], gr[2], gr[3], grads=self.grads, accumulate=True)
             lat2.backward(bw2["d_latents"])
-        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+        if world > 1:
             dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.group)
             dist.all_reduce(self.lat.latents.grad, op=dist.ReduceOp.SUM, group=self.group)
+            for t in (loss_rgb, loss_logp):
+                dist.all_reduce(t.detach_(), op=dist.ReduceOp.SUM, group=self.group)
+            loss = loss_rgb + loss_logp + ((self.lam_coh * loss_coh) if use_coh else 0.0)
         self.step_count += 1
         self.r.adam_step(self.flat, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count, lr=self.lr)   # style_optimizer (:54)
         self.lat.opt.step()                                          # latents_model_1.optimize (:495)
