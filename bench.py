@@ -297,7 +297,9 @@ TRAIN_WORKLOAD = ("training step: 32768-ray batch (rays of one fern-shaped 1008x
                   "gradient all-reduce")
 TRAIN_RAYS = 32768
 TRAIN_FLOP_PER_SAMPLE = 3489024.0    # fwd + wgrad + dgrad
-DGRAD_BYTES_PER_SAMPLE = 9 * 512 + 256 + 32 + 9 * 512 + 256 + 128   # stash read (h, f, d_rgbsigma, rgbsigma) + dz/dzf/dhead written
+DGRAD_BYTES_PER_SAMPLE = 10 * 32 + 32 + 9 * 512 + 256 + 128   # mask words + (d_rgbsigma, rgbsigma) read; dz/dzf/dhead tile images written
+# wgrad reads every dz and every layer-input image once (dz5 and the PE tile twice: layer 5 is two jobs)
+WGRAD_BYTES_PER_SAMPLE = (9 * 512 + 256 + 128) + (9 * 512 + 256) + 2 * 128 + 512
 
 
 STYLE_WORKLOAD = ("stylised render (render_style loop body, rendering.py:118-178): fern-shaped 1008x756 frame in 4096-ray batches, NeRF "
@@ -605,9 +607,15 @@ def run_train(args):
         hbm = peaks.get("hbm_gbs", 6650.0)
         ms_total = ms.item()
         value = TRAIN_RAYS * args.steps / (ms_total * 1e-3)
-        n_d, ms_d, _ = kinds["mlp_dgrad_kernel"]
+        n_d, ms_d, _ = kinds["mlp_wgrad_kernel"]       # the longest of the three kernels of a step
         samples_local = n_local * SAMPLES_PER_RAY * args.steps
-        ach = samples_local * DGRAD_BYTES_PER_SAMPLE / (ms_d * 1e-3) / 1e9 if ms_d > 0 else None
+        ach = samples_local * WGRAD_BYTES_PER_SAMPLE / (ms_d * 1e-3) / 1e9 if ms_d > 0 else None
+        traffic = None
+        try:    # DRAM bytes per sample of the same kernel from one `ncu --set full` capture, scaled to this run's launches
+            per_sample = json.load(open(os.path.join(ROOT, "profiles", "mlp_bwd_traffic.json")))["wgrad_dram_bytes_per_sample"]
+            traffic = per_sample * samples_local / max(n_d, 1)
+        except Exception:
+            pass
         res = {
             "metric": "rays/s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
@@ -620,9 +628,11 @@ def run_train(args):
                     "d2h_bytes_per_step": 4, "ms_per_step": ms2.item() / args.steps, "api": "NerfTrainer.step (tgtc_train_step + all-reduce + Adam)",
                     "loss": loss_val},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if ach else None, "traffic": None,
-                         "kernel": "mlp_dgrad_kernel", "launches_timed": int(n_d), "avg_launch_ms": ms_d / max(n_d, 1),
-                         "bytes_per_sample": DGRAD_BYTES_PER_SAMPLE, "peak_source": "MEASURED_PEAKS.json hbm_gbs"},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if ach else None, "traffic": traffic,
+                         "kernel": "mlp_wgrad_kernel", "launches_timed": int(n_d), "avg_launch_ms": ms_d / max(n_d, 1),
+                         "bytes_per_sample": WGRAD_BYTES_PER_SAMPLE, "algorithmic_bytes_per_launch": samples_local * WGRAD_BYTES_PER_SAMPLE / max(n_d, 1),
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs",
+                         "other_kernels_bytes_per_sample": {"mlp_dgrad_kernel": DGRAD_BYTES_PER_SAMPLE, "mlp_tc_kernel<train>": 9 * 512 + 256 + 128 + 320}},
             "kernels": {k: {"launches": int(v[0]), "ms_per_step": v[1] / args.steps,
                             "tflops": (v[2] / (v[1] * 1e-3) / 1e12) if v[1] > 0 else None} for k, v in kinds.items()},
             "clocks": clocks.window(t_wall0, t_wall1),

@@ -232,6 +232,23 @@ int tgtc_profile_read_kind(tgtc_ctx* ctx, int kind, int64_t* launches, double* m
  * gpu_launches claim is counted here, not estimated) */
 int64_t tgtc_launch_count(const tgtc_ctx* ctx);
 
+/* ---- in-kernel random streams for the training step -----------------------------------------------------
+ * tgtc_train_step_seeded = tgtc_train_step with the reference's stochastic options drawn inside the kernels instead of read
+ * from caller tensors: perturb != 0 -> stratified jitter (utils.py:518-524) generated in the sampling kernel;
+ * sigma_noise_std > 0 -> randn * std (utils.py:372-374) generated in the compositing forward and regenerated in its backward.
+ * Generator: Philox4x32-10, counter = element index, key = seed (csrc/philox.cuh; CPU restatement oracle/philox_oracle.py).
+ * Element e of a stream is a pure function of (seed, stream, e): use a different seed for every call of a step (ray chunks)
+ * and every step.  The reference's own streams (torch's global generator) are not reproduced, only the distributions.
+ * tgtc_philox_fill writes the same streams as tensors: stream_id 0 = jitter uniforms [n_rays*n_samples] (normal = 0),
+ * 1 / 2 = coarse / fine sigma noise [n_rays*S] (normal = 1, std) -- feeding them to tgtc_train_step(rand, noise_*) gives
+ * bit-identical results to the seeded call. */
+int tgtc_train_step_seeded(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, const float* rgb_gt, int64_t n_rays,
+                           int64_t n_rays_total, double near, double far, int n_samples, int n_fine, unsigned long long seed,
+                           int perturb, double sigma_noise_std, float* grads, int accumulate, float* loss_sums, float* rgb_coarse,
+                           float* rgb_fine, void* workspace, size_t workspace_bytes, tgtc_stream stream);
+int tgtc_philox_fill(tgtc_ctx* ctx, unsigned long long seed, int stream_id, int normal, double std, int64_t n, float* out,
+                     tgtc_stream stream);
+
 /* ---- Style_train: the second training phase (train_tgtcs.py:311-495) ------------------------------------
  * The reference's step: perturbed coarse samples (train_tgtcs.py:362) -> frozen NeRF net -> style module 1 with the ray's
  * latent (latents_model_1(style_id, frame_id), :409) -> style module 2 with mean(latent) (:410-421) -> compositing (:424) ->

@@ -196,3 +196,38 @@ def test_trainer_steps_reduce_loss(renderer_bf16):
     assert (tr.flat - before).abs().max().item() > 0
     sdc, sdf = tr.state_dicts()
     assert set(sdc) == set(wc) and sdc["net.base_layers.5.weight"].shape == (256, 319)
+
+
+def test_philox_streams_vs_oracle(renderer_bf16):
+    """the in-kernel generator (csrc/philox.cuh) against its CPU restatement: uniforms bit for bit, normals to fp32 rounding"""
+    import philox_oracle as P
+    r = renderer_bf16
+    n = 100003
+    for seed in (0, 7, 0xDEADBEEF12345678):
+        u = r.philox_fill(seed, 0, n).cpu().numpy()
+        assert np.array_equal(u, P.uniform(seed, 0, n)), seed
+        z = r.philox_fill(seed, 2, n, normal=True, std=0.75).cpu().numpy()
+        np.testing.assert_allclose(z, P.normal(seed, 2, n, std=0.75), rtol=2e-5, atol=2e-6)
+    assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 5e-3 and abs(z.std() - 0.75) < 5e-3
+
+
+def test_train_step_seeded_equals_replay(renderer_bf16):
+    """tgtc_train_step_seeded (jitter + noise drawn inside the kernels) == tgtc_train_step fed the same streams as tensors"""
+    n = 192
+    wc, wf, ro, rd, gt = _train_inputs(n, seed=13)
+    r = renderer_bf16
+    r.set_weights(wc, wf)
+    seed, std = 1234567, 0.5
+    a = r.train_step(ro, rd, gt, seed=seed, perturb=True, sigma_noise_std=std)
+    ga, la = a["grads"].clone(), a["loss"].item()
+    rand = r.philox_fill(seed, 0, n * 64).view(n, 64)
+    nzc = r.philox_fill(seed, 1, n * 64, normal=True, std=std).view(n, 64)
+    nzf = r.philox_fill(seed, 2, n * 128, normal=True, std=std).view(n, 128)
+    b = r.train_step(ro, rd, gt, rand=rand, noise_coarse=nzc, noise_fine=nzf)
+    torch.cuda.synchronize()
+    assert torch.equal(ga, b["grads"]) and la == b["loss"].item()
+    # and the options matter
+    c = r.train_step(ro, rd, gt)
+    assert not torch.equal(c["grads"], ga)
+    d = r.train_step(ro, rd, gt, seed=seed + 1, perturb=True, sigma_noise_std=std)
+    assert not torch.equal(d["grads"], ga)

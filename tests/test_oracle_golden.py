@@ -200,3 +200,15 @@ def test_style_train_step_vs_golden():
             sl = gr.numpy().reshape(-1)[::97]
             assert abs(np.linalg.norm(gr.numpy().astype(np.float64)) - ref_norm) <= 1e-3 * ref_norm + 1e-9, (tag, k)
             np.testing.assert_allclose(sl, g["gslice_%s/%s" % (tag, k)], rtol=5e-3, atol=1e-5 * ref_norm + 1e-9, err_msg="%s %s" % (tag, k))
+
+
+def test_philox_known_answers():
+    """oracle/philox_oracle.py against the Random123 known-answer vectors of philox4x32-10"""
+    import philox_oracle as P
+    for ctr, key, exp in P.KAT:
+        out = P.philox4x32_10(np.array(ctr, dtype=np.uint32), np.array(key, dtype=np.uint32))
+        assert [int(x) for x in out] == list(exp)
+    u = P.uniform(3, 0, 200000)
+    z = P.normal(3, 1, 200000)
+    assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 3e-3
+    assert abs(z.mean()) < 1e-2 and abs(z.std() - 1.0) < 1e-2

@@ -69,6 +69,10 @@ PROTOTYPES = {
     "tgtc_render_style": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                          ctypes.c_int, c_i64, c_void_p, c_void_p, ctypes.POINTER(RenderOut), c_void_p,
                                          ctypes.c_size_t, c_void_p]),
+    "tgtc_train_step_seeded": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, ctypes.c_double, ctypes.c_double,
+                                              ctypes.c_int, ctypes.c_int, ctypes.c_ulonglong, ctypes.c_int, ctypes.c_double, c_void_p,
+                                              ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_size_t, c_void_p]),
+    "tgtc_philox_fill": (ctypes.c_int, [c_void_p, ctypes.c_ulonglong, ctypes.c_int, ctypes.c_int, ctypes.c_double, c_i64, c_void_p, c_void_p]),
     "tgtc_style_train_workspace_bytes": (ctypes.c_size_t, [c_void_p, c_i64, ctypes.c_int, ctypes.c_int]),
     "tgtc_style_num_params": (c_i64, []),
     "tgtc_style_train_forward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_int,

@@ -533,9 +533,9 @@ extern "C" int64_t tgtc_num_params(void) { return (int64_t)bwd_flat_floats(); }
 // one network pass: forward (stash) -> compositing -> [caller hook: resampling] -> loss gradient -> compositing backward ->
 // activation gradients -> weight gradients
 static int train_pass(tgtc_ctx* ctx, int net, const float* rays_o, const float* rays_d, const float* ts, int64_t ts_stride, int64_t n,
-                      int S, double near, double far, const float* noise, const float* rgb_gt, float scale, const TrainWs& ws,
-                      uint8_t* base, float* grads, int accumulate, float* sq_sum, float* rgb_out, float* weights_out,
-                      cudaStream_t st) {
+                      int S, double near, double far, const float* noise, const PhiloxSrc* prng, const float* rgb_gt, float scale,
+                      const TrainWs& ws, uint8_t* base, float* grads, int accumulate, float* sq_sum, float* rgb_out,
+                      float* weights_out, cudaStream_t st) {
   TcStash stash;
   stash.h = base + ws.off_stash_h; stash.f = base + ws.off_stash_f; stash.pe = base + ws.off_stash_pe;
   stash.mask = reinterpret_cast<uint32_t*>(base + ws.off_stash_mask);
@@ -558,11 +558,11 @@ static int train_pass(tgtc_ctx* ctx, int net, const float* rays_o, const float* 
   rc = launch_mlp_tc_train(ctx, net, io, stash, st);
   if (rc) return rc;
   if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
-  rc = launch_composite(ctx, nullptr, nullptr, rs, ts, ts_stride, noise, 0, n, S, rgb, nullptr, nullptr, weights_out, st);
+  rc = launch_composite(ctx, nullptr, nullptr, rs, ts, ts_stride, noise, 0, n, S, rgb, nullptr, nullptr, weights_out, st, prng);
   if (rc) return rc;
   rc = launch_mse_grad(ctx, rgb, rgb_gt, n, scale, g, sq_sum, st);
   if (rc) return rc;
-  rc = launch_composite_backward(ctx, rs, ts, ts_stride, noise, 0, n, S, g, nullptr, nullptr, drs, st);
+  rc = launch_composite_backward(ctx, rs, ts, ts_stride, noise, 0, n, S, g, nullptr, nullptr, drs, st, prng);
   if (rc) return rc;
   // algorithmic FLOPs: dgrad skips the three slices into non-differentiable inputs (PE->L0, PE->L5, dirPE->rgb0)
   rc = prof_begin(ctx, 2, samples * 2.0 * (593408.0 - 16128.0 - 16128.0 - 3456.0), st, &e1);
@@ -578,11 +578,11 @@ static int train_pass(tgtc_ctx* ctx, int net, const float* rays_o, const float* 
   return TGTC_OK;
 }
 
-extern "C" int tgtc_train_step(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, const float* rgb_gt, int64_t n_rays,
-                               int64_t n_rays_total, double near, double far, int n_samples, int n_fine, const float* rand,
-                               const float* noise_coarse, const float* noise_fine, float* grads, int accumulate,
-                               float* loss_sums, float* rgb_coarse, float* rgb_fine, void* workspace, size_t workspace_bytes,
-                               tgtc_stream stream) {
+static int train_step_impl(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, const float* rgb_gt, int64_t n_rays,
+                           int64_t n_rays_total, double near, double far, int n_samples, int n_fine, const float* rand,
+                           const float* noise_coarse, const float* noise_fine, const PhiloxSrc* jitter, const PhiloxSrc* prng_c,
+                           const PhiloxSrc* prng_f, float* grads, int accumulate, float* loss_sums, float* rgb_coarse, float* rgb_fine,
+                           void* workspace, size_t workspace_bytes, tgtc_stream stream) {
   CHECK_CTX(ctx);
   CHECK_NET(ctx, TGTC_NET_COARSE);
   CHECK_NET(ctx, TGTC_NET_FINE);
@@ -605,19 +605,56 @@ extern "C" int tgtc_train_step(tgtc_ctx* ctx, const float* rays_o, const float* 
   const size_t np = bwd_flat_floats();
   // loss = mse(rgb_gt, rgb_coarse) + mse(rgb_gt, rgb_fine), each a mean over n_rays_total*3 values (train_tgtcs.py:238-251)
   const float scale = 2.0f / (3.0f * (float)n_rays_total);
-  // coarse sample positions: one shared row (perturb=False, utils.py:512-516) or per-ray stratified positions replaying the
-  // caller's uniforms (perturb=True, utils.py:518-524)
-  const int64_t ts_c_stride = rand != nullptr ? S : 0;
-  int rc = launch_sample_uniform(ctx, nullptr, nullptr, rand != nullptr ? n_rays : 1, S, near, far, rand, nullptr, ts_c, st);
+  // coarse sample positions: one shared row (perturb=False, utils.py:512-516) or per-ray stratified positions from the
+  // caller's uniforms / the in-kernel Philox stream (perturb=True, utils.py:518-524)
+  const bool per_ray = rand != nullptr || jitter != nullptr;
+  const int64_t ts_c_stride = per_ray ? S : 0;
+  int rc = launch_sample_uniform(ctx, nullptr, nullptr, per_ray ? n_rays : 1, S, near, far, rand, nullptr, ts_c, st, jitter);
   if (rc) return rc;
-  rc = train_pass(ctx, TGTC_NET_COARSE, rays_o, rays_d, ts_c, ts_c_stride, n_rays, S, near, far, noise_coarse, rgb_gt, scale, ws, base,
-                  grads, accumulate, loss_sums, rgb_coarse, w_c, st);
+  rc = train_pass(ctx, TGTC_NET_COARSE, rays_o, rays_d, ts_c, ts_c_stride, n_rays, S, near, far, noise_coarse, prng_c, rgb_gt, scale, ws,
+                  base, grads, accumulate, loss_sums, rgb_coarse, w_c, st);
   if (rc) return rc;
   // no gradient flows through the resampling (utils.py:576-579): the two nets' backward passes are independent
   rc = launch_sample_fine(ctx, nullptr, nullptr, ts_c, ts_c_stride, w_c, n_rays, S, F, nullptr, ts_f, nullptr, nullptr, st);
   if (rc) return rc;
-  return train_pass(ctx, TGTC_NET_FINE, rays_o, rays_d, ts_f, S + F, n_rays, S + F, near, far, noise_fine, rgb_gt, scale, ws, base,
-                    grads + np, accumulate, loss_sums != nullptr ? loss_sums + 1 : nullptr, rgb_fine, nullptr, st);
+  return train_pass(ctx, TGTC_NET_FINE, rays_o, rays_d, ts_f, S + F, n_rays, S + F, near, far, noise_fine, prng_f, rgb_gt, scale, ws,
+                    base, grads + np, accumulate, loss_sums != nullptr ? loss_sums + 1 : nullptr, rgb_fine, nullptr, st);
+}
+
+extern "C" int tgtc_train_step(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, const float* rgb_gt, int64_t n_rays,
+                               int64_t n_rays_total, double near, double far, int n_samples, int n_fine, const float* rand,
+                               const float* noise_coarse, const float* noise_fine, float* grads, int accumulate,
+                               float* loss_sums, float* rgb_coarse, float* rgb_fine, void* workspace, size_t workspace_bytes,
+                               tgtc_stream stream) {
+  return train_step_impl(ctx, rays_o, rays_d, rgb_gt, n_rays, n_rays_total, near, far, n_samples, n_fine, rand, noise_coarse, noise_fine,
+                         nullptr, nullptr, nullptr, grads, accumulate, loss_sums, rgb_coarse, rgb_fine, workspace, workspace_bytes, stream);
+}
+
+// the same step with the reference's stochastic options drawn INSIDE the kernels from Philox4x32-10 (philox.cuh): stratified
+// jitter in the sampling kernel, sigma noise in the compositing forward and (regenerated, not stored) backward
+extern "C" int tgtc_train_step_seeded(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, const float* rgb_gt, int64_t n_rays,
+                                      int64_t n_rays_total, double near, double far, int n_samples, int n_fine,
+                                      unsigned long long seed, int perturb, double sigma_noise_std, float* grads, int accumulate,
+                                      float* loss_sums, float* rgb_coarse, float* rgb_fine, void* workspace, size_t workspace_bytes,
+                                      tgtc_stream stream) {
+  const PhiloxSrc jit = {seed, kStreamJitter, 1.0f, 1};
+  const PhiloxSrc nc = {seed, kStreamNoiseCoarse, (float)sigma_noise_std, 1};
+  const PhiloxSrc nf = {seed, kStreamNoiseFine, (float)sigma_noise_std, 1};
+  const bool noise = sigma_noise_std > 0.0;
+  return train_step_impl(ctx, rays_o, rays_d, rgb_gt, n_rays, n_rays_total, near, far, n_samples, n_fine, nullptr, nullptr, nullptr,
+                         perturb ? &jit : nullptr, noise ? &nc : nullptr, noise ? &nf : nullptr, grads, accumulate, loss_sums, rgb_coarse,
+                         rgb_fine, workspace, workspace_bytes, stream);
+}
+
+// element e of stream `stream` (0 = jitter uniforms, 1 / 2 = coarse / fine sigma noise) under `seed`, as a tensor
+extern "C" int tgtc_philox_fill(tgtc_ctx* ctx, unsigned long long seed, int stream_id, int normal, double std, int64_t n, float* out,
+                                tgtc_stream stream) {
+  CHECK_CTX(ctx);
+  TGTC_REQUIRE(n >= 0 && stream_id >= 0, TGTC_ERR_ARG, "bad n=%lld / stream_id=%d", (long long)n, stream_id);
+  if (n == 0) return TGTC_OK;
+  CHECK_PTR(out, "out");
+  DeviceGuard g(ctx->device);
+  return launch_philox_fill(ctx, seed, (uint32_t)stream_id, normal, (float)std, n, out, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/tgtc_b200.h"
+#include "philox.cuh"
 
 // ---------------------------------------------------------------------------
 // network geometry (models.py:63-117 with D=8, W=256, skips=[4], L_pts=10, L_dir=4)
@@ -153,7 +154,7 @@ int launch_raygen(tgtc_ctx* ctx, int H, int W, const double* K, const double* c2
 
 // sampling.cu
 int launch_sample_uniform(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n, int S, double near,
-                          double far, const float* rnd, float* pts, float* ts, cudaStream_t st);
+                          double far, const float* rnd, float* pts, float* ts, cudaStream_t st, const PhiloxSrc* prng = nullptr);
 int launch_sample_fine(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, const float* ts, int64_t ts_stride,
                        const float* weights, int64_t n, int S, int n_fine, float* pts_out, float* ts_out,
                        int64_t* inds_out, float* samples_out, cudaStream_t st);
@@ -161,11 +162,12 @@ int launch_sample_fine(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, 
 // composite.cu
 int launch_composite(tgtc_ctx* ctx, const float* rgb, const float* sigma, const float* rgbsigma, const float* ts,
                      int64_t ts_stride, const float* noise, int white_bkgd, int64_t n, int S, float* rgb_out,
-                     float* depth_out, float* acc_out, float* weights_out, cudaStream_t st);
+                     float* depth_out, float* acc_out, float* weights_out, cudaStream_t st, const PhiloxSrc* prng = nullptr);
+int launch_philox_fill(tgtc_ctx* ctx, unsigned long long seed, uint32_t stream, int normal, float std, int64_t n, float* out, cudaStream_t st);
 
 int launch_composite_backward(tgtc_ctx* ctx, const float* rgbsigma, const float* ts, int64_t ts_stride, const float* noise,
                               int white_bkgd, int64_t n, int S, const float* g_rgb, const float* g_depth, const float* g_acc,
-                              float* d_rgbsigma, cudaStream_t st);
+                              float* d_rgbsigma, cudaStream_t st, const PhiloxSrc* prng = nullptr);
 
 // how the MLP kernels get their per-sample inputs and where results go
 struct MlpIO {

@@ -9,6 +9,7 @@
 // chunks are not read (bit-identical to not terminating).
 // HBM-bound: fine pass reads 16 B/sample + 4 B/sample ts, writes 4 B/sample + 20 B/ray.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace {
 
@@ -17,8 +18,8 @@ constexpr int kWarps = 8;
 template <bool PACKED>
 __global__ void __launch_bounds__(32 * kWarps) composite_kernel(
     const float* __restrict__ rgb, const float* __restrict__ sigma, const float4* __restrict__ rgbsigma,
-    const float* __restrict__ ts, int64_t ts_stride, const float* __restrict__ noise, int white_bkgd, int64_t n, int S,
-    float* __restrict__ rgb_out, float* __restrict__ depth_out, float* __restrict__ acc_out,
+    const float* __restrict__ ts, int64_t ts_stride, const float* __restrict__ noise, const PhiloxSrc prng, int white_bkgd, int64_t n,
+    int S, float* __restrict__ rgb_out, float* __restrict__ depth_out, float* __restrict__ acc_out,
     float* __restrict__ weights_out) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
@@ -45,6 +46,8 @@ __global__ void __launch_bounds__(32 * kWarps) composite_kernel(
           cr = c[0]; cg = c[1]; cb = c[2];
         }
         if (noise != nullptr) sg = __fadd_rn(sg, noise[ray * S + i]);
+        else if (prng.on) sg = __fadd_rn(sg, __fmul_rn(prng.std, philox_normal(prng.seed, prng.stream, (uint64_t)(ray * S + i))));
+        else if (prng.on) sg = __fadd_rn(sg, __fmul_rn(prng.std, philox_normal(prng.seed, prng.stream, (uint64_t)(ray * S + i))));
         t = tsr[i];
         tn = (i + 1 < S) ? tsr[i + 1] : 0.f;
       }
@@ -90,17 +93,18 @@ __global__ void __launch_bounds__(32 * kWarps) composite_kernel(
 
 int launch_composite(tgtc_ctx* ctx, const float* rgb, const float* sigma, const float* rgbsigma, const float* ts,
                      int64_t ts_stride, const float* noise, int white_bkgd, int64_t n, int S, float* rgb_out,
-                     float* depth_out, float* acc_out, float* weights_out, cudaStream_t st) {
+                     float* depth_out, float* acc_out, float* weights_out, cudaStream_t st, const PhiloxSrc* prng_p) {
+  const PhiloxSrc prng = prng_p != nullptr ? *prng_p : PhiloxSrc{0, 0, 0.f, 0};
   const int64_t blocks_needed = (n + kWarps - 1) / kWarps;
   const int64_t cap = (int64_t)ctx->num_sms * 8 * 4;  // 8 resident 256-thread CTAs per SM, 4 waves
   const int64_t grid = blocks_needed < cap ? blocks_needed : cap;
   if (rgbsigma != nullptr) {
     composite_kernel<true><<<(unsigned)grid, 32 * kWarps, 0, st>>>(nullptr, nullptr, reinterpret_cast<const float4*>(rgbsigma), ts,
-                                                                  ts_stride, noise, white_bkgd, n, S, rgb_out, depth_out,
+                                                                  ts_stride, noise, prng, white_bkgd, n, S, rgb_out, depth_out,
                                                                   acc_out, weights_out);
   } else {
-    composite_kernel<false><<<(unsigned)grid, 32 * kWarps, 0, st>>>(rgb, sigma, nullptr, ts, ts_stride, noise, white_bkgd, n, S,
-                                                                   rgb_out, depth_out, acc_out, weights_out);
+    composite_kernel<false><<<(unsigned)grid, 32 * kWarps, 0, st>>>(rgb, sigma, nullptr, ts, ts_stride, noise, prng, white_bkgd, n,
+                                                                   S, rgb_out, depth_out, acc_out, weights_out);
   }
   TGTC_LAUNCH_CHECK(ctx);
   return TGTC_OK;
@@ -122,7 +126,7 @@ constexpr int kBwdMaxS = 256;
 
 __global__ void __launch_bounds__(32 * kWarps) composite_backward_kernel(
     const float4* __restrict__ rgbsigma, const float* __restrict__ ts, int64_t ts_stride, const float* __restrict__ noise,
-    int white_bkgd, int64_t n, int S, const float* __restrict__ g_rgb, const float* __restrict__ g_depth,
+    const PhiloxSrc prng, int white_bkgd, int64_t n, int S, const float* __restrict__ g_rgb, const float* __restrict__ g_depth,
     const float* __restrict__ g_acc, float4* __restrict__ d_rgbsigma) {
   __shared__ float s_e[kWarps][kBwdMaxS], s_T[kWarps][kBwdMaxS], s_gw[kWarps][kBwdMaxS];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -144,6 +148,7 @@ __global__ void __launch_bounds__(32 * kWarps) composite_backward_kernel(
       if (valid) {
         v = rgbsigma[ray * S + i];
         if (noise != nullptr) v.w = __fadd_rn(v.w, noise[ray * S + i]);
+        else if (prng.on) v.w = __fadd_rn(v.w, __fmul_rn(prng.std, philox_normal(prng.seed, prng.stream, (uint64_t)(ray * S + i))));
         t = tsr[i];
         tn = (i + 1 < S) ? tsr[i + 1] : 0.f;
       }
@@ -191,6 +196,7 @@ __global__ void __launch_bounds__(32 * kWarps) composite_backward_kernel(
         const float4 v = rgbsigma[ray * S + i];
         float sg = v.w;
         if (noise != nullptr) sg = __fadd_rn(sg, noise[ray * S + i]);
+        else if (prng.on) sg = __fadd_rn(sg, __fmul_rn(prng.std, philox_normal(prng.seed, prng.stream, (uint64_t)(ray * S + i))));
         const float t = tsr[i];
         const float delta = (i + 1 < S) ? __fsub_rn(tsr[i + 1], t) : 1e10f;
         const float fac = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
@@ -207,14 +213,32 @@ __global__ void __launch_bounds__(32 * kWarps) composite_backward_kernel(
 
 int launch_composite_backward(tgtc_ctx* ctx, const float* rgbsigma, const float* ts, int64_t ts_stride, const float* noise,
                               int white_bkgd, int64_t n, int S, const float* g_rgb, const float* g_depth, const float* g_acc,
-                              float* d_rgbsigma, cudaStream_t st) {
+                              float* d_rgbsigma, cudaStream_t st, const PhiloxSrc* prng_p) {
+  const PhiloxSrc prng = prng_p != nullptr ? *prng_p : PhiloxSrc{0, 0, 0.f, 0};
   TGTC_REQUIRE(S <= kBwdMaxS, TGTC_ERR_UNSUPPORTED, "composite_backward: S=%d > %d", S, kBwdMaxS);
   const int64_t blocks_needed = (n + kWarps - 1) / kWarps;
   const int64_t cap = (int64_t)ctx->num_sms * 8 * 4;
   const int64_t grid = blocks_needed < cap ? blocks_needed : cap;
-  composite_backward_kernel<<<(unsigned)grid, 32 * kWarps, 0, st>>>(reinterpret_cast<const float4*>(rgbsigma), ts, ts_stride, noise,
+  composite_backward_kernel<<<(unsigned)grid, 32 * kWarps, 0, st>>>(reinterpret_cast<const float4*>(rgbsigma), ts, ts_stride, noise, prng,
                                                                    white_bkgd, n, S, g_rgb, g_depth, g_acc,
                                                                    reinterpret_cast<float4*>(d_rgbsigma));
+  TGTC_LAUNCH_CHECK(ctx);
+  return TGTC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// the same streams as stand-alone tensors (tests, and callers that want to look at what a seeded step drew)
+namespace {
+__global__ void philox_fill_kernel(unsigned long long seed, uint32_t stream, int normal, float std, int64_t n, float* __restrict__ out) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+    out[e] = normal ? __fmul_rn(std, philox_normal(seed, stream, (uint64_t)e)) : philox_uniform(seed, stream, (uint64_t)e);
+}
+}  // namespace
+int launch_philox_fill(tgtc_ctx* ctx, unsigned long long seed, uint32_t stream, int normal, float std, int64_t n, float* out, cudaStream_t st) {
+  if (n == 0) return TGTC_OK;
+  const int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)ctx->num_sms * 16;
+  philox_fill_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(seed, stream, normal, std, n, out);
   TGTC_LAUNCH_CHECK(ctx);
   return TGTC_OK;
 }

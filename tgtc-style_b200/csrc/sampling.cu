@@ -4,6 +4,7 @@
 // Both are HBM-bound when run stand-alone (sample_fine: read w 4S + write
 // ts_fine 4(S+F) bytes per ray = 768 B/ray at S=F=64).  One warp per ray.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace {
 
@@ -11,20 +12,21 @@ namespace {
 // K2
 __global__ void __launch_bounds__(256) sample_uniform_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                              int64_t n, int S, float t_scale, float t_near,
-                                                             const float* __restrict__ rnd, float* __restrict__ pts,
-                                                             float* __restrict__ ts) {
+                                                             const float* __restrict__ rnd, const PhiloxSrc prng,
+                                                             float* __restrict__ pts, float* __restrict__ ts) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * S) return;
   const int64_t ray = idx / S;
   const int k = (int)(idx - ray * S);
   float t = coarse_t(k, S, t_scale, t_near);
-  if (rnd != nullptr) {
+  if (rnd != nullptr || prng.on) {
     // utils.py:518-524: mid=(ts[1:]+ts[:-1])/2; upper=[mid, ts[-1]]; lower=[ts[0], mid]; ts=lower+(upper-lower)*rand
     const float tp = coarse_t(k > 0 ? k - 1 : 0, S, t_scale, t_near);
     const float tn = coarse_t(k < S - 1 ? k + 1 : S - 1, S, t_scale, t_near);
     const float lower = (k == 0) ? t : __fdiv_rn(__fadd_rn(t, tp), 2.0f);
     const float upper = (k == S - 1) ? t : __fdiv_rn(__fadd_rn(tn, t), 2.0f);
-    t = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), rnd[idx]));
+    const float u = rnd != nullptr ? rnd[idx] : philox_uniform(prng.seed, prng.stream, (uint64_t)idx);
+    t = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), u));
   }
   ts[idx] = t;
   if (pts != nullptr) {
@@ -214,12 +216,13 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_fine_kernel(
 }  // namespace
 
 int launch_sample_uniform(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n, int S, double near,
-                          double far, const float* rnd, float* pts, float* ts, cudaStream_t st) {
+                          double far, const float* rnd, float* pts, float* ts, cudaStream_t st, const PhiloxSrc* prng) {
   const int64_t total = n * S;
   const int block = 256;
   const int64_t grid = (total + block - 1) / block;
   TGTC_REQUIRE(grid <= 0x7fffffff, TGTC_ERR_UNSUPPORTED, "sample_uniform: too many samples in one call");
-  sample_uniform_kernel<<<(unsigned)grid, block, 0, st>>>(rays_o, rays_d, n, S, (float)(far - near), (float)near, rnd, pts, ts);
+  sample_uniform_kernel<<<(unsigned)grid, block, 0, st>>>(rays_o, rays_d, n, S, (float)(far - near), (float)near, rnd,
+                                                          prng != nullptr ? *prng : PhiloxSrc{0, 0, 0.f, 0}, pts, ts);
   TGTC_LAUNCH_CHECK(ctx);
   return TGTC_OK;
 }

@@ -409,13 +409,14 @@ class NerfRenderer:
 
     # ------------------------------------------------------------------ training step (a11)
     def train_step(self, rays_o, rays_d, rgb_gt, n_total=None, near=0., far=1., n_samples=64, n_fine=64, grads=None,
-                   accumulate=False, rand=None, noise_coarse=None, noise_fine=None):
+                   accumulate=False, rand=None, noise_coarse=None, noise_fine=None, seed=None, perturb=False, sigma_noise_std=0.):
         """Forward + backward of Origin_train's loss (train_tgtcs.py:228-255, perturb=0, noise=0) for one batch of rays:
         loss = mse(rgb_gt, rgb_coarse) + mse(rgb_gt, rgb_fine), means taken over n_total rays (default: this batch).
         Returns {"loss" (device scalar), "grads" (flat fp32 [2*P]: coarse net then fine net, tgtc_set_weights order),
         "rgb_coarse", "rgb_fine"}.  Pass the same `grads` with accumulate=True for the later ray chunks of one step.
         rand [n,S] (uniforms, perturb=True of utils.py:518-524) and noise_coarse [n,S] / noise_fine [n,S+F] (randn*std,
-        utils.py:372-374) replay the reference's stochastic options with caller-drawn tensors."""
+        utils.py:372-374) replay the reference's stochastic options with caller-drawn tensors; with `seed` (an int) they are
+        drawn inside the kernels instead (Philox4x32-10, tgtc_train_step_seeded): perturb / sigma_noise_std select which."""
         self.refresh_weights()
         ro, rd, gt = self._dev(rays_o), self._dev(rays_d), self._dev(rgb_gt)
         n = ro.shape[0]
@@ -433,10 +434,18 @@ class NerfRenderer:
         rnd = self._dev(rand) if rand is not None else None
         nzc = self._dev(noise_coarse) if noise_coarse is not None else None
         nzf = self._dev(noise_fine) if noise_fine is not None else None
-        _lib.check(self.lib.tgtc_train_step(self._h, _ptr(ro), _ptr(rd), _ptr(gt), n, n_total, float(near), float(far), n_samples,
-                                            n_fine, _ptr(rnd), _ptr(nzc), _ptr(nzf), _ptr(grads), int(accumulate), _ptr(sums),
-                                            _ptr(rgb_c), _ptr(rgb_f),
-                                            ctypes.c_void_p(ws.data_ptr() + off), wsb, self._stream))
+        if seed is not None:
+            if rnd is not None or nzc is not None or nzf is not None:
+                raise ValueError("pass either replay tensors or a seed")
+            _lib.check(self.lib.tgtc_train_step_seeded(self._h, _ptr(ro), _ptr(rd), _ptr(gt), n, n_total, float(near), float(far),
+                                                       n_samples, n_fine, int(seed) & 0xFFFFFFFFFFFFFFFF, int(bool(perturb)),
+                                                       float(sigma_noise_std), _ptr(grads), int(accumulate), _ptr(sums), _ptr(rgb_c),
+                                                       _ptr(rgb_f), ctypes.c_void_p(ws.data_ptr() + off), wsb, self._stream))
+        else:
+            _lib.check(self.lib.tgtc_train_step(self._h, _ptr(ro), _ptr(rd), _ptr(gt), n, n_total, float(near), float(far), n_samples,
+                                                n_fine, _ptr(rnd), _ptr(nzc), _ptr(nzf), _ptr(grads), int(accumulate), _ptr(sums),
+                                                _ptr(rgb_c), _ptr(rgb_f),
+                                                ctypes.c_void_p(ws.data_ptr() + off), wsb, self._stream))
         return {"loss": sums.sum() / (3.0 * n_total), "grads": grads, "rgb_coarse": rgb_c, "rgb_fine": rgb_f}
 
     # ------------------------------------------------------------------ Style_train (train_tgtcs.py:311-495)
@@ -501,6 +510,13 @@ class NerfRenderer:
                 o += no
             out.append(d)
         return tuple(out)
+
+    def philox_fill(self, seed, stream_id, n, normal=False, std=1.0):
+        """The tensor a seeded training step draws in-kernel: stream 0 = jitter uniforms, 1 / 2 = coarse / fine sigma noise."""
+        out = torch.empty(int(n), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.tgtc_philox_fill(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_id), int(bool(normal)), float(std), int(n),
+                                             _ptr(out), self._stream))
+        return out
 
     def adam_step(self, params, grads, exp_avg, exp_avg_sq, step, lr=5e-4, betas=(0.9, 0.999), eps=1e-8):
         """torch.optim.Adam's update (train_tgtcs.py:39) on flat fp32 device buffers, one kernel (tgtc_adam_step)."""

@@ -16,12 +16,14 @@ from .render import LAYER_NAMES, LAYER_SHAPES
 
 
 class NerfTrainer:
-    def __init__(self, renderer, coarse, fine, lr=5e-4, lr_decay_steps=100000, lr_decay_rate=0.1, group=None, max_rays_per_pass=8192):
+    def __init__(self, renderer, coarse, fine, lr=5e-4, lr_decay_steps=100000, lr_decay_rate=0.1, group=None, max_rays_per_pass=8192,
+                 seed=None):
         """coarse / fine: state_dicts (or nn.Modules) with the reference's parameter names (models.py:75-91).
         lr schedule: lr * rate^(step/decay_steps) as train_tgtcs.py:272-276."""
         self.r = renderer
         self.group = group
         self.max_rays = int(max_rays_per_pass)
+        self.seed = seed   # int: perturb / sigma noise are drawn inside the kernels (Philox) instead of by torch's generator
         dev = renderer.device
         # fp32 masters of both nets live in ONE flat buffer laid out like the gradient buffer; the per-parameter tensors are
         # views into it (state_dict export, re-packing) and the optimizer is one fused kernel over the flat buffers
@@ -67,6 +69,13 @@ class NerfTrainer:
         for b in range(0, max(n, 1), self.max_rays):
             e = min(n, b + self.max_rays)
             rand = nzc = nzf = None
+            if self.seed is not None and (perturb or sigma_noise_std > 0):
+                # one Philox key per (step, rank, ray chunk): elements are indexed from 0 inside every library call
+                key = (int(self.seed) * 0x9E3779B97F4A7C15 + (self.step_count << 24) + (self.rank() << 12) + b // self.max_rays) & (2 ** 64 - 1)
+                out = self.r.train_step(rays_o[b:e], rays_d[b:e], rgb_gt[b:e], n_total=n_total, grads=self.grads, accumulate=b > 0,
+                                        seed=key, perturb=perturb, sigma_noise_std=sigma_noise_std)
+                loss = out["loss"] if loss is None else loss + out["loss"]
+                continue
             if perturb:             # the generator call of utils.py:519-520
                 rand = torch.zeros([e - b, 64], device=rays_o.device)
                 torch.nn.init.uniform_(rand, 0, 1)
