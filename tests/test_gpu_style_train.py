@@ -190,3 +190,28 @@ def test_style_train_forward_vs_reference_golden(renderer_bf16):
     # minus_logp of the host latent model against the reference's (models.py:531-537)
     lp = 0.1 * lat.minus_logp(torch.from_numpy(g["b1/style_id"]).to(dev), torch.from_numpy(g["b1/frame_id"]).to(dev))
     assert abs(lp.item() - float(g["loss_logp"])) <= 1e-5 * max(1.0, float(g["loss_logp"]))
+
+
+@pytest.mark.parametrize("n", [1, 3, 130])
+def test_style_train_ragged_batches(renderer_bf16, n):
+    """ray counts that leave half-filled / padding tiles in both passes (coarse tile = 2 rays, fine tile = 1 ray, tiles are
+    handed out in quads): forward, parameter gradients and latent gradients still match autograd"""
+    r = renderer_bf16
+    (wc, wf, cs, ws), ro, rd, lat, rand, g_c, g_f = _inputs(n, seed=17 + n)
+    r.set_weights(wc, wf)
+    r.set_style_weights(cs, ws)
+    ref_c, ref_f, gcs, gws, dlat_ref = O.style_train_forward_backward(wc, wf, cs, ws, ro, rd, lat, g_c, g_f, rand=rand)
+    fw = r.style_train_forward(ro, rd, lat, rand=rand)
+    bw = r.style_train_backward(fw["state"], g_c, g_f)
+    torch.cuda.synchronize()
+    assert (fw["rgb_coarse"].cpu() - ref_c).abs().max().item() <= 3e-2
+    assert (fw["rgb_fine"].cpu() - ref_f).abs().max().item() <= 5e-2
+    ours_c, ours_w = r.style_grad_views(bw["grads"])
+    for ref, ours, tag in ((gcs, ours_c, "concat"), (gws, ours_w, "wild")):
+        for k, gr in ref.items():
+            a, b = ours[k].cpu().double().flatten(), gr.double().flatten()
+            assert torch.isfinite(a).all(), (tag, k)
+            rel = ((a - b).norm() / (b.norm() + 1e-30)).item()
+            assert rel <= 0.2, (n, tag, k, rel)
+    a, b = bw["d_latents"].cpu().double().flatten(), dlat_ref.double().flatten()
+    assert ((a - b).norm() / b.norm()).item() <= 0.1
