@@ -539,14 +539,18 @@ __global__ void __launch_bounds__(256) style_latgrad_kernel(const float* __restr
 #pragma unroll
   for (int q = 0; q < kLatRays; ++q) a1[q] = a2[q] = 0.f;
   for (int l = 0; l < 13; ++l) {
-    __syncthreads();
+    // all of the layer's R rows of this block's rays in flight at once (spr <= 2: S is 64 or 128)
+    float v[kLatRays][2];
+#pragma unroll
     for (int q = 0; q < kLatRays; ++q) {
       const int64_t ray = ray0 + q;
-      float a = 0.f;
-      if (ray < n_rays && !(l == 12 && threadIdx.x >= 3))
-        for (int s = 0; s < spr; ++s) a += R[((size_t)l * nstages + ray * spr + s) * 256 + threadIdx.x];
-      rr[q][threadIdx.x] = a;
+      const bool ok = ray < n_rays && !(l == 12 && threadIdx.x >= 3);
+#pragma unroll
+      for (int s = 0; s < 2; ++s) v[q][s] = (ok && s < spr) ? __ldg(R + ((size_t)l * nstages + ray * spr + s) * 256 + threadIdx.x) : 0.f;
     }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kLatRays; ++q) rr[q][threadIdx.x] = v[q][0] + v[q][1];
     __syncthreads();
     const float* w = wlat + (size_t)l * 256 * 33;
     float acc[kLatRays];
@@ -721,7 +725,7 @@ int launch_style_wgrad(tgtc_ctx* ctx, const StyleStash& stash, const uint8_t* re
                        int dlat_accumulate, cudaStream_t st) {
   const int64_t M = n_rays * S;
   if (M == 0) return TGTC_OK;
-  TGTC_REQUIRE(S % 64 == 0, TGTC_ERR_UNSUPPORTED, "style wgrad needs n_samples a multiple of 64");
+  TGTC_REQUIRE(S == 64 || S == 128, TGTC_ERR_UNSUPPORTED, "style wgrad needs 64 or 128 samples per ray");
   const int64_t ntiles = (M + kTileM - 1) / kTileM;
   const StyleJobPlan plan = style_plan();
   const StyleFlat flat = style_flat();

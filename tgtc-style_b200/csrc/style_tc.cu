@@ -64,6 +64,7 @@ struct ChainParams {
   uint32_t* mask;            // [ntiles][mask_layers][8][128] ReLU mask words (common.cuh: TcStash.mask), this module at mask_slot0
   int mask_layers, mask_slot0;
   uint8_t* stash_pe;         // [ntiles][16 KB] positional-encoding tile image, or nullptr
+  int dbg_flags;             // timing experiments (results garbage): 1 no mask words, 4 no image store, 8 no drain wait
 };
 
 constexpr int kOffAct = 0;
@@ -328,7 +329,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
           if constexpr (kTrain) {
             // every layer's output image goes to the stash; the epilogue of the next layer waits for the store to have drained
             mbar_wait(bar(kBarOutDone + t), od_par); od_par ^= 1;
-            if (tile_ok) {
+            if (tile_ok && !(P.dbg_flags & 4)) {
               bulk_s2g(P.stash + ((size_t)tile * P.stash_layers + l) * 65536, sbase + kOffAct + t * kActBytes, 65536u);
               bulk_commit_group();
             }
@@ -360,12 +361,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
     uint32_t acc_par[2] = {0, 0}, sf_par[2] = {0, 0};
     float hb[3] = {0.f, 0.f, 0.f};
     if (P.head_b != nullptr) { hb[0] = P.head_b[0]; hb[1] = P.head_b[1]; hb[2] = P.head_b[2]; }
+    // kTrain: the per-ray effective biases of a step (one layer of one slot: the two half-tiles' rays x 256 outputs) are staged
+    // in shared memory one step ahead -- [slot][parity][half][256] fp32 in the (otherwise unused) bias area; fetching them
+    // from global memory inside the epilogue cost 35 % of the kernel
+    float* bias_w = reinterpret_cast<float*>(smem + kOffBias);
+    const int e256 = threadIdx.x - kEpiWarp0 * 32;
+    uint32_t use[2] = {0, 0};
+    auto bias_rows = [&](int64_t it_, int l_, int t_, float& b0, float& b1) {
+      const int64_t tile_ = pair_tile(it_, t_, rank);
+      int64_t m0 = tile_ * kTileM, m1 = tile_ * kTileM + 64;
+      if (m0 >= P.M) m0 = P.M - 1;
+      if (m1 >= P.M) m1 = P.M - 1;
+      b0 = __ldg(P.bias_rays + (m0 / P.S) * P.bias_ray_stride + l_ * 256 + e256);
+      b1 = __ldg(P.bias_rays + (m1 / P.S) * P.bias_ray_stride + l_ * 256 + e256);
+    };
+    if constexpr (kTrain) {
+      if (iters > 0) {
+        for (int t = 0; t < 2; ++t) {
+          float b0, b1;
+          bias_rows(0, 0, t, b0, b1);
+          bias_w[((t * 2 + 0) * 2 + 0) * 256 + e256] = b0;
+          bias_w[((t * 2 + 0) * 2 + 1) * 256 + e256] = b1;
+        }
+      }
+    }
     for (int64_t it = 0; it < iters; ++it) {
       for (int l = 0; l < nl; ++l) {
         const int okind = P.layer[l].out;
         for (int t = 0; t < 2; ++t) {
           const int64_t tile = pair_tile(it, t, rank);
           const int64_t m = tile * kTileM + row;
+          float nb0 = 0.f, nb1 = 0.f;
+          const bool has_next = kTrain && !(it == iters - 1 && l == nl - 1);
+          if constexpr (kTrain) {
+            if (has_next) bias_rows(l + 1 < nl ? it : it + 1, l + 1 < nl ? l + 1 : 0, t, nb0, nb1);
+            named_bar_sync(3, kNumEpiThreads);   // this step's rows (written at the end of the slot's previous step) are visible
+          }
           mbar_wait(bar(kBarAccFull + t), acc_par[t]); acc_par[t] ^= 1;
           tc_fence_after();
           const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 * t) + (uint32_t)(hc * 128);
@@ -373,10 +404,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
           float p0 = 0.f, p1 = 0.f, p2 = 0.f;
           if constexpr (kTrain) {
             // per-ray effective biases (the latent columns folded per ray); all 32 rows of a warp belong to one ray
-            const int64_t mc = m < P.M ? m : P.M - 1;
-            const float* bl = P.bias_rays + (mc / P.S) * P.bias_ray_stride + l * 256 + hc * 128;
-            uint32_t* mrow = tile < P.ntiles ? P.mask + (((size_t)tile * P.mask_layers + P.mask_slot0 + l) * 8 + hc * 4) * 128 + row : nullptr;
-            mbar_wait(bar(kBarSlotFree + t), sf_par[t]); sf_par[t] ^= 1;   // the previous image store has drained act[t]
+            const float* bl = bias_w + ((t * 2 + (int)(use[t] & 1)) * 2 + (row >> 6)) * 256 + hc * 128;
+            uint32_t* mrow = (tile < P.ntiles && !(P.dbg_flags & 1)) ? P.mask + (((size_t)tile * P.mask_layers + P.mask_slot0 + l) * 8 + hc * 4) * 128 + row : nullptr;
+            if (!(P.dbg_flags & 8)) { mbar_wait(bar(kBarSlotFree + t), sf_par[t]); sf_par[t] ^= 1; }   // the previous image store has drained act[t]
 #pragma unroll 1
             for (int blk = 0; blk < 4; ++blk) {
               uint32_t v[32];
@@ -385,7 +415,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
               const uint32_t kb = arow + (uint32_t)(blk >> 1) * 16384u;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(bl + blk * 32 + 4 * j));
+                const float4 b = *reinterpret_cast<const float4*>(bl + blk * 32 + 4 * j);
                 add2(v[4 * j + 0], v[4 * j + 1], b.x, b.y);
                 add2(v[4 * j + 2], v[4 * j + 3], b.z, b.w);
               }
@@ -407,6 +437,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
                              pack_bf16_relu(v[8 * j + 4], v[8 * j + 5]), pack_bf16_relu(v[8 * j + 6], v[8 * j + 7]));
               }
             }
+            if (has_next) {
+              bias_w[((t * 2 + (int)((use[t] + 1) & 1)) * 2 + 0) * 256 + e256] = nb0;
+              bias_w[((t * 2 + (int)((use[t] + 1) & 1)) * 2 + 1) * 256 + e256] = nb1;
+            }
+            ++use[t];
           } else {
           const float* bl = bias_s + l * 256 + hc * 128;
 #pragma unroll 1
@@ -683,7 +718,12 @@ static void fill_common(ChainParams& P, const MlpIO& io) {
   P.img0_stride = P.img1_stride = 65536;
 }
 
-static int launch_chain(tgtc_ctx* ctx, const ChainParams& P, cudaStream_t st, bool train = false) {
+static int g_chain_dbg = 0;
+extern "C" void tgtc_debug_chain_flags(int f) { g_chain_dbg = f; }
+
+static int launch_chain(tgtc_ctx* ctx, const ChainParams& P_in, cudaStream_t st, bool train = false) {
+  ChainParams P = P_in;
+  P.dbg_flags = g_chain_dbg;
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
     TGTC_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
