@@ -215,3 +215,30 @@ def test_style_train_ragged_batches(renderer_bf16, n):
             assert rel <= 0.2, (n, tag, k, rel)
     a, b = bw["d_latents"].cpu().double().flatten(), dlat_ref.double().flatten()
     assert ((a - b).norm() / b.norm()).item() <= 0.1
+
+
+def test_style_wgrad_work_splits_agree(renderer_bf16):
+    """the two work splits of style_wgrad_kernel (all jobs per CTA for large batches / one job per CTA for small ones) give the
+    same gradients up to summation order"""
+    import ctypes
+    from tgtc_style_b200 import _lib
+    r = renderer_bf16
+    (wc, wf, cs, ws), ro, rd, lat, rand, g_c, g_f = _inputs(200, seed=31)
+    r.set_weights(wc, wf)
+    r.set_style_weights(cs, ws)
+    lib = _lib.load()
+    lib.tgtc_debug_style_wgrad_mode.argtypes = [ctypes.c_int]
+    fw = r.style_train_forward(ro, rd, lat, rand=rand)
+    res = []
+    try:
+        for mode in (0, 1):
+            lib.tgtc_debug_style_wgrad_mode(mode)
+            bw = r.style_train_backward(fw["state"], g_c, g_f)
+            torch.cuda.synchronize()
+            res.append((bw["grads"].clone(), bw["d_latents"].clone()))
+    finally:
+        lib.tgtc_debug_style_wgrad_mode(-1)
+    (ga, la), (gb, lb) = res
+    assert ga.abs().max().item() > 0
+    assert ((ga - gb).norm() / ga.norm()).item() <= 1e-5
+    assert torch.equal(la, lb)          # the R rows do not depend on the split

@@ -336,7 +336,13 @@ struct SWgradParams {
   int64_t colsum_off;   // floats: [njobs][256]
   float* R;             // [13][2 * ntiles][256] per-64-sample column sums of dz
   int64_t ntiles;
+  // Work split.  job_parallel = 0: every CTA walks all jobs over its tiles (tile = blockIdx.x + k * gridDim.x): best HBM
+  // streaming at large batches, but each CTA flushes 17 partial matrices (3.5 MB).  job_parallel = 1 (small batches, the
+  // reference's batch_size_style is 256..1024 rays): CTAs first[j] .. first[j+1]-1 share job j, a CTA's partial is one matrix.
+  int job_parallel;
+  int first[kMaxJobs + 1];
 };
+constexpr int64_t kCtaFloatsParallel = 256 * 256 + 256;   // job-parallel partial of one CTA: matrix, then column sums
 
 __global__ void __launch_bounds__(kWThreads, 1) style_wgrad_kernel(const __grid_constant__ SWgradParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -345,10 +351,17 @@ __global__ void __launch_bounds__(kWThreads, 1) style_wgrad_kernel(const __grid_
   const int lane = threadIdx.x & 31;
   const uint32_t bars = sbase + kWOffBars;
   auto bar = [&](int i) { return bars + 8u * i; };
-  const int64_t n_my = P.ntiles > (int64_t)blockIdx.x ? (P.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  int j0 = 0, j1 = P.njobs;
+  int64_t slice = blockIdx.x, nsl = gridDim.x;
+  if (P.job_parallel) {
+    while (j0 + 1 < P.njobs && (int)blockIdx.x >= P.first[j0 + 1]) ++j0;
+    j1 = j0 + 1;
+    slice = (int)blockIdx.x - P.first[j0];
+    nsl = P.first[j0 + 1] - P.first[j0];
+  }
+  const int64_t n_my = P.ntiles > slice ? (P.ntiles - slice + nsl - 1) / nsl : 0;   // tiles slice, slice + nsl, ...
   const int64_t nst = 2 * n_my;   // 64-sample stages per job
-  float* part = P.partial + (size_t)blockIdx.x * P.part_floats;
-  const int nj = P.njobs;
+  float* part = P.partial + (size_t)blockIdx.x * (P.job_parallel ? kCtaFloatsParallel : P.part_floats);
 
   if (threadIdx.x == 0) {
     if ((sbase & 1023u) != 0) { printf("tgtc style_wgrad: shared memory base not 1024-aligned\n"); __trap(); }
@@ -373,11 +386,11 @@ __global__ void __launch_bounds__(kWThreads, 1) style_wgrad_kernel(const __grid_
     // ===================================================================== producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int j = 0; j < nj; ++j) {
+    for (int j = j0; j < j1; ++j) {
       const SJob& jb = P.job[j];
       const uint32_t bytes = (uint32_t)(jb.a_blocks + jb.b_blocks) * 8192u;
       for (int64_t s = 0; s < nst; ++s) {
-        const int64_t tile = (int64_t)blockIdx.x + (s >> 1) * gridDim.x;
+        const int64_t tile = slice + (s >> 1) * nsl;
         const size_t half = (size_t)(s & 1) * 8192;   // rows [64*half, 64*half+64) of a block are contiguous
         mbar_wait(bar(kWBarEmpty + stage), phase ^ 1);
         if (elect_one()) {
@@ -396,12 +409,12 @@ __global__ void __launch_bounds__(kWThreads, 1) style_wgrad_kernel(const __grid_
     // ===================================================================== MMA issuer
     int stage = 0;
     uint32_t phase = 0;
-    for (int j = 0; j < nj; ++j) {
+    for (int j = j0; j < j1; ++j) {
       const SJob& jb = P.job[j];
       const int nm = jb.a_blocks >= 4 ? 2 : 1;                          // 128-row halves of the output
       const uint32_t a_lbo = jb.a_blocks >= 2 ? 8192u : 0u;            // a single 64-feature block is replicated (rows 64..127 unused)
       const uint32_t idesc = make_idesc_mn(128, jb.b_blocks * 64);
-      if (j > 0) { mbar_wait_uniform(bar(kWBarAccFree), (uint32_t)((j - 1) & 1)); tc_fence_after(); }
+      if (j > j0) { mbar_wait_uniform(bar(kWBarAccFree), (uint32_t)((j - j0 - 1) & 1)); tc_fence_after(); }
       for (int64_t s = 0; s < nst; ++s) {
         mbar_wait_uniform(bar(kWBarFull + stage), phase);
         tc_fence_after();
@@ -426,13 +439,13 @@ __global__ void __launch_bounds__(kWThreads, 1) style_wgrad_kernel(const __grid_
     // ===================================================================== drain: TMEM -> per-CTA partial
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    for (int j = 0; j < nj; ++j) {
+    for (int j = j0; j < j1; ++j) {
       const SJob& jb = P.job[j];
       const int nm = jb.a_blocks >= 4 ? 2 : 1;
       const int ni = jb.b_blocks * 64;
-      float* dst = part + jb.out_off;
+      float* dst = part + (P.job_parallel ? 0 : jb.out_off);
       if (nst > 0) {
-        mbar_wait(bar(kWBarAccDone), (uint32_t)(j & 1));
+        mbar_wait(bar(kWBarAccDone), (uint32_t)((j - j0) & 1));
         tc_fence_after();
       }
       for (int mh = 0; mh < nm; ++mh) {
@@ -461,7 +474,7 @@ __global__ void __launch_bounds__(kWThreads, 1) style_wgrad_kernel(const __grid_
     int stage = 0;
     uint32_t phase = 0;
     const int64_t nstages_total = 2 * P.ntiles;
-    for (int j = 0; j < nj; ++j) {
+    for (int j = j0; j < j1; ++j) {
       const SJob& jb = P.job[j];
       const bool mine = jb.r_slot >= 0 && cb < jb.a_blocks;
       float total = 0.f;
@@ -479,14 +492,14 @@ __global__ void __launch_bounds__(kWThreads, 1) style_wgrad_kernel(const __grid_
             }
             total += acc;
           }
-          const int64_t sg = 2 * ((int64_t)blockIdx.x + (s >> 1) * gridDim.x) + (s & 1);
+          const int64_t sg = 2 * (slice + (s >> 1) * nsl) + (s & 1);
           Rj[sg * 256 + c] = acc;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(kWBarEmpty + stage));
         if (++stage == kWStages) { stage = 0; phase ^= 1; }
       }
-      part[P.colsum_off + j * 256 + c] = total;
+      part[P.job_parallel ? 256 * 256 + c : P.colsum_off + j * 256 + c] = total;
     }
   }
 
@@ -500,7 +513,7 @@ __global__ void __launch_bounds__(kWThreads, 1) style_wgrad_kernel(const __grid_
 
 // ---------------------------------------------------------------------------
 // partial -> flat gradients.  One region = a [rows x cols] sub-matrix of a parameter.
-struct SRegion { int64_t part_off; int ni; int rows; int cols; int64_t dst_off; int dst_ld; int dst_col0; };
+struct SRegion { int64_t part_off; int job; int colsum; int ni; int rows; int cols; int64_t dst_off; int dst_ld; int dst_col0; };
 constexpr int kMaxRegions = 40;
 struct SReduceParams {
   SRegion reg[kMaxRegions];
@@ -510,15 +523,21 @@ struct SReduceParams {
   int nparts;
   float* grads;
   int accumulate;
+  int job_parallel;
+  int first[kMaxJobs + 1];
 };
 __global__ void style_reduce_kernel(const __grid_constant__ SReduceParams P) {
   const SRegion& rg = P.reg[blockIdx.y];
   const int64_t total = (int64_t)rg.rows * rg.cols;
+  // job-serial: every CTA holds a partial of this region at part_off; job-parallel: only the CTAs of the region's job do
+  const int p0 = P.job_parallel ? P.first[rg.job] : 0, p1 = P.job_parallel ? P.first[rg.job + 1] : P.nparts;
+  const int64_t stride = P.job_parallel ? kCtaFloatsParallel : P.part_floats;
+  const int64_t base = P.job_parallel ? (rg.colsum ? 256 * 256 : 0) : rg.part_off;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int row = (int)(i / rg.cols), col = (int)(i % rg.cols);
-    const float* src = P.partial + rg.part_off + (int64_t)row * rg.ni + col;
+    const float* src = P.partial + base + (int64_t)row * rg.ni + col;
     float acc = 0.f;
-    for (int p = 0; p < P.nparts; ++p) acc += src[(int64_t)p * P.part_floats];
+    for (int p = p0; p < p1; ++p) acc += src[(int64_t)p * stride];
     float* dst = P.grads + rg.dst_off + (int64_t)row * rg.dst_ld + rg.dst_col0 + col;
     *dst = P.accumulate ? *dst + acc : acc;
   }
@@ -719,6 +738,9 @@ int launch_style_dgrad(tgtc_ctx* ctx, const float* rgbsigma, const float* d_rgbs
   return TGTC_OK;
 }
 
+static int g_style_wgrad_mode = -1;   // test hook: -1 automatic, 0 force job-serial, 1 force job-parallel
+extern "C" void tgtc_debug_style_wgrad_mode(int m) { g_style_wgrad_mode = m; }
+
 // dW of both style modules into grads (flat, style_flat layout) and d lat1 [n_rays][32]
 int launch_style_wgrad(tgtc_ctx* ctx, const StyleStash& stash, const uint8_t* remap_img, const StyleDz& dz, const float* lat1,
                        int64_t n_rays, int S, float* partial, float* R, float* wlat_part, float* grads, int accumulate, float* dlat,
@@ -762,7 +784,30 @@ int launch_style_wgrad(tgtc_ctx* ctx, const StyleStash& stash, const uint8_t* re
   P.colsum_off = plan.colsum_off;
   P.R = R;
   P.ntiles = ntiles;
-  const int grid = (int)(ntiles < ctx->num_sms ? ntiles : ctx->num_sms);
+  // small batches: one job per CTA (CTAs per job proportional to the job's bytes per stage)
+  P.job_parallel = (ntiles <= 1536 && ctx->num_sms >= kMaxJobs) ? 1 : 0;
+  if (g_style_wgrad_mode >= 0 && ctx->num_sms >= kMaxJobs) P.job_parallel = g_style_wgrad_mode;
+  int grid = (int)(ntiles < ctx->num_sms ? ntiles : ctx->num_sms);
+  if (P.job_parallel) {
+    grid = ctx->num_sms;
+    int k[kMaxJobs], total = 0, csum = 0;
+    for (int j = 0; j < kMaxJobs; ++j) csum += kJobABlocks[j] + kJobBBlocks[j];
+    for (int j = 0; j < kMaxJobs; ++j) { k[j] = grid * (kJobABlocks[j] + kJobBBlocks[j]) / csum; if (k[j] < 1) k[j] = 1; total += k[j]; }
+    while (total < grid) {   // the remaining CTAs go to the jobs with the most bytes per CTA
+      int best = 0;
+      for (int j = 1; j < kMaxJobs; ++j)
+        if ((kJobABlocks[j] + kJobBBlocks[j]) * k[best] > (kJobABlocks[best] + kJobBBlocks[best]) * k[j]) best = j;
+      ++k[best]; ++total;
+    }
+    while (total > grid) {
+      int best = -1;
+      for (int j = 0; j < kMaxJobs; ++j)
+        if (k[j] > 1 && (best < 0 || (kJobABlocks[j] + kJobBBlocks[j]) * k[best] < (kJobABlocks[best] + kJobBBlocks[best]) * k[j])) best = j;
+      --k[best]; --total;
+    }
+    P.first[0] = 0;
+    for (int j = 0; j < kMaxJobs; ++j) P.first[j + 1] = P.first[j] + k[j];
+  }
   style_wgrad_kernel<<<grid, kWThreads, kWSmemBytes, st>>>(P);
   TGTC_LAUNCH_CHECK(ctx);
 
@@ -770,9 +815,9 @@ int launch_style_wgrad(tgtc_ctx* ctx, const StyleStash& stash, const uint8_t* re
   SReduceParams Q = {};
   int nr = 0;
   auto region = [&](int j, int64_t dst_off, int ld, int col0, int cols, int rows) {
-    Q.reg[nr++] = {(int64_t)plan.out_off[j], plan.ni[j], rows, cols, dst_off, ld, col0};
+    Q.reg[nr++] = {(int64_t)plan.out_off[j], j, 0, plan.ni[j], rows, cols, dst_off, ld, col0};
   };
-  auto bias = [&](int j, int64_t dst_off, int rows) { Q.reg[nr++] = {plan.colsum_off + (int64_t)j * 256, 1, rows, 1, dst_off, 1, 0}; };
+  auto bias = [&](int j, int64_t dst_off, int rows) { Q.reg[nr++] = {plan.colsum_off + (int64_t)j * 256, j, 1, 1, rows, 1, dst_off, 1, 0}; };
   const int W0 = 5;   // index of module 2's first layer in flat.w / flat.b
   region(0, flat.w[W0 + 7], 288, 0, 256, 3);      bias(0, flat.b[W0 + 7], 3);
   region(1, flat.w[W0 + 6], 288, 0, 256, 256);    bias(1, flat.b[W0 + 6], 256);
@@ -797,6 +842,8 @@ int launch_style_wgrad(tgtc_ctx* ctx, const StyleStash& stash, const uint8_t* re
   Q.nparts = grid;
   Q.grads = grads;
   Q.accumulate = accumulate;
+  Q.job_parallel = P.job_parallel;
+  for (int j = 0; j <= kMaxJobs; ++j) Q.first[j] = P.first[j];
   style_reduce_kernel<<<dim3(64, nr), 256, 0, st>>>(Q);
   TGTC_LAUNCH_CHECK(ctx);
 

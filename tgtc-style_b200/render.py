@@ -357,6 +357,11 @@ class NerfRenderer:
     def set_style_weights(self, concat_style, style):
         """concat_style: models.StyleMLP_before_concat, style: models.StyleMLP_Wild_multilayers (nn.Modules or state_dicts with
         keys layers.{i}.weight / layers.{i}.bias; models.py:120-180)."""
+        cached = getattr(self, "_style_src", None)
+        if cached is not None and cached[0] is concat_style and cached[1] is style and isinstance(style, dict):
+            # the same two dicts of device tensors as last time (a trainer re-packing after an optimizer step): skip the checks
+            _lib.check(self.lib.tgtc_set_style_weights(self._h, self._style_arr, self._stream))
+            return
         tensors = []
         for src, shapes in ((concat_style, self.STYLE_C_SHAPES), (style, self.STYLE_W_SHAPES)):
             sd = src.state_dict() if hasattr(src, "state_dict") else src
@@ -368,6 +373,9 @@ class NerfRenderer:
         arr = (ctypes.c_void_p * 26)(*[t.data_ptr() for t in tensors])
         _lib.check(self.lib.tgtc_set_style_weights(self._h, arr, self._stream))
         self._style_keep = tensors
+        on_device = all(t.data_ptr() == sd_t.data_ptr() for t, sd_t in zip(tensors[:2], (concat_style["layers.0.weight"], concat_style["layers.0.bias"]))) \
+            if isinstance(concat_style, dict) else False
+        self._style_src, self._style_arr = ((concat_style, style), arr) if on_device else (None, None)
 
     def render_style(self, rays_o, rays_d, latents, near=0., far=1., chunk=None, n_samples=64, n_fine=64, extras=False,
                      want_weights=False, out=None):

@@ -138,26 +138,57 @@ class StyleLatents:
     mu / logvar, `forward` = mu + sigma_scale * (latents[id] - mu), `minus_logp`, Adam(lr=1e-3) on the table.  Tiny tensors:
     plain torch on the device (plumbing); the per-ray latents it returns feed tgtc_style_train_forward."""
 
-    def __init__(self, latents, mu, logvar, dataset_type="llff", sigma_scale=1.0, lr=1e-3):
-        self.latents = latents.detach().clone().requires_grad_(True)
+    def __init__(self, latents, mu, logvar, dataset_type="llff", sigma_scale=1.0, lr=1e-3, renderer=None):
+        self.latents = latents.detach().clone().contiguous().requires_grad_(True)
         self.mu, self.logvar = mu.detach(), logvar.detach()
         self.frame_num = latents.shape[1]
         self.dataset_type = dataset_type
         self.sigma_scale = sigma_scale
-        self.opt = torch.optim.Adam([self.latents], lr=lr)          # models.py:541-542
+        self.lr = lr
+        # Adam(lr=1e-3) on the table (models.py:541-542): the library's fused kernel when a renderer is given, else torch's
+        self.r = renderer
+        self.step_count = 0
+        if renderer is not None:
+            self.exp_avg = torch.zeros_like(self.latents)
+            self.exp_avg_sq = torch.zeros_like(self.latents)
+            self.opt = None
+        else:
+            self.opt = torch.optim.Adam([self.latents], lr=lr)
 
     def __call__(self, style_ids, frame_ids):
         flat = style_ids * self.frame_num + frame_ids
         tab = self.latents.reshape(-1, self.latents.shape[-1])
         if self.dataset_type == "llff":
-            tab = tab.repeat((7, 1))                                 # models.py:496 (SURVEY App. D)
+            flat = flat % tab.shape[0]      # == indexing the 7x tiled table of models.py:496 (SURVEY App. D), without the copy
         mu = self.mu[style_ids]
         return mu + self.sigma_scale * (tab[flat] - mu)              # models.py:506
 
-    def minus_logp(self, style_ids, frame_ids):
-        lat = self(style_ids, frame_ids)
+    def minus_logp(self, style_ids, frame_ids, lat=None):
+        if lat is None:
+            lat = self(style_ids, frame_ids)
         mu, logvar = self.mu[style_ids], self.logvar[style_ids]
         return torch.sum((lat - mu) ** 2 / (torch.exp(0.5 * logvar) + 1e-3), -1).mean()   # models.py:531-537
+
+    def use_fused_adam(self, renderer):
+        if self.opt is not None and self.step_count == 0 and hasattr(renderer, "adam_step"):
+            self.r = renderer
+            self.exp_avg = torch.zeros_like(self.latents)
+            self.exp_avg_sq = torch.zeros_like(self.latents)
+            self.opt = None
+
+    def zero_grad(self):
+        self.latents.grad = None
+
+    def step(self):
+        if self.latents.grad is None:
+            return
+        self.step_count += 1
+        if self.opt is not None:
+            self.opt.step()
+        else:
+            with torch.no_grad():
+                self.r.adam_step(self.latents.view(-1), self.latents.grad.contiguous().view(-1), self.exp_avg.view(-1),
+                                 self.exp_avg_sq.view(-1), self.step_count, lr=self.lr)
 
 
 class StyleTrainer:
@@ -177,6 +208,7 @@ class StyleTrainer:
         self.r = renderer
         self.group = group
         self.lat = latents
+        self.lat.use_fused_adam(renderer)
         dev = renderer.device
         P = renderer.style_num_params()
         self.flat = torch.zeros(P, dtype=torch.float32, device=dev)
@@ -233,7 +265,7 @@ class StyleTrainer:
         # single-process ones
         loss_rgb = self.lam_rgb * (torch.mean((rgb_c - gt) ** 2) + torch.mean((rgb_f - gt) ** 2)) / world   # train_tgtcs.py:425, :480-481
         lam = self.lam_logp * (self.logp_decay ** int((gstep - self.origin_step) / 1000))             # train_tgtcs.py:426
-        loss_logp = lam * self.lat.minus_logp(sid, fid) / world
+        loss_logp = lam * self.lat.minus_logp(sid, fid, lat1) / world
         loss_coh = torch.zeros((), device=dev)       # value of the term (global)
         coh_local = None                             # this rank's differentiable share: its gradient is d(term)/d(local rows)
         fw2 = None
@@ -268,16 +300,17 @@ class StyleTrainer:
         loss = loss_rgb + loss_logp + ((self.lam_coh * loss_coh) if use_coh else 0.0)
         objective = loss_rgb + loss_logp + ((self.lam_coh * coh_local) if (use_coh and coh_local is not None) else 0.0)
         # d loss / d (rgb maps) and the direct latent term (minus_logp) by torch on the tiny tensors
-        self.lat.opt.zero_grad()
+        self.lat.zero_grad()
         with_coh = use_coh and coh_local is not None
         leaves = [rgb_c, rgb_f] + ([c2, f2] if with_coh else [])
         gr = torch.autograd.grad(objective, leaves, retain_graph=True)
-        loss_logp.backward()                                         # -> latents table (direct term)
         bw = self.r.style_train_backward(fw["state"], gr[0], gr[1], grads=self.grads, accumulate=False)
-        lat1.backward(bw["d_latents"])                               # -> latents table (through the style modules)
+        roots, seeds = [loss_logp, lat1], [None, bw["d_latents"]]    # direct term + the path through the style modules
         if with_coh:
             bw2 = self.r.style_train_backward(fw2["state"], gr[2], gr[3], grads=self.grads, accumulate=True)
-            lat2.backward(bw2["d_latents"])
+            roots.append(lat2)
+            seeds.append(bw2["d_latents"])
+        torch.autograd.backward(roots, seeds)                        # one engine run -> latents table
         if world > 1:
             dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.group)
             dist.all_reduce(self.lat.latents.grad, op=dist.ReduceOp.SUM, group=self.group)
@@ -286,7 +319,7 @@ class StyleTrainer:
             loss = loss_rgb + loss_logp + ((self.lam_coh * loss_coh) if use_coh else 0.0)
         self.step_count += 1
         self.r.adam_step(self.flat, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count, lr=self.lr)   # style_optimizer (:54)
-        self.lat.opt.step()                                          # latents_model_1.optimize (:495)
+        self.lat.step()                                              # latents_model_1.optimize (:495)
         self.r.set_style_weights(*self.params)
         return {"loss": loss.detach(), "loss_rgb": loss_rgb.detach(), "loss_logp": loss_logp.detach(), "loss_coh": loss_coh.detach()}
 
