@@ -91,6 +91,11 @@ def test_style_train_gradients_vs_autograd(renderer_bf16):
     torch.cuda.synchronize()
     assert torch.allclose(bw2["grads"], 2 * bw["grads"], rtol=1e-6, atol=1e-12)
     assert torch.equal(bw2["d_latents"], bw["d_latents"])
+    # a fresh forward + backward of the same batch reproduces everything bit for bit (ordered reductions, no atomics)
+    fw3 = r.style_train_forward(ro, rd, lat, rand=rand)
+    bw3 = r.style_train_backward(fw3["state"], g_c, g_f)
+    torch.cuda.synchronize()
+    assert torch.equal(fw3["rgb_fine"], fw["rgb_fine"]) and torch.equal(bw3["grads"], bw["grads"]) and torch.equal(bw3["d_latents"], bw["d_latents"])
 
 
 def test_style_train_rejects_bad_arguments(renderer_bf16):
