@@ -260,7 +260,9 @@ int tgtc_philox_fill(tgtc_ctx* ctx, unsigned long long seed, int stream_id, int 
  *   grads  flat fp32 [tgtc_style_num_params()] in tgtc_set_style_weights order (module 1 (W,b) x 5, module 2 (W,b) x 8)
  *   dlat1  [n,32]  dL/d lat1 (module 2 sees mean(lat1) broadcast to 32 dims; its share comes back as 1/32 per component)
  * lat1 [n,32]: per-ray latents.  rand [n,S] uniforms or NULL (perturb=False).  noise_*: randn*sigma_noise_std or NULL.
- * The NeRF nets are constants here (they are not in style_optimizer); no gradient flows through the resampling. */
+ * The NeRF nets are constants here (they are not in style_optimizer); no gradient flows through the resampling.
+ * The context remembers which workspaces hold a forward stash and for which (n, samples, has_rand): a backward on any other
+ * workspace, or with different arguments, fails with TGTC_ERR_STATE instead of reading garbage. */
 size_t tgtc_style_train_workspace_bytes(tgtc_ctx* ctx, int64_t n_rays, int n_samples, int n_fine);
 int64_t tgtc_style_num_params(void);
 int tgtc_style_train_forward(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n_rays, double near, double far,

@@ -107,6 +107,21 @@ def test_style_train_rejects_bad_arguments(renderer_bf16):
         r.style_train_forward(ro, rd, lat[:10])
     with pytest.raises(Exception):
         r.style_train_forward(ro, rd, lat, n_samples=32)
+    # a backward needs the workspace of a matching forward
+    import tgtc_style_b200 as T
+    fw = r.style_train_forward(ro, rd, lat)
+    g = torch.zeros(64, 3)
+    r2 = T.NerfRenderer(device=r.device, mode="bf16")       # a context that never ran a forward
+    r2.set_weights(wc, wf)
+    r2.set_style_weights(cs, ws)
+    with pytest.raises(Exception, match="no tgtc_style_train_forward"):
+        r2.style_train_backward(fw["state"], g, g)
+    r2.close()
+    bad2 = dict(fw["state"])
+    bad2["rand"] = torch.zeros(64, 64)
+    with pytest.raises(Exception, match="different batch"):
+        r.style_train_backward(bad2, g, g)
+    r.style_train_backward(fw["state"], g, g)
 
 
 def _batch(ro, rd, idx, style_num, frame_num, g, origin=False):

@@ -887,6 +887,15 @@ extern "C" int tgtc_style_train_forward(tgtc_ctx* ctx, const float* rays_o, cons
       if (rc) return rc;
     }
   }
+  // remember what this workspace holds (at most a handful of pending batches: the oldest record is recycled)
+  tgtc_ctx::StyleFwdRec rec = {workspace, n_rays, S, F, rand != nullptr ? 1 : 0};
+  bool found = false;
+  for (auto& r : ctx->style_fwd)
+    if (r.ws == workspace) { r = rec; found = true; }
+  if (!found) {
+    if (ctx->style_fwd.size() >= 16) ctx->style_fwd.erase(ctx->style_fwd.begin());
+    ctx->style_fwd.push_back(rec);
+  }
   return TGTC_OK;
 }
 
@@ -896,6 +905,15 @@ extern "C" int tgtc_style_train_backward(tgtc_ctx* ctx, int64_t n_rays, int n_sa
                                          size_t workspace_bytes, tgtc_stream stream) {
   STYLE_TRAIN_PROLOGUE();
   CHECK_PTR(lat1, "lat1"); CHECK_PTR(d_rgb_coarse, "d_rgb_coarse"); CHECK_PTR(d_rgb_fine, "d_rgb_fine"); CHECK_PTR(grads, "grads");
+  {
+    const tgtc_ctx::StyleFwdRec* rec = nullptr;
+    for (const auto& r : ctx->style_fwd)
+      if (r.ws == workspace) rec = &r;
+    TGTC_REQUIRE(rec != nullptr, TGTC_ERR_STATE, "tgtc_style_train_backward: no tgtc_style_train_forward has filled this workspace");
+    TGTC_REQUIRE(rec->n == n_rays && rec->S == S && rec->F == F && rec->has_rand == (has_rand ? 1 : 0), TGTC_ERR_STATE,
+                 "tgtc_style_train_backward: the workspace holds the stash of a different batch (n=%lld, %d+%d samples, has_rand=%d)",
+                 (long long)rec->n, rec->S, rec->F, rec->has_rand);
+  }
   StyleDz dz;
   dz.dz = base + ws.off_dz; dz.dhead = base + ws.off_dhead;
   float* drs = reinterpret_cast<float*>(base + ws.off_drs);

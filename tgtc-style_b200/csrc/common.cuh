@@ -101,6 +101,9 @@ struct tgtc_ctx {
   std::vector<int> ev_kind;           // kind of pair i (TGTC_PROF_*)
   double prof_flops = 0.0;            // forward MLP (kind 0) algorithmic FLOPs since the last read
   double prof_work[4] = {0, 0, 0, 0}; // algorithmic FLOPs per kind
+  // Style_train: which workspaces hold a forward stash (tgtc_style_train_backward refuses anything else)
+  struct StyleFwdRec { const void* ws; int64_t n; int S, F, has_rand; };
+  std::vector<StyleFwdRec> style_fwd;
 };
 
 // ---------------------------------------------------------------------------
