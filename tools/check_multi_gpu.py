@@ -2,6 +2,8 @@
   * a frame rendered as N ray shards + NCCL tile all-gather == the same frame rendered whole on rank 0's GPU, bit for bit
   * a training step with the batch split over N ranks + ONE gradient all-reduce == the single-GPU step (fp32 reduction
     tolerance), and every rank ends with identical parameters
+  * two Style_train iterations (the second with the coherence term) with both batches split over N ranks == the single-GPU
+    iterations: losses, style-module gradients, latent table
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_multi_gpu.py
 """
 import os, sys, json
@@ -54,8 +56,45 @@ def main():
     pm = [torch.empty_like(p_multi) for _ in range(world)]
     dist.all_gather(pm, p_multi)
     res["params_identical_across_ranks"] = all(bool(torch.equal(pm[0], x)) for x in pm)
+    # ---- Style_train: both batches of an iteration split over the ranks vs one GPU
+    cs, ws = O.init_style_like_reference(1)
+    ns = 512
+    table = torch.randn(2, 5, 32, generator=g) * 0.5
+    mu, logvar = torch.randn(2, 32, generator=g) * 0.3, torch.randn(2, 32, generator=g) * 0.2
+    its = []
+    for it in range(2):
+        pair = []
+        for origin in (False, True):
+            idx = torch.randperm(n, generator=g)[:ns]
+            b = {"rays_o": torch.from_numpy(ro_np)[idx].to(dev), "rays_d": torch.from_numpy(rd_np)[idx].to(dev),
+                 "rgb_gt": torch.rand(ns, 3, generator=g).to(dev), "style_id": torch.randint(0, 2, (ns,), generator=g).to(dev),
+                 "frame_id": torch.randint(0, 5, (ns,), generator=g).to(dev), "rand": torch.rand(ns, 64, generator=g).to(dev)}
+            if origin:
+                b["rgb_origin"] = torch.rand(ns, 3, generator=g).to(dev)
+            pair.append(b)
+        its.append(pair)
+
+    def style_run(renderer, group, lo, hi):
+        lat = T.StyleLatents(table.to(dev), mu.to(dev), logvar.to(dev))
+        st = T.StyleTrainer(renderer, cs, ws, lat, frame_num=5, group=group)
+        out = None
+        for pair in its:
+            out = st.step(*({k: v[lo:hi] for k, v in d.items()} for d in pair))
+        torch.cuda.synchronize()
+        return st.grads.clone(), lat.latents.detach().clone(), {k: float(v) for k, v in out.items()}
+
+    r.set_weights(wc, wf)
+    b0, b1 = rank * ns // world, (rank + 1) * ns // world
+    gm, tm, lm = style_run(r, None, b0, b1)
+    r1.set_weights(wc, wf)
+    gs, ts_, ls = style_run(r1, dist.new_group([rank]), 0, ns)
+    res["style_grad_rel_err_vs_single_gpu"] = float((gm - gs).norm() / gs.norm())
+    res["style_table_max_abs_diff_vs_single_gpu"] = float((tm - ts_).abs().max())
+    res["style_losses"] = {"multi": lm, "single": ls}
+    style_ok = (res["style_grad_rel_err_vs_single_gpu"] < 1e-3 and res["style_table_max_abs_diff_vs_single_gpu"] < 2e-3
+                and ls["loss_coh"] > 0 and abs(lm["loss"] - ls["loss"]) <= 1e-3 * max(1.0, abs(ls["loss"])))
     ok = (res["render_bit_identical"] and res["frames_split_bit_identical"] and res["grad_rel_err_vs_single_gpu"] < 1e-4
-          and res["params_identical_across_ranks"])
+          and res["params_identical_across_ranks"] and style_ok)
     res["ok"] = bool(ok)
     if rank == 0:
         print(json.dumps(res))
