@@ -72,6 +72,15 @@ def synth_style_weights(seed=1):
 _REAL_STDOUT = None
 
 
+def _profile_traffic(fname, key, samples_per_launch):
+    """DRAM bytes per launch of a kernel: bytes per sample from one committed `ncu --set full` capture (profiles/), scaled to
+    this run's launch size.  None when the capture is missing."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", fname)))[key] * samples_per_launch
+    except Exception:
+        return None
+
+
 def claim_stdout():
     """stdout carries exactly ONE JSON line (the contract): library chatter on fd 1 (NCCL prints its version banner there)
     is sent to stderr for the whole run and the result line is written to the saved descriptor."""
@@ -463,7 +472,8 @@ def run_style(args):
                     "ms_per_step": ms2.item() / args.steps, "api": "NerfRenderer.render_style -> tgtc_render_style", "checksum": checksum},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
-                         "traffic": None, "kernel": "mlp_chain_kernel (style module 2)", "launches_timed": int(n2),
+                         "traffic": _profile_traffic("ncu_style_chain_r1.json", "module2_dram_bytes_per_sample", n * SAMPLES_PER_RAY * args.steps / max(n2, 1)),
+                         "kernel": "mlp_chain_kernel (style module 2)", "launches_timed": int(n2),
                          "avg_launch_ms": ms2k / max(n2, 1), "flop_per_sample": STYLE_M2_FLOP_PER_SAMPLE,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"},
             "kernels": {k: {"launches": int(v[0]), "ms_per_step": v[1] / args.steps,
@@ -828,7 +838,8 @@ def run_style_train(args):
                     "d2h_bytes_per_step": 4, "ms_per_step": ms2.item() / args.steps,
                     "api": "StyleTrainer.step (tgtc_style_train_forward/backward x 2 batches + losses + Adam)", "loss": loss_val},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if ach else None, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if ach else None,
+                         "traffic": _profile_traffic("style_train_traffic.json", "wgrad_dram_bytes_per_sample", samples_local / max(n_w, 1)),
                          "kernel": "style_wgrad_kernel", "launches_timed": int(n_w), "avg_launch_ms": ms_w / max(n_w, 1),
                          "bytes_per_sample": wbytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs",
                          "note": "timed interval includes the partial reduction and the two latent kernels"},
