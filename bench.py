@@ -784,7 +784,7 @@ def run_style_train(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = r.launch_count() - l0
     kinds = {name: r.profile_read_kind(k) for name, k in (("mlp_tc_kernel<trunk>", 0), ("mlp_chain_kernel<train> (modules 1+2)", 1),
-                                                            ("style_dgrad_kernel", 2), ("style_wgrad_kernel (+reduce, latents)", 3))}
+                                                            ("style_dgrad_kernel", 2), ("style_wgrad_kernel", 3))}
     r.profile_enable(False)
 
     # end to end: both batches from pinned host memory every iteration, the loss read back
@@ -819,7 +819,7 @@ def run_style_train(args):
         hbm = peaks.get("hbm_gbs", 6650.0)
         ms_total = ms.item()
         rays_step = 2 * STYLE_TRAIN_RAYS
-        n_w, ms_w, _ = kinds["style_wgrad_kernel (+reduce, latents)"]
+        n_w, ms_w, _ = kinds["style_wgrad_kernel"]
         # wgrad reads per sample: 17 jobs' A and B blocks = (1 + 4*16 + 4*12 + 5) blocks of 128 B rows
         wbytes = (1 + 16 * 4 + 12 * 4 + 5) * 128
         samples_local = 2 * n_local * SAMPLES_PER_RAY * args.steps
@@ -841,8 +841,7 @@ def run_style_train(args):
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if ach else None,
                          "traffic": _profile_traffic("style_train_traffic.json", "wgrad_dram_bytes_per_sample", samples_local / max(n_w, 1)),
                          "kernel": "style_wgrad_kernel", "launches_timed": int(n_w), "avg_launch_ms": ms_w / max(n_w, 1),
-                         "bytes_per_sample": wbytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs",
-                         "note": "timed interval includes the partial reduction and the two latent kernels"},
+                         "bytes_per_sample": wbytes, "peak_source": "MEASURED_PEAKS.json hbm_gbs"},
             "kernels": {k: {"launches": int(v[0]), "ms_per_step": v[1] / args.steps,
                             "tflops": (v[2] / (v[1] * 1e-3) / 1e12) if v[1] > 0 else None} for k, v in kinds.items()},
             "clocks": clocks.window(t_wall0, t_wall1),

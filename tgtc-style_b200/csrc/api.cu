@@ -939,9 +939,8 @@ extern "C" int tgtc_style_train_backward(tgtc_ctx* ctx, int64_t n_rays, int n_sa
     if (rc) return rc;
     rc = launch_style_wgrad(ctx, stash, base + ws.off_remap[p], dz, lat1, n_rays, Sp, partial, R,
                             reinterpret_cast<float*>(base + ws.off_wlat), grads, (p == 0) ? accumulate : 1, dlat1,
-                            p == 0 ? 0 : 1, st);
+                            p == 0 ? 0 : 1, st, e1);
     if (rc) return rc;
-    if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
   }
   return TGTC_OK;
 }

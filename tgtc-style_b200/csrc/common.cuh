@@ -236,7 +236,7 @@ int launch_style_dgrad(tgtc_ctx* ctx, const float* rgbsigma, const float* d_rgbs
                        cudaStream_t st);
 int launch_style_wgrad(tgtc_ctx* ctx, const StyleStash& stash, const uint8_t* remap_img, const StyleDz& dz, const float* lat1,
                        int64_t n_rays, int S, float* partial, float* R, float* wlat_part, float* grads, int accumulate, float* dlat,
-                       int dlat_accumulate, cudaStream_t st);
+                       int dlat_accumulate, cudaStream_t st, cudaEvent_t ev_after_kernel = nullptr);
 size_t style_wlat_part_floats();
 int launch_style_bias_rays(tgtc_ctx* ctx, const float* lat1, int64_t n_rays, float* bias_rays, cudaStream_t st);
 int launch_style_concat_train(tgtc_ctx* ctx, const MlpIO& io, const float* bias_rays, const StyleStash& stash, cudaStream_t st);

@@ -744,7 +744,7 @@ extern "C" void tgtc_debug_style_wgrad_mode(int m) { g_style_wgrad_mode = m; }
 // dW of both style modules into grads (flat, style_flat layout) and d lat1 [n_rays][32]
 int launch_style_wgrad(tgtc_ctx* ctx, const StyleStash& stash, const uint8_t* remap_img, const StyleDz& dz, const float* lat1,
                        int64_t n_rays, int S, float* partial, float* R, float* wlat_part, float* grads, int accumulate, float* dlat,
-                       int dlat_accumulate, cudaStream_t st) {
+                       int dlat_accumulate, cudaStream_t st, cudaEvent_t ev_after_kernel) {
   const int64_t M = n_rays * S;
   if (M == 0) return TGTC_OK;
   TGTC_REQUIRE(S == 64 || S == 128, TGTC_ERR_UNSUPPORTED, "style wgrad needs 64 or 128 samples per ray");
@@ -810,6 +810,7 @@ int launch_style_wgrad(tgtc_ctx* ctx, const StyleStash& stash, const uint8_t* re
   }
   style_wgrad_kernel<<<grid, kWThreads, kWSmemBytes, st>>>(P);
   TGTC_LAUNCH_CHECK(ctx);
+  if (ev_after_kernel != nullptr) TGTC_CUDA(cudaEventRecord(ev_after_kernel, st));   // profiling: the main kernel alone
 
   // regions: (job, parameter, destination column offset, valid columns, rows)
   SReduceParams Q = {};
