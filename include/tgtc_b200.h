@@ -272,6 +272,15 @@ int tgtc_style_train_forward(tgtc_ctx* ctx, const float* rays_o, const float* ra
 int tgtc_style_train_backward(tgtc_ctx* ctx, int64_t n_rays, int n_samples, int n_fine, const float* lat1, int has_rand,
                               const float* noise_coarse, const float* noise_fine, const float* d_rgb_coarse, const float* d_rgb_fine,
                               float* grads, int accumulate, float* dlat1, void* workspace, size_t workspace_bytes, tgtc_stream stream);
+/* the same pair with perturb / sigma noise drawn inside the kernels from Philox4x32-10 (see tgtc_train_step_seeded): pass the
+ * same (seed, perturb, sigma_noise_std) to the backward, which regenerates the noise instead of reading it */
+int tgtc_style_train_forward_seeded(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n_rays, double near, double far,
+                                    int n_samples, int n_fine, const float* lat1, unsigned long long seed, int perturb,
+                                    double sigma_noise_std, float* rgb_coarse, float* rgb_fine, void* workspace, size_t workspace_bytes,
+                                    tgtc_stream stream);
+int tgtc_style_train_backward_seeded(tgtc_ctx* ctx, int64_t n_rays, int n_samples, int n_fine, const float* lat1, unsigned long long seed,
+                                     int perturb, double sigma_noise_std, const float* d_rgb_coarse, const float* d_rgb_fine, float* grads,
+                                     int accumulate, float* dlat1, void* workspace, size_t workspace_bytes, tgtc_stream stream);
 
 #ifdef __cplusplus
 }

@@ -262,3 +262,25 @@ def test_style_wgrad_work_splits_agree(renderer_bf16):
     assert ga.abs().max().item() > 0
     assert ((ga - gb).norm() / ga.norm()).item() <= 1e-5
     assert torch.equal(la, lb)          # the R rows do not depend on the split
+
+
+def test_style_train_seeded_equals_replay(renderer_bf16):
+    """tgtc_style_train_forward/backward_seeded (jitter + sigma noise drawn in-kernel) == the replay entries fed the same streams"""
+    r = renderer_bf16
+    n = 96
+    (wc, wf, cs, ws), ro, rd, lat, _, g_c, g_f = _inputs(n, seed=41)
+    r.set_weights(wc, wf)
+    r.set_style_weights(cs, ws)
+    seed, std = 987654321, 0.5
+    fa = r.style_train_forward(ro, rd, lat, seed=seed, perturb=True, sigma_noise_std=std)
+    ba = r.style_train_backward(fa["state"], g_c, g_f)
+    rand = r.philox_fill(seed, 0, n * 64).view(n, 64)
+    nzc = r.philox_fill(seed, 1, n * 64, normal=True, std=std).view(n, 64)
+    nzf = r.philox_fill(seed, 2, n * 128, normal=True, std=std).view(n, 128)
+    fb = r.style_train_forward(ro, rd, lat, rand=rand, noise_coarse=nzc, noise_fine=nzf)
+    bb = r.style_train_backward(fb["state"], g_c, g_f)
+    torch.cuda.synchronize()
+    assert torch.equal(fa["rgb_coarse"], fb["rgb_coarse"]) and torch.equal(fa["rgb_fine"], fb["rgb_fine"])
+    assert torch.equal(ba["grads"], bb["grads"]) and torch.equal(ba["d_latents"], bb["d_latents"])
+    fc = r.style_train_forward(ro, rd, lat, seed=seed + 1, perturb=True, sigma_noise_std=std)
+    assert not torch.equal(fc["rgb_fine"], fa["rgb_fine"])

@@ -837,10 +837,10 @@ static StyleStash style_stash_of(const StyleTrainWs& ws, uint8_t* base, int p) {
   cudaStream_t st = (cudaStream_t)stream;                                                                                       \
   uint8_t* base = static_cast<uint8_t*>(workspace)
 
-extern "C" int tgtc_style_train_forward(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n_rays, double near, double far,
-                                        int n_samples, int n_fine, const float* lat1, const float* rand, const float* noise_coarse,
-                                        const float* noise_fine, float* rgb_coarse, float* rgb_fine, void* workspace,
-                                        size_t workspace_bytes, tgtc_stream stream) {
+static int style_train_forward_impl(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n_rays, double near, double far,
+                                    int n_samples, int n_fine, const float* lat1, const float* rand, const float* noise_coarse,
+                                    const float* noise_fine, const PhiloxSrc* jitter, const PhiloxSrc* prng_c, const PhiloxSrc* prng_f,
+                                    float* rgb_coarse, float* rgb_fine, void* workspace, size_t workspace_bytes, tgtc_stream stream) {
   STYLE_TRAIN_PROLOGUE();
   CHECK_PTR(rays_o, "rays_o"); CHECK_PTR(rays_d, "rays_d"); CHECK_PTR(lat1, "lat1");
   CHECK_PTR(rgb_coarse, "rgb_coarse"); CHECK_PTR(rgb_fine, "rgb_fine");
@@ -850,8 +850,9 @@ extern "C" int tgtc_style_train_forward(tgtc_ctx* ctx, const float* rays_o, cons
   if (rc) return rc;
   float* ts_c = reinterpret_cast<float*>(base + ws.off_ts[0]);
   float* ts_f = reinterpret_cast<float*>(base + ws.off_ts[1]);
-  const int64_t ts_c_stride = rand != nullptr ? S : 0;
-  rc = launch_sample_uniform(ctx, nullptr, nullptr, rand != nullptr ? n_rays : 1, S, near, far, rand, nullptr, ts_c, st);
+  const bool per_ray_ts = rand != nullptr || jitter != nullptr;
+  const int64_t ts_c_stride = per_ray_ts ? S : 0;
+  rc = launch_sample_uniform(ctx, nullptr, nullptr, per_ray_ts ? n_rays : 1, S, near, far, rand, nullptr, ts_c, st, jitter);
   if (rc) return rc;
   for (int p = 0; p < 2; ++p) {
     const StyleStash stash = style_stash_of(ws, base, p);
@@ -878,17 +879,18 @@ extern "C" int tgtc_style_train_forward(tgtc_ctx* ctx, const float* rays_o, cons
     if (rc) return rc;
     if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
     if (p == 0) {
-      rc = launch_composite(ctx, nullptr, nullptr, rs, ts_c, ts_c_stride, noise_coarse, 0, n_rays, S, rgb_coarse, nullptr, nullptr, w_c, st);
+      rc = launch_composite(ctx, nullptr, nullptr, rs, ts_c, ts_c_stride, noise_coarse, 0, n_rays, S, rgb_coarse, nullptr, nullptr, w_c, st,
+                            prng_c);
       if (rc) return rc;
       rc = launch_sample_fine(ctx, nullptr, nullptr, ts_c, ts_c_stride, w_c, n_rays, S, F, nullptr, ts_f, nullptr, nullptr, st);
       if (rc) return rc;
     } else {
-      rc = launch_composite(ctx, nullptr, nullptr, rs, ts_f, T, noise_fine, 0, n_rays, T, rgb_fine, nullptr, nullptr, nullptr, st);
+      rc = launch_composite(ctx, nullptr, nullptr, rs, ts_f, T, noise_fine, 0, n_rays, T, rgb_fine, nullptr, nullptr, nullptr, st, prng_f);
       if (rc) return rc;
     }
   }
   // remember what this workspace holds (at most a handful of pending batches: the oldest record is recycled)
-  tgtc_ctx::StyleFwdRec rec = {workspace, n_rays, S, F, rand != nullptr ? 1 : 0};
+  tgtc_ctx::StyleFwdRec rec = {workspace, n_rays, S, F, per_ray_ts ? 1 : 0};
   bool found = false;
   for (auto& r : ctx->style_fwd)
     if (r.ws == workspace) { r = rec; found = true; }
@@ -899,10 +901,32 @@ extern "C" int tgtc_style_train_forward(tgtc_ctx* ctx, const float* rays_o, cons
   return TGTC_OK;
 }
 
-extern "C" int tgtc_style_train_backward(tgtc_ctx* ctx, int64_t n_rays, int n_samples, int n_fine, const float* lat1, int has_rand,
-                                         const float* noise_coarse, const float* noise_fine, const float* d_rgb_coarse,
-                                         const float* d_rgb_fine, float* grads, int accumulate, float* dlat1, void* workspace,
-                                         size_t workspace_bytes, tgtc_stream stream) {
+extern "C" int tgtc_style_train_forward(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n_rays, double near, double far,
+                                        int n_samples, int n_fine, const float* lat1, const float* rand, const float* noise_coarse,
+                                        const float* noise_fine, float* rgb_coarse, float* rgb_fine, void* workspace,
+                                        size_t workspace_bytes, tgtc_stream stream) {
+  return style_train_forward_impl(ctx, rays_o, rays_d, n_rays, near, far, n_samples, n_fine, lat1, rand, noise_coarse, noise_fine, nullptr,
+                                  nullptr, nullptr, rgb_coarse, rgb_fine, workspace, workspace_bytes, stream);
+}
+
+// the stochastic options drawn inside the kernels (Philox4x32-10, philox.cuh) instead of read from caller tensors
+extern "C" int tgtc_style_train_forward_seeded(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n_rays, double near,
+                                               double far, int n_samples, int n_fine, const float* lat1, unsigned long long seed,
+                                               int perturb, double sigma_noise_std, float* rgb_coarse, float* rgb_fine, void* workspace,
+                                               size_t workspace_bytes, tgtc_stream stream) {
+  const PhiloxSrc jit = {seed, kStreamJitter, 1.0f, 1};
+  const PhiloxSrc nc = {seed, kStreamNoiseCoarse, (float)sigma_noise_std, 1};
+  const PhiloxSrc nf = {seed, kStreamNoiseFine, (float)sigma_noise_std, 1};
+  const bool noise = sigma_noise_std > 0.0;
+  return style_train_forward_impl(ctx, rays_o, rays_d, n_rays, near, far, n_samples, n_fine, lat1, nullptr, nullptr, nullptr,
+                                  perturb ? &jit : nullptr, noise ? &nc : nullptr, noise ? &nf : nullptr, rgb_coarse, rgb_fine, workspace,
+                                  workspace_bytes, stream);
+}
+
+static int style_train_backward_impl(tgtc_ctx* ctx, int64_t n_rays, int n_samples, int n_fine, const float* lat1, int has_rand,
+                                     const float* noise_coarse, const float* noise_fine, const PhiloxSrc* prng_c, const PhiloxSrc* prng_f,
+                                     const float* d_rgb_coarse, const float* d_rgb_fine, float* grads, int accumulate, float* dlat1,
+                                     void* workspace, size_t workspace_bytes, tgtc_stream stream) {
   STYLE_TRAIN_PROLOGUE();
   CHECK_PTR(lat1, "lat1"); CHECK_PTR(d_rgb_coarse, "d_rgb_coarse"); CHECK_PTR(d_rgb_fine, "d_rgb_fine"); CHECK_PTR(grads, "grads");
   {
@@ -926,7 +950,7 @@ extern "C" int tgtc_style_train_backward(tgtc_ctx* ctx, int64_t n_rays, int n_sa
     const int Sp = p == 0 ? S : T;
     const int64_t ts_stride = p == 0 ? (has_rand ? S : 0) : T;
     int rc = launch_composite_backward(ctx, rs, ts, ts_stride, p == 0 ? noise_coarse : noise_fine, 0, n_rays, Sp,
-                                       p == 0 ? d_rgb_coarse : d_rgb_fine, nullptr, nullptr, drs, st);
+                                       p == 0 ? d_rgb_coarse : d_rgb_fine, nullptr, nullptr, drs, st, p == 0 ? prng_c : prng_f);
     if (rc) return rc;
     const double samples = (double)n_rays * Sp;
     cudaEvent_t e1 = nullptr;
@@ -943,6 +967,26 @@ extern "C" int tgtc_style_train_backward(tgtc_ctx* ctx, int64_t n_rays, int n_sa
     if (rc) return rc;
   }
   return TGTC_OK;
+}
+
+extern "C" int tgtc_style_train_backward(tgtc_ctx* ctx, int64_t n_rays, int n_samples, int n_fine, const float* lat1, int has_rand,
+                                         const float* noise_coarse, const float* noise_fine, const float* d_rgb_coarse,
+                                         const float* d_rgb_fine, float* grads, int accumulate, float* dlat1, void* workspace,
+                                         size_t workspace_bytes, tgtc_stream stream) {
+  return style_train_backward_impl(ctx, n_rays, n_samples, n_fine, lat1, has_rand, noise_coarse, noise_fine, nullptr, nullptr, d_rgb_coarse,
+                                   d_rgb_fine, grads, accumulate, dlat1, workspace, workspace_bytes, stream);
+}
+
+extern "C" int tgtc_style_train_backward_seeded(tgtc_ctx* ctx, int64_t n_rays, int n_samples, int n_fine, const float* lat1,
+                                                unsigned long long seed, int perturb, double sigma_noise_std, const float* d_rgb_coarse,
+                                                const float* d_rgb_fine, float* grads, int accumulate, float* dlat1, void* workspace,
+                                                size_t workspace_bytes, tgtc_stream stream) {
+  const PhiloxSrc nc = {seed, kStreamNoiseCoarse, (float)sigma_noise_std, 1};
+  const PhiloxSrc nf = {seed, kStreamNoiseFine, (float)sigma_noise_std, 1};
+  const bool noise = sigma_noise_std > 0.0;
+  return style_train_backward_impl(ctx, n_rays, n_samples, n_fine, lat1, perturb ? 1 : 0, nullptr, nullptr, noise ? &nc : nullptr,
+                                   noise ? &nf : nullptr, d_rgb_coarse, d_rgb_fine, grads, accumulate, dlat1, workspace, workspace_bytes,
+                                   stream);
 }
 
 // torch.optim.Adam on flat fp32 buffers (the optimizer of train_tgtcs.py:39)

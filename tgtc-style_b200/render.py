@@ -458,11 +458,12 @@ class NerfRenderer:
 
     # ------------------------------------------------------------------ Style_train (train_tgtcs.py:311-495)
     def style_train_forward(self, rays_o, rays_d, latents, near=0., far=1., n_samples=64, n_fine=64, rand=None, noise_coarse=None,
-                            noise_fine=None, workspace=None):
+                            noise_fine=None, workspace=None, seed=None, perturb=True, sigma_noise_std=0.):
         """Forward of one Style_train batch (train_tgtcs.py:404-479): frozen NeRF nets, both style modules with per-ray
         latents [N,32], stratified positions replaying `rand` [N,S] (perturb=True) -> {"rgb_coarse", "rgb_fine"} plus an
         opaque "state" for style_train_backward (the activation stash lives in `workspace`, a uint8 device tensor; by default
-        one owned by this call's state -- use separate workspaces for batches whose backward passes are both pending)."""
+        one owned by this call's state -- use separate workspaces for batches whose backward passes are both pending).
+        With `seed` (an int) the jitter (perturb) and sigma noise are drawn inside the kernels (Philox) instead of replayed."""
         self.refresh_weights()
         ro, rd = self._dev(rays_o), self._dev(rays_d)
         lat = self._dev(latents).contiguous()
@@ -479,10 +480,19 @@ class NerfRenderer:
         nzf = self._dev(noise_fine) if noise_fine is not None else None
         rgb_c = torch.empty(n, 3, dtype=torch.float32, device=self.device)
         rgb_f = torch.empty(n, 3, dtype=torch.float32, device=self.device)
-        _lib.check(self.lib.tgtc_style_train_forward(self._h, _ptr(ro), _ptr(rd), n, float(near), float(far), n_samples, n_fine, _ptr(lat),
-                                                     _ptr(rnd), _ptr(nzc), _ptr(nzf), _ptr(rgb_c), _ptr(rgb_f),
-                                                     ctypes.c_void_p(ws.data_ptr() + off), wsb, self._stream))
-        state = dict(n=n, S=n_samples, F=n_fine, lat=lat, rand=rnd, nzc=nzc, nzf=nzf, ws=ws, off=off, wsb=wsb)
+        seeded = None
+        if seed is not None:
+            if rnd is not None or nzc is not None or nzf is not None:
+                raise ValueError("pass either replay tensors or a seed")
+            seeded = (int(seed) & 0xFFFFFFFFFFFFFFFF, int(bool(perturb)), float(sigma_noise_std))
+            _lib.check(self.lib.tgtc_style_train_forward_seeded(self._h, _ptr(ro), _ptr(rd), n, float(near), float(far), n_samples, n_fine,
+                                                                _ptr(lat), seeded[0], seeded[1], seeded[2], _ptr(rgb_c), _ptr(rgb_f),
+                                                                ctypes.c_void_p(ws.data_ptr() + off), wsb, self._stream))
+        else:
+            _lib.check(self.lib.tgtc_style_train_forward(self._h, _ptr(ro), _ptr(rd), n, float(near), float(far), n_samples, n_fine,
+                                                         _ptr(lat), _ptr(rnd), _ptr(nzc), _ptr(nzf), _ptr(rgb_c), _ptr(rgb_f),
+                                                         ctypes.c_void_p(ws.data_ptr() + off), wsb, self._stream))
+        state = dict(n=n, S=n_samples, F=n_fine, lat=lat, rand=rnd, nzc=nzc, nzf=nzf, ws=ws, off=off, wsb=wsb, seeded=seeded)
         return {"rgb_coarse": rgb_c, "rgb_fine": rgb_f, "state": state}
 
     def style_train_workspace_bytes(self, n, n_samples=64, n_fine=64):
@@ -500,6 +510,13 @@ class NerfRenderer:
             grads = torch.empty(P, dtype=torch.float32, device=self.device)
             accumulate = False
         dlat = torch.empty(state["n"], 32, dtype=torch.float32, device=self.device)
+        if state.get("seeded") is not None:
+            sd = state["seeded"]
+            _lib.check(self.lib.tgtc_style_train_backward_seeded(self._h, state["n"], state["S"], state["F"], _ptr(state["lat"]), sd[0],
+                                                                 sd[1], sd[2], _ptr(gc), _ptr(gf), _ptr(grads), int(accumulate), _ptr(dlat),
+                                                                 ctypes.c_void_p(state["ws"].data_ptr() + state["off"]), state["wsb"],
+                                                                 self._stream))
+            return {"grads": grads, "d_latents": dlat}
         _lib.check(self.lib.tgtc_style_train_backward(self._h, state["n"], state["S"], state["F"], _ptr(state["lat"]),
                                                       int(state["rand"] is not None), _ptr(state["nzc"]), _ptr(state["nzf"]), _ptr(gc),
                                                       _ptr(gf), _ptr(grads), int(accumulate), _ptr(dlat),

@@ -204,7 +204,7 @@ class StyleTrainer:
     backward serves both optimizers."""
 
     def __init__(self, renderer, concat_style, style, latents, lr=5e-4, rgb_loss_lambda=1.0, logp_loss_lambda=0.1, logp_loss_decay=1.0,
-                 loss_coh_lambda=1e2, origin_step=0, frame_num=None, sigma_noise_std=0.0, group=None):
+                 loss_coh_lambda=1e2, origin_step=0, frame_num=None, sigma_noise_std=0.0, group=None, seed=None):
         self.r = renderer
         self.group = group
         self.lat = latents
@@ -225,6 +225,7 @@ class StyleTrainer:
         self.origin_step = origin_step
         self.frame_num = frame_num if frame_num is not None else latents.frame_num
         self.noise_std = sigma_noise_std
+        self.seed = seed                   # int: jitter / sigma noise from the in-kernel Philox streams instead of torch's generator
         self.step_count = 0
         self.cnt = 0                       # the reference's `cnt` (train_tgtcs.py:347)
         self.prev = None                   # (x, y, x_origin): previous loss_coh batch's coarse / fine maps and its originals
@@ -237,6 +238,11 @@ class StyleTrainer:
         if self._ws[slot] is None or self._ws[slot].numel() < need:      # one persistent stash per pending batch
             self._ws[slot] = None
             self._ws[slot] = torch.empty(need, dtype=torch.uint8, device=self.r.device)
+        if rand is None and self.seed is not None:
+            rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+            key = (int(self.seed) * 0x9E3779B97F4A7C15 + (self.step_count << 24) + (rank << 12) + slot) & (2 ** 64 - 1)
+            return self.r.style_train_forward(rays_o, rays_d, lat.detach(), workspace=self._ws[slot], seed=key, perturb=True,
+                                              sigma_noise_std=self.noise_std)
         if rand is None:
             rand = torch.rand(n, 64, device=rays_o.device)           # perturb=True (train_tgtcs.py:362)
         nzc = nzf = None
