@@ -282,6 +282,24 @@ int tgtc_style_train_backward_seeded(tgtc_ctx* ctx, int64_t n_rays, int n_sample
                                      int perturb, double sigma_noise_std, const float* d_rgb_coarse, const float* d_rgb_fine, float* grads,
                                      int accumulate, float* dlat1, void* workspace, size_t workspace_bytes, tgtc_stream stream);
 
+/* ---- the per-ray losses of Style_train on the composited maps (train_tgtcs.py:397-404, :425, :449-459, :480-484) --------------
+ * tgtc_style_loss_sums:  sums[0] = sum (rgb_coarse - gt)^2, sums[1] = sum (rgb_fine - gt)^2 over [n,3];
+ *   sums[2] = sum_i (cos(coh_coarse_i, prev_coarse_i) - cos(rgb_origin_i, prev_origin_i))^2,
+ *   sums[3] = sum_i (cos(coh_fine_i, prev_fine_i) - cos(rgb_origin_i, rgb_origin_i))^2 over [n_coh,3]   (VGGNet.py:204-210;
+ *   the fine term's reference similarity uses this batch's own originals: train_tgtcs.py:403 precedes :456).
+ *   coh_coarse == NULL: no coherence term (sums[2] = sums[3] = 0).
+ * tgtc_style_loss_grads: gradients of  scale_rgb * (sums[0] + sums[1]) + scale_coh * (sqrt(coh_ss[0] + 1e-8) + sqrt(coh_ss[1] + 1e-8))
+ *   (utils.L2_norm, utils.py:459) w.r.t. the four maps; coh_ss = sums[2..3], summed over all ranks when the batch is sharded.
+ * With scale_rgb = rgb_loss_lambda / (3 n world) and scale_coh = loss_coh_lambda these are d loss / d maps of the iteration. */
+int tgtc_style_loss_sums(tgtc_ctx* ctx, const float* rgb_coarse, const float* rgb_fine, const float* rgb_gt, int64_t n,
+                         const float* coh_coarse, const float* coh_fine, const float* prev_coarse, const float* prev_fine,
+                         const float* rgb_origin, const float* prev_origin, int64_t n_coh, float* sums, tgtc_stream stream);
+int tgtc_style_loss_grads(tgtc_ctx* ctx, const float* rgb_coarse, const float* rgb_fine, const float* rgb_gt, int64_t n,
+                          const float* coh_coarse, const float* coh_fine, const float* prev_coarse, const float* prev_fine,
+                          const float* rgb_origin, const float* prev_origin, int64_t n_coh, const float* coh_ss, double scale_rgb,
+                          double scale_coh, float* d_rgb_coarse, float* d_rgb_fine, float* d_coh_coarse, float* d_coh_fine,
+                          tgtc_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -284,3 +284,39 @@ def test_style_train_seeded_equals_replay(renderer_bf16):
     assert torch.equal(ba["grads"], bb["grads"]) and torch.equal(ba["d_latents"], bb["d_latents"])
     fc = r.style_train_forward(ro, rd, lat, seed=seed + 1, perturb=True, sigma_noise_std=std)
     assert not torch.equal(fc["rgb_fine"], fa["rgb_fine"])
+
+
+def test_style_trainer_fused_losses_equal_torch_losses(renderer_bf16):
+    """tgtc_style_loss_sums / tgtc_style_loss_grads against the same losses written with torch ops + autograd: two iterations
+    (the second with the coherence term), same batches, same jitter"""
+    import tgtc_style_b200 as T
+    r = renderer_bf16
+    (wc, wf, cs, ws), _, _, _, _, _, _ = _inputs(8)
+    ro_all, rd_all = small_rays()
+    r.set_weights(wc, wf)
+    dev = r.device
+    g = torch.Generator().manual_seed(77)
+    style_num, frame_num, n = 2, 5, 96
+    table = torch.randn(style_num, frame_num, 32, generator=g) * 0.5
+    mu, logvar = torch.randn(style_num, 32, generator=g) * 0.3, torch.randn(style_num, 32, generator=g) * 0.2
+    perm = torch.randperm(ro_all.shape[0], generator=g)
+    its = [(_batch(ro_all, rd_all, perm[(2 * i) * n:(2 * i + 1) * n], style_num, frame_num, g),
+            _batch(ro_all, rd_all, perm[(2 * i + 1) * n:(2 * i + 2) * n], style_num, frame_num, g, True)) for i in range(2)]
+    # a zero row in the originals: cos(0, .) = 0 and its gradient is the zero subgradient, as in torch
+    its[1][1]["rgb_origin"][3] = 0.0
+    res = []
+    for fused in (True, False):
+        lat = T.StyleLatents(table.to(dev), mu.to(dev), logvar.to(dev))
+        tr = T.StyleTrainer(r, cs, ws, lat, frame_num=frame_num, fused_losses=fused)
+        assert tr.fused_losses == fused
+        out = None
+        for b, c in its:
+            out = tr.step({k: v.to(dev) for k, v in b.items()}, {k: v.to(dev) for k, v in c.items()})
+        torch.cuda.synchronize()
+        res.append((tr.grads.clone(), lat.latents.grad.clone(), {k: v.item() for k, v in out.items()}))
+    (ga, ta, la), (gb, tb, lb) = res
+    assert la["loss_coh"] > 0
+    for k in la:
+        assert abs(la[k] - lb[k]) <= 1e-5 * max(1.0, abs(lb[k])), (k, la[k], lb[k])
+    assert ((ga - gb).norm() / gb.norm()).item() <= 2e-4
+    assert ((ta - tb).norm() / tb.norm()).item() <= 2e-4

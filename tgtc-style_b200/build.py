@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "pack.cu", "raygen.cu", "sampling.cu", "composite.cu", "mlp_fp32.cu", "mlp_tc.cu", "mlp_bwd.cu", "style_tc.cu", "style_bwd.cu"]
+SOURCES = ["api.cu", "pack.cu", "raygen.cu", "sampling.cu", "composite.cu", "mlp_fp32.cu", "mlp_tc.cu", "mlp_bwd.cu", "style_tc.cu", "style_bwd.cu", "style_loss.cu"]
 LIB = os.path.join(HERE, "libtgtc_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--threads", "8",

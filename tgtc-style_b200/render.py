@@ -523,6 +523,32 @@ class NerfRenderer:
                                                       ctypes.c_void_p(state["ws"].data_ptr() + state["off"]), state["wsb"], self._stream))
         return {"grads": grads, "d_latents": dlat}
 
+    def style_loss_sums(self, rgb_c, rgb_f, gt, coh=None):
+        """-> device tensor [4]: squared-error sums of the two maps and, with coh = (c2, f2, x, y, rgb_origin, prev_origin), the two
+        sums of squared cosine-similarity differences of the coherence term (tgtc_style_loss_sums)."""
+        sums = torch.empty(4, dtype=torch.float32, device=self.device)
+        c = [self._dev(t).contiguous() for t in coh] if coh is not None else [None] * 6
+        n2 = c[0].shape[0] if coh is not None else 0
+        _lib.check(self.lib.tgtc_style_loss_sums(self._h, _ptr(rgb_c), _ptr(rgb_f), _ptr(gt), rgb_c.shape[0], _ptr(c[0]), _ptr(c[1]),
+                                                 _ptr(c[2]), _ptr(c[3]), _ptr(c[4]), _ptr(c[5]), n2, _ptr(sums), self._stream))
+        return sums
+
+    def style_loss_grads(self, rgb_c, rgb_f, gt, scale_rgb, coh=None, coh_ss=None, scale_coh=0.0, out=None):
+        """-> (d rgb_c, d rgb_f, d c2 or None, d f2 or None): gradients of scale_rgb * (sum sq err) + scale_coh * (the two L2 norms
+        built from coh_ss [2], device) (tgtc_style_loss_grads).  out: the four result tensors to write into (contiguous)."""
+        n = rgb_c.shape[0]
+        d_c, d_f = (out[0], out[1]) if out is not None else (torch.empty_like(rgb_c), torch.empty_like(rgb_f))
+        if coh is None:
+            c, d2c, d2f, n2 = [None] * 6, None, None, 0
+        else:
+            c = [self._dev(t).contiguous() for t in coh]
+            n2 = c[0].shape[0]
+            d2c, d2f = (out[2], out[3]) if out is not None else (torch.empty_like(c[0]), torch.empty_like(c[1]))
+        _lib.check(self.lib.tgtc_style_loss_grads(self._h, _ptr(rgb_c), _ptr(rgb_f), _ptr(gt), n, _ptr(c[0]), _ptr(c[1]), _ptr(c[2]),
+                                                  _ptr(c[3]), _ptr(c[4]), _ptr(c[5]), n2, _ptr(coh_ss), float(scale_rgb),
+                                                  float(scale_coh), _ptr(d_c), _ptr(d_f), _ptr(d2c), _ptr(d2f), self._stream))
+        return d_c, d_f, d2c, d2f
+
     def style_grad_views(self, flat):
         """Per-parameter views into a flat style gradient buffer: (concat-module dict, wild-module dict), state_dict keys."""
         out, o = [], 0

@@ -204,7 +204,7 @@ class StyleTrainer:
     backward serves both optimizers."""
 
     def __init__(self, renderer, concat_style, style, latents, lr=5e-4, rgb_loss_lambda=1.0, logp_loss_lambda=0.1, logp_loss_decay=1.0,
-                 loss_coh_lambda=1e2, origin_step=0, frame_num=None, sigma_noise_std=0.0, group=None, seed=None):
+                 loss_coh_lambda=1e2, origin_step=0, frame_num=None, sigma_noise_std=0.0, group=None, seed=None, fused_losses=True):
         self.r = renderer
         self.group = group
         self.lat = latents
@@ -226,6 +226,9 @@ class StyleTrainer:
         self.frame_num = frame_num if frame_num is not None else latents.frame_num
         self.noise_std = sigma_noise_std
         self.seed = seed                   # int: jitter / sigma noise from the in-kernel Philox streams instead of torch's generator
+        # the losses on the [N,3] maps and their gradients: two library kernels (tgtc_style_loss_sums / _grads) or, for
+        # stand-in renderers and as the test oracle of those kernels, torch ops + autograd
+        self.fused_losses = bool(fused_losses) and hasattr(renderer, "style_loss_sums")
         self.step_count = 0
         self.cnt = 0                       # the reference's `cnt` (train_tgtcs.py:347)
         self.prev = None                   # (x, y, x_origin): previous loss_coh batch's coarse / fine maps and its originals
@@ -252,14 +255,78 @@ class StyleTrainer:
         return self.r.style_train_forward(rays_o, rays_d, lat.detach(), rand=rand, noise_coarse=nzc, noise_fine=nzf,
                                           workspace=self._ws[slot])
 
-    def step(self, batch, coh_batch=None, global_step=None):
-        """batch / coh_batch: dicts with rays_o, rays_d [N,3], rgb_gt [N,3], style_id, frame_id [N] (+ rgb_origin [N,3] in
-        coh_batch), as LightDataLoader.get_batch / loss_coh_get_batch return them (train_tgtcs.py:356-370); an optional
-        "rand" [N,64] replays the stratified-sampling uniforms (tests).
-        Returns {"loss", "loss_rgb", "loss_logp", "loss_coh"} (device scalars)."""
-        gstep = self.step_count if global_step is None else global_step
+    def _coh_active(self):
+        """the reference's `cnt` bookkeeping (train_tgtcs.py:397-404, :449-459): -> whether this iteration's coherence batch is
+        compared with the previous one"""
+        if self.cnt == self.frame_num:
+            self.cnt = 1
+            return False
+        active = self.cnt != 0 and self.prev is not None
+        self.cnt += 1
+        return active
+
+    def _step_fused(self, batch, coh_batch, gstep, world):
         dev = self.r.device
-        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        sid, fid = batch["style_id"].long().to(dev), batch["frame_id"].long().to(dev)
+        lat1 = self.lat(sid, fid)                                    # [N,32], differentiable w.r.t. the table
+        gt = batch["rgb_gt"].contiguous()
+        n = gt.shape[0]
+        lam = self.lam_logp * (self.logp_decay ** int((gstep - self.origin_step) / 1000))             # train_tgtcs.py:426
+        loss_logp = lam * self.lat.minus_logp(sid, fid, lat1) / world
+        use_coh = gstep <= 122000                                    # train_tgtcs.py:486-493
+        active = coh_batch is not None and self._coh_active()
+        with_coh = use_coh and active
+        lat2 = coh = None
+        if coh_batch is not None:
+            sid2, fid2 = coh_batch["style_id"].long().to(dev), coh_batch["frame_id"].long().to(dev)
+            lat2 = self.lat(sid2, fid2)
+            org2 = coh_batch["rgb_origin"].contiguous()
+        if with_coh:
+            # both batches of the iteration through ONE forward / backward (latents are per ray anyway): half the launches
+            ro = torch.cat([batch["rays_o"], coh_batch["rays_o"]])
+            rd = torch.cat([batch["rays_d"], coh_batch["rays_d"]])
+            rand = torch.cat([batch["rand"], coh_batch["rand"]]) if ("rand" in batch and "rand" in coh_batch) else None
+            lat_all = torch.cat([lat1, lat2])
+            fw = self._forward(ro, rd, lat_all, rand)
+            rc, rf = fw["rgb_coarse"], fw["rgb_fine"]
+            rgb_c, rgb_f, c2, f2 = rc[:n], rf[:n], rc[n:], rf[n:]
+            coh = (c2, f2, self.prev[0], self.prev[1], org2, self.prev[2])
+        else:
+            fw = self._forward(batch["rays_o"], batch["rays_d"], lat1, batch.get("rand"))
+            rgb_c, rgb_f = fw["rgb_coarse"], fw["rgb_fine"]
+            if coh_batch is not None:                                # forward only: its maps are the next iteration's x / y
+                fw2 = self._forward(coh_batch["rays_o"], coh_batch["rays_d"], lat2, coh_batch.get("rand"), slot=1)
+                c2, f2 = fw2["rgb_coarse"], fw2["rgb_fine"]
+                if active:
+                    coh = (c2, f2, self.prev[0], self.prev[1], org2, self.prev[2])
+        sums = self.r.style_loss_sums(rgb_c, rgb_f, gt, coh)        # [sq err coarse, sq err fine, coh ss coarse, coh ss fine]
+        if world > 1:                                                # batch means and coherence norms are over all ranks' rows
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+        scale_rgb = self.lam_rgb / (3.0 * n * world)
+        self.lat.zero_grad()
+        if with_coh:
+            d_c, d_f = torch.empty_like(rc), torch.empty_like(rf)
+            self.r.style_loss_grads(rgb_c, rgb_f, gt, scale_rgb, coh, sums[2:4], self.lam_coh, out=(d_c[:n], d_f[:n], d_c[n:], d_f[n:]))
+            bw = self.r.style_train_backward(fw["state"], d_c, d_f, grads=self.grads, accumulate=False)
+            torch.autograd.backward([loss_logp, lat_all], [None, bw["d_latents"]])      # one engine run -> latents table
+        else:
+            d_c, d_f, _, _ = self.r.style_loss_grads(rgb_c, rgb_f, gt, scale_rgb)
+            bw = self.r.style_train_backward(fw["state"], d_c, d_f, grads=self.grads, accumulate=False)
+            torch.autograd.backward([loss_logp, lat1], [None, bw["d_latents"]])
+        if coh_batch is not None:
+            self.prev = (c2, f2, org2)
+        loss_rgb = self.lam_rgb * (sums[0] + sums[1]) / (3.0 * n * world)
+        loss_coh = (torch.sqrt(sums[2] + 1e-8) + torch.sqrt(sums[3] + 1e-8)) if coh is not None else torch.zeros((), device=dev)
+        loss_logp = loss_logp.detach()
+        if world > 1:
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(self.lat.latents.grad, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(loss_logp, op=dist.ReduceOp.SUM, group=self.group)
+        loss = loss_rgb + loss_logp + ((self.lam_coh * loss_coh) if use_coh else 0.0)
+        return loss, loss_rgb, loss_logp, loss_coh
+
+    def _step_torch(self, batch, coh_batch, gstep, world):
+        dev = self.r.device
         sid, fid = batch["style_id"].long().to(dev), batch["frame_id"].long().to(dev)
         lat1 = self.lat(sid, fid)                                    # [N,32], differentiable w.r.t. the table
         fw = self._forward(batch["rays_o"], batch["rays_d"], lat1, batch.get("rand"))
@@ -323,6 +390,20 @@ class StyleTrainer:
             for t in (loss_rgb, loss_logp):
                 dist.all_reduce(t.detach_(), op=dist.ReduceOp.SUM, group=self.group)
             loss = loss_rgb + loss_logp + ((self.lam_coh * loss_coh) if use_coh else 0.0)
+        return loss, loss_rgb, loss_logp, loss_coh
+
+    def step(self, batch, coh_batch=None, global_step=None):
+        """batch / coh_batch: dicts with rays_o, rays_d [N,3], rgb_gt [N,3], style_id, frame_id [N] (+ rgb_origin [N,3] in
+        coh_batch), as LightDataLoader.get_batch / loss_coh_get_batch return them (train_tgtcs.py:356-370); an optional
+        "rand" [N,64] replays the stratified-sampling uniforms (tests).
+        Returns {"loss", "loss_rgb", "loss_logp", "loss_coh"} (device scalars)."""
+        gstep = self.step_count if global_step is None else global_step
+        dev = self.r.device
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if self.fused_losses:
+            loss, loss_rgb, loss_logp, loss_coh = self._step_fused(batch, coh_batch, gstep, world)
+        else:
+            loss, loss_rgb, loss_logp, loss_coh = self._step_torch(batch, coh_batch, gstep, world)
         self.step_count += 1
         self.r.adam_step(self.flat, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count, lr=self.lr)   # style_optimizer (:54)
         self.lat.step()                                              # latents_model_1.optimize (:495)
