@@ -75,3 +75,26 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "render_oracle" not in txt and "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_header_is_plain_c():
+    """include/tgtc_b200.h is the C ABI a cgo / JNI / ctypes binding would consume: it must compile as C99 and as C++"""
+    import shutil
+    import subprocess
+    import tempfile
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "hdr.c")
+        open(src, "w").write('#include "include/tgtc_b200.h"\nint main(void) { return 0; }\n')
+        subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I", ROOT, src], check=True)
+        subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I", ROOT, "-x", "c++", src], check=True)
+
+
+def test_oracle_files_say_test_infrastructure():
+    """every file under oracle/ declares itself test infrastructure (it must never be mistaken for a product path)"""
+    odir = os.path.join(ROOT, "oracle")
+    for f in sorted(os.listdir(odir)):
+        if f.endswith((".py", ".c", ".h")):
+            head = open(os.path.join(odir, f)).read(600)
+            assert "TEST INFRASTRUCTURE" in head.upper(), f
