@@ -300,6 +300,19 @@ int tgtc_style_loss_grads(tgtc_ctx* ctx, const float* rgb_coarse, const float* r
                           double scale_coh, float* d_rgb_coarse, float* d_rgb_fine, float* d_coh_coarse, float* d_coh_fine,
                           tgtc_stream stream);
 
+/* ---- the latent model of Style_train (models.StyleLatents_variational, models.py:475-549) -----------------------------------
+ * forward:  lat[i] = mu[style_id[i]] + sigma_scale * (table[(style_id[i] * frame_num + frame_id[i]) mod rows] - mu[style_id[i]])
+ *           (models.py:490-506; the modulo is the reference's 7x tiling of the LLFF table, :496), and
+ *           logp_sum = sum_{i < n_logp} sum_k (lat_ik - mu_k)^2 / (exp(0.5 logvar_k) + 1e-3)   (minus_logp = logp_sum / n_logp, :531-537)
+ * backward: table_grad[row] (+)= d/d table of  sum_i <dlat[i], lat[i]> + logp_scale * logp_sum  -- row by row, in ray order.
+ * table [rows,32], mu / logvar [style_num,32], style_id / frame_id int64 [n], lat / dlat [n,32] fp32, all on the device. */
+int tgtc_style_latents_forward(tgtc_ctx* ctx, const float* table, const float* mu, const float* logvar, const int64_t* style_id,
+                               const int64_t* frame_id, int64_t n, int64_t n_logp, int rows, int frame_num, double sigma_scale,
+                               float* lat, float* logp_sum, tgtc_stream stream);
+int tgtc_style_latents_backward(tgtc_ctx* ctx, const float* table, const float* mu, const float* logvar, const int64_t* style_id,
+                                const int64_t* frame_id, int64_t n, int64_t n_logp, int rows, int frame_num, double sigma_scale,
+                                const float* dlat, double logp_scale, float* table_grad, int accumulate, tgtc_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,11 @@ PROTOTYPES = {
     "tgtc_style_loss_grads": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_i64, c_void_p, ctypes.c_double, ctypes.c_double, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p]),
+    "tgtc_style_latents_forward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, ctypes.c_int,
+                                                  ctypes.c_int, ctypes.c_double, c_void_p, c_void_p, c_void_p]),
+    "tgtc_style_latents_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, ctypes.c_int,
+                                                   ctypes.c_int, ctypes.c_double, c_void_p, ctypes.c_double, c_void_p, ctypes.c_int,
+                                                   c_void_p]),
     "tgtc_profile_enable": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "tgtc_profile_read": (ctypes.c_int, [c_void_p, ctypes.POINTER(c_i64), c_double_p, c_double_p]),
     "tgtc_profile_read_kind": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.POINTER(c_i64), c_double_p, c_double_p]),

@@ -91,6 +91,75 @@ __global__ void style_loss_grads_kernel(const LossArgs A, const float* __restric
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// models.StyleLatents_variational (models.py:475-549) as two kernels: the per-ray latents
+//   lat_i = mu[s_i] + sigma_scale * (table[(s_i * frame_num + f_i) mod rows] - mu[s_i])                     models.py:490-506
+// (the modulo is the reference's 7x tiling of the LLFF table, models.py:496), minus_logp (models.py:531-537)
+//   logp = mean_i sum_k (lat_ik - mu_k)^2 / (exp(0.5 logvar_k) + 1e-3)
+// and the gradient of  (upstream d lat) + logp_scale * logp_sum  w.r.t. the table, reduced row by row in ray order (no atomics).
+struct LatArgs {
+  const float* table; const float* mu; const float* logvar;   // [rows,32], [style_num,32] x 2
+  const int64_t* sid; const int64_t* fid;                      // [n]
+  int64_t n, n_logp;                                           // rays; the first n_logp of them enter minus_logp
+  int rows, frame_num;
+  float sigma_scale;
+};
+__device__ __forceinline__ int lat_row(const LatArgs& A, int64_t i) { return (int)((A.sid[i] * A.frame_num + A.fid[i]) % A.rows); }
+
+__global__ void __launch_bounds__(1024) style_latents_forward_kernel(const LatArgs A, float* __restrict__ lat, float* __restrict__ logp_sum) {
+  __shared__ float red[32];
+  const int k = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int64_t i = threadIdx.x >> 5; i < A.n; i += blockDim.x >> 5) {
+    const int64_t s = A.sid[i];
+    const float m = A.mu[s * 32 + k];
+    const float v = m + A.sigma_scale * (A.table[(size_t)lat_row(A, i) * 32 + k] - m);
+    lat[i * 32 + k] = v;
+    if (i < A.n_logp) acc += (v - m) * (v - m) / (expf(0.5f * A.logvar[s * 32 + k]) + 1e-3f);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  if (k == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    *logp_sum = t;
+  }
+}
+
+// one block per table row: grad[row][k] = sigma_scale * sum_{i: row(i) == row} (dlat[i][k] + [i < n_logp] logp_scale * d logp_sum / d lat_ik)
+__global__ void __launch_bounds__(256) style_latents_backward_kernel(const LatArgs A, const float* __restrict__ dlat, float logp_scale,
+                                                                     float* __restrict__ grad, int accumulate) {
+  __shared__ float red[8][32];
+  const int row = blockIdx.x;
+  const int k = threadIdx.x & 31, g = threadIdx.x >> 5;
+  float acc = 0.f;
+  for (int64_t i0 = 0; i0 < A.n; i0 += 8) {       // the 8 warps take consecutive rays; each warp's partial is summed in ray order
+    const int64_t i = i0 + g;
+    if (i < A.n && lat_row(A, i) == row) {
+      float v = dlat != nullptr ? dlat[i * 32 + k] : 0.f;
+      if (i < A.n_logp) {
+        const int64_t s = A.sid[i];
+        const float m = A.mu[s * 32 + k];
+        const float d = A.sigma_scale * (A.table[(size_t)row * 32 + k] - m);          // lat - mu
+        v += logp_scale * 2.0f * d / (expf(0.5f * A.logvar[s * 32 + k]) + 1e-3f);
+      }
+      acc += v;
+    }
+  }
+  red[g][k] = acc;
+  __syncthreads();
+  if (g == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w][k];
+    t *= A.sigma_scale;
+    float* dst = grad + (size_t)row * 32 + k;
+    *dst = accumulate ? *dst + t : t;
+  }
+}
+
 }  // namespace
 
 namespace {
@@ -139,6 +208,45 @@ extern "C" int tgtc_style_loss_grads(tgtc_ctx* ctx, const float* rgb_coarse, con
   style_loss_grads_kernel<<<(unsigned)((m + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       loss_args(rgb_coarse, rgb_fine, rgb_gt, n, coh_coarse, coh_fine, prev_coarse, prev_fine, rgb_origin, prev_origin, n_coh), coh_ss,
       (float)scale_rgb, (float)scale_coh, d_rgb_coarse, d_rgb_fine, d_coh_coarse, d_coh_fine);
+  TGTC_LAUNCH_CHECK(ctx);
+  return TGTC_OK;
+}
+
+static int lat_args(tgtc_ctx* ctx, LatArgs& A, const float* table, const float* mu, const float* logvar, const int64_t* style_id,
+                    const int64_t* frame_id, int64_t n, int64_t n_logp, int rows, int frame_num, double sigma_scale) {
+  TGTC_REQUIRE(table && mu && logvar && style_id && frame_id, TGTC_ERR_ARG, "style latents: null argument");
+  TGTC_REQUIRE(n > 0 && n_logp >= 0 && n_logp <= n && rows > 0 && frame_num > 0, TGTC_ERR_ARG, "style latents: bad n=%lld / n_logp=%lld / rows=%d",
+               (long long)n, (long long)n_logp, rows);
+  (void)ctx;
+  A.table = table; A.mu = mu; A.logvar = logvar; A.sid = style_id; A.fid = frame_id;
+  A.n = n; A.n_logp = n_logp; A.rows = rows; A.frame_num = frame_num; A.sigma_scale = (float)sigma_scale;
+  return TGTC_OK;
+}
+
+extern "C" int tgtc_style_latents_forward(tgtc_ctx* ctx, const float* table, const float* mu, const float* logvar, const int64_t* style_id,
+                                          const int64_t* frame_id, int64_t n, int64_t n_logp, int rows, int frame_num, double sigma_scale,
+                                          float* lat, float* logp_sum, tgtc_stream stream) {
+  if (ctx == nullptr) { tgtc_set_error("ctx is null"); return TGTC_ERR_ARG; }
+  LatArgs A;
+  int rc = lat_args(ctx, A, table, mu, logvar, style_id, frame_id, n, n_logp, rows, frame_num, sigma_scale);
+  if (rc) return rc;
+  TGTC_REQUIRE(lat && logp_sum, TGTC_ERR_ARG, "tgtc_style_latents_forward: null output");
+  DevGuard guard(ctx->device);
+  style_latents_forward_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(A, lat, logp_sum);
+  TGTC_LAUNCH_CHECK(ctx);
+  return TGTC_OK;
+}
+
+extern "C" int tgtc_style_latents_backward(tgtc_ctx* ctx, const float* table, const float* mu, const float* logvar, const int64_t* style_id,
+                                           const int64_t* frame_id, int64_t n, int64_t n_logp, int rows, int frame_num, double sigma_scale,
+                                           const float* dlat, double logp_scale, float* table_grad, int accumulate, tgtc_stream stream) {
+  if (ctx == nullptr) { tgtc_set_error("ctx is null"); return TGTC_ERR_ARG; }
+  LatArgs A;
+  int rc = lat_args(ctx, A, table, mu, logvar, style_id, frame_id, n, n_logp, rows, frame_num, sigma_scale);
+  if (rc) return rc;
+  TGTC_REQUIRE(table_grad != nullptr, TGTC_ERR_ARG, "tgtc_style_latents_backward: null output");
+  DevGuard guard(ctx->device);
+  style_latents_backward_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(A, dlat, (float)logp_scale, table_grad, accumulate);
   TGTC_LAUNCH_CHECK(ctx);
   return TGTC_OK;
 }

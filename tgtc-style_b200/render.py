@@ -549,6 +549,31 @@ class NerfRenderer:
                                                   float(scale_coh), _ptr(d_c), _ptr(d_f), _ptr(d2c), _ptr(d2f), self._stream))
         return d_c, d_f, d2c, d2f
 
+    def style_latents_forward(self, table, mu, logvar, style_id, frame_id, n_logp, frame_num, sigma_scale=1.0):
+        """models.StyleLatents_variational.forward for every ray + the minus_logp sum of the first n_logp rays
+        (tgtc_style_latents_forward) -> (lat [n,32], logp_sum [1])."""
+        n = style_id.shape[0]
+        lat = torch.empty(n, 32, dtype=torch.float32, device=self.device)
+        logp = torch.empty(1, dtype=torch.float32, device=self.device)
+        rows = table.numel() // 32
+        _lib.check(self.lib.tgtc_style_latents_forward(self._h, _ptr(table), _ptr(mu), _ptr(logvar), _ptr(style_id), _ptr(frame_id), n,
+                                                       int(n_logp), rows, int(frame_num), float(sigma_scale), _ptr(lat), _ptr(logp),
+                                                       self._stream))
+        return lat, logp
+
+    def style_latents_backward(self, table, mu, logvar, style_id, frame_id, n_logp, frame_num, dlat, logp_scale, sigma_scale=1.0,
+                               out=None, accumulate=False):
+        """gradient of <dlat, lat> + logp_scale * logp_sum w.r.t. the table (tgtc_style_latents_backward) -> tensor like table."""
+        n = style_id.shape[0]
+        if out is None:
+            out = torch.empty_like(table)
+            accumulate = False
+        rows = table.numel() // 32
+        _lib.check(self.lib.tgtc_style_latents_backward(self._h, _ptr(table), _ptr(mu), _ptr(logvar), _ptr(style_id), _ptr(frame_id), n,
+                                                        int(n_logp), rows, int(frame_num), float(sigma_scale), _ptr(dlat),
+                                                        float(logp_scale), _ptr(out), int(accumulate), self._stream))
+        return out
+
     def style_grad_views(self, flat):
         """Per-parameter views into a flat style gradient buffer: (concat-module dict, wild-module dict), state_dict keys."""
         out, o = [], 0

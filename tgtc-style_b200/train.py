@@ -176,6 +176,19 @@ class StyleLatents:
             self.exp_avg_sq = torch.zeros_like(self.latents)
             self.opt = None
 
+    def fused_ok(self):
+        return self.r is not None and hasattr(self.r, "style_latents_forward")
+
+    def forward_fused(self, style_ids, frame_ids, n_logp):
+        """-> (per-ray latents [n,32] without autograd history, minus_logp SUM of the first n_logp rays [1])"""
+        return self.r.style_latents_forward(self.latents.detach(), self.mu, self.logvar, style_ids, frame_ids, n_logp, self.frame_num,
+                                            self.sigma_scale)
+
+    def backward_fused(self, style_ids, frame_ids, n_logp, dlat, logp_scale):
+        """table gradient of <dlat, lat> + logp_scale * logp_sum, written to self.latents.grad"""
+        self.latents.grad = self.r.style_latents_backward(self.latents.detach(), self.mu, self.logvar, style_ids, frame_ids, n_logp,
+                                                          self.frame_num, dlat, logp_scale, self.sigma_scale)
+
     def zero_grad(self):
         self.latents.grad = None
 
@@ -228,7 +241,7 @@ class StyleTrainer:
         self.seed = seed                   # int: jitter / sigma noise from the in-kernel Philox streams instead of torch's generator
         # the losses on the [N,3] maps and their gradients: two library kernels (tgtc_style_loss_sums / _grads) or, for
         # stand-in renderers and as the test oracle of those kernels, torch ops + autograd
-        self.fused_losses = bool(fused_losses) and hasattr(renderer, "style_loss_sums")
+        self.fused_losses = bool(fused_losses) and hasattr(renderer, "style_loss_sums") and self.lat.fused_ok()
         self.step_count = 0
         self.cnt = 0                       # the reference's `cnt` (train_tgtcs.py:347)
         self.prev = None                   # (x, y, x_origin): previous loss_coh batch's coarse / fine maps and its originals
@@ -266,35 +279,37 @@ class StyleTrainer:
         return active
 
     def _step_fused(self, batch, coh_batch, gstep, world):
+        """every per-sample and per-ray operation of the iteration is a library call; torch only concatenates the two batches"""
         dev = self.r.device
-        sid, fid = batch["style_id"].long().to(dev), batch["frame_id"].long().to(dev)
-        lat1 = self.lat(sid, fid)                                    # [N,32], differentiable w.r.t. the table
+        sid, fid = batch["style_id"].long().to(dev).contiguous(), batch["frame_id"].long().to(dev).contiguous()
         gt = batch["rgb_gt"].contiguous()
         n = gt.shape[0]
         lam = self.lam_logp * (self.logp_decay ** int((gstep - self.origin_step) / 1000))             # train_tgtcs.py:426
-        loss_logp = lam * self.lat.minus_logp(sid, fid, lat1) / world
         use_coh = gstep <= 122000                                    # train_tgtcs.py:486-493
         active = coh_batch is not None and self._coh_active()
         with_coh = use_coh and active
-        lat2 = coh = None
+        coh = None
         if coh_batch is not None:
-            sid2, fid2 = coh_batch["style_id"].long().to(dev), coh_batch["frame_id"].long().to(dev)
-            lat2 = self.lat(sid2, fid2)
+            sid2, fid2 = coh_batch["style_id"].long().to(dev).contiguous(), coh_batch["frame_id"].long().to(dev).contiguous()
             org2 = coh_batch["rgb_origin"].contiguous()
         if with_coh:
             # both batches of the iteration through ONE forward / backward (latents are per ray anyway): half the launches
+            ids = (torch.cat([sid, sid2]), torch.cat([fid, fid2]))
+            lat_all, logp_sum = self.lat.forward_fused(ids[0], ids[1], n)          # minus_logp covers the shuffled batch only
             ro = torch.cat([batch["rays_o"], coh_batch["rays_o"]])
             rd = torch.cat([batch["rays_d"], coh_batch["rays_d"]])
             rand = torch.cat([batch["rand"], coh_batch["rand"]]) if ("rand" in batch and "rand" in coh_batch) else None
-            lat_all = torch.cat([lat1, lat2])
             fw = self._forward(ro, rd, lat_all, rand)
             rc, rf = fw["rgb_coarse"], fw["rgb_fine"]
             rgb_c, rgb_f, c2, f2 = rc[:n], rf[:n], rc[n:], rf[n:]
             coh = (c2, f2, self.prev[0], self.prev[1], org2, self.prev[2])
         else:
+            ids = (sid, fid)
+            lat1, logp_sum = self.lat.forward_fused(sid, fid, n)
             fw = self._forward(batch["rays_o"], batch["rays_d"], lat1, batch.get("rand"))
             rgb_c, rgb_f = fw["rgb_coarse"], fw["rgb_fine"]
             if coh_batch is not None:                                # forward only: its maps are the next iteration's x / y
+                lat2 = self.lat.forward_fused(sid2, fid2, 0)[0]
                 fw2 = self._forward(coh_batch["rays_o"], coh_batch["rays_d"], lat2, coh_batch.get("rand"), slot=1)
                 c2, f2 = fw2["rgb_coarse"], fw2["rgb_fine"]
                 if active:
@@ -303,21 +318,19 @@ class StyleTrainer:
         if world > 1:                                                # batch means and coherence norms are over all ranks' rows
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
         scale_rgb = self.lam_rgb / (3.0 * n * world)
-        self.lat.zero_grad()
         if with_coh:
             d_c, d_f = torch.empty_like(rc), torch.empty_like(rf)
             self.r.style_loss_grads(rgb_c, rgb_f, gt, scale_rgb, coh, sums[2:4], self.lam_coh, out=(d_c[:n], d_f[:n], d_c[n:], d_f[n:]))
-            bw = self.r.style_train_backward(fw["state"], d_c, d_f, grads=self.grads, accumulate=False)
-            torch.autograd.backward([loss_logp, lat_all], [None, bw["d_latents"]])      # one engine run -> latents table
         else:
             d_c, d_f, _, _ = self.r.style_loss_grads(rgb_c, rgb_f, gt, scale_rgb)
-            bw = self.r.style_train_backward(fw["state"], d_c, d_f, grads=self.grads, accumulate=False)
-            torch.autograd.backward([loss_logp, lat1], [None, bw["d_latents"]])
+        bw = self.r.style_train_backward(fw["state"], d_c, d_f, grads=self.grads, accumulate=False)
+        # latent table: the path through the style modules (d_latents) + the direct minus_logp term, one kernel
+        self.lat.backward_fused(ids[0], ids[1], n, bw["d_latents"], lam / (n * world))
         if coh_batch is not None:
             self.prev = (c2, f2, org2)
         loss_rgb = self.lam_rgb * (sums[0] + sums[1]) / (3.0 * n * world)
         loss_coh = (torch.sqrt(sums[2] + 1e-8) + torch.sqrt(sums[3] + 1e-8)) if coh is not None else torch.zeros((), device=dev)
-        loss_logp = loss_logp.detach()
+        loss_logp = lam * logp_sum[0] / (n * world)
         if world > 1:
             dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.group)
             dist.all_reduce(self.lat.latents.grad, op=dist.ReduceOp.SUM, group=self.group)
