@@ -9,7 +9,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("workload", ["render", "train", "style"])
+@pytest.mark.parametrize("workload", ["render", "train", "style", "style-train"])
 def test_reference_arm_json_contract(workload):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", workload, "--steps", "1",
                         "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
