@@ -210,8 +210,9 @@ class StyleTrainer:
          with per-ray latents and perturbed samples (tgtc_style_train_forward), compositing, resampling, fine pass;
          loss = lambda_rgb (mse(coarse) + mse(fine)) + lambda_logp(step) * minus_logp  [+ lambda_coh * loss_coh];
          backward into the style modules (tgtc_style_train_backward) and the latents; Adam on both.
-    The per-ray losses on the [N,3] maps are evaluated with torch on the device and differentiated there; everything
-    per-sample runs in the CUDA library.  Two deviations from the reference loop, both forced by it not running as written on
+    With a real renderer every operation of the iteration is a library call (style_loss.cu for the losses on the [N,3] maps and
+    the latent model); the same losses written with torch ops + autograd are the second path (`fused_losses=False`, stand-in
+    renderers).  Two deviations from the reference loop, both forced by it not running as written on
     torch >= 1.5 (it backpropagates twice through a graph whose weights the first optimizer step modified in place, and
     through the previous iteration's graph via `x` / `y`): the previous batch's maps enter loss_coh as constants, and one
     backward serves both optimizers."""
