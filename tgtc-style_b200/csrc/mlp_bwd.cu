@@ -728,18 +728,26 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
-// g = scale * (rgb - gt); block-summed squared error atomically added to *sq_sum (the loss value, for logging only)
-__global__ void mse_grad_kernel(const float* __restrict__ rgb, const float* __restrict__ gt, int64_t n3, float scale,
-                                float* __restrict__ g, float* __restrict__ sq_sum) {
+// g = scale * (rgb - gt); the squared error is added to *sq_sum (the loss value).  One block, fixed summation order: the loss is
+// bit-reproducible like everything else of the step (an atomicAdd over blocks made it depend on scheduling).
+__global__ void __launch_bounds__(1024) mse_grad_kernel(const float* __restrict__ rgb, const float* __restrict__ gt, int64_t n3, float scale,
+                                                        float* __restrict__ g, float* __restrict__ sq_sum) {
+  __shared__ float red[32];
   float acc = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n3; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = threadIdx.x; i < n3; i += blockDim.x) {
     const float d = rgb[i] - gt[i];
     g[i] = scale * d;
     acc += d * d;
   }
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-  if ((threadIdx.x & 31) == 0 && sq_sum != nullptr) atomicAdd(sq_sum, acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0 && sq_sum != nullptr) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    *sq_sum += t;
+  }
 }
 
 }  // namespace
@@ -816,8 +824,7 @@ int launch_adam(tgtc_ctx* ctx, float* p, const float* g, float* m, float* v, int
 int launch_mse_grad(tgtc_ctx* ctx, const float* rgb, const float* gt, int64_t n, float scale, float* g, float* sq_sum, cudaStream_t st) {
   if (n == 0) return TGTC_OK;
   const int64_t n3 = n * 3;
-  const int64_t blocks = (n3 + 255) / 256;
-  mse_grad_kernel<<<(unsigned)(blocks < 4096 ? blocks : 4096), 256, 0, st>>>(rgb, gt, n3, scale, g, sq_sum);
+  mse_grad_kernel<<<1, 1024, 0, st>>>(rgb, gt, n3, scale, g, sq_sum);
   TGTC_LAUNCH_CHECK(ctx);
   return TGTC_OK;
 }
