@@ -265,3 +265,37 @@ def test_style_trainer_data_parallel_matches_single_process():
         np.testing.assert_allclose(tab, tab_ref, rtol=1e-4, atol=2e-6)
         for k in ("loss", "loss_rgb", "loss_logp", "loss_coh"):
             assert abs(losses[k] - l_ref[k]) <= 1e-4 * max(1.0, abs(l_ref[k])), (k, losses[k], l_ref[k])
+
+
+def test_style_trainer_coherence_bookkeeping_matches_reference_loop():
+    """StyleTrainer._coh_active against a transcription of the reference's `cnt` logic (train_tgtcs.py:347, :397-404, :449-459):
+    which iterations compare the coherence batch with the previous one"""
+    def reference_sequence(frame_num, iters):
+        cnt, out = 0, []
+        for _ in range(iters):
+            coarse_term = False
+            if cnt == frame_num:                  # :397-399
+                pass
+            else:
+                if cnt != 0:                      # :400-401
+                    coarse_term = True
+            fine_term = False
+            if cnt == frame_num:                  # :449-451
+                cnt = 1
+            else:
+                if cnt != 0:                      # :453-456
+                    fine_term = True
+                cnt += 1                          # :458
+            assert coarse_term == fine_term
+            out.append(coarse_term)
+        return out
+
+    for frame_num in (1, 3, 5):
+        its, table, mu, logvar = _style_iteration_inputs(8)
+        r = _FakeStyleRenderer()
+        tr = T.StyleTrainer(r, _style_sd(r.STYLE_C_SHAPES, 1), _style_sd(r.STYLE_W_SHAPES, 2), T.StyleLatents(table, mu, logvar), frame_num=frame_num)
+        got = []
+        for i in range(12):
+            out = tr.step(*its[i % 2])
+            got.append(float(out["loss_coh"]) > 0.0)
+        assert got == reference_sequence(frame_num, 12), (frame_num, got)

@@ -364,24 +364,20 @@ class StyleTrainer:
             f2 = fw2["rgb_fine"].requires_grad_(True)
             org2 = coh_batch["rgb_origin"]
             # train_tgtcs.py:397-404, :449-459: compare with the previous batch unless a new pass over the frames starts
-            if self.cnt == self.frame_num:
-                self.cnt = 1
-            else:
-                if self.cnt != 0 and self.prev is not None:
-                    x, y, x_org = self.prev
-                    # :401 compares with the previous originals; :456 runs after :403 replaced x_origin by THIS batch's originals
-                    terms = (cosine_similarity_rows(c2, x) - cosine_similarity_rows(org2, x_org),
-                             cosine_similarity_rows(f2, y) - cosine_similarity_rows(org2, org2))
-                    coh_local = 0.0
-                    for v in terms:
-                        ss = torch.sum(v ** 2)
-                        ss_all = ss.detach().clone()
-                        if world > 1:
-                            dist.all_reduce(ss_all, op=dist.ReduceOp.SUM, group=self.group)
-                        norm = torch.sqrt(ss_all + 1e-8)                # utils.L2_norm over all ranks' rows
-                        loss_coh = loss_coh + norm
-                        coh_local = coh_local + ss / (2.0 * norm)        # d/dv = v / norm = d L2_norm / dv
-                self.cnt += 1
+            if self._coh_active():
+                x, y, x_org = self.prev
+                # :401 compares with the previous originals; :456 runs after :403 replaced x_origin by THIS batch's originals
+                terms = (cosine_similarity_rows(c2, x) - cosine_similarity_rows(org2, x_org),
+                         cosine_similarity_rows(f2, y) - cosine_similarity_rows(org2, org2))
+                coh_local = 0.0
+                for v in terms:
+                    ss = torch.sum(v ** 2)
+                    ss_all = ss.detach().clone()
+                    if world > 1:
+                        dist.all_reduce(ss_all, op=dist.ReduceOp.SUM, group=self.group)
+                    norm = torch.sqrt(ss_all + 1e-8)                # utils.L2_norm over all ranks' rows
+                    loss_coh = loss_coh + norm
+                    coh_local = coh_local + ss / (2.0 * norm)        # d/dv = v / norm = d L2_norm / dv
             self.prev = (c2.detach(), f2.detach(), org2)
         use_coh = gstep <= 122000                                    # train_tgtcs.py:486-493
         loss = loss_rgb + loss_logp + ((self.lam_coh * loss_coh) if use_coh else 0.0)
