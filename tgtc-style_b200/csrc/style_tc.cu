@@ -442,6 +442,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
               bias_w[((t * 2 + (int)((use[t] + 1) & 1)) * 2 + 1) * 256 + e256] = nb1;
             }
             ++use[t];
+          } else if (okind != OUT_HEAD) {
+            // hidden layer: packed bias add + ReLU + bf16 pack, the TMEM load of block b+1 in flight while block b is processed
+            const float* bl = bias_s + l * 256 + hc * 128;
+            auto blk_store = [&](uint32_t (&v)[32], int blk) {
+              const uint32_t kb = arow + (uint32_t)(blk >> 1) * 16384u;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int c = blk * 32 + 8 * j;
+                const float4 b0 = *reinterpret_cast<const float4*>(bl + c);
+                const float4 b1 = *reinterpret_cast<const float4*>(bl + c + 4);
+                add2(v[8 * j + 0], v[8 * j + 1], b0.x, b0.y);
+                add2(v[8 * j + 2], v[8 * j + 3], b0.z, b0.w);
+                add2(v[8 * j + 4], v[8 * j + 5], b1.x, b1.y);
+                add2(v[8 * j + 6], v[8 * j + 7], b1.z, b1.w);
+                const uint32_t dst = kb + ((uint32_t)((((blk & 1) * 4) + j) << 4) ^ rx);
+                st_shared_v4(dst, pack_bf16_relu(v[8 * j + 0], v[8 * j + 1]), pack_bf16_relu(v[8 * j + 2], v[8 * j + 3]),
+                             pack_bf16_relu(v[8 * j + 4], v[8 * j + 5]), pack_bf16_relu(v[8 * j + 6], v[8 * j + 7]));
+              }
+            };
+            uint32_t va[32], vb[32];
+            tmem_ld32(tcol, va);
+            tmem_ld_wait_dep(va);
+            tmem_ld32(tcol + 32, vb);
+            blk_store(va, 0);
+            tmem_ld_wait_dep(vb);
+            tmem_ld32(tcol + 64, va);
+            blk_store(vb, 1);
+            tmem_ld_wait_dep(va);
+            tmem_ld32(tcol + 96, vb);
+            blk_store(va, 2);
+            tmem_ld_wait_dep(vb);
+            blk_store(vb, 3);
           } else {
           const float* bl = bias_s + l * 256 + hc * 128;
 #pragma unroll 1
