@@ -200,8 +200,10 @@ __device__ __forceinline__ int64_t my_tile(int64_t it, int t, uint32_t rank) {
 }
 
 // ---------------------------------------------------------------------------
-// kTrain: also write the activation stash (training forward); the inference instantiation carries none of that code
-template <bool kTrain>
+// kTrain: also write the activation stash (training forward); the inference instantiation carries none of that code.
+// kTrunk (style path; implies P.trunk): the inference epilogue on L0..L7 + remap, and only the remap tile leaves as an image --
+// two barriers per tile instead of the training instantiation's one per layer.
+template <bool kTrain, bool kTrunk = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -466,6 +468,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 * t);
           const int64_t tile = my_tile(it, t, rank);
           const int64_t m = tile * kTileM + row;
+          if constexpr (kTrunk) {
+            // the previous tile's remap image store out of act[t] must have drained before this tile's first epilogue overwrites it:
+            // slot 0 may leave the store of slot 1 (issued one epilogue ago) in flight, slot 1 waits for everything
+            if (l == 0 && it > 0) {
+              if (warp == kEpiWarp0 && lane == 0) { if (t == 0) bulk_wait_read1(); else bulk_wait_read0(); }
+              named_bar_sync(3, kNumEpiThreads);
+            }
+          }
 
           if (P.dbg_layers > 0 && l == nlayers - 1) {
             // test hook: dump the raw fp32 accumulator of the last executed layer
@@ -520,6 +530,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
                 // head kernels fill in (r,g,b).  sigpart_s was written by the hc==1 threads one layer ago (ordered through the
                 // ActReady -> MMA -> AccFull chain).
                 reinterpret_cast<float*>(P.io.rgbsigma)[m * 4 + 3] = sig_keep[t] + sigpart_s[t * 128 + row] + b_sigma;
+              }
+            }
+            if constexpr (kTrunk) {
+              if (l == 8) {
+                named_bar_sync(3, kNumEpiThreads);   // every thread's tile writes are fenced: the image may leave
+                if (warp == kEpiWarp0 && lane == 0) {
+                  if (tile < P.ntiles) bulk_s2g(P.stash_h + (size_t)tile * 65536, sbase + kOffAct + t * kActBytes, 65536u);
+                  bulk_commit_group();   // one group per slot and tile (empty for padding tiles): the drain waits count groups
+                }
+                if (hc == 0 && m < P.M)   // sigma (fp32 head, models.py:103) -> .w lane; the style head kernels fill in (r,g,b)
+                  reinterpret_cast<float*>(P.io.rgbsigma)[m * 4 + 3] = sig_keep[t] + sigpart_s[t * 128 + row] + b_sigma;
               }
             }
             tc_fence_before();
@@ -597,7 +618,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
   }
 
   // ---- teardown
-  if constexpr (kTrain) {
+  if constexpr (kTrain || kTrunk) {
     if (warp == kEpiWarp0 && lane == 0) bulk_wait_all0();
   }
   tc_fence_before();
@@ -649,12 +670,14 @@ static int launch_tc_common(tgtc_ctx* ctx, int net, const MlpIO& io, int dbg_lay
   if (!attr_set[ctx->device & 63]) {
     TGTC_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     TGTC_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    TGTC_CUDA((cudaFuncSetAttribute(mlp_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)));
     attr_set[ctx->device & 63] = true;
   }
   const int64_t nquads = (P.ntiles + 3) / 4;
   const int64_t max_pairs = ctx->num_sms / 2;
   const int grid = 2 * (int)(nquads < max_pairs ? nquads : max_pairs);   // CTA pairs (clusters of 2)
-  if (stash != nullptr) mlp_tc_kernel<true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
+  if (trunk) mlp_tc_kernel<false, true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
+  else if (stash != nullptr) mlp_tc_kernel<true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
   else mlp_tc_kernel<false><<<grid, kNumThreads, kSmemBytes, st>>>(P);
   TGTC_LAUNCH_CHECK(ctx);
   return TGTC_OK;
