@@ -393,7 +393,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
           for (int a = 0; a < 3; ++a) fast_sincos(__fmul_rn(x[a], fr), &e[3 + 6 * f + a], &e[3 + 6 * f + 3 + a]);
         }
         e[63] = 0.f;
-        uint8_t* const gpe = (kTrain && !P.trunk && tile < P.ntiles) ? P.stash_pe + (size_t)tile * 16384 + (r >> 3) * 1024 + (r & 7) * 128 : nullptr;
+        uint8_t* const gpe = (kTrain && tile < P.ntiles) ? P.stash_pe + (size_t)tile * 16384 + (r >> 3) * 1024 + (r & 7) * 128 : nullptr;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
           const uint32_t q0 = pack_bf16(e[8 * ch + 0], e[8 * ch + 1]), q1 = pack_bf16(e[8 * ch + 2], e[8 * ch + 3]),
@@ -520,16 +520,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
                 if (issuer) bulk_wait_read0();
                 named_bar_sync(3, kNumEpiThreads);
               }
-              if (issuer && tile < P.ntiles && (!P.trunk || l == 8) && !(P.dbg_flags & 32)) {
-                uint8_t* gimg = P.trunk ? P.stash_h + (size_t)tile * 65536 : P.stash_h + ((size_t)tile * 9 + l) * 65536;
-                bulk_s2g(gimg, sbase + kOffAct + t * kActBytes, 65536u);
+              if (issuer && tile < P.ntiles && !(P.dbg_flags & 32)) {
+                bulk_s2g(P.stash_h + ((size_t)tile * 9 + l) * 65536, sbase + kOffAct + t * kActBytes, 65536u);
                 bulk_commit_group();
-              }
-              if (P.trunk && l == 8 && hc == 0 && m < P.M) {
-                // trunk mode ends here: sigma (fp32 head, models.py:103) goes to the .w lane of the per-sample float4; the style
-                // head kernels fill in (r,g,b).  sigpart_s was written by the hc==1 threads one layer ago (ordered through the
-                // ActReady -> MMA -> AccFull chain).
-                reinterpret_cast<float*>(P.io.rgbsigma)[m * 4 + 3] = sig_keep[t] + sigpart_s[t * 128 + row] + b_sigma;
               }
             }
             if constexpr (kTrunk) {
@@ -539,7 +532,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
                   if (tile < P.ntiles) bulk_s2g(P.stash_h + (size_t)tile * 65536, sbase + kOffAct + t * kActBytes, 65536u);
                   bulk_commit_group();   // one group per slot and tile (empty for padding tiles): the drain waits count groups
                 }
-                if (hc == 0 && m < P.M)   // sigma (fp32 head, models.py:103) -> .w lane; the style head kernels fill in (r,g,b)
+                // trunk mode ends here: sigma (fp32 head, models.py:103) goes to the .w lane of the per-sample float4; the style head
+                // kernels fill in (r,g,b).  sigpart_s was written by the hc==1 threads one layer ago (ordered through the
+                // ActReady -> MMA -> AccFull chain).
+                if (hc == 0 && m < P.M)
                   reinterpret_cast<float*>(P.io.rgbsigma)[m * 4 + 3] = sig_keep[t] + sigpart_s[t * 128 + row] + b_sigma;
               }
             }
