@@ -124,6 +124,42 @@ def spiral_poses(n=120):
     return np.stack(poses, 0)
 
 
+def _setup(args):
+    """rank / world / device of this process; NCCL process group and the in-tree build, once per process."""
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run --nproc-per-node %d" % (args.gpus, world, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+        if rank == 0:
+            entry.build()
+        dist.barrier()
+    elif world == 1:
+        entry.build()
+    return rank, world, local, dev
+
+
+def _finish(args, res, sub):
+    """standalone workload: rank 0 prints the line and the process group goes away; as a sub-workload of the headline run
+    (extra_workloads) the dict is returned to the caller instead."""
+    import torch.distributed as dist
+    if sub:
+        return res
+    if res is not None:
+        emit(json.dumps(res))
+    if dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
+    return res
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -172,26 +208,51 @@ class ClockSampler:
             self.proc.terminate()
 
 
-def cpu_chain_rays_per_s(n_rays, chunk=1024, min_seconds=8.0, max_chunks=16):
-    """The oracle's CPU chain (oracle/render_oracle.py = the reference's arithmetic, rendering.py:27-51) on a
-    bounded sample of the SAME workload: chunks of `chunk` rays spread over the frame, all host threads."""
+def _reference_chain_fn():
+    """-> (fn(ray index array) running one batch through the CPU chain, kind).  kind = "reference": the reference's OWN modules
+    (utils / models from /root/reference or the staged copy oracle/_ref, see oracle/stage_ref.py), driven as rendering.py:27-51
+    drives them; kind = "port": the oracle restatement (bit-identical on the golden vectors) when no copy is available."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import torch
     import render_oracle as O
+    import ref_import
+    ro, rd = O.make_rays(H, W, FOCAL, np.eye(4)[:3, :4])
+    if ref_import.reference_available():
+        try:
+            utils, models, _, _ = ref_import.import_reference()
+            mc, mf = ref_import.reference_nets(models, 0)
+            ro_t, rd_t = torch.from_numpy(ro), torch.from_numpy(rd)
+
+            def fn(sel, chunk=1024):
+                return ref_import.reference_chain(utils, mc, mf, ro_t[sel], rd_t[sel], 0., 1., N_SAMPLES, N_FINE, chunk)
+            fn(np.arange(4))
+            return fn, "reference"
+        except Exception as e:      # a missing optional import of the reference on this box: fall back to the port, and say so
+            sys.stderr.write("bench: reference modules not importable (%s); timing the oracle port instead\n" % e)
+    wc, wf = O.init_linear_like_reference(0)
+
+    def fn_port(sel, chunk=1024):
+        return O.render_chain(wc, wf, ro[sel], rd[sel], 0., 1., N_SAMPLES, N_FINE, chunk)
+    return fn_port, "port"
+
+
+def cpu_chain_rays_per_s(n_rays, chunk=1024, min_seconds=8.0, max_chunks=16):
+    """The reference's CPU chain (rendering.py:27-51; see _reference_chain_fn) on a bounded sample of the SAME workload:
+    chunks of `chunk` rays spread over the frame, all host threads."""
+    import numpy as np
+    import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    wc, wf = O.init_linear_like_reference(0)
-    ro, rd = O.make_rays(H, W, FOCAL, np.eye(4)[:3, :4])
+    fn, kind = _reference_chain_fn()
     sel = np.linspace(0, H * W - 1, chunk * (max_chunks + 1)).astype(np.int64)
-    O.render_chain(wc, wf, ro[sel[:chunk]], rd[sel[:chunk]], 0., 1., N_SAMPLES, N_FINE, chunk)   # warm-up chunk
+    fn(sel[:chunk], chunk)   # warm-up chunk
     done, t0 = 0, time.perf_counter()
     while done < max_chunks and (done < 3 or time.perf_counter() - t0 < min_seconds) and done * chunk < n_rays:
-        s = sel[(done + 1) * chunk:(done + 2) * chunk]
-        O.render_chain(wc, wf, ro[s], rd[s], 0., 1., N_SAMPLES, N_FINE, chunk)
+        fn(sel[(done + 1) * chunk:(done + 2) * chunk], chunk)
         done += 1
     dt = time.perf_counter() - t0
-    return done * chunk / dt, cores, "%d chunks of %d rays of the 1008x756 frame, chunk=%d, %.1f s" % (done, chunk, chunk, dt)
+    return done * chunk / dt, cores, "%d chunks of %d rays of the 1008x756 frame, chunk=%d, %.1f s" % (done, chunk, chunk, dt), kind
 
 
 def run_eager_gpu_arm(args):
@@ -264,27 +325,24 @@ def run_eager_gpu_arm(args):
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's own CPU implementation of the path (its arithmetic restated in
-    oracle/render_oracle.py, pinned bit-for-bit to /root/reference in the build container; the reference tree
-    itself cannot travel to the GPU box), timed on the host cores.  Each step = a bounded sample of the frame."""
+    """--impl reference: the reference's own CPU implementation of the path, timed on the host cores -- its OWN modules from the
+    staged copy oracle/_ref (kind "reference"; the oracle port, pinned bit-for-bit to the reference, only when no copy exists).
+    Each step = a bounded sample of the frame."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
     import torch
-    import render_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    wc, wf = O.init_linear_like_reference(0)
-    ro, rd = O.make_rays(H, W, FOCAL, np.eye(4)[:3, :4])
+    fn, kind = _reference_chain_fn()
     per_step = 2048
     sel = np.linspace(0, H * W - 1, per_step * (args.steps + args.warmup)).astype(np.int64)
     t_steps = []
     for i in range(args.warmup + args.steps):
         s = sel[i * per_step:(i + 1) * per_step]
         t0 = time.perf_counter()
-        O.render_chain(wc, wf, ro[s], rd[s], 0., 1., N_SAMPLES, N_FINE, 1024)
+        fn(s, 1024)
         if i >= args.warmup:
             t_steps.append(time.perf_counter() - t0)
     total = sum(t_steps)
@@ -295,7 +353,7 @@ def run_reference_arm(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "mlp_samples_per_s": value * SAMPLES_PER_RAY,
     }))
@@ -353,7 +411,7 @@ def run_style_reference_arm(args):
     }))
 
 
-def run_style(args):
+def run_style(args, sub=False):
     """--workload style (BASELINE config 4): one stylised 1008x756 frame per step and per GPU, 4096-ray batches."""
     import numpy as np
     import torch
@@ -361,22 +419,11 @@ def run_style(args):
     import __graft_entry__ as entry
     import tgtc_style_b200 as T
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    if rank == 0:
-        entry.build()
-    if world > 1:
-        dist.barrier()
+    rank, world, local, dev = _setup(args)
     wc, wf = synth_nerf_weights(0)
     cs, ws = synth_style_weights(1)
-    r = T.NerfRenderer(device=dev, mode="bf16")
+    smode = args.mode if getattr(args, "mode", "f16") in ("f16", "bf16") else "f16"
+    r = T.NerfRenderer(device=dev, mode=smode)
     r.set_weights(wc, wf)
     r.set_style_weights(cs, ws)
     K = np.array([[FOCAL, 0, 0.5 * W], [0, FOCAL, 0.5 * H], [0, 0, 1]])
@@ -463,7 +510,7 @@ def run_style(args):
         res = {
             "metric": "rays/s", "value": rays_total / (ms_total * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": smode, "data": "synthetic",
             "config": {"workload": STYLE_WORKLOAD, "rays_per_step_per_gpu": n, "batch_rays": 4096, "samples_per_ray": SAMPLES_PER_RAY,
                        "parallelism": "one frame per GPU per step, NCCL all-gather of rgb/depth/acc tiles" if world > 1 else "1 GPU",
                        "l2_policy": "frame working set (rays, outputs, per-batch feature tiles) cycles through HBM; weights stay L2-resident"},
@@ -480,10 +527,7 @@ def run_style(args):
                             "tflops": (v[2] / (v[1] * 1e-3) / 1e12) if v[1] > 0 else None} for k, v in kinds.items()},
             "clocks": clocks.window(t_wall0, t_wall1),
         }
-        emit(json.dumps(res))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    return _finish(args, res if rank == 0 else None, sub)
 
 
 def run_train_reference_arm(args):
@@ -521,7 +565,7 @@ def run_train_reference_arm(args):
     }))
 
 
-def run_train(args):
+def run_train(args, sub=False):
     """--workload train (BASELINE config 5): one optimisation step per bench step, strong scaling over --gpus."""
     import numpy as np
     import torch
@@ -529,19 +573,7 @@ def run_train(args):
     import __graft_entry__ as entry
     import tgtc_style_b200 as T
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    if rank == 0:
-        entry.build()
-    if world > 1:
-        dist.barrier()
+    rank, world, local, dev = _setup(args)
     wc, wf = synth_nerf_weights(0)
     r = T.NerfRenderer(device=dev, mode="bf16")
     tr = T.NerfTrainer(r, wc, wf, max_rays_per_pass=32768)
@@ -647,10 +679,7 @@ def run_train(args):
                             "tflops": (v[2] / (v[1] * 1e-3) / 1e12) if v[1] > 0 else None} for k, v in kinds.items()},
             "clocks": clocks.window(t_wall0, t_wall1),
         }
-        emit(json.dumps(res))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    return _finish(args, res if rank == 0 else None, sub)
 
 
 STYLE_TRAIN_WORKLOAD = ("Style_train iteration (train_tgtcs.py:354-495): a shuffled 4096-ray batch plus the 4096-ray coherence batch, "
@@ -720,7 +749,7 @@ def run_style_train_reference_arm(args):
     }))
 
 
-def run_style_train(args):
+def run_style_train(args, sub=False):
     """--workload style-train (BASELINE config 4's batch, training side): one Style_train iteration per bench step."""
     import numpy as np
     import torch
@@ -728,19 +757,7 @@ def run_style_train(args):
     import __graft_entry__ as entry
     import tgtc_style_b200 as T
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    if rank == 0:
-        entry.build()
-    if world > 1:
-        dist.barrier()
+    rank, world, local, dev = _setup(args)
     wc, wf = synth_nerf_weights(0)
     cs, ws = synth_style_weights(1)
     r = T.NerfRenderer(device=dev, mode="bf16")
@@ -846,10 +863,51 @@ def run_style_train(args):
                             "tflops": (v[2] / (v[1] * 1e-3) / 1e12) if v[1] > 0 else None} for k, v in kinds.items()},
             "clocks": clocks.window(t_wall0, t_wall1),
         }
-        emit(json.dumps(res))
+    return _finish(args, res if rank == 0 else None, sub)
+
+
+def _render_mode_quick(args, dev, rank, world, mode, steps):
+    """the headline workload (device-resident rays, one frame per GPU per step + tile all-gather) in another MLP mode, a few steps"""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import tgtc_style_b200 as T
+    wc, wf = synth_nerf_weights(0)
+    r = T.NerfRenderer(device=dev, mode=mode)
+    r.set_weights(wc, wf)
+    K = np.array([[FOCAL, 0, 0.5 * W], [0, FOCAL, 0.5 * H], [0, 0, 1]])
+    poses = spiral_poses(120)
+    n = H * W
+    rays = [r.raygen(H, W, K, np.eye(4)[:3, :4] if world == 1 else poses[(s * world + rank) % 120]) for s in range(2)]
+    out = r._alloc_out(n, N_SAMPLES, N_FINE, False, dev)
+    out.pop("weights")
+
+    def step(s):
+        r.render(rays[s % 2][0], rays[s % 2][1], 0., 1., n_samples=N_SAMPLES, n_fine=N_FINE, out=out)
+        if world > 1:
+            T.gather_tiles({"rgb": out["rgb"], "depth": out["depth"], "acc": out["acc"]}, n * world)
+
+    for s in range(3):
+        step(s)
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+    r.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(steps):
+        step(s)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    _, mlp_ms, mlp_flops = r.profile_read()
+    r.profile_enable(False)
+    r.close()
+    del rays, out
+    return {"value": n * world * steps / (ms.item() * 1e-3), "unit": "rays/s", "steps": steps, "ms_per_step": ms.item() / steps,
+            "mlp_tflops": (mlp_flops / (mlp_ms * 1e-3) / 1e12) if mlp_ms > 0 else None}
 
 
 def main():
@@ -858,7 +916,11 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "eager-gpu"])
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--mode", default="f16", choices=["f16", "bf16", "fp32"],
+                    help="MLP arithmetic of the render / style workloads: f16 = fp16 operands on tcgen05 (default: the mode that meets "
+                         "the 1e-2 parity bound on every non-knife-edge ray), bf16 = bf16 operands, fp32 = CUDA-core reference path")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="headline only: skip the extra_workloads (configs 4/5 + Style_train) and the bf16-mode comparison")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="render", choices=["render", "train", "style", "style-train"],
                     help="render = BASELINE config 2 (the headline; default); train = config 5 (training step); "
@@ -896,19 +958,7 @@ def main():
     import __graft_entry__ as entry
     import tgtc_style_b200 as T
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        raise SystemExit("--gpus %d but WORLD_SIZE=%d: launch with torch.distributed.run --nproc-per-node %d" % (args.gpus, world, args.gpus))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    if rank == 0:
-        entry.build()
-    if world > 1:
-        dist.barrier()
+    rank, world, local, dev = _setup(args)
 
     wc, wf = synth_nerf_weights(0)    # the oracle is imported only by the cpu_baseline leg (cpu_chain_rays_per_s) below
     r = T.NerfRenderer(device=dev, mode=args.mode)
@@ -1011,7 +1061,7 @@ def main():
         res = {
             "metric": "rays/s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.mode if args.mode != "fp32" else "f32", "data": "synthetic",
+            "dtype": {"f16": "f16", "bf16": "bf16", "fp32": "f32"}[args.mode], "data": "synthetic",
             "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n, "samples_per_ray": SAMPLES_PER_RAY,
                        "parallelism": "ray-sharded, one frame per GPU per step, NCCL all-gather of rgb/depth/acc tiles" if world > 1 else "1 GPU",
                        "l2_policy": "per-step working set 2.4 GB (rgb-sigma workspace) >> 126 MB L2; no flush needed"},
@@ -1020,7 +1070,7 @@ def main():
                     "ms_per_step": ms2.item() / args.steps, "api": "NerfRenderer.render_host -> tgtc_render_host", "checksum": checksum},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": traffic, "kernel": "mlp_tc_kernel" if args.mode == "bf16" else "mlp_fp32_kernel",
+                         "traffic": traffic, "kernel": {"f16": "mlp_tc_kernel<fp16 operands>", "bf16": "mlp_tc_kernel<bf16 operands>", "fp32": "mlp_fp32_kernel"}[args.mode],
                          "launches_timed": int(mlp_launches), "avg_launch_ms": mlp_ms / max(mlp_launches, 1),
                          "flop_per_launch_avg": mlp_flops / max(mlp_launches, 1), "peak_source": peak_src,
                          "frac_of_burst_peak": (achieved / peaks["bf16_tflops"]) if (achieved and peaks.get("bf16_tflops")) else None,
@@ -1028,8 +1078,39 @@ def main():
             "clocks": clocks.window(t_wall0, t_wall1),
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, sample = cpu_chain_rays_per_s(16 * 1024)
-            res["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
+            v, cores, sample, kind = cpu_chain_rays_per_s(16 * 1024)
+            res["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": kind, "sample": sample}
+    else:
+        res = None
+
+    # ---------------- the other BASELINE configs, measured by the same (driver-observed) process: the bf16-operand mode of the
+    # headline workload, config 5 (training step, strong scaling, gradient all-reduce), config 4 (stylised render, 4096-ray
+    # batches; at N > 1 this is config 3's per-frame work with its tile all-gather) and one Style_train iteration.
+    if not args.no_extra:
+        del rays, out, h_rays, h_out
+        r.close()
+        torch.cuda.empty_cache()
+        extra = {}
+        if args.mode == "f16":
+            extra_bf16 = _render_mode_quick(args, dev, rank, world, "bf16", min(args.steps, 5))
+            if rank == 0:
+                res["other_modes"] = {"bf16": extra_bf16}
+        sub = argparse.Namespace(**vars(args))
+        for name, fn, steps in (("train", run_train, min(args.steps, 10)), ("style", run_style, min(args.steps, 4)),
+                                ("style_train", run_style_train, min(args.steps, 10))):
+            sub.steps, sub.warmup = max(steps, 1), 3
+            t0 = time.time()
+            try:
+                out_w = fn(sub, sub=True)
+            except Exception as e:     # an extra workload must never cost the headline line
+                out_w = {"error": "%s: %s" % (type(e).__name__, e)}
+            torch.cuda.empty_cache()
+            if rank == 0 and out_w is not None:
+                out_w["wall_s"] = time.time() - t0
+                extra[name] = out_w
+        if rank == 0:
+            res["extra_workloads"] = extra
+    if rank == 0:
         emit(json.dumps(res))
     if world > 1:
         dist.barrier()

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define TGTC_ABI_VERSION 1
+#define TGTC_ABI_VERSION 2
 
 typedef struct tgtc_ctx tgtc_ctx;
 typedef void* tgtc_stream; /* cudaStream_t */
@@ -42,8 +42,12 @@ enum { TGTC_NET_COARSE = 0, TGTC_NET_FINE = 1 };
 
 /* arithmetic of the MLP (K3+K4).  FP32: CUDA-core FFMA, reference-grade
  * (<=1e-3 end to end).  BF16: bf16 operands on tcgen05 tensor cores, fp32
- * accumulation in TMEM, fp32 sigma/rgb heads (<=1e-2 teacher-forced). */
-enum { TGTC_MLP_FP32 = 0, TGTC_MLP_BF16 = 1 };
+ * accumulation in TMEM, fp32 sigma/rgb heads.  F16: the same kernel with fp16
+ * operands (11-bit significand: 8x smaller operand rounding error than bf16 at
+ * the same tensor-core rate; operand values saturate at +-65504) -- the mode
+ * that meets the 1e-2 teacher-forced bound on every non-knife-edge ray
+ * (DESIGN.md section 2); inference entry points only, training is bf16. */
+enum { TGTC_MLP_FP32 = 0, TGTC_MLP_BF16 = 1, TGTC_MLP_F16 = 2 };
 
 #define TGTC_NUM_PARAMS 24 /* 12 layers x (weight, bias) */
 
@@ -211,10 +215,11 @@ int tgtc_set_style_weights(tgtc_ctx* ctx, const float* const* params, tgtc_strea
  * module 1 (concat_features) -> style module 2 (stylised rgb) -> compositing with the NeRF sigma -> resampling -> the
  * same on the fine net.  latent1 / latent2: device pointers to the 32 latent values of module 1 / module 2 for this
  * batch (one (style, frame) per call: latent1 = latents_model_1(...) row, rendering.py:125; latent2 = its mean over the
- * latent dim broadcast to 32, rendering.py:126,:139).  Outputs as tgtc_render.  bf16 tcgen05 path; 64 + 64 samples;
+ * latent dim broadcast to 32, rendering.py:126,:139).  Outputs as tgtc_render.  tcgen05 path (mode = TGTC_MLP_BF16 or
+ * TGTC_MLP_F16: operand format of all three kernels and of the feature tiles between them); 64 + 64 samples;
  * chunk <= 0 means passes of 32768 rays (128 KB of feature tiles per 128 samples live in the workspace). */
 size_t tgtc_render_style_workspace_bytes(int64_t n_rays, int n_samples, int n_fine, int64_t chunk);
-int tgtc_render_style(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n_rays, double near, double far,
+int tgtc_render_style(tgtc_ctx* ctx, int mode, const float* rays_o, const float* rays_d, int64_t n_rays, double near, double far,
                       int n_samples, int n_fine, int64_t chunk, const float* latent1, const float* latent2,
                       const tgtc_render_out* out, void* workspace, size_t workspace_bytes, tgtc_stream stream);
 

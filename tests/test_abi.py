@@ -35,7 +35,7 @@ def test_header_symbols_exported(lib):
 
 
 def test_abi_version(lib):
-    assert lib.tgtc_abi_version() == 1
+    assert lib.tgtc_abi_version() == 2   # matches TGTC_ABI_VERSION in include/tgtc_b200.h
 
 
 def test_workspace_bytes_arithmetic(lib):

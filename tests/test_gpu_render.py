@@ -41,30 +41,38 @@ def test_render_bf16_end_to_end_default_init(renderer_bf16):
     assert np.abs(out["acc"].cpu().numpy() - g["acc"]).max() <= tol
 
 
-def test_render_bf16_teacher_forced_protocol(renderer_bf16):
-    """bf16 mode on the sigma-recalibrated set W1 (sigma ~ N(0,30^2): deliberately hard, every sigma error is
-    amplified by the compositing), SURVEY H1 protocol: fine pass teacher-forced on the reference's ts_fine.
-    Tolerance 1e-2 (north star, bf16-MLP): holds for >= 98% of rays, the raw max is bounded by 3e-2 and by
-    3x what a bf16-operand emulation of the same arithmetic gives (5.7e-3 on these rays); knife-edge rays
-    (oracle moves > 1e-2 under a +-1% sigma perturbation) are excluded from the max and counted."""
+@pytest.mark.parametrize("mode", ["f16", "bf16"])
+def test_render_tc_teacher_forced_protocol(mode):
+    """Tensor-core modes on the sigma-recalibrated set W1 (sigma ~ N(0,30^2): deliberately hard, every sigma error is
+    amplified by the compositing), SURVEY H1 protocol: fine pass teacher-forced on the reference's ts_fine, knife-edge rays
+    (oracle moves > 1e-2 under a small sigma perturbation, helpers.knife_edge_mask) flagged, < 0.5 % of the rays.
+    fp16 operands: max <= 1e-2 over the non-flagged rays (north star).  bf16 operands: the format itself leaves ~0.3 % of such
+    rays above 1e-2 (tools/precision_study.py, tests/test_gpu_parity_fullsize.py), so on these 160 rays: at most one ray above
+    1e-2, raw max <= 3e-2."""
+    r = T.NerfRenderer(device="cuda:0", mode=mode)
     g = golden("chain_w1")
     wc, wf = weights("w1")
-    renderer_bf16.set_weights(wc, wf)
-    rs = renderer_bf16.nerf_forward_rays(T.NET_FINE, g["rays_o"], g["rays_d"], g["ts_fine"], 128, 0., 1.)
-    rgb, depth, w, acc = renderer_bf16.composite(t_values=g["ts_fine"], rgbsigma=rs)
+    r.set_weights(wc, wf)
+    rs = r.nerf_forward_rays(T.NET_FINE, g["rays_o"], g["rays_d"], g["ts_fine"], 128, 0., 1.)
+    rgb, depth, w, acc = r.composite(t_values=g["ts_fine"], rgbsigma=rs)
     flagged = knife_edge_mask(torch.from_numpy(g["sigma_fine"]), torch.from_numpy(g["ts_fine"])).numpy()
     ok = ~flagged
     assert flagged.mean() <= 0.005
     e_rgb = np.abs(rgb.cpu().numpy() - g["rgb"]).max(-1)
     e_acc = np.abs(acc.cpu().numpy() - g["acc"])
     e_dep = np.abs(depth.cpu().numpy() - g["depth"])
-    print("bf16 teacher-forced: max drgb %.2e dacc %.2e ddepth %.2e, frac>1e-2 %.4f" % (e_rgb[ok].max(), e_acc[ok].max(), e_dep[ok].max(), (e_rgb > 1e-2).mean()))
+    print("%s teacher-forced: max drgb %.2e dacc %.2e ddepth %.2e, frac>1e-2 %.4f" % (mode, e_rgb[ok].max(), e_acc[ok].max(), e_dep[ok].max(), (e_rgb > 1e-2).mean()))
     for e in (e_rgb, e_acc, e_dep):
-        assert (e[ok] <= 1e-2).mean() >= 0.98
-        assert e[ok].max() <= 3e-2
-        assert e.mean() <= 2e-3
-    out = renderer_bf16.render(g["rays_o"], g["rays_d"], 0., 1., n_samples=64, n_fine=64)
-    assert np.abs(out["rgb"].cpu().numpy() - g["rgb"]).mean() <= 5e-3      # end to end (resampling moves ts_fine)
+        if mode == "f16":
+            assert e[ok].max() <= 1e-2
+            assert e.mean() <= 3e-4
+        else:
+            assert (e[ok] > 1e-2).sum() <= 1
+            assert e[ok].max() <= 3e-2
+            assert e.mean() <= 2e-3
+    out = r.render(g["rays_o"], g["rays_d"], 0., 1., n_samples=64, n_fine=64)
+    assert np.abs(out["rgb"].cpu().numpy() - g["rgb"]).mean() <= (1e-3 if mode == "f16" else 5e-3)      # end to end (resampling moves ts_fine)
+    r.close()
 
 
 def test_render_host_chunk_and_shard_invariance(renderer_fp32):

@@ -9,7 +9,7 @@ Public surface:
 The directory name contains a hyphen; import it as `tgtc_style_b200` (root-level loader module).
 """
 from . import _lib
-from ._lib import MLP_BF16, MLP_FP32, NET_COARSE, NET_FINE, TgtcError
+from ._lib import MLP_BF16, MLP_F16, MLP_FP32, NET_COARSE, NET_FINE, TgtcError
 from .dist import gather_tiles, render_frame_sharded, render_path_sharded, shard_range, shard_sizes
 from .geometry import cal_geometry, frame_geometry, save_frame
 from .render import LAYER_NAMES, LAYER_SHAPES, NerfRenderer
@@ -17,4 +17,4 @@ from .shims import make_callables, patch
 from .train import NerfTrainer, StyleLatents, StyleTrainer
 
 __all__ = ["NerfRenderer", "NerfTrainer", "StyleTrainer", "StyleLatents", "make_callables", "patch", "shard_range", "shard_sizes", "gather_tiles", "render_frame_sharded", "render_path_sharded",
-           "cal_geometry", "frame_geometry", "save_frame", "TgtcError", "MLP_FP32", "MLP_BF16", "NET_COARSE", "NET_FINE", "LAYER_NAMES", "LAYER_SHAPES"]
+           "cal_geometry", "frame_geometry", "save_frame", "TgtcError", "MLP_FP32", "MLP_BF16", "MLP_F16", "NET_COARSE", "NET_FINE", "LAYER_NAMES", "LAYER_SHAPES"]

@@ -16,6 +16,7 @@ c_i64 = ctypes.c_int64
 
 MLP_FP32 = 0
 MLP_BF16 = 1
+MLP_F16 = 2
 NET_COARSE = 0
 NET_FINE = 1
 NUM_PARAMS = 24
@@ -66,7 +67,7 @@ PROTOTYPES = {
                                       ctypes.c_double, ctypes.c_double, c_i64, c_void_p]),
     "tgtc_set_style_weights": (ctypes.c_int, [c_void_p, ctypes.POINTER(c_void_p), c_void_p]),
     "tgtc_render_style_workspace_bytes": (ctypes.c_size_t, [c_i64, ctypes.c_int, ctypes.c_int, c_i64]),
-    "tgtc_render_style": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+    "tgtc_render_style": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p, c_void_p, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                          ctypes.c_int, c_i64, c_void_p, c_void_p, ctypes.POINTER(RenderOut), c_void_p,
                                          ctypes.c_size_t, c_void_p]),
     "tgtc_train_step_seeded": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, ctypes.c_double, ctypes.c_double,
@@ -107,6 +108,7 @@ PROTOTYPES = {
 DEBUG_PROTOTYPES = {
     "tgtc_debug_tc_layers": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p, c_void_p, c_void_p, c_i64, ctypes.c_int, ctypes.c_double,
                                             ctypes.c_double, ctypes.c_int, c_void_p, c_void_p]),
+    "tgtc_debug_tc_f16": (None, [ctypes.c_int]),
 }
 
 _lib = None
@@ -130,7 +132,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.tgtc_abi_version() != 1:
+    if lib.tgtc_abi_version() != 2:
         raise TgtcError("libtgtc_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -33,7 +33,7 @@ extern "C" int tgtc_abi_version(void) { return TGTC_ABI_VERSION; }
   TGTC_REQUIRE((ctx)->net[(which)].set, TGTC_ERR_STATE, "weights of net %d not set (call tgtc_set_weights)", (which))
 
 #define CHECK_MODE(mode) \
-  TGTC_REQUIRE((mode) == TGTC_MLP_FP32 || (mode) == TGTC_MLP_BF16, TGTC_ERR_ARG, "bad MLP mode %d", (mode))
+  TGTC_REQUIRE((mode) == TGTC_MLP_FP32 || (mode) == TGTC_MLP_BF16 || (mode) == TGTC_MLP_F16, TGTC_ERR_ARG, "bad MLP mode %d", (mode))
 
 #define CHECK_PTR(p, name) TGTC_REQUIRE((p) != nullptr && aligned4(p), TGTC_ERR_ARG, "%s is null or misaligned", name)
 
@@ -62,11 +62,12 @@ extern "C" int tgtc_destroy(tgtc_ctx* ctx) {
     if (ctx->net[i].f32_gemm) cudaFree(ctx->net[i].f32_gemm);
     if (ctx->net[i].smalls) cudaFree(ctx->net[i].smalls);
     if (ctx->net[i].tc_blob) cudaFree(ctx->net[i].tc_blob);
+    if (ctx->net[i].tc_blob_h) cudaFree(ctx->net[i].tc_blob_h);
     if (ctx->net[i].tc_blobT) cudaFree(ctx->net[i].tc_blobT);
   }
   {
     StyleImage& si = ctx->style;
-    void* bufs[] = {si.blob_c, si.blob_w, si.blob_T, si.head_w, si.bias_c, si.bias_w, si.head_b, si.latents, si.tables, si.wlat, si.wlatT};
+    void* bufs[] = {si.blob_c, si.blob_w, si.blob_c_h, si.blob_w_h, si.blob_T, si.head_w, si.bias_c, si.bias_w, si.head_b, si.latents, si.tables, si.wlat, si.wlatT};
     for (void* b : bufs) if (b) cudaFree(b);
   }
   if (ctx->arena) cudaFree(ctx->arena);
@@ -136,10 +137,10 @@ static int run_mlp(tgtc_ctx* ctx, int net, int mode, const MlpIO& io, cudaStream
   int prc = prof_begin(ctx, 0, (double)io.n_rays * io.S * 1186816.0, st, &e1);
   if (prc) return prc;
   int rc;
-  if (mode == TGTC_MLP_BF16) {
+  if (mode == TGTC_MLP_BF16 || mode == TGTC_MLP_F16) {
     TGTC_REQUIRE(mlp_tc_supports(io), TGTC_ERR_UNSUPPORTED,
-                 "bf16 MLP needs per-ray view dirs, S in {64,128} or a multiple of 128, and no feature outputs (S=%d)", io.S);
-    rc = launch_mlp_tc(ctx, net, io, st);
+                 "tensor-core MLP needs per-ray view dirs, S in {64,128} or a multiple of 128, and no feature outputs (S=%d)", io.S);
+    rc = launch_mlp_tc(ctx, net, io, st, mode == TGTC_MLP_F16);
   } else {
     rc = launch_mlp_fp32(ctx, net, io, st);
   }
@@ -692,10 +693,12 @@ extern "C" size_t tgtc_render_style_workspace_bytes(int64_t n_rays, int n_sample
   return style_ws_layout(style_pass(n_rays, chunk), n_samples, n_fine).total;
 }
 
-extern "C" int tgtc_render_style(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n_rays, double near, double far,
+extern "C" int tgtc_render_style(tgtc_ctx* ctx, int mode, const float* rays_o, const float* rays_d, int64_t n_rays, double near, double far,
                                  int n_samples, int n_fine, int64_t chunk, const float* latent1, const float* latent2,
                                  const tgtc_render_out* out_p, void* workspace, size_t workspace_bytes, tgtc_stream stream) {
   CHECK_CTX(ctx);
+  TGTC_REQUIRE(mode == TGTC_MLP_BF16 || mode == TGTC_MLP_F16, TGTC_ERR_ARG, "stylised render runs on the tensor-core path: mode must be BF16 or F16 (got %d)", mode);
+  const bool f16 = mode == TGTC_MLP_F16;
   CHECK_NET(ctx, TGTC_NET_COARSE);
   CHECK_NET(ctx, TGTC_NET_FINE);
   TGTC_REQUIRE(ctx->style.set, TGTC_ERR_STATE, "style weights not set (tgtc_set_style_weights)");
@@ -738,19 +741,19 @@ extern "C" int tgtc_render_style(tgtc_ctx* ctx, const float* rays_o, const float
       cudaEvent_t e1 = nullptr;
       rc = prof_begin(ctx, 0, (double)m * io.S * 2.0 * (593408.0 - 36224.0 - 384.0), st, &e1);
       if (rc) return rc;
-      rc = launch_mlp_tc_trunk(ctx, which, io, remap, st);
+      rc = launch_mlp_tc_trunk(ctx, which, io, remap, st, f16);
       if (rc) return rc;
       if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
       // style module 1 -> concat_features tile images (rendering.py:129-130)
       rc = prof_begin(ctx, 1, (double)m * io.S * 2.0 * 335360.0, st, &e1);
       if (rc) return rc;
-      rc = launch_style_concat(ctx, io, cf, st);
+      rc = launch_style_concat(ctx, io, cf, st, f16);
       if (rc) return rc;
       if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
       // style module 2 -> stylised rgb (rendering.py:132-142)
       rc = prof_begin(ctx, 2, (double)m * io.S * 2.0 * 614752.0, st, &e1);
       if (rc) return rc;
-      rc = launch_style_wild(ctx, io, remap, cf, st);
+      rc = launch_style_wild(ctx, io, remap, cf, st, f16);
       if (rc) return rc;
       if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
       if (which == 0) {

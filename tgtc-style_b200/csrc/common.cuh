@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -63,6 +64,7 @@ struct NetImage {
   float* f32_gemm = nullptr;   // kF32GemmFloats
   float* smalls = nullptr;     // kSmallFloats
   uint8_t* tc_blob = nullptr;  // kTcBlobBytes
+  uint8_t* tc_blob_h = nullptr;  // the same image with fp16 elements (TGTC_MLP_F16)
   uint8_t* tc_blobT = nullptr; // transposed weights for the activation-gradient kernel (mlp_bwd.cu), bwd_blobT_bytes()
   bool set = false;
 };
@@ -71,6 +73,8 @@ struct NetImage {
 struct StyleImage {
   uint8_t* blob_c = nullptr;   // module 1: 18 chunks [256 x 64] bf16
   uint8_t* blob_w = nullptr;   // module 2: 34 chunks
+  uint8_t* blob_c_h = nullptr; // the same two images with fp16 elements (TGTC_MLP_F16 stylised render)
+  uint8_t* blob_w_h = nullptr;
   uint8_t* blob_T = nullptr;   // 45 transposed chunks for the style dgrad (style_bwd.cu)
   float* head_w = nullptr;     // [3][256] output layer of module 2
   float* bias_c = nullptr;     // [5][256] effective biases for the current latents
@@ -246,8 +250,8 @@ int launch_style_wild_train(tgtc_ctx* ctx, const MlpIO& io, const float* bias_ra
 // style_tc.cu
 int style_set_weights(tgtc_ctx* ctx, const float* const* params, cudaStream_t st);
 int style_set_latents(tgtc_ctx* ctx, const float* latent1, const float* latent2, cudaStream_t st);
-int launch_style_concat(tgtc_ctx* ctx, const MlpIO& io, uint8_t* cf_img, cudaStream_t st);
-int launch_style_wild(tgtc_ctx* ctx, const MlpIO& io, const uint8_t* remap_img, const uint8_t* cf_img, cudaStream_t st);
+int launch_style_concat(tgtc_ctx* ctx, const MlpIO& io, uint8_t* cf_img, cudaStream_t st, bool f16 = false);
+int launch_style_wild(tgtc_ctx* ctx, const MlpIO& io, const uint8_t* remap_img, const uint8_t* cf_img, cudaStream_t st, bool f16 = false);
 
 // mlp_bwd.cu
 size_t bwd_partial_floats();
@@ -263,9 +267,9 @@ int launch_mse_grad(tgtc_ctx* ctx, const float* rgb, const float* gt, int64_t n,
 
 // mlp_fp32.cu / mlp_tc.cu
 int launch_mlp_fp32(tgtc_ctx* ctx, int net, const MlpIO& io, cudaStream_t st);
-int launch_mlp_tc(tgtc_ctx* ctx, int net, const MlpIO& io, cudaStream_t st);
+int launch_mlp_tc(tgtc_ctx* ctx, int net, const MlpIO& io, cudaStream_t st, bool f16 = false);
 int launch_mlp_tc_train(tgtc_ctx* ctx, int net, const MlpIO& io, const TcStash& stash, cudaStream_t st);
-int launch_mlp_tc_trunk(tgtc_ctx* ctx, int net, const MlpIO& io, uint8_t* remap_img, cudaStream_t st);
+int launch_mlp_tc_trunk(tgtc_ctx* ctx, int net, const MlpIO& io, uint8_t* remap_img, cudaStream_t st, bool f16 = false);
 bool mlp_tc_supports(const MlpIO& io);
 
 // ---------------------------------------------------------------------------

@@ -78,7 +78,7 @@ using namespace tcptx;
 // blk = 32-column block index inside this thread's 128 columns; kb = row base of the 64-column K block.
 // mrow: when training, the block's ReLU mask word (bit 31-c = sign of pre-activation c, i.e. 1 = gradient blocked) goes to the
 // mask stash in HBM that mlp_dgrad_kernel reads instead of the 16x larger activation image; nullptr otherwise.
-template <bool kSigma, bool kMask>
+template <bool kSigma, bool kMask, bool kF16>
 __device__ __forceinline__ void epi_block(uint32_t (&v)[32], const float* bl, const float* wsig, uint32_t kb, uint32_t rx, int blk,
                                           float& sig, uint32_t* mrow) {
   if constexpr (kMask) {
@@ -117,15 +117,15 @@ __device__ __forceinline__ void epi_block(uint32_t (&v)[32], const float* bl, co
         const float4 w1 = *reinterpret_cast<const float4*>(wsig + c + 4);
         sig = fmaf(h[0], w0.x, sig); sig = fmaf(h[1], w0.y, sig); sig = fmaf(h[2], w0.z, sig); sig = fmaf(h[3], w0.w, sig);
         sig = fmaf(h[4], w1.x, sig); sig = fmaf(h[5], w1.y, sig); sig = fmaf(h[6], w1.z, sig); sig = fmaf(h[7], w1.w, sig);
-        const uint32_t q0 = pack_bf16(h[0], h[1]), q1 = pack_bf16(h[2], h[3]), q2 = pack_bf16(h[4], h[5]), q3 = pack_bf16(h[6], h[7]);
+        const uint32_t q0 = pack_op<kF16>(h[0], h[1]), q1 = pack_op<kF16>(h[2], h[3]), q2 = pack_op<kF16>(h[4], h[5]), q3 = pack_op<kF16>(h[6], h[7]);
         st_shared_v4(dst, q0, q1, q2, q3);
       } else {
         add2(v[8 * j + 0], v[8 * j + 1], b0.x, b0.y);
         add2(v[8 * j + 2], v[8 * j + 3], b0.z, b0.w);
         add2(v[8 * j + 4], v[8 * j + 5], b1.x, b1.y);
         add2(v[8 * j + 6], v[8 * j + 7], b1.z, b1.w);
-        const uint32_t q0 = pack_bf16_relu(v[8 * j + 0], v[8 * j + 1]), q1 = pack_bf16_relu(v[8 * j + 2], v[8 * j + 3]),
-                       q2 = pack_bf16_relu(v[8 * j + 4], v[8 * j + 5]), q3 = pack_bf16_relu(v[8 * j + 6], v[8 * j + 7]);
+        const uint32_t q0 = pack_op_relu<kF16>(v[8 * j + 0], v[8 * j + 1]), q1 = pack_op_relu<kF16>(v[8 * j + 2], v[8 * j + 3]),
+                       q2 = pack_op_relu<kF16>(v[8 * j + 4], v[8 * j + 5]), q3 = pack_op_relu<kF16>(v[8 * j + 6], v[8 * j + 7]);
         st_shared_v4(dst, q0, q1, q2, q3);
       }
     } else {
@@ -138,8 +138,8 @@ __device__ __forceinline__ void epi_block(uint32_t (&v)[32], const float* bl, co
 #pragma unroll
         for (int e = 0; e < 8; ++e) sig = fmaf(fmaxf(__uint_as_float(v[8 * j + e]), 0.f), ws[e], sig);
       }
-      const uint32_t q0 = pack_bf16_relu(v[8 * j + 0], v[8 * j + 1]), q1 = pack_bf16_relu(v[8 * j + 2], v[8 * j + 3]),
-                     q2 = pack_bf16_relu(v[8 * j + 4], v[8 * j + 5]), q3 = pack_bf16_relu(v[8 * j + 6], v[8 * j + 7]);
+      const uint32_t q0 = pack_op_relu<kF16>(v[8 * j + 0], v[8 * j + 1]), q1 = pack_op_relu<kF16>(v[8 * j + 2], v[8 * j + 3]),
+                     q2 = pack_op_relu<kF16>(v[8 * j + 4], v[8 * j + 5]), q3 = pack_op_relu<kF16>(v[8 * j + 6], v[8 * j + 7]);
       st_shared_v4(dst, q0, q1, q2, q3);
     }
   }
@@ -147,7 +147,7 @@ __device__ __forceinline__ void epi_block(uint32_t (&v)[32], const float* bl, co
 
 // this thread's 128 columns of one hidden layer: TMEM loads software-pipelined against the math
 // (the load of block b+1 is in flight while block b is converted and stored)
-template <bool kSigma, bool kMask>
+template <bool kSigma, bool kMask, bool kF16>
 __device__ __forceinline__ float hidden_epilogue(uint32_t tcol, const float* bl, const float* wsig, uint32_t arow, uint32_t rx,
                                                  uint32_t* mrow) {
   float sig = 0.f;
@@ -155,15 +155,15 @@ __device__ __forceinline__ float hidden_epilogue(uint32_t tcol, const float* bl,
   tmem_ld32(tcol, va);
   tmem_ld_wait_dep(va);
   tmem_ld32(tcol + 32, vb);
-  epi_block<kSigma, kMask>(va, bl, wsig, arow, rx, 0, sig, mrow);
+  epi_block<kSigma, kMask, kF16>(va, bl, wsig, arow, rx, 0, sig, mrow);
   tmem_ld_wait_dep(vb);
   tmem_ld32(tcol + 64, va);
-  epi_block<kSigma, kMask>(vb, bl, wsig, arow, rx, 1, sig, mrow);
+  epi_block<kSigma, kMask, kF16>(vb, bl, wsig, arow, rx, 1, sig, mrow);
   tmem_ld_wait_dep(va);
   tmem_ld32(tcol + 96, vb);
-  epi_block<kSigma, kMask>(va, bl, wsig, arow + 16384, rx, 2, sig, mrow);
+  epi_block<kSigma, kMask, kF16>(va, bl, wsig, arow + 16384, rx, 2, sig, mrow);
   tmem_ld_wait_dep(vb);
-  epi_block<kSigma, kMask>(vb, bl, wsig, arow + 16384, rx, 3, sig, mrow);
+  epi_block<kSigma, kMask, kF16>(vb, bl, wsig, arow + 16384, rx, 3, sig, mrow);
   return sig;
 }
 
@@ -203,8 +203,10 @@ __device__ __forceinline__ int64_t my_tile(int64_t it, int t, uint32_t rank) {
 // kTrain: also write the activation stash (training forward); the inference instantiation carries none of that code.
 // kTrunk (style path; implies P.trunk): the inference epilogue on L0..L7 + remap, and only the remap tile leaves as an image --
 // two barriers per tile instead of the training instantiation's one per layer.
-template <bool kTrain, bool kTrunk = false>
+// kF16: fp16 instead of bf16 operands (weights image, PE tile, activations); inference only.
+template <bool kTrain, bool kTrunk = false, bool kF16 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P) {
+  static_assert(!(kTrain && kF16), "the training stash / backward kernels are bf16");
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5;
@@ -322,7 +324,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
     };
     for (int64_t it = 0; it < iters; ++it) {
       for (int l = 0; l < nlayers; ++l) {
-        const uint32_t idesc = make_idesc(2 * kTileM, tc_layer_n(l));
+        const uint32_t idesc = make_idesc_op<kF16>(2 * kTileM, tc_layer_n(l));
         const bool has_pe = (l == 0 || l == 5);
         const bool has_act = (l != 0);
 #pragma unroll
@@ -396,8 +398,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
         uint8_t* const gpe = (kTrain && tile < P.ntiles) ? P.stash_pe + (size_t)tile * 16384 + (r >> 3) * 1024 + (r & 7) * 128 : nullptr;
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
-          const uint32_t q0 = pack_bf16(e[8 * ch + 0], e[8 * ch + 1]), q1 = pack_bf16(e[8 * ch + 2], e[8 * ch + 3]),
-                         q2 = pack_bf16(e[8 * ch + 4], e[8 * ch + 5]), q3 = pack_bf16(e[8 * ch + 6], e[8 * ch + 7]);
+          const uint32_t q0 = pack_op<kF16>(e[8 * ch + 0], e[8 * ch + 1]), q1 = pack_op<kF16>(e[8 * ch + 2], e[8 * ch + 3]),
+                         q2 = pack_op<kF16>(e[8 * ch + 4], e[8 * ch + 5]), q3 = pack_op<kF16>(e[8 * ch + 6], e[8 * ch + 7]);
           st_shared_v4(prow + ((ch ^ (r & 7)) << 4), q0, q1, q2, q3);
           if (gpe != nullptr) st_global_v4(gpe + ((ch ^ (r & 7)) << 4), q0, q1, q2, q3);
         }
@@ -505,10 +507,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
             }
             if (P.dbg_flags & 2) {
             } else if (l == 7) {
-              const float sig = hidden_epilogue<true, kTrain>(tcol, bl, wsig_s + hc * 128, arow, rx, mrow);
+              const float sig = hidden_epilogue<true, kTrain, kF16>(tcol, bl, wsig_s + hc * 128, arow, rx, mrow);
               if (hc == 1) sigpart_s[t * 128 + row] = sig; else sig_keep[t] = sig;
             } else {
-              hidden_epilogue<false, kTrain>(tcol, bl, nullptr, arow, rx, mrow);
+              hidden_epilogue<false, kTrain, kF16>(tcol, bl, nullptr, arow, rx, mrow);
             }
             fence_proxy_async();
             if constexpr (kTrain) {
@@ -643,10 +645,10 @@ extern "C" void tgtc_debug_tc_flags(int f) { g_dbg_flags = f; }
 extern "C" void tgtc_debug_tc_trace(long long* dev_buf) { g_dbg_trace = dev_buf; }
 
 static int launch_tc_common(tgtc_ctx* ctx, int net, const MlpIO& io, int dbg_layers, float* dbg_out, const TcStash* stash,
-                            cudaStream_t st, int trunk = 0) {
+                            cudaStream_t st, int trunk = 0, bool f16 = false) {
   const NetImage& im = ctx->net[net];
   TcParams P;
-  P.blob = im.tc_blob;
+  P.blob = f16 ? im.tc_blob_h : im.tc_blob;
   P.smalls = im.smalls;
   P.io = io;
   P.M = io.n_rays * io.S;
@@ -667,23 +669,27 @@ static int launch_tc_common(tgtc_ctx* ctx, int net, const MlpIO& io, int dbg_lay
     TGTC_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     TGTC_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     TGTC_CUDA((cudaFuncSetAttribute(mlp_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)));
+    TGTC_CUDA((cudaFuncSetAttribute(mlp_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)));
+    TGTC_CUDA((cudaFuncSetAttribute(mlp_tc_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)));
     attr_set[ctx->device & 63] = true;
   }
   const int64_t nquads = (P.ntiles + 3) / 4;
   const int64_t max_pairs = ctx->num_sms / 2;
   const int grid = 2 * (int)(nquads < max_pairs ? nquads : max_pairs);   // CTA pairs (clusters of 2)
-  if (trunk) mlp_tc_kernel<false, true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
+  if (trunk && f16) mlp_tc_kernel<false, true, true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
+  else if (trunk) mlp_tc_kernel<false, true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
   else if (stash != nullptr) mlp_tc_kernel<true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
+  else if (f16) mlp_tc_kernel<false, false, true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
   else mlp_tc_kernel<false><<<grid, kNumThreads, kSmemBytes, st>>>(P);
   TGTC_LAUNCH_CHECK(ctx);
   return TGTC_OK;
 }
 
 // style path: NeRF trunk only (L0..L7, sigma head, remap); remap tile images -> remap_img [ntiles][64 KB], sigma -> rgbsigma[.].w
-int launch_mlp_tc_trunk(tgtc_ctx* ctx, int net, const MlpIO& io, uint8_t* remap_img, cudaStream_t st) {
+int launch_mlp_tc_trunk(tgtc_ctx* ctx, int net, const MlpIO& io, uint8_t* remap_img, cudaStream_t st, bool f16) {
   TcStash stash;
   stash.h = remap_img;
-  return launch_tc_common(ctx, net, io, 0, nullptr, &stash, st, 1);
+  return launch_tc_common(ctx, net, io, 0, nullptr, &stash, st, 1, f16);
 }
 
 // training forward: same kernel, additionally writing the activation stash the backward kernels read
@@ -691,12 +697,14 @@ int launch_mlp_tc_train(tgtc_ctx* ctx, int net, const MlpIO& io, const TcStash& 
   return launch_tc_common(ctx, net, io, 0, nullptr, &stash, st);
 }
 
-int launch_mlp_tc(tgtc_ctx* ctx, int net, const MlpIO& io, cudaStream_t st) {
-  return launch_tc_common(ctx, net, io, 0, nullptr, nullptr, st);
+int launch_mlp_tc(tgtc_ctx* ctx, int net, const MlpIO& io, cudaStream_t st, bool f16) {
+  return launch_tc_common(ctx, net, io, 0, nullptr, nullptr, st, 0, f16);
 }
 
 // test hook (not part of the public header): run the first `layers` GEMM layers of the bf16 kernel and dump
 // the raw fp32 accumulator of the last one ([n_rays*S, 256], columns >= N untouched)
+static int g_dbg_f16 = 0;
+extern "C" void tgtc_debug_tc_f16(int on) { g_dbg_f16 = on; }   // the hook below runs the fp16-operand instantiation
 extern "C" int tgtc_debug_tc_layers(tgtc_ctx* ctx, int net, const float* rays_o, const float* rays_d, const float* ts,
                                     int64_t n_rays, int S, double near, double far, int layers, float* acc_out, void* stream) {
   if (ctx == nullptr || !ctx->net[net].set || layers < 1 || layers > kTcNumGemm) { tgtc_set_error("bad debug args"); return TGTC_ERR_ARG; }
@@ -706,5 +714,5 @@ extern "C" int tgtc_debug_tc_layers(tgtc_ctx* ctx, int net, const float* rays_o,
   io.t_scale = (float)(far - near); io.t_near = (float)near;
   io.n_rays = n_rays; io.S = S;
   if (!mlp_tc_supports(io)) { tgtc_set_error("unsupported S"); return TGTC_ERR_UNSUPPORTED; }
-  return launch_tc_common(ctx, net, io, layers, acc_out, nullptr, (cudaStream_t)stream);
+  return launch_tc_common(ctx, net, io, layers, acc_out, nullptr, (cudaStream_t)stream, 0, g_dbg_f16 != 0);
 }

@@ -48,7 +48,12 @@ __global__ void pack_f32_kernel(Params24 P, float* __restrict__ out) {
   }
 }
 
-__global__ void pack_tc_kernel(Params24 P, __nv_bfloat16* __restrict__ out) {
+template <typename T> __device__ __forceinline__ T to_op(float v);
+template <> __device__ __forceinline__ __nv_bfloat16 to_op<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half to_op<__half>(float v) { return __float2half_rn(v); }
+
+template <typename T>
+__global__ void pack_tc_kernel(Params24 P, T* __restrict__ out) {
   const size_t total = kTcBlobBytes / 2;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     int l = 0;
@@ -70,7 +75,7 @@ __global__ void pack_tc_kernel(Params24 P, __nv_bfloat16* __restrict__ out) {
     const int c16 = c16p ^ rr;
     const int n = grp * 8 + rr;
     const int k = chunk * kTcChunkK + c16 * 8 + within;
-    out[idx] = __float2bfloat16_rn(gemm_w(P, l, n, k, /*with_dir=*/false));
+    out[idx] = to_op<T>(gemm_w(P, l, n, k, /*with_dir=*/false));
   }
 }
 
@@ -136,13 +141,16 @@ int pack_weights(tgtc_ctx* ctx, int net, const float* const* params, cudaStream_
     TGTC_CUDA(cudaMalloc(&im.f32_gemm, kF32GemmFloats * sizeof(float)));
     TGTC_CUDA(cudaMalloc(&im.smalls, kSmallFloats * sizeof(float)));
     TGTC_CUDA(cudaMalloc(&im.tc_blob, kTcBlobBytes));
+    TGTC_CUDA(cudaMalloc(&im.tc_blob_h, kTcBlobBytes));
     TGTC_CUDA(cudaMalloc(&im.tc_blobT, bwd_blobT_bytes()));
   }
   Params24 P;
   for (int i = 0; i < TGTC_NUM_PARAMS; ++i) P.p[i] = params[i];
   pack_f32_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(P, im.f32_gemm);
   TGTC_LAUNCH_CHECK(ctx);
-  pack_tc_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(P, reinterpret_cast<__nv_bfloat16*>(im.tc_blob));
+  pack_tc_kernel<__nv_bfloat16><<<ctx->num_sms * 4, 256, 0, st>>>(P, reinterpret_cast<__nv_bfloat16*>(im.tc_blob));
+  TGTC_LAUNCH_CHECK(ctx);
+  pack_tc_kernel<__half><<<ctx->num_sms * 4, 256, 0, st>>>(P, reinterpret_cast<__half*>(im.tc_blob_h));
   TGTC_LAUNCH_CHECK(ctx);
   pack_tcT_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(P, reinterpret_cast<__nv_bfloat16*>(im.tc_blobT), bwd_blobT_bytes() / 2);
   TGTC_LAUNCH_CHECK(ctx);

@@ -94,8 +94,11 @@ __device__ __forceinline__ int seg_chunks(int s) { return s == SEG_PE ? 1 : 4; }
 
 // kTrain: the training forward of Style_train (train_tgtcs.py:311-483) -- per-ray latents (effective biases per ray from
 // global memory), every layer's output image and ReLU mask words stashed for the backward, the PE tile stashed once.
-template <bool kTrain>
+// kF16 (inference only): fp16 instead of bf16 operands -- weights image, PE tile, activations and the feature tile images that
+// travel between the trunk / module 1 / module 2 launches (TGTC_MLP_F16).
+template <bool kTrain, bool kF16 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_chain_kernel(const __grid_constant__ ChainParams P) {
+  static_assert(!(kTrain && kF16), "the Style_train stash / backward kernels are bf16");
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5;
@@ -198,7 +201,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
     uint32_t phase = 0;
     uint32_t act_par[2] = {0, 0}, pe_par[2] = {0, 0}, af_par[2] = {0, 0}, of_par[2] = {0, 0};
     const uint32_t w_lo0 = (((sbase + kOffW) & 0x3FFFFu) >> 4) | (1u << 16);
-    const uint32_t idesc = make_idesc(2 * kTileM, 256);
+    const uint32_t idesc = make_idesc_op<kF16>(2 * kTileM, 256);
     auto issue_chunk = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t accumulate) {
       mbar_wait_uniform(bar(kBarWFull + stage), phase);
       tc_fence_after();
@@ -290,8 +293,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
         }
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch) {
-          const uint32_t q0 = pack_bf16(e[8 * ch + 0], e[8 * ch + 1]), q1 = pack_bf16(e[8 * ch + 2], e[8 * ch + 3]),
-                         q2 = pack_bf16(e[8 * ch + 4], e[8 * ch + 5]), q3 = pack_bf16(e[8 * ch + 6], e[8 * ch + 7]);
+          const uint32_t q0 = pack_op<kF16>(e[8 * ch + 0], e[8 * ch + 1]), q1 = pack_op<kF16>(e[8 * ch + 2], e[8 * ch + 3]),
+                         q2 = pack_op<kF16>(e[8 * ch + 4], e[8 * ch + 5]), q3 = pack_op<kF16>(e[8 * ch + 6], e[8 * ch + 7]);
           st_shared_v4(prow + ((ch ^ (r & 7)) << 4), q0, q1, q2, q3);
           if (gpe != nullptr) *reinterpret_cast<uint4*>(gpe + ((ch ^ (r & 7)) << 4)) = make_uint4(q0, q1, q2, q3);
         }
@@ -433,8 +436,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
                   }
                 }
                 const uint32_t dst = kb + ((uint32_t)((((blk & 1) * 4) + j) << 4) ^ rx);
-                st_shared_v4(dst, pack_bf16_relu(v[8 * j + 0], v[8 * j + 1]), pack_bf16_relu(v[8 * j + 2], v[8 * j + 3]),
-                             pack_bf16_relu(v[8 * j + 4], v[8 * j + 5]), pack_bf16_relu(v[8 * j + 6], v[8 * j + 7]));
+                st_shared_v4(dst, pack_op_relu<kF16>(v[8 * j + 0], v[8 * j + 1]), pack_op_relu<kF16>(v[8 * j + 2], v[8 * j + 3]),
+                             pack_op_relu<kF16>(v[8 * j + 4], v[8 * j + 5]), pack_op_relu<kF16>(v[8 * j + 6], v[8 * j + 7]));
               }
             }
             if (has_next) {
@@ -457,8 +460,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
                 add2(v[8 * j + 4], v[8 * j + 5], b1.x, b1.y);
                 add2(v[8 * j + 6], v[8 * j + 7], b1.z, b1.w);
                 const uint32_t dst = kb + ((uint32_t)((((blk & 1) * 4) + j) << 4) ^ rx);
-                st_shared_v4(dst, pack_bf16_relu(v[8 * j + 0], v[8 * j + 1]), pack_bf16_relu(v[8 * j + 2], v[8 * j + 3]),
-                             pack_bf16_relu(v[8 * j + 4], v[8 * j + 5]), pack_bf16_relu(v[8 * j + 6], v[8 * j + 7]));
+                st_shared_v4(dst, pack_op_relu<kF16>(v[8 * j + 0], v[8 * j + 1]), pack_op_relu<kF16>(v[8 * j + 2], v[8 * j + 3]),
+                             pack_op_relu<kF16>(v[8 * j + 4], v[8 * j + 5]), pack_op_relu<kF16>(v[8 * j + 6], v[8 * j + 7]));
               }
             };
             uint32_t va[32], vb[32];
@@ -502,7 +505,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
                 }
               } else {
                 const uint32_t dst = kb + ((uint32_t)((((blk & 1) * 4) + j) << 4) ^ rx);
-                st_shared_v4(dst, pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+                st_shared_v4(dst, pack_op<kF16>(h[0], h[1]), pack_op<kF16>(h[2], h[3]), pack_op<kF16>(h[4], h[5]), pack_op<kF16>(h[6], h[7]));
               }
             }
           }
@@ -551,7 +554,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
 // transposed chunks (the dgrad of style_bwd.cu): row n = input feature col0 + n, value = W[k0 + k][col0 + n] for k < ncols else 0
 struct ChunkSrc { const float* W; int ld; int col0; int ncols; int k0; int trans; };
 
-__global__ void pack_chunks_kernel(const ChunkSrc* __restrict__ table, int nchunks, __nv_bfloat16* __restrict__ out) {
+template <typename T> __device__ __forceinline__ T to_op(float v);
+template <> __device__ __forceinline__ __nv_bfloat16 to_op<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half to_op<__half>(float v) { return __float2half_rn(v); }
+
+template <typename T>
+__global__ void pack_chunks_kernel(const ChunkSrc* __restrict__ table, int nchunks, T* __restrict__ out) {
   const size_t total = (size_t)nchunks * 256 * 64;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int chunk = (int)(idx / (256 * 64));
@@ -564,7 +572,7 @@ __global__ void pack_chunks_kernel(const ChunkSrc* __restrict__ table, int nchun
     const ChunkSrc s = table[chunk];
     float v = 0.f;
     if (k < s.ncols) v = s.trans ? s.W[(size_t)(s.k0 + k) * s.ld + s.col0 + n] : s.W[(size_t)n * s.ld + s.col0 + k];
-    out[idx] = __float2bfloat16_rn(v);
+    out[idx] = to_op<T>(v);
   }
 }
 
@@ -649,6 +657,8 @@ int style_set_weights(tgtc_ctx* ctx, const float* const* params, cudaStream_t st
   if (im.blob_c == nullptr) {
     TGTC_CUDA(cudaMalloc(&im.blob_c, (size_t)kCChunks * 32768));
     TGTC_CUDA(cudaMalloc(&im.blob_w, (size_t)kWChunks * 32768));
+    TGTC_CUDA(cudaMalloc(&im.blob_c_h, (size_t)kCChunks * 32768));
+    TGTC_CUDA(cudaMalloc(&im.blob_w_h, (size_t)kWChunks * 32768));
     TGTC_CUDA(cudaMalloc(&im.head_w, 3 * 256 * sizeof(float)));
     TGTC_CUDA(cudaMalloc(&im.bias_c, 5 * 256 * sizeof(float)));
     TGTC_CUDA(cudaMalloc(&im.bias_w, 7 * 256 * sizeof(float)));
@@ -717,11 +727,15 @@ int style_set_weights(tgtc_ctx* ctx, const float* const* params, cudaStream_t st
     TGTC_CUDA(cudaStreamSynchronize(st));   // the host vectors go out of scope
     for (int i = 0; i < 26; ++i) im.src[i] = params[i];
   }
-  pack_chunks_kernel<<<ctx->num_sms * 2, 256, 0, st>>>(dtab, kCChunks, reinterpret_cast<__nv_bfloat16*>(im.blob_c));
+  pack_chunks_kernel<__half><<<ctx->num_sms * 2, 256, 0, st>>>(dtab, kCChunks, reinterpret_cast<__half*>(im.blob_c_h));
   TGTC_LAUNCH_CHECK(ctx);
-  pack_chunks_kernel<<<ctx->num_sms * 2, 256, 0, st>>>(dtab + 64, kWChunks, reinterpret_cast<__nv_bfloat16*>(im.blob_w));
+  pack_chunks_kernel<__half><<<ctx->num_sms * 2, 256, 0, st>>>(dtab + 64, kWChunks, reinterpret_cast<__half*>(im.blob_w_h));
   TGTC_LAUNCH_CHECK(ctx);
-  pack_chunks_kernel<<<ctx->num_sms * 2, 256, 0, st>>>(dtab + 128, kTChunks, reinterpret_cast<__nv_bfloat16*>(im.blob_T));
+  pack_chunks_kernel<__nv_bfloat16><<<ctx->num_sms * 2, 256, 0, st>>>(dtab, kCChunks, reinterpret_cast<__nv_bfloat16*>(im.blob_c));
+  TGTC_LAUNCH_CHECK(ctx);
+  pack_chunks_kernel<__nv_bfloat16><<<ctx->num_sms * 2, 256, 0, st>>>(dtab + 64, kWChunks, reinterpret_cast<__nv_bfloat16*>(im.blob_w));
+  TGTC_LAUNCH_CHECK(ctx);
+  pack_chunks_kernel<__nv_bfloat16><<<ctx->num_sms * 2, 256, 0, st>>>(dtab + 128, kTChunks, reinterpret_cast<__nv_bfloat16*>(im.blob_T));
   TGTC_LAUNCH_CHECK(ctx);
   head_copy_kernel<<<1, 256, 0, st>>>(Wp[14], 288, im.head_w);
   TGTC_LAUNCH_CHECK(ctx);
@@ -753,26 +767,28 @@ static void fill_common(ChainParams& P, const MlpIO& io) {
 static int g_chain_dbg = 0;
 extern "C" void tgtc_debug_chain_flags(int f) { g_chain_dbg = f; }
 
-static int launch_chain(tgtc_ctx* ctx, const ChainParams& P_in, cudaStream_t st, bool train = false) {
+static int launch_chain(tgtc_ctx* ctx, const ChainParams& P_in, cudaStream_t st, bool train = false, bool f16 = false) {
   ChainParams P = P_in;
   P.dbg_flags = g_chain_dbg;
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
     TGTC_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     TGTC_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    TGTC_CUDA((cudaFuncSetAttribute(mlp_chain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)));
     attr_set[ctx->device & 63] = true;
   }
   const int64_t nquads = (P.ntiles + 3) / 4;
   const int64_t max_pairs = ctx->num_sms / 2;
   const int grid = 2 * (int)(nquads < max_pairs ? nquads : max_pairs);
   if (train) mlp_chain_kernel<true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
+  else if (f16) mlp_chain_kernel<false, true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
   else mlp_chain_kernel<false><<<grid, kNumThreads, kSmemBytes, st>>>(P);
   TGTC_LAUNCH_CHECK(ctx);
   return TGTC_OK;
 }
 
 // module 1: concat_features tile images for the samples of io -> cf_img [ntiles][64 KB]
-int launch_style_concat(tgtc_ctx* ctx, const MlpIO& io, uint8_t* cf_img, cudaStream_t st) {
+int launch_style_concat(tgtc_ctx* ctx, const MlpIO& io, uint8_t* cf_img, cudaStream_t st, bool f16) {
   if (io.n_rays == 0) return TGTC_OK;
   ChainParams P = {};
   fill_common(P, io);
@@ -780,14 +796,14 @@ int launch_style_concat(tgtc_ctx* ctx, const MlpIO& io, uint8_t* cf_img, cudaStr
   P.layer[0] = {{SEG_PE, 0, 0}, 1, OUT_ACT, 0};
   for (int l = 1; l <= 3; ++l) P.layer[l] = {{SEG_ACT, 0, 0}, 1, OUT_ACT, 0};
   P.layer[4] = {{SEG_PE, SEG_ACT, 0}, 2, OUT_ACT_IMG, 1};
-  P.blob = ctx->style.blob_c;
+  P.blob = f16 ? ctx->style.blob_c_h : ctx->style.blob_c;
   P.bias = ctx->style.bias_c;
   P.img_out = cf_img;
-  return launch_chain(ctx, P, st);
+  return launch_chain(ctx, P, st, false, f16);
 }
 
 // module 2: stylised rgb -> rgbsigma[.].xyz from base_remap images (NeRF trunk) and concat_features images (module 1)
-int launch_style_wild(tgtc_ctx* ctx, const MlpIO& io, const uint8_t* remap_img, const uint8_t* cf_img, cudaStream_t st) {
+int launch_style_wild(tgtc_ctx* ctx, const MlpIO& io, const uint8_t* remap_img, const uint8_t* cf_img, cudaStream_t st, bool f16) {
   if (io.n_rays == 0) return TGTC_OK;
   ChainParams P = {};
   fill_common(P, io);
@@ -797,14 +813,14 @@ int launch_style_wild(tgtc_ctx* ctx, const MlpIO& io, const uint8_t* remap_img, 
   P.layer[4] = {{SEG_PE, SEG_ACT, 0}, 2, OUT_ACT, 1};
   P.layer[5] = {{SEG_ACT, 0, 0}, 1, OUT_ACT, 0};
   P.layer[6] = {{SEG_ACT, 0, 0}, 1, OUT_HEAD, 0};
-  P.blob = ctx->style.blob_w;
+  P.blob = f16 ? ctx->style.blob_w_h : ctx->style.blob_w;
   P.bias = ctx->style.bias_w;
   P.head_w = ctx->style.head_w;
   P.head_b = ctx->style.head_b;
   P.img0 = remap_img;
   P.img1 = cf_img;
   P.rgbsigma = io.rgbsigma;
-  return launch_chain(ctx, P, st);
+  return launch_chain(ctx, P, st, false, f16);
 }
 
 // ---------------------------------------------------------------------------

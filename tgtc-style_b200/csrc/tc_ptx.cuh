@@ -203,6 +203,27 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// ---- operand format of the inference kernels: bf16 (the training format) or fp16 (TGTC_MLP_F16: 11-bit significand, 8x smaller
+// operand rounding error at the same tensor-core rate; fp32 values beyond +-65504 saturate instead of becoming inf)
+template <bool kF16>
+__device__ __forceinline__ uint32_t pack_op(float lo, float hi) {
+  uint32_t r;
+  if constexpr (kF16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <bool kF16>
+__device__ __forceinline__ uint32_t pack_op_relu(uint32_t lo, uint32_t hi) {
+  uint32_t r;
+  if constexpr (kF16) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return r;
+}
+// instruction descriptor with the A/B format field: 1 = bf16, 0 = f16 (cute::UMMA::F16F32Format)
+template <bool kF16>
+__host__ __device__ constexpr uint32_t make_idesc_op(int M, int N) {
+  return (1u << 4) | (kF16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }

@@ -22,7 +22,8 @@ LAYER_NAMES = (["net.base_layers.%d" % i for i in range(8)]
 LAYER_SHAPES = ([(256, 63)] + [(256, 256)] * 4 + [(256, 319)] + [(256, 256)] * 2
                 + [(1, 256), (256, 256), (128, 283), (3, 128)])
 
-_MODES = {"fp32": _lib.MLP_FP32, "bf16": _lib.MLP_BF16, _lib.MLP_FP32: _lib.MLP_FP32, _lib.MLP_BF16: _lib.MLP_BF16}
+_MODES = {"fp32": _lib.MLP_FP32, "bf16": _lib.MLP_BF16, "f16": _lib.MLP_F16, "fp16": _lib.MLP_F16,
+          _lib.MLP_FP32: _lib.MLP_FP32, _lib.MLP_BF16: _lib.MLP_BF16, _lib.MLP_F16: _lib.MLP_F16}
 
 
 def _ptr(t):
@@ -174,7 +175,7 @@ class NerfRenderer:
         p = self._dev(pts_t)
         rgb = torch.empty(n, S, 3, dtype=torch.float32, device=self.device)
         sigma = torch.empty(n, S, dtype=torch.float32, device=self.device)
-        if want_features and mode == _lib.MLP_BF16:
+        if want_features and mode != _lib.MLP_FP32:
             mode = _lib.MLP_FP32  # feature outputs exist on the general path only
         remap = torch.empty(n, S, 256, dtype=torch.float32, device=self.device) if want_features else None
         pe = torch.empty(n, S, 63, dtype=torch.float32, device=self.device) if want_features else None
@@ -378,13 +379,16 @@ class NerfRenderer:
         self._style_src, self._style_arr = ((concat_style, style), arr) if on_device else (None, None)
 
     def render_style(self, rays_o, rays_d, latents, near=0., far=1., chunk=None, n_samples=64, n_fine=64, extras=False,
-                     want_weights=False, out=None):
+                     want_weights=False, out=None, mode=None):
         """The loop body of render_style (rendering.py:118-178, perturb=False) for one batch of rays.
         latents = the output of latents_model_1 (rendering.py:125): [32] for a batch that shares one (style, frame), or [N,32];
         per-ray latents are handled as runs of consecutive rays with equal latents (the reference's loaders walk frames in
         order, train_tgtcs.py:170), one library call per run.
         -> {rgb, depth, acc} (+ weights / coarse outputs / ts_fine like render())."""
         self.refresh_weights()
+        mode = self.mode if mode is None else _MODES[mode]
+        if mode == _lib.MLP_FP32:
+            raise _lib.TgtcError("the stylised render runs on the tensor-core path: mode must be 'bf16' or 'f16'")
         ro, rd = self._dev(rays_o), self._dev(rays_d)
         n = ro.shape[0]
         lat = self._dev(latents)
@@ -399,7 +403,7 @@ class NerfRenderer:
             bounds = [0] + change + [n]
             for b, e in zip(bounds[:-1], bounds[1:]):
                 self.render_style(ro[b:e], rd[b:e], lat[b], near, far, chunk, n_samples, n_fine, extras, want_weights,
-                                  out={k: v[b:e] for k, v in out.items()})
+                                  out={k: v[b:e] for k, v in out.items()}, mode=mode)
             return out
         if lat.dim() == 2:
             lat = lat[0]
@@ -410,7 +414,7 @@ class NerfRenderer:
         ws = self._workspace(wsb + 1024)
         off = (-ws.data_ptr()) % 1024
         s = self._out_struct(out)
-        _lib.check(self.lib.tgtc_render_style(self._h, _ptr(ro), _ptr(rd), n, float(near), float(far), n_samples, n_fine, ck,
+        _lib.check(self.lib.tgtc_render_style(self._h, mode, _ptr(ro), _ptr(rd), n, float(near), float(far), n_samples, n_fine, ck,
                                               _ptr(lat1), _ptr(lat2), ctypes.byref(s), ctypes.c_void_p(ws.data_ptr() + off), wsb,
                                               self._stream))
         return out
@@ -616,6 +620,7 @@ class NerfRenderer:
 
     # ------------------------------------------------------------------ test hook
     def debug_tc_layers(self, net, rays_o, rays_d, ts, n_samples, near, far, layers):
+        self.lib.tgtc_debug_tc_f16(int(self.mode == _lib.MLP_F16))
         ro, rd = self._dev(rays_o), self._dev(rays_d)
         n = ro.shape[0]
         tsd = self._dev(ts) if ts is not None else None
