@@ -80,10 +80,10 @@ int tgtc_raygen(tgtc_ctx* ctx, int H, int W, const double* K, const double* c2w,
                 tgtc_stream stream);
 
 /* K2 -- stratified sample positions.  Replaces utils.sampling_pts_uniform
- * (utils.py:509-531, harmony=False).  rand: NULL for perturb=False, else [n,S]
- * uniforms replaying utils.py:518-524.  pts [n,S,3] may be NULL. ts [n,S]. */
+ * (utils.py:509-531).  harmony != 0: ts = 1/(1/near*(1-ts) + 1/far*ts) (utils.py:516; near, far non-zero) instead of the
+ * linear row.  rand: NULL for perturb=False, else [n,S] uniforms replaying utils.py:518-524.  pts [n,S,3] may be NULL. ts [n,S]. */
 int tgtc_sample_uniform(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n, int n_samples,
-                        double near, double far, const float* rand, float* pts, float* ts, tgtc_stream stream);
+                        double near, double far, int harmony, const float* rand, float* pts, float* ts, tgtc_stream stream);
 
 /* K3+K4 -- positional encoding + MLP on explicit points.  Replaces
  * models.StyleNerf.forward (models.py:216-223) = Embedder x2 (models.py:46-60)
@@ -170,11 +170,12 @@ int tgtc_render_host(tgtc_ctx* ctx, int mode, const float* rays_o, const float* 
 
 /* Frame operator: K1 fused in front of tgtc_render for pixels
  * [pix_begin, pix_begin+n) of an H x W pinhole frame (replaces the
- * RaySampler precompute dataset.py:105-118 + the cal_geometry batch loop).
+ * RaySampler precompute dataset.py:105-118 + the cal_geometry batch loop;
+ * pixel_alignment as in tgtc_raygen / get_rays_np, dataset.py:33-36).
  * Device outputs; workspace as for tgtc_render plus 24*n bytes for the rays. */
 size_t tgtc_render_frame_workspace_bytes(int64_t n_rays, int n_samples, int n_fine, int64_t chunk);
 int tgtc_render_frame(tgtc_ctx* ctx, int mode, int H, int W, const double* K, const double* c2w, int ndc,
-                      double ndc_near, int64_t pix_begin, int64_t n, double near, double far, int n_samples,
+                      double ndc_near, int pixel_alignment, int64_t pix_begin, int64_t n, double near, double far, int n_samples,
                       int n_fine, int64_t chunk, int white_bkgd, const tgtc_render_out* out, void* workspace,
                       size_t workspace_bytes, tgtc_stream stream);
 
@@ -190,12 +191,35 @@ int tgtc_render_frame(tgtc_ctx* ctx, int mode, int H, int W, const double* K, co
  * Stochastic options of the reference replay caller-drawn tensors (so a torch generator stream can be reproduced):
  * rand [n,64] uniforms = perturb=True (utils.py:518-524), noise_coarse [n,64] / noise_fine [n,128] =
  * randn * sigma_noise_std (utils.py:372-374); each may be NULL (= off). */
+/* Overlap hook for data-parallel training: `cuda_event` (a caller-owned cudaEvent_t, NULL to clear) is recorded
+ * on the step's stream by every following tgtc_train_step* call at the point where the COARSE net's half of `grads` is final,
+ * i.e. before the fine net's forward / backward is enqueued -- the caller's gradient all-reduce of that half can then run on
+ * another stream underneath the fine net's work (no gradient links the two nets: utils.py:576-579). */
+int tgtc_train_set_coarse_event(tgtc_ctx* ctx, void* cuda_event);
 size_t tgtc_train_workspace_bytes(tgtc_ctx* ctx, int64_t n_rays, int n_samples, int n_fine);
 int64_t tgtc_num_params(void); /* 595 844 per net */
 int tgtc_train_step(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, const float* rgb_gt, int64_t n_rays,
                     int64_t n_rays_total, double near, double far, int n_samples, int n_fine, const float* rand,
                     const float* noise_coarse, const float* noise_fine, float* grads, int accumulate, float* loss_sums,
                     float* rgb_coarse, float* rgb_fine, void* workspace, size_t workspace_bytes, tgtc_stream stream);
+
+/* Stage-level training entries: the forward of ONE net with its activation stash, and the matching backward.  They replace
+ * the autograd graph that PyTorch records for models.StyleNerf.forward (models.py:216-223, through utils.batchify,
+ * utils.py:435-456) inside Origin_train (train_tgtcs.py:234, :246 -> loss.backward() :254), so that loop runs unchanged with the
+ * model_forward drop-in (tgtc-style_b200/shims.py wraps these two calls in a torch.autograd.Function).
+ *   forward : pts [n_rays*S,3], dirs [n_rays,3] (the reference passes a stride-0 expand of rays_d) -> rgbsigma [n_rays*S,4];
+ *             the activation stash of the pass stays in `stash` (tgtc_nerf_stash_bytes, 1024-byte aligned, ~5.2 KB/sample)
+ *   backward: dL/d(r,g,b,sigma) per sample [n_rays*S,4] + the forward's rgbsigma and stash -> grads, a flat fp32 buffer of
+ *             tgtc_num_params() values in tgtc_set_weights order (accumulate != 0 adds); `scratch` (tgtc_nerf_backward_scratch_bytes)
+ *             is free again when the call's work has run.  bf16 tcgen05 kernels; S in {64, 128}.  No gradient w.r.t. pts / dirs
+ *             (they are data in the reference's graph too). */
+size_t tgtc_nerf_stash_bytes(int64_t n_rays, int S);
+size_t tgtc_nerf_backward_scratch_bytes(tgtc_ctx* ctx, int64_t n_rays, int S);
+int tgtc_nerf_forward_stash(tgtc_ctx* ctx, int net, const float* pts, const float* dirs, int64_t n_rays, int S, float* rgbsigma,
+                            void* stash, size_t stash_bytes, tgtc_stream stream);
+int tgtc_nerf_backward(tgtc_ctx* ctx, int net, const float* dirs, int64_t n_rays, int S, const float* rgbsigma, const float* d_rgbsigma,
+                       float* grads, int accumulate, void* stash, size_t stash_bytes, void* scratch, size_t scratch_bytes,
+                       tgtc_stream stream);
 
 /* The reference's optimizer step (torch.optim.Adam, betas (0.9, 0.999), eps 1e-8; train_tgtcs.py:39, :255) on flat fp32
  * device buffers of n values -- e.g. the 2 * tgtc_num_params() masters laid out like the gradient buffer of
@@ -307,15 +331,16 @@ int tgtc_style_loss_grads(tgtc_ctx* ctx, const float* rgb_coarse, const float* r
 
 /* ---- the latent model of Style_train (models.StyleLatents_variational, models.py:475-549) -----------------------------------
  * forward:  lat[i] = mu[style_id[i]] + sigma_scale * (table[(style_id[i] * frame_num + frame_id[i]) mod rows] - mu[style_id[i]])
- *           (models.py:490-506; the modulo is the reference's 7x tiling of the LLFF table, :496), and
+ *           (models.py:490-506; the modulo is the reference's 7x tiling of the LLFF table, :496: table_tiles = 7 for
+ *           dataset_type 'llff', 1 otherwise; a flat id at or beyond rows * table_tiles -- an IndexError in the reference -- traps), and
  *           logp_sum = sum_{i < n_logp} sum_k (lat_ik - mu_k)^2 / (exp(0.5 logvar_k) + 1e-3)   (minus_logp = logp_sum / n_logp, :531-537)
  * backward: table_grad[row] (+)= d/d table of  sum_i <dlat[i], lat[i]> + logp_scale * logp_sum  -- row by row, in ray order.
  * table [rows,32], mu / logvar [style_num,32], style_id / frame_id int64 [n], lat / dlat [n,32] fp32, all on the device. */
 int tgtc_style_latents_forward(tgtc_ctx* ctx, const float* table, const float* mu, const float* logvar, const int64_t* style_id,
-                               const int64_t* frame_id, int64_t n, int64_t n_logp, int rows, int frame_num, double sigma_scale,
+                               const int64_t* frame_id, int64_t n, int64_t n_logp, int rows, int frame_num, int table_tiles, double sigma_scale,
                                float* lat, float* logp_sum, tgtc_stream stream);
 int tgtc_style_latents_backward(tgtc_ctx* ctx, const float* table, const float* mu, const float* logvar, const int64_t* style_id,
-                                const int64_t* frame_id, int64_t n, int64_t n_logp, int rows, int frame_num, double sigma_scale,
+                                const int64_t* frame_id, int64_t n, int64_t n_logp, int rows, int frame_num, int table_tiles, double sigma_scale,
                                 const float* dlat, double logp_scale, float* table_grad, int accumulate, tgtc_stream stream);
 
 #ifdef __cplusplus

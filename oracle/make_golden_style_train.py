@@ -92,13 +92,16 @@ def main():
     rgb_c, rgb_f = forward(b1)
     loss_rgb = 1.0 * utils.img2mse(rgb_c, b1["rgb_gt"]) + 1.0 * utils.img2mse(rgb_f, b1["rgb_gt"])                          # :425, :480-481
     loss_logp = 0.1 * lm.minus_logp(style_ids=b1["style_id"], frame_ids=b1["frame_id"], data_type="llff")                   # :426-427
-    loss = loss_rgb + loss_logp + 1e2 * loss_coh                                                                              # :484
-    loss.backward()
+    loss = loss_rgb + loss_logp + 1e2 * loss_coh                                                                              # loss_for_style, :482
+    loss.backward(retain_graph=True)                     # style_optimizer: loss_for_style.backward (:490) -> the two style modules
+    # the latent table: latents_model_1.optimize(loss) with loss = loss_rgb + loss_logp (:481, :495; models.py:544-549) zeroes
+    # the table's gradient and backpropagates WITHOUT the coherence term
+    grad_table = torch.autograd.grad(loss_rgb + loss_logp, lm.latents)[0]
     out = dict(style_num=style_num, frame_num=frame_num, table=lm.latents.detach().numpy(), mu=lm.style_latents_mu.detach().numpy(),
                logvar=lm.style_latents_logvar.detach().numpy(), prev_x=x.numpy(), prev_y=y.numpy(), prev_x_origin=x_org.numpy(),
                loss=loss.item(), loss_rgb=loss_rgb.item(), loss_logp=loss_logp.item(), loss_coh=loss_coh.item(),
                rgb_coarse=rgb_c.detach().numpy(), rgb_fine=rgb_f.detach().numpy(), coh_rgb_coarse=c2.detach().numpy(),
-               coh_rgb_fine=f2.detach().numpy(), grad_table=lm.latents.grad.numpy())
+               coh_rgb_fine=f2.detach().numpy(), grad_table=grad_table.numpy())
     for tag, b in (("b1", b1), ("b2", b2)):
         for k, v in b.items():
             if k != "seed":

@@ -39,11 +39,21 @@ def _stub(name, **attrs):
     return m
 
 
+def import_rendering():
+    """The reference's rendering module (cal_geometry, render_style, render_train_style: the caller loops of the hot path);
+    its only imports are `from utils import *` and time."""
+    import_reference()
+    m = sys.modules.get("rendering")
+    if m is not None and not getattr(m, "__file__", "").startswith(REFERENCE_ROOT):
+        del sys.modules["rendering"]
+    return importlib.import_module("rendering")
+
+
 def import_reference():
     """Returns (utils, models, dataset, load_llff) modules of the reference."""
     if not reference_available():
         raise RuntimeError("reference tree not present at " + REFERENCE_ROOT)
-    _stub("imageio")
+    _stub("imageio", imwrite=lambda *a, **k: None, mimwrite=lambda *a, **k: None)
     _stub("plyfile", PlyElement=object, PlyData=object)
     _stub("pyrender")
     mpl = _stub("matplotlib")

@@ -532,7 +532,10 @@ def style_train_step_reference(sd_coarse, sd_fine, sd_concat, sd_wild, lat_table
         l2 = lambda v: torch.sqrt(torch.sum(v ** 2) + 1e-8)          # utils.py:459
         # train_tgtcs.py:401 / :456 -- the fine term compares with x_origin AFTER line 403 replaced it by this batch's originals
         loss_coh = l2(_cos_rows(c2, x) - _cos_rows(org2, x_org)) + l2(_cos_rows(f2, y) - _cos_rows(org2, org2))
-    loss = loss_rgb + loss_logp + loss_coh_lambda * loss_coh
-    loss.backward()
+    loss = loss_rgb + loss_logp + loss_coh_lambda * loss_coh         # loss_for_style (train_tgtcs.py:482): style_optimizer's objective
+    loss.backward(retain_graph=True)
+    # the latent table is optimised on loss = loss_rgb + loss_logp only: latents_model_1.optimize(loss) zeroes its gradient and
+    # backpropagates without the coherence term (train_tgtcs.py:481, :495; models.py:544-549)
+    grad_tab = torch.autograd.grad(loss_rgb + loss_logp, tab)[0]
     losses = {"loss": loss.detach(), "loss_rgb": loss_rgb.detach(), "loss_logp": loss_logp.detach(), "loss_coh": loss_coh.detach()}
-    return losses, {k: v.grad for k, v in pc.items()}, {k: v.grad for k, v in pw.items()}, tab.grad
+    return losses, {k: v.grad for k, v in pc.items()}, {k: v.grad for k, v in pw.items()}, grad_tab

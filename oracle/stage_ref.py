@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY (and the CPU baseline of bench.py) -- stages the reference's own hot-path modules for the GPU box.
 
 The reference is pure Python (no build step), so "building" it for the box is a copy: the four modules the ray-render path
-lives in (utils.py, models.py, dataset.py, load_llff.py) are copied, unmodified, from /root/reference -- where they lie --
+lives in (utils.py, models.py, dataset.py, load_llff.py) and the three small modules dataset.py imports are copied, unmodified, from /root/reference -- where they lie --
 into oracle/_ref/ (git-ignored build output: it travels with the gpurun snapshot like the built .so, and never enters the
 history).  __graft_entry__.build() calls this when /root/reference is present; on the GPU box the prebuilt copy is used as is.
 bench.py's `--impl reference` arm and `cpu_baseline` then time the reference's OWN code (kind = "reference"); without the staged
@@ -17,7 +17,9 @@ import shutil
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = "/root/reference"
 DST = os.path.join(HERE, "_ref")
-FILES = ("utils.py", "models.py", "dataset.py", "load_llff.py")
+# the four hot-path modules + the three small modules dataset.py imports at module scope (dataset.py:8,:16,:17)
+# ... and rendering.py: the caller loops (cal_geometry) the drop-in tests drive unchanged
+FILES = ("utils.py", "models.py", "dataset.py", "load_llff.py", "VGGNet.py", "Style_function.py", "ray_utils.py", "rendering.py")
 
 
 def stage(force=False):

@@ -67,6 +67,46 @@ def test_sharded_render_gather_gloo(world, n_total):
     assert sorted(res) == [(r, True) for r in range(world)]
 
 
+def _gather_worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        tg = T.TileGatherer(n, "cpu")
+        ok = True
+        handles = []
+        for frame in range(3):          # three frames through two buffer pairs: the first pair is reused
+            out = tg.outputs()
+            assert out["rgb"].shape == (n, 3) and out["depth"].shape == (n,) and out["acc"].shape == (n,)
+            src = _fake_render(frame * 1000 + rank * n, frame * 1000 + (rank + 1) * n)
+            for k in out:
+                out[k].copy_(src[k])     # what NerfRenderer.render(out=...) does: writes into the packed send buffer
+            handles.append((frame, tg.gather_async()))
+            f, h = handles[-1]
+            full = h.wait()
+            for r in range(world):
+                ref = _fake_render(f * 1000 + r * n, f * 1000 + (r + 1) * n)
+                ok = ok and all(torch.equal(full[k][r], ref[k]) for k in ref)
+        tg.finish()
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_packed_tile_gather_gloo():
+    world, n = 2, 257
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(r, True) for r in range(world)]
+
+
 # ------------------------------------------------------------------ data-parallel training step (host logic, gloo)
 class _FakeRenderer:
     """CPU stand-in for NerfRenderer in NerfTrainer: the 'gradient' is a deterministic linear function of the rays,
@@ -131,7 +171,7 @@ def _train_worker(rank, world, port, n, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n", [(2, 1000), (2, 333)])
+@pytest.mark.parametrize("world,n", [(2, 1000), (2, 333), (2, 1)])     # n = 1 < world: rank 1 owns an EMPTY shard
 def test_trainer_data_parallel_matches_single_process(world, n):
     single = T.NerfTrainer(_FakeRenderer(), _sd(), _sd(), max_rays_per_pass=97)
     ro, rd, gt = _train_batch(n)

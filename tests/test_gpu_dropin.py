@@ -1,0 +1,169 @@
+"""GPU: the reference's own caller loops on the B200 kernels through the drop-in seam (tgtc_style_b200.patch).
+  * rendering.cal_geometry (the reference's function object, from the staged copy oracle/_ref on the GPU box) with
+    NerfRenderer behind the rebound names -- results vs the oracle;
+  * the loop body of Origin_train (train_tgtcs.py:223-255, restated line by line: the function itself is a closure inside
+    train(), which needs configargparse, LLFF images and a DataLoader) on the reference's OWN nn.Modules and
+    torch.optim.Adam: `loss.backward()` flows through the autograd-capable model_forward / alpha_composition drop-ins into
+    the modules' .grad -- compared with fp32 autograd through the oracle fed the same jitter / noise draws; then
+    optimizer.step() and a second iteration (the packed weight images follow the parameters)."""
+import numpy as np
+import pytest
+import torch
+
+import ref_import
+import render_oracle as O
+import tgtc_style_b200 as T
+from dropin_common import Args, FakeDataset, FakeLoader, POSES
+from helpers import small_rays, weights
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_import.reference_available(), reason="needs the staged reference modules (oracle/stage_ref.py)")]
+
+
+@pytest.fixture()
+def patched():
+    utils, models, _, _ = ref_import.import_reference()
+    rendering = ref_import.import_rendering()
+    saved = {(m, n): getattr(m, n) for m in (utils, rendering) for n in T.shims.PATCHED_NAMES}
+    yield utils, models, rendering
+    for (m, n), v in saved.items():
+        setattr(m, n, v)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "f16"])
+def test_reference_cal_geometry_on_the_kernels(patched, tmp_path, mode):
+    utils, models, rendering = patched
+    r = T.NerfRenderer(device="cuda:0", mode=mode)
+    T.patch(r, [utils, rendering])
+    dev = torch.device("cuda:0")
+    mc, mf = ref_import.reference_nets(models, 0)
+    wc, wf = weights("w1")                       # a non-degenerate field (sigma recalibrated), loaded the way a checkpoint is
+    mc.load_state_dict(wc)
+    mf.load_state_dict(wf)
+    mc, mf = mc.to(dev), mf.to(dev)
+    model_forward = rendering.batchify(lambda **kwargs: mc(**kwargs), Args.chunk)            # train_tgtcs.py:30
+    model_forward_fine = rendering.batchify(lambda **kwargs: mf(**kwargs), Args.chunk)       # train_tgtcs.py:37
+    H, W, f = 24, 32, 26.0
+    ds = FakeDataset(H, W, f, POSES)
+    with torch.no_grad():
+        rgb_map, t_map = rendering.cal_geometry(model_forward, rendering.sampling_pts_uniform, FakeLoader(ds, 512), Args, dev,
+                                                sv_path=str(tmp_path), model_forward_fine=model_forward_fine,
+                                                samp_func_fine=rendering.sampling_pts_fine_torch)
+    ref = O.render_chain(wc, wf, ds.rays_o, ds.rays_d, 0., 1., 64, 64, 1024)
+    e_rgb = np.abs(rgb_map.reshape(-1, 3) - ref["rgb"].numpy())
+    e_t = np.abs(t_map.reshape(-1) - ref["depth"].numpy())
+    print("cal_geometry %s: max drgb %.2e ddepth %.2e mean %.2e" % (mode, e_rgb.max(), e_t.max(), e_rgb.mean()))
+    if mode == "fp32":
+        assert e_rgb.max() <= 1e-3 and e_t.max() <= 1e-3
+    else:
+        assert e_rgb.mean() <= 1e-3 and np.quantile(e_rgb.max(-1), 0.99) <= 1e-2      # end to end (resampling on its own weights)
+    assert r.launch_count() > 0
+    r.close()
+
+
+def test_origin_train_loop_body_backward_through_the_dropins(patched):
+    utils, models, rendering = patched
+    r = T.NerfRenderer(device="cuda:0", mode="bf16")
+    T.patch(r, [utils, rendering])
+    dev = torch.device("cuda:0")
+    n = 256
+    ro_np, rd_np = small_rays()
+    sel = np.random.RandomState(3).choice(ro_np.shape[0], n, replace=False)
+    w0c, w0f = weights("w0")
+    probe = np.arange(0, ro_np.shape[0], 743)
+    wc = O.recalibrate_sigma(w0c, ro_np[probe], rd_np[probe], gain=4.0, shift=10.0)   # smooth density, last sigma away from 0
+    wf = O.recalibrate_sigma(w0f, ro_np[probe], rd_np[probe], gain=4.0, shift=10.0)
+    model, model_fine = ref_import.reference_nets(models, 0)
+    model.load_state_dict(wc)
+    model_fine.load_state_dict(wf)
+    model, model_fine = model.to(dev), model_fine.to(dev)
+    # ---- train_tgtcs.py:14-39, verbatim in structure
+    samp_func = rendering.sampling_pts_uniform
+    samp_func_fine = rendering.sampling_pts_fine_torch
+    model.train()
+    grad_vars = list(model.parameters())
+    model_forward = rendering.batchify(lambda **kwargs: model(**kwargs), Args.chunk)
+    model_fine.train()
+    grad_vars += list(model_fine.parameters())
+    model_forward_fine = rendering.batchify(lambda **kwargs: model_fine(**kwargs), Args.chunk)
+    optimizer = torch.optim.Adam(params=grad_vars, lr=5e-4, betas=(0.9, 0.999))
+    img2mse = utils.img2mse
+    alpha_composition = rendering.alpha_composition
+    gt_cpu = torch.rand(n, 3, generator=torch.Generator().manual_seed(2))
+    batch_data = {"rgb_gt": gt_cpu.to(dev), "rays_o": torch.from_numpy(ro_np[sel]).to(dev), "rays_d": torch.from_numpy(rd_np[sel]).to(dev)}
+
+    # the draws the loop body will make from torch's CUDA generator, in its order (utils.py:519-520, :373-374 twice)
+    torch.manual_seed(11)
+    rand = torch.zeros([n, 64], device=dev)
+    torch.nn.init.uniform_(rand, 0, 1)
+    nzc = torch.randn([n, 64], device=dev) * Args.sigma_noise_std
+    nzf = torch.randn([n, 128], device=dev) * Args.sigma_noise_std
+    loss_ref, gc, gf, rgbc_ref, rgbf_ref, _ = O.train_step_reference(wc, wf, ro_np[sel], rd_np[sel], gt_cpu, rand=rand.cpu(),
+                                                                     noise_coarse=nzc.cpu(), noise_fine=nzf.cpu())
+
+    def loop_body():
+        # ---- train_tgtcs.py:226-255
+        rgb_gt, rays_o, rays_d = batch_data['rgb_gt'], batch_data['rays_o'], batch_data['rays_d']
+        pts, ts = samp_func(rays_o=rays_o, rays_d=rays_d, N_samples=Args.N_samples, near=0., far=1., perturb=True)
+        ray_num, pts_num = rays_o.shape[0], Args.N_samples
+        rays_d_forward = rays_d.unsqueeze(1).expand([ray_num, pts_num, 3])
+        ret = model_forward(pts=pts, dirs=rays_d_forward)
+        pts_rgb, pts_sigma = ret['rgb'], ret['sigma']
+        rgb_exp, t_exp, weights_ = alpha_composition(pts_rgb, pts_sigma, ts, Args.sigma_noise_std)
+        loss_rgb = img2mse(rgb_gt, rgb_exp)
+        loss = loss_rgb
+        pts_fine, ts_fine = samp_func_fine(rays_o, rays_d, ts, weights_, Args.N_samples_fine)
+        pts_num = Args.N_samples + Args.N_samples_fine
+        rays_d_forward = rays_d.unsqueeze(1).expand([ray_num, pts_num, 3])
+        ret = model_forward_fine(pts=pts_fine, dirs=rays_d_forward)
+        pts_rgb_fine, pts_sigma_fine = ret['rgb'], ret['sigma']
+        rgb_exp_fine, t_exp_fine, _ = alpha_composition(pts_rgb_fine, pts_sigma_fine, ts_fine, Args.sigma_noise_std)
+        loss_rgb_fine = img2mse(rgb_gt, rgb_exp_fine)
+        loss = loss + loss_rgb_fine
+        optimizer.zero_grad()
+        loss.backward()
+        return loss, rgb_exp, rgb_exp_fine
+
+    torch.manual_seed(11)
+    loss, rgb_c, rgb_f = loop_body()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - loss_ref.item()) <= 2e-3 * max(1.0, abs(loss_ref.item()))
+    assert (rgb_c.detach().cpu() - rgbc_ref).abs().max().item() <= 2e-2
+    worst = 0.0
+    for mod, ref in ((model, gc), (model_fine, gf)):
+        for k, p in mod.named_parameters():
+            assert p.grad is not None and torch.isfinite(p.grad).all(), k
+            g, g_ref = p.grad.cpu(), ref[k]
+            rel = (g - g_ref).norm().item() / max(g_ref.norm().item(), 1e-12)
+            cos = torch.nn.functional.cosine_similarity(g.flatten(), g_ref.flatten(), dim=0).item()
+            worst = max(worst, rel)
+            assert rel <= 0.12 and cos >= 0.995, (k, rel, cos)
+    print("Origin_train loop body through the drop-ins: loss %.5f (oracle %.5f), worst per-tensor gradient error %.3e" % (loss.item(), loss_ref.item(), worst))
+    # ---- optimizer.step() (train_tgtcs.py:255) moves the reference's own parameters; the next forward sees the new weights
+    before = model.net.sigma_layer.weight.detach().clone()
+    optimizer.step()
+    assert not torch.equal(before, model.net.sigma_layer.weight.detach())
+    with torch.no_grad():
+        pts, ts = samp_func(rays_o=batch_data['rays_o'], rays_d=batch_data['rays_d'], N_samples=64, near=0., far=1.)
+        got = model_forward(pts=pts, dirs=batch_data['rays_d'].unsqueeze(1).expand([n, 64, 3]))
+        sd_new = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        want = O.nerf_forward(sd_new, pts.cpu(), batch_data['rays_d'].cpu().unsqueeze(1).expand(n, 64, 3))
+    assert (got["rgb"].cpu() - want["rgb"]).abs().max().item() <= 1e-2
+    assert (got["sigma"].cpu() - want["sigma"]).abs().max().item() <= 2e-2 * want["sigma"].abs().max().item()
+    assert got["base_remap"].shape == (n, 64, 256)          # the reference dict's other keys, produced on demand
+    torch.manual_seed(12)
+    loss2, _, _ = loop_body()
+    assert torch.isfinite(loss2) and loss2.item() != loss.item()
+    r.close()
+
+
+def test_harmony_sampling_matches_reference(patched):
+    utils, models, rendering = patched
+    ref_fn = [v for (m, n), v in [((m, n), getattr(m, n)) for m in (utils,) for n in ("sampling_pts_uniform",)]][0]
+    r = T.NerfRenderer(device="cuda:0", mode="fp32")
+    ro_np, rd_np = small_rays()
+    o, d = torch.from_numpy(ro_np[:50]), torch.from_numpy(rd_np[:50])
+    want_pts, want_ts = ref_fn(rays_o=o, rays_d=d, N_samples=64, near=0.5, far=6.0, harmony=True)     # the reference's own function (CPU)
+    s = T.shims.Shims(r)
+    pts, ts = s.sampling_pts_uniform(rays_o=o.cuda(), rays_d=d.cuda(), N_samples=64, near=0.5, far=6.0, harmony=True)
+    assert torch.equal(ts.cpu(), want_ts.contiguous()) and torch.equal(pts.cpu(), want_pts)
+    r.close()

@@ -82,13 +82,14 @@ def test_bf16_teacher_forced_is_at_the_format_limit(renderer_bf16, kind):
     ce = O.alpha_composition(emu["rgb"].reshape(len(sub), 128, 3), emu["sigma"].reshape(len(sub), 128), ref["ts_fine"][sub])
     ee = torch.stack([(ce[0] - ref["rgb"][sub]).abs().max(-1)[0], (ce[1] - ref["depth"][sub]).abs(), (ce[3] - ref["acc"][sub]).abs()], 0).max(0)[0]
     frac_k = (e[ok] > 1e-2).float().mean().item()
+    frac_ks = (e[sub][ok[sub]] > 1e-2).float().mean().item()      # the kernel on the emulated subset
     frac_e = (ee[ok[sub]] > 1e-2).float().mean().item()
     print("bf16 %s fine: flagged %.4f%%  rays>1e-2 kernel %.4f%% / emulation %.4f%%  max(not flagged) kernel %.2e / emulation %.2e  mean %.2e / %.2e" %
           (kind, 100 * flagged.float().mean(), 100 * frac_k, 100 * frac_e, e[ok].max(), ee[ok[sub]].max(), e.mean(), ee.mean()))
     assert flagged.float().mean().item() < 0.005
     assert frac_k <= 0.005                                      # >= 99.5 % of non-flagged rays within 1e-2
-    assert frac_k <= 1.5 * frac_e + 0.001                       # and that residue is the operand format's, not the kernel's
-    assert e.mean().item() <= 1.25 * ee.mean().item() + 1e-5
+    assert frac_ks <= frac_e + 0.002                            # and that residue is the operand format's, not the kernel's
+    assert e[sub].mean().item() <= 1.25 * ee.mean().item() + 1e-5   # (same rays: within 4 rays of 2048 and 25 % of the mean)
     ec, fc = _pass_stats(got["coarse"], ref, "coarse")
     assert (ec[~fc] > 1e-2).float().mean().item() <= 0.005
 

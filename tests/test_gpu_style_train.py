@@ -320,3 +320,40 @@ def test_style_trainer_fused_losses_equal_torch_losses(renderer_bf16):
         assert abs(la[k] - lb[k]) <= 1e-5 * max(1.0, abs(lb[k])), (k, la[k], lb[k])
     assert ((ga - gb).norm() / gb.norm()).item() <= 2e-4
     assert ((ta - tb).norm() / tb.norm()).item() <= 2e-4
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_latent_table_gradient_ignores_the_coherence_term(renderer_bf16, fused):
+    """latents_model_1.optimize(loss) backpropagates loss = loss_rgb + loss_logp (train_tgtcs.py:481, :495; models.py:544-549):
+    the coherence term reaches the two style modules (loss_for_style, :482-493) but never the latent table -- its gradient must
+    not depend on loss_coh_lambda, while the style gradient does."""
+    import tgtc_style_b200 as T
+    r = renderer_bf16
+    (wc, wf, cs, ws), _, _, _, _, _, _ = _inputs(8)
+    ro_all, rd_all = small_rays()
+    r.set_weights(wc, wf)
+    dev = r.device
+    g = torch.Generator().manual_seed(78)
+    style_num, frame_num, n = 2, 5, 64
+    table = torch.randn(style_num, frame_num, 32, generator=g) * 0.5
+    mu, logvar = torch.randn(style_num, 32, generator=g) * 0.3, torch.randn(style_num, 32, generator=g) * 0.2
+    perm = torch.randperm(ro_all.shape[0], generator=g)
+    its = [(_batch(ro_all, rd_all, perm[(2 * i) * n:(2 * i + 1) * n], style_num, frame_num, g),
+            _batch(ro_all, rd_all, perm[(2 * i + 1) * n:(2 * i + 2) * n], style_num, frame_num, g, True)) for i in range(2)]
+    res = []
+    for lam in (1e2, 0.0):
+        lat = T.StyleLatents(table.to(dev), mu.to(dev), logvar.to(dev))
+        # lr = 0: the first iteration leaves every parameter where it was, so both runs reach iteration 2 in the same state
+        tr = T.StyleTrainer(r, cs, ws, lat, lr=0.0, frame_num=frame_num, loss_coh_lambda=lam, fused_losses=fused)
+        lat.lr = 0.0
+        if lat.opt is not None:
+            for gp in lat.opt.param_groups:
+                gp["lr"] = 0.0
+        for b, c in its:
+            out = tr.step({k: v.to(dev) for k, v in b.items()}, {k: v.to(dev) for k, v in c.items()})
+        torch.cuda.synchronize()
+        assert out["loss_coh"].item() > 0
+        res.append((tr.grads.clone(), lat.latents.grad.clone()))
+    (g_with, t_with), (g_without, t_without) = res
+    assert ((t_with - t_without).norm() / t_without.norm()).item() <= 1e-5
+    assert ((g_with - g_without).norm() / g_without.norm()).item() >= 1e-3

@@ -38,7 +38,7 @@ PROTOTYPES = {
     "tgtc_raygen": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, ctypes.c_int, ctypes.c_double,
                                    ctypes.c_int, c_i64, c_i64, c_void_p, c_void_p, c_void_p]),
     "tgtc_sample_uniform": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_i64, ctypes.c_int, ctypes.c_double, ctypes.c_double,
-                                           c_void_p, c_void_p, c_void_p, c_void_p]),
+                                           ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tgtc_nerf_forward": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, ctypes.c_int, c_i64, ctypes.c_int,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tgtc_nerf_forward_rays": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p, c_i64, ctypes.c_int,
@@ -56,8 +56,9 @@ PROTOTYPES = {
                                         ctypes.c_int, ctypes.c_int, c_i64, ctypes.c_int, ctypes.POINTER(RenderOut), c_void_p]),
     "tgtc_render_frame_workspace_bytes": (ctypes.c_size_t, [c_i64, ctypes.c_int, ctypes.c_int, c_i64]),
     "tgtc_render_frame": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, ctypes.c_int,
-                                         ctypes.c_double, c_i64, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_double, ctypes.c_int, c_i64, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int,
                                          c_i64, ctypes.c_int, ctypes.POINTER(RenderOut), c_void_p, ctypes.c_size_t, c_void_p]),
+    "tgtc_train_set_coarse_event": (ctypes.c_int, [c_void_p, c_void_p]),
     "tgtc_train_workspace_bytes": (ctypes.c_size_t, [c_void_p, c_i64, ctypes.c_int, ctypes.c_int]),
     "tgtc_num_params": (c_i64, []),
     "tgtc_train_step": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, ctypes.c_double, ctypes.c_double,
@@ -94,10 +95,16 @@ PROTOTYPES = {
                                              c_void_p, c_i64, c_void_p, ctypes.c_double, ctypes.c_double, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p]),
     "tgtc_style_latents_forward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, ctypes.c_int,
-                                                  ctypes.c_int, ctypes.c_double, c_void_p, c_void_p, c_void_p]),
+                                                  ctypes.c_int, ctypes.c_int, ctypes.c_double, c_void_p, c_void_p, c_void_p]),
     "tgtc_style_latents_backward": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, ctypes.c_int,
-                                                   ctypes.c_int, ctypes.c_double, c_void_p, ctypes.c_double, c_void_p, ctypes.c_int,
-                                                   c_void_p]),
+                                                   ctypes.c_int, ctypes.c_int, ctypes.c_double, c_void_p, ctypes.c_double, c_void_p,
+                                                   ctypes.c_int, c_void_p]),
+    "tgtc_nerf_stash_bytes": (ctypes.c_size_t, [c_i64, ctypes.c_int]),
+    "tgtc_nerf_backward_scratch_bytes": (ctypes.c_size_t, [c_void_p, c_i64, ctypes.c_int]),
+    "tgtc_nerf_forward_stash": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p, c_void_p, c_i64, ctypes.c_int, c_void_p, c_void_p,
+                                               ctypes.c_size_t, c_void_p]),
+    "tgtc_nerf_backward": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p, c_i64, ctypes.c_int, c_void_p, c_void_p, c_void_p, ctypes.c_int,
+                                          c_void_p, ctypes.c_size_t, c_void_p, ctypes.c_size_t, c_void_p]),
     "tgtc_profile_enable": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "tgtc_profile_read": (ctypes.c_int, [c_void_p, ctypes.POINTER(c_i64), c_double_p, c_double_p]),
     "tgtc_profile_read_kind": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.POINTER(c_i64), c_double_p, c_double_p]),

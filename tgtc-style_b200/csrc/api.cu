@@ -102,13 +102,13 @@ extern "C" int tgtc_raygen(tgtc_ctx* ctx, int H, int W, const double* K, const d
 }
 
 extern "C" int tgtc_sample_uniform(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n, int n_samples,
-                                   double near, double far, const float* rnd, float* pts, float* ts, tgtc_stream stream) {
+                                   double near, double far, int harmony, const float* rnd, float* pts, float* ts, tgtc_stream stream) {
   CHECK_CTX(ctx);
   TGTC_REQUIRE(n >= 0 && n_samples >= 1, TGTC_ERR_ARG, "bad sizes n=%lld S=%d", (long long)n, n_samples);
   if (n == 0) return TGTC_OK;
   CHECK_PTR(ts, "ts");
   if (pts != nullptr) { CHECK_PTR(rays_o, "rays_o"); CHECK_PTR(rays_d, "rays_d"); }
-  return launch_sample_uniform(ctx, rays_o, rays_d, n, n_samples, near, far, rnd, pts, ts, (cudaStream_t)stream);
+  return launch_sample_uniform(ctx, rays_o, rays_d, n, n_samples, near, far, rnd, pts, ts, (cudaStream_t)stream, nullptr, harmony);
 }
 
 // per-launch device timing: a pair of events of kind `kind` around the next launch(es) on `st`
@@ -467,7 +467,7 @@ extern "C" size_t tgtc_render_frame_workspace_bytes(int64_t n_rays, int n_sample
 }
 
 extern "C" int tgtc_render_frame(tgtc_ctx* ctx, int mode, int H, int W, const double* K, const double* c2w, int ndc,
-                                 double ndc_near, int64_t pix_begin, int64_t n, double near, double far, int n_samples,
+                                 double ndc_near, int pixel_alignment, int64_t pix_begin, int64_t n, double near, double far, int n_samples,
                                  int n_fine, int64_t chunk, int white_bkgd, const tgtc_render_out* out, void* workspace,
                                  size_t workspace_bytes, tgtc_stream stream) {
   CHECK_CTX(ctx);
@@ -485,7 +485,7 @@ extern "C" int tgtc_render_frame(tgtc_ctx* ctx, int mode, int H, int W, const do
   float* ro = reinterpret_cast<float*>(base);
   float* rd = reinterpret_cast<float*>(base + ray_bytes);
   cudaStream_t st = (cudaStream_t)stream;
-  rc = launch_raygen(ctx, H, W, K, c2w, ndc, ndc_near, 0, pix_begin, n, ro, rd, st);
+  rc = launch_raygen(ctx, H, W, K, c2w, ndc, ndc_near, pixel_alignment, pix_begin, n, ro, rd, st);
   if (rc) return rc;
   return render_impl(ctx, mode, ro, rd, n, near, far, n_samples, n_fine, chunk, white_bkgd, *out, base + 2 * ray_bytes,
                      workspace_bytes - 2 * ray_bytes, st);
@@ -589,7 +589,12 @@ static int train_step_impl(tgtc_ctx* ctx, const float* rays_o, const float* rays
   CHECK_NET(ctx, TGTC_NET_FINE);
   TGTC_REQUIRE(n_rays >= 0 && n_rays_total >= n_rays, TGTC_ERR_ARG, "bad n_rays=%lld / n_rays_total=%lld", (long long)n_rays,
                (long long)n_rays_total);
-  if (n_rays == 0) return TGTC_OK;
+  if (n_rays == 0) {
+    // an empty shard (global batch < world size) still owns a gradient buffer that the caller all-reduces: it must read as zero
+    if (!accumulate && grads != nullptr) TGTC_CUDA(cudaMemsetAsync(grads, 0, 2 * bwd_flat_floats() * sizeof(float), (cudaStream_t)stream));
+    if (ctx->coarse_done != nullptr) TGTC_CUDA(cudaEventRecord(ctx->coarse_done, (cudaStream_t)stream));
+    return TGTC_OK;
+  }
   const int S = n_samples, F = n_fine;
   TGTC_REQUIRE(S == 64 && (S + F) == 128, TGTC_ERR_UNSUPPORTED,
                "training supports n_samples=64, n_fine=64 (configs/fern.txt:16-17); got %d+%d", S, F);
@@ -615,11 +620,136 @@ static int train_step_impl(tgtc_ctx* ctx, const float* rays_o, const float* rays
   rc = train_pass(ctx, TGTC_NET_COARSE, rays_o, rays_d, ts_c, ts_c_stride, n_rays, S, near, far, noise_coarse, prng_c, rgb_gt, scale, ws,
                   base, grads, accumulate, loss_sums, rgb_coarse, w_c, st);
   if (rc) return rc;
+  // the coarse net's half of the gradient buffer is final here: a caller that all-reduces it on another stream waits for this
+  // event while the fine net's forward / backward below still runs
+  if (ctx->coarse_done != nullptr) TGTC_CUDA(cudaEventRecord(ctx->coarse_done, st));
   // no gradient flows through the resampling (utils.py:576-579): the two nets' backward passes are independent
   rc = launch_sample_fine(ctx, nullptr, nullptr, ts_c, ts_c_stride, w_c, n_rays, S, F, nullptr, ts_f, nullptr, nullptr, st);
   if (rc) return rc;
   return train_pass(ctx, TGTC_NET_FINE, rays_o, rays_d, ts_f, S + F, n_rays, S + F, near, far, noise_fine, prng_f, rgb_gt, scale, ws,
                     base, grads + np, accumulate, loss_sums != nullptr ? loss_sums + 1 : nullptr, rgb_fine, nullptr, st);
+}
+
+// ---------------------------------------------------------------------------
+// stage-level training entries: the forward of ONE net with its activation stash, and the matching backward.  They back the
+// torch.autograd.Function behind the model_forward drop-in (shims.py), so the reference's own Origin_train loop
+// (train_tgtcs.py:228-255: model_forward -> alpha_composition -> loss.backward()) runs unchanged on the tensor-core kernels.
+struct StageStash { size_t off_h, off_f, off_pe, off_mask, total; };
+static StageStash stage_stash_layout(int64_t M) {
+  StageStash w;
+  const size_t tiles = (size_t)((M + 127) / 128);
+  size_t o = 0;
+  w.off_h = o;    o = align_up(o + tiles * kStashHBytesPerTile, 1024);
+  w.off_f = o;    o = align_up(o + tiles * kStashFBytesPerTile, 1024);
+  w.off_pe = o;   o = align_up(o + tiles * kStashPeBytesPerTile, 1024);
+  w.off_mask = o; o = align_up(o + tiles * kStashMaskBytesPerTile, 1024);
+  w.total = o;
+  return w;
+}
+struct StageScratch { size_t off_dz, off_dzf, off_dhead, off_partial, total; };
+static StageScratch stage_scratch_layout(tgtc_ctx* ctx, int64_t M) {
+  StageScratch w;
+  const size_t tiles = (size_t)((M + 127) / 128);
+  size_t o = 0;
+  w.off_dz = o;      o = align_up(o + tiles * kStashHBytesPerTile, 1024);
+  w.off_dzf = o;     o = align_up(o + tiles * kStashFBytesPerTile, 1024);
+  w.off_dhead = o;   o = align_up(o + tiles * kStashPeBytesPerTile, 1024);
+  w.off_partial = o; o = align_up(o + (size_t)ctx->num_sms * bwd_partial_floats() * 4, 256);
+  w.total = o;
+  return w;
+}
+extern "C" size_t tgtc_nerf_stash_bytes(int64_t n_rays, int S) {
+  if (n_rays <= 0 || S <= 0) return 0;
+  return stage_stash_layout(n_rays * S).total;
+}
+extern "C" size_t tgtc_nerf_backward_scratch_bytes(tgtc_ctx* ctx, int64_t n_rays, int S) {
+  if (ctx == nullptr || n_rays <= 0 || S <= 0) return 0;
+  return stage_scratch_layout(ctx, n_rays * S).total;
+}
+
+static int stage_args(tgtc_ctx* ctx, int net, int64_t n_rays, int S, const void* stash, size_t stash_bytes) {
+  CHECK_NET(ctx, net);
+  TGTC_REQUIRE(n_rays >= 0, TGTC_ERR_ARG, "bad n_rays=%lld", (long long)n_rays);
+  TGTC_REQUIRE(S == 64 || S == 128, TGTC_ERR_UNSUPPORTED, "the training kernels take S in {64,128} samples per ray; got %d", S);
+  if (n_rays == 0) return TGTC_OK;
+  const StageStash w = stage_stash_layout(n_rays * S);
+  TGTC_REQUIRE(stash != nullptr && (reinterpret_cast<uintptr_t>(stash) & 1023) == 0 && stash_bytes >= w.total, TGTC_ERR_STATE,
+               "stash too small or not 1024-byte aligned: need %zu bytes, got %zu", w.total, stash_bytes);
+  return TGTC_OK;
+}
+
+extern "C" int tgtc_nerf_forward_stash(tgtc_ctx* ctx, int net, const float* pts, const float* dirs, int64_t n_rays, int S, float* rgbsigma,
+                                       void* stash_p, size_t stash_bytes, tgtc_stream stream) {
+  CHECK_CTX(ctx);
+  int rc = stage_args(ctx, net, n_rays, S, stash_p, stash_bytes);
+  if (rc) return rc;
+  if (n_rays == 0) return TGTC_OK;
+  CHECK_PTR(pts, "pts"); CHECK_PTR(dirs, "dirs"); CHECK_PTR(rgbsigma, "rgbsigma");
+  TGTC_REQUIRE(aligned16(rgbsigma), TGTC_ERR_ARG, "rgbsigma not 16-byte aligned");
+  const StageStash w = stage_stash_layout(n_rays * S);
+  uint8_t* base = static_cast<uint8_t*>(stash_p);
+  TcStash stash;
+  stash.h = base + w.off_h; stash.f = base + w.off_f; stash.pe = base + w.off_pe;
+  stash.mask = reinterpret_cast<uint32_t*>(base + w.off_mask);
+  MlpIO io;
+  io.pts = pts; io.dirs = dirs; io.dirs_per_ray = 1;
+  io.n_rays = n_rays; io.S = S; io.rgbsigma = rgbsigma;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t e1 = nullptr;
+  rc = prof_begin(ctx, 1, (double)n_rays * S * 1186816.0, st, &e1);
+  if (rc) return rc;
+  rc = launch_mlp_tc_train(ctx, net, io, stash, st);
+  if (rc) return rc;
+  if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
+  return TGTC_OK;
+}
+
+extern "C" int tgtc_nerf_backward(tgtc_ctx* ctx, int net, const float* dirs, int64_t n_rays, int S, const float* rgbsigma,
+                                  const float* d_rgbsigma, float* grads, int accumulate, void* stash_p, size_t stash_bytes, void* scratch_p,
+                                  size_t scratch_bytes, tgtc_stream stream) {
+  CHECK_CTX(ctx);
+  int rc = stage_args(ctx, net, n_rays, S, stash_p, stash_bytes);
+  if (rc) return rc;
+  CHECK_PTR(grads, "grads");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_rays == 0) {
+    if (!accumulate) TGTC_CUDA(cudaMemsetAsync(grads, 0, bwd_flat_floats() * sizeof(float), st));
+    return TGTC_OK;
+  }
+  CHECK_PTR(dirs, "dirs"); CHECK_PTR(rgbsigma, "rgbsigma"); CHECK_PTR(d_rgbsigma, "d_rgbsigma");
+  TGTC_REQUIRE(aligned16(rgbsigma) && aligned16(d_rgbsigma), TGTC_ERR_ARG, "rgbsigma / d_rgbsigma not 16-byte aligned");
+  const int64_t M = n_rays * S;
+  const StageStash w = stage_stash_layout(M);
+  const StageScratch sc = stage_scratch_layout(ctx, M);
+  TGTC_REQUIRE(scratch_p != nullptr && (reinterpret_cast<uintptr_t>(scratch_p) & 1023) == 0 && scratch_bytes >= sc.total, TGTC_ERR_STATE,
+               "backward scratch too small or not 1024-byte aligned: need %zu bytes, got %zu", sc.total, scratch_bytes);
+  uint8_t* base = static_cast<uint8_t*>(stash_p);
+  uint8_t* sb = static_cast<uint8_t*>(scratch_p);
+  TcStash stash;
+  stash.h = base + w.off_h; stash.f = base + w.off_f; stash.pe = base + w.off_pe;
+  stash.mask = reinterpret_cast<uint32_t*>(base + w.off_mask);
+  TcDz dz;
+  dz.dz = sb + sc.off_dz; dz.dzf = sb + sc.off_dzf; dz.dhead = sb + sc.off_dhead;
+  float* partial = reinterpret_cast<float*>(sb + sc.off_partial);
+  const double samples = (double)M;
+  cudaEvent_t e1 = nullptr;
+  rc = prof_begin(ctx, 2, samples * 2.0 * (593408.0 - 16128.0 - 16128.0 - 3456.0), st, &e1);
+  if (rc) return rc;
+  rc = launch_mlp_dgrad(ctx, net, rgbsigma, d_rgbsigma, stash, dz, M, st);
+  if (rc) return rc;
+  if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
+  rc = prof_begin(ctx, 3, samples * 1186816.0, st, &e1);
+  if (rc) return rc;
+  rc = launch_mlp_wgrad(ctx, stash, dz, dirs, d_rgbsigma, M, S, partial, grads, accumulate, st);
+  if (rc) return rc;
+  if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
+  return TGTC_OK;
+}
+
+extern "C" int tgtc_train_set_coarse_event(tgtc_ctx* ctx, void* cuda_event) {
+  TGTC_REQUIRE(ctx != nullptr, TGTC_ERR_ARG, "null context");
+  ctx->coarse_done = (cudaEvent_t)cuda_event;
+  return TGTC_OK;
 }
 
 extern "C" int tgtc_train_step(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, const float* rgb_gt, int64_t n_rays,
@@ -930,6 +1060,11 @@ static int style_train_backward_impl(tgtc_ctx* ctx, int64_t n_rays, int n_sample
                                      const float* noise_coarse, const float* noise_fine, const PhiloxSrc* prng_c, const PhiloxSrc* prng_f,
                                      const float* d_rgb_coarse, const float* d_rgb_fine, float* grads, int accumulate, float* dlat1,
                                      void* workspace, size_t workspace_bytes, tgtc_stream stream) {
+  if (ctx != nullptr && n_rays == 0 && !accumulate && grads != nullptr) {
+    // an empty shard still owns a gradient buffer that the caller all-reduces: it must read as zero (no d latent rows exist)
+    DeviceGuard g0(ctx->device);
+    TGTC_CUDA(cudaMemsetAsync(grads, 0, style_flat_floats() * sizeof(float), (cudaStream_t)stream));
+  }
   STYLE_TRAIN_PROLOGUE();
   CHECK_PTR(lat1, "lat1"); CHECK_PTR(d_rgb_coarse, "d_rgb_coarse"); CHECK_PTR(d_rgb_fine, "d_rgb_fine"); CHECK_PTR(grads, "grads");
   {

@@ -105,6 +105,7 @@ struct tgtc_ctx {
   std::vector<int> ev_kind;           // kind of pair i (TGTC_PROF_*)
   double prof_flops = 0.0;            // forward MLP (kind 0) algorithmic FLOPs since the last read
   double prof_work[4] = {0, 0, 0, 0}; // algorithmic FLOPs per kind
+  cudaEvent_t coarse_done = nullptr;  // caller-owned: recorded by tgtc_train_step when the coarse net's gradient half is final
   // Style_train: which workspaces hold a forward stash (tgtc_style_train_backward refuses anything else)
   struct StyleFwdRec { const void* ws; int64_t n; int S, F, has_rand; };
   std::vector<StyleFwdRec> style_fwd;
@@ -161,7 +162,8 @@ int launch_raygen(tgtc_ctx* ctx, int H, int W, const double* K, const double* c2
 
 // sampling.cu
 int launch_sample_uniform(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n, int S, double near,
-                          double far, const float* rnd, float* pts, float* ts, cudaStream_t st, const PhiloxSrc* prng = nullptr);
+                          double far, const float* rnd, float* pts, float* ts, cudaStream_t st, const PhiloxSrc* prng = nullptr,
+                          int harmony = 0);
 int launch_sample_fine(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, const float* ts, int64_t ts_stride,
                        const float* weights, int64_t n, int S, int n_fine, float* pts_out, float* ts_out,
                        int64_t* inds_out, float* samples_out, cudaStream_t st);

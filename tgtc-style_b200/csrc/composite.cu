@@ -47,7 +47,6 @@ __global__ void __launch_bounds__(32 * kWarps) composite_kernel(
         }
         if (noise != nullptr) sg = __fadd_rn(sg, noise[ray * S + i]);
         else if (prng.on) sg = __fadd_rn(sg, __fmul_rn(prng.std, philox_normal(prng.seed, prng.stream, (uint64_t)(ray * S + i))));
-        else if (prng.on) sg = __fadd_rn(sg, __fmul_rn(prng.std, philox_normal(prng.seed, prng.stream, (uint64_t)(ray * S + i))));
         t = tsr[i];
         tn = (i + 1 < S) ? tsr[i + 1] : 0.f;
       }

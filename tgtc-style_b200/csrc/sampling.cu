@@ -10,19 +10,28 @@ namespace {
 
 // ---------------------------------------------------------------------------
 // K2
+// utils.py:513-516: ts = linspace*(far-near)+near, or with harmony=True ts = 1/(1/near*(1-ts) + 1/far*ts) (fp32 tensor ops with
+// the Python-float scalars 1/near, 1/far rounded to fp32)
+struct TRow { float t_scale, t_near, inv_near, inv_far; int harmony; };
+__device__ __forceinline__ float row_t(int k, int S, const TRow& r) {
+  if (!r.harmony) return coarse_t(k, S, r.t_scale, r.t_near);
+  const float u = linspace01(k, S);
+  return __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(r.inv_near, __fsub_rn(1.0f, u)), __fmul_rn(r.inv_far, u)));
+}
+
 __global__ void __launch_bounds__(256) sample_uniform_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                                                             int64_t n, int S, float t_scale, float t_near,
+                                                             int64_t n, int S, const TRow row,
                                                              const float* __restrict__ rnd, const PhiloxSrc prng,
                                                              float* __restrict__ pts, float* __restrict__ ts) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * S) return;
   const int64_t ray = idx / S;
   const int k = (int)(idx - ray * S);
-  float t = coarse_t(k, S, t_scale, t_near);
+  float t = row_t(k, S, row);
   if (rnd != nullptr || prng.on) {
     // utils.py:518-524: mid=(ts[1:]+ts[:-1])/2; upper=[mid, ts[-1]]; lower=[ts[0], mid]; ts=lower+(upper-lower)*rand
-    const float tp = coarse_t(k > 0 ? k - 1 : 0, S, t_scale, t_near);
-    const float tn = coarse_t(k < S - 1 ? k + 1 : S - 1, S, t_scale, t_near);
+    const float tp = row_t(k > 0 ? k - 1 : 0, S, row);
+    const float tn = row_t(k < S - 1 ? k + 1 : S - 1, S, row);
     const float lower = (k == 0) ? t : __fdiv_rn(__fadd_rn(t, tp), 2.0f);
     const float upper = (k == S - 1) ? t : __fdiv_rn(__fadd_rn(tn, t), 2.0f);
     const float u = rnd != nullptr ? rnd[idx] : philox_uniform(prng.seed, prng.stream, (uint64_t)idx);
@@ -216,12 +225,18 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_fine_kernel(
 }  // namespace
 
 int launch_sample_uniform(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, int64_t n, int S, double near,
-                          double far, const float* rnd, float* pts, float* ts, cudaStream_t st, const PhiloxSrc* prng) {
+                          double far, const float* rnd, float* pts, float* ts, cudaStream_t st, const PhiloxSrc* prng, int harmony) {
   const int64_t total = n * S;
   const int block = 256;
   const int64_t grid = (total + block - 1) / block;
   TGTC_REQUIRE(grid <= 0x7fffffff, TGTC_ERR_UNSUPPORTED, "sample_uniform: too many samples in one call");
-  sample_uniform_kernel<<<(unsigned)grid, block, 0, st>>>(rays_o, rays_d, n, S, (float)(far - near), (float)near, rnd,
+  TRow row = {(float)(far - near), (float)near, 0.f, 0.f, harmony ? 1 : 0};
+  if (harmony) {
+    TGTC_REQUIRE(near != 0.0 && far != 0.0, TGTC_ERR_ARG, "harmony sampling divides by near and far (utils.py:516): both must be non-zero");
+    row.inv_near = (float)(1.0 / near);
+    row.inv_far = (float)(1.0 / far);
+  }
+  sample_uniform_kernel<<<(unsigned)grid, block, 0, st>>>(rays_o, rays_d, n, S, row, rnd,
                                                           prng != nullptr ? *prng : PhiloxSrc{0, 0, 0.f, 0}, pts, ts);
   TGTC_LAUNCH_CHECK(ctx);
   return TGTC_OK;

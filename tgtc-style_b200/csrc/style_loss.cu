@@ -95,7 +95,7 @@ __global__ void style_loss_grads_kernel(const LossArgs A, const float* __restric
 // ---------------------------------------------------------------------------
 // models.StyleLatents_variational (models.py:475-549) as two kernels: the per-ray latents
 //   lat_i = mu[s_i] + sigma_scale * (table[(s_i * frame_num + f_i) mod rows] - mu[s_i])                     models.py:490-506
-// (the modulo is the reference's 7x tiling of the LLFF table, models.py:496), minus_logp (models.py:531-537)
+// (the modulo is the reference's 7x tiling of the LLFF table, models.py:496: table_tiles = 7; 1 for other dataset types), minus_logp (models.py:531-537)
 //   logp = mean_i sum_k (lat_ik - mu_k)^2 / (exp(0.5 logvar_k) + 1e-3)
 // and the gradient of  (upstream d lat) + logp_scale * logp_sum  w.r.t. the table, reduced row by row in ray order (no atomics).
 struct LatArgs {
@@ -103,9 +103,19 @@ struct LatArgs {
   const int64_t* sid; const int64_t* fid;                      // [n]
   int64_t n, n_logp;                                           // rays; the first n_logp of them enter minus_logp
   int rows, frame_num;
+  int64_t limit;                                               // rows * table_tiles: flat ids at or beyond it are out of range
   float sigma_scale;
 };
-__device__ __forceinline__ int lat_row(const LatArgs& A, int64_t i) { return (int)((A.sid[i] * A.frame_num + A.fid[i]) % A.rows); }
+// the reference indexes `latents.reshape(-1, 32).repeat((7, 1))` for dataset_type == 'llff' and the plain table otherwise
+// (models.py:495-498): a flat id wraps modulo `rows` inside the tiled range, and is an IndexError beyond it -- here a trap
+__device__ __forceinline__ int lat_row(const LatArgs& A, int64_t i) {
+  const int64_t flat = A.sid[i] * A.frame_num + A.fid[i];
+  if (flat < 0 || flat >= A.limit) {
+    printf("tgtc style latents: id %lld of ray %lld outside the table (%lld rows incl. tiling)\n", (long long)flat, (long long)i, (long long)A.limit);
+    __trap();
+  }
+  return (int)(flat % A.rows);
+}
 
 __global__ void __launch_bounds__(1024) style_latents_forward_kernel(const LatArgs A, float* __restrict__ lat, float* __restrict__ logp_sum) {
   __shared__ float red[32];
@@ -213,22 +223,22 @@ extern "C" int tgtc_style_loss_grads(tgtc_ctx* ctx, const float* rgb_coarse, con
 }
 
 static int lat_args(tgtc_ctx* ctx, LatArgs& A, const float* table, const float* mu, const float* logvar, const int64_t* style_id,
-                    const int64_t* frame_id, int64_t n, int64_t n_logp, int rows, int frame_num, double sigma_scale) {
+                    const int64_t* frame_id, int64_t n, int64_t n_logp, int rows, int frame_num, int table_tiles, double sigma_scale) {
   TGTC_REQUIRE(table && mu && logvar && style_id && frame_id, TGTC_ERR_ARG, "style latents: null argument");
-  TGTC_REQUIRE(n > 0 && n_logp >= 0 && n_logp <= n && rows > 0 && frame_num > 0, TGTC_ERR_ARG, "style latents: bad n=%lld / n_logp=%lld / rows=%d",
-               (long long)n, (long long)n_logp, rows);
+  TGTC_REQUIRE(n > 0 && n_logp >= 0 && n_logp <= n && rows > 0 && frame_num > 0 && table_tiles >= 1, TGTC_ERR_ARG,
+               "style latents: bad n=%lld / n_logp=%lld / rows=%d / table_tiles=%d", (long long)n, (long long)n_logp, rows, table_tiles);
   (void)ctx;
   A.table = table; A.mu = mu; A.logvar = logvar; A.sid = style_id; A.fid = frame_id;
-  A.n = n; A.n_logp = n_logp; A.rows = rows; A.frame_num = frame_num; A.sigma_scale = (float)sigma_scale;
+  A.n = n; A.n_logp = n_logp; A.rows = rows; A.frame_num = frame_num; A.limit = (int64_t)rows * table_tiles; A.sigma_scale = (float)sigma_scale;
   return TGTC_OK;
 }
 
 extern "C" int tgtc_style_latents_forward(tgtc_ctx* ctx, const float* table, const float* mu, const float* logvar, const int64_t* style_id,
-                                          const int64_t* frame_id, int64_t n, int64_t n_logp, int rows, int frame_num, double sigma_scale,
+                                          const int64_t* frame_id, int64_t n, int64_t n_logp, int rows, int frame_num, int table_tiles, double sigma_scale,
                                           float* lat, float* logp_sum, tgtc_stream stream) {
   if (ctx == nullptr) { tgtc_set_error("ctx is null"); return TGTC_ERR_ARG; }
   LatArgs A;
-  int rc = lat_args(ctx, A, table, mu, logvar, style_id, frame_id, n, n_logp, rows, frame_num, sigma_scale);
+  int rc = lat_args(ctx, A, table, mu, logvar, style_id, frame_id, n, n_logp, rows, frame_num, table_tiles, sigma_scale);
   if (rc) return rc;
   TGTC_REQUIRE(lat && logp_sum, TGTC_ERR_ARG, "tgtc_style_latents_forward: null output");
   DevGuard guard(ctx->device);
@@ -238,11 +248,11 @@ extern "C" int tgtc_style_latents_forward(tgtc_ctx* ctx, const float* table, con
 }
 
 extern "C" int tgtc_style_latents_backward(tgtc_ctx* ctx, const float* table, const float* mu, const float* logvar, const int64_t* style_id,
-                                           const int64_t* frame_id, int64_t n, int64_t n_logp, int rows, int frame_num, double sigma_scale,
+                                           const int64_t* frame_id, int64_t n, int64_t n_logp, int rows, int frame_num, int table_tiles, double sigma_scale,
                                            const float* dlat, double logp_scale, float* table_grad, int accumulate, tgtc_stream stream) {
   if (ctx == nullptr) { tgtc_set_error("ctx is null"); return TGTC_ERR_ARG; }
   LatArgs A;
-  int rc = lat_args(ctx, A, table, mu, logvar, style_id, frame_id, n, n_logp, rows, frame_num, sigma_scale);
+  int rc = lat_args(ctx, A, table, mu, logvar, style_id, frame_id, n, n_logp, rows, frame_num, table_tiles, sigma_scale);
   if (rc) return rc;
   TGTC_REQUIRE(table_grad != nullptr, TGTC_ERR_ARG, "tgtc_style_latents_backward: null output");
   DevGuard guard(ctx->device);

@@ -148,15 +148,15 @@ class NerfRenderer:
         return ro, rd
 
     # ------------------------------------------------------------------ K2
-    def sample_uniform(self, rays_o, rays_d, n_samples=64, near=0., far=1.05, rand=None, want_pts=True):
+    def sample_uniform(self, rays_o, rays_d, n_samples=64, near=0., far=1.05, rand=None, want_pts=True, harmony=False):
         """utils.sampling_pts_uniform (utils.py:509-531).  Returns (pts [N,S,3], ts [N,S])."""
         ro, rd = self._dev(rays_o), self._dev(rays_d)
         n = ro.shape[0]
         ts = torch.empty(n, n_samples, dtype=torch.float32, device=self.device)
         pts = torch.empty(n, n_samples, 3, dtype=torch.float32, device=self.device) if want_pts else None
         rnd = self._dev(rand) if rand is not None else None
-        _lib.check(self.lib.tgtc_sample_uniform(self._h, _ptr(ro), _ptr(rd), n, n_samples, float(near), float(far), _ptr(rnd),
-                                                _ptr(pts), _ptr(ts), self._stream))
+        _lib.check(self.lib.tgtc_sample_uniform(self._h, _ptr(ro), _ptr(rd), n, n_samples, float(near), float(far), int(bool(harmony)),
+                                                _ptr(rnd), _ptr(pts), _ptr(ts), self._stream))
         return pts, ts
 
     # ------------------------------------------------------------------ K3+K4
@@ -198,6 +198,37 @@ class NerfRenderer:
         _lib.check(self.lib.tgtc_nerf_forward_rays(self._h, net, mode, _ptr(ro), _ptr(rd), _ptr(tsd), n, S, float(near), float(far),
                                                    _ptr(out), self._stream))
         return out
+
+    # stage-level training entries (the autograd.Function behind the model_forward drop-in, shims.py)
+    def nerf_forward_stash(self, net, pts, dirs):
+        """Training forward of one net on explicit points: pts [N,S,3], dirs [N,3] -> (rgbsigma [N,S,4], stash).  The stash (a uint8
+        device tensor owned by the caller) holds the activations nerf_backward needs; S in {64,128}; bf16 tcgen05 kernels."""
+        p, d = self._dev(pts), self._dev(dirs)
+        n, S = p.shape[0], p.shape[1]
+        sb = int(self.lib.tgtc_nerf_stash_bytes(n, S))
+        stash = torch.empty(sb + 1024, dtype=torch.uint8, device=self.device)
+        off = (-stash.data_ptr()) % 1024
+        rs = torch.empty(n, S, 4, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.tgtc_nerf_forward_stash(self._h, net, _ptr(p), _ptr(d), n, S, _ptr(rs), ctypes.c_void_p(stash.data_ptr() + off), sb,
+                                                    self._stream))
+        return rs, (stash, off, sb)
+
+    def nerf_backward(self, net, dirs, rgbsigma, d_rgbsigma, stash, grads=None, accumulate=False):
+        """dL/d(r,g,b,sigma) [N,S,4] -> flat fp32 gradient [tgtc_num_params()] of net `net` (tgtc_set_weights order)."""
+        d, rs, drs = self._dev(dirs), self._dev(rgbsigma), self._dev(d_rgbsigma)
+        n, S = rs.shape[0], rs.shape[1]
+        P = int(self.lib.tgtc_num_params())
+        if grads is None:
+            grads = torch.empty(P, dtype=torch.float32, device=self.device)
+            accumulate = False
+        scb = int(self.lib.tgtc_nerf_backward_scratch_bytes(self._h, n, S))
+        ws = self._workspace(scb + 1024)
+        woff = (-ws.data_ptr()) % 1024
+        buf, off, sb = stash
+        _lib.check(self.lib.tgtc_nerf_backward(self._h, net, _ptr(d), n, S, _ptr(rs), _ptr(drs), _ptr(grads), int(accumulate),
+                                               ctypes.c_void_p(buf.data_ptr() + off), sb, ctypes.c_void_p(ws.data_ptr() + woff), scb,
+                                               self._stream))
+        return grads
 
     # ------------------------------------------------------------------ K5
     def composite(self, pts_rgb=None, pts_sigma=None, t_values=None, noise=None, white_bkgd=False, rgbsigma=None):
@@ -331,7 +362,7 @@ class NerfRenderer:
         return out
 
     def render_frame(self, H, W, K, c2w, pix_begin=0, n=None, near=0., far=1., chunk=None, n_samples=64, n_fine=64, ndc=True,
-                     ndc_near=1.0, white_bkgd=False, extras=False, want_weights=False, mode=None, out=None):
+                     ndc_near=1.0, white_bkgd=False, extras=False, want_weights=False, mode=None, out=None, pixel_alignment=False):
         """Ray generation (K1) fused in front of render() for pixels [pix_begin, pix_begin+n) of an HxW frame."""
         self.refresh_weights()
         mode = self.mode if mode is None else _MODES[mode]
@@ -346,7 +377,7 @@ class NerfRenderer:
         Ka, Kp = _dptr(np.asarray(K, np.float64).reshape(9))
         Ca, Cp = _dptr(np.asarray(c2w, np.float64)[:3, :4].reshape(12))
         s = self._out_struct(out)
-        _lib.check(self.lib.tgtc_render_frame(self._h, mode, H, W, Kp, Cp, int(ndc), float(ndc_near), pix_begin, n, float(near),
+        _lib.check(self.lib.tgtc_render_frame(self._h, mode, H, W, Kp, Cp, int(ndc), float(ndc_near), int(bool(pixel_alignment)), pix_begin, n, float(near),
                                               float(far), n_samples, n_fine, ck, int(white_bkgd), ctypes.byref(s), _ptr(ws), wsb,
                                               self._stream))
         return out
@@ -418,6 +449,17 @@ class NerfRenderer:
                                               _ptr(lat1), _ptr(lat2), ctypes.byref(s), ctypes.c_void_p(ws.data_ptr() + off), wsb,
                                               self._stream))
         return out
+
+    def set_coarse_event(self, event):
+        """torch.cuda.Event (or None) that every following train_step records once the coarse net's gradient half is final
+        (tgtc_train_set_coarse_event): lets the caller all-reduce that half underneath the fine net's work."""
+        if event is not None:
+            event.record(torch.cuda.current_stream(self.device))      # materialises the lazily-created CUDA event
+            handle = ctypes.c_void_p(event.cuda_event)
+        else:
+            handle = None
+        _lib.check(self.lib.tgtc_train_set_coarse_event(self._h, handle))
+        self._coarse_event = event
 
     # ------------------------------------------------------------------ training step (a11)
     def train_step(self, rays_o, rays_d, rgb_gt, n_total=None, near=0., far=1., n_samples=64, n_fine=64, grads=None,
@@ -553,7 +595,7 @@ class NerfRenderer:
                                                   float(scale_coh), _ptr(d_c), _ptr(d_f), _ptr(d2c), _ptr(d2f), self._stream))
         return d_c, d_f, d2c, d2f
 
-    def style_latents_forward(self, table, mu, logvar, style_id, frame_id, n_logp, frame_num, sigma_scale=1.0):
+    def style_latents_forward(self, table, mu, logvar, style_id, frame_id, n_logp, frame_num, sigma_scale=1.0, table_tiles=7):
         """models.StyleLatents_variational.forward for every ray + the minus_logp sum of the first n_logp rays
         (tgtc_style_latents_forward) -> (lat [n,32], logp_sum [1])."""
         n = style_id.shape[0]
@@ -561,12 +603,12 @@ class NerfRenderer:
         logp = torch.empty(1, dtype=torch.float32, device=self.device)
         rows = table.numel() // 32
         _lib.check(self.lib.tgtc_style_latents_forward(self._h, _ptr(table), _ptr(mu), _ptr(logvar), _ptr(style_id), _ptr(frame_id), n,
-                                                       int(n_logp), rows, int(frame_num), float(sigma_scale), _ptr(lat), _ptr(logp),
+                                                       int(n_logp), rows, int(frame_num), int(table_tiles), float(sigma_scale), _ptr(lat), _ptr(logp),
                                                        self._stream))
         return lat, logp
 
     def style_latents_backward(self, table, mu, logvar, style_id, frame_id, n_logp, frame_num, dlat, logp_scale, sigma_scale=1.0,
-                               out=None, accumulate=False):
+                               out=None, accumulate=False, table_tiles=7):
         """gradient of <dlat, lat> + logp_scale * logp_sum w.r.t. the table (tgtc_style_latents_backward) -> tensor like table."""
         n = style_id.shape[0]
         if out is None:
@@ -574,7 +616,7 @@ class NerfRenderer:
             accumulate = False
         rows = table.numel() // 32
         _lib.check(self.lib.tgtc_style_latents_backward(self._h, _ptr(table), _ptr(mu), _ptr(logvar), _ptr(style_id), _ptr(frame_id), n,
-                                                        int(n_logp), rows, int(frame_num), float(sigma_scale), _ptr(dlat),
+                                                        int(n_logp), rows, int(frame_num), int(table_tiles), float(sigma_scale), _ptr(dlat),
                                                         float(logp_scale), _ptr(out), int(accumulate), self._stream))
         return out
 

@@ -1,71 +1,296 @@
 """Drop-in callables with the reference's own signatures.
 
-The reference injects four callables into its render/training loops:
-  samp_func        = utils.sampling_pts_uniform        (train_tgtcs.py:14)
-  samp_func_fine   = utils.sampling_pts_fine_torch     (train_tgtcs.py:16)
-  model_forward    = utils.batchify(lambda **kw: model(**kw), chunk)   (train_tgtcs.py:30, :37)
+The reference injects its hot path into the render / training loops as callables:
+  samp_func        = utils.sampling_pts_uniform                          (train_tgtcs.py:14)
+  samp_func_fine   = utils.sampling_pts_fine_torch                       (train_tgtcs.py:16)
+  model_forward    = utils.batchify(lambda **kw: model(**kw), chunk)     (train_tgtcs.py:30, :37)
+  concat_style_forward / style_forward = utils.batchify(...) of the two style modules   (train_tgtcs.py:46, :53)
   alpha_composition (module global via `from utils import *`, rendering.py:1)
-`make_callables(renderer)` returns B200 versions with the same names, argument
-meaning and return structure; `patch(renderer, modules)` rebinds them in the
-reference's module globals (star-imports copy names, so each module's copy is
-patched) so train_tgtcs.py / rendering.py run unchanged.
+`patch(renderer, modules)` rebinds sampling_pts_uniform, sampling_pts_fine_torch, alpha_composition AND batchify in the
+reference's module globals (star-imports copy names, so each module's copy is patched).  train() then builds its wrappers
+through OUR batchify, which recognises the nn.Module captured by the lambda (models.StyleNerf -> the fused PE+MLP kernels) --
+so train_tgtcs.train(), rendering.cal_geometry and Origin_train run with ZERO edits.
 
-These stage shims are forward-only (their tensors carry no grad): training goes through the fused step
-(NerfTrainer / tgtc_train_step, train.py), stylised rendering through NerfRenderer.render_style.
+Autograd: model_forward and alpha_composition are torch.autograd.Functions over the library's stage-level training entries
+(tgtc_nerf_forward_stash / tgtc_nerf_backward, tgtc_composite / tgtc_composite_backward), so `loss.backward()` of Origin_train
+(train_tgtcs.py:253-255) fills `.grad` of the reference's own nn.Parameters and its torch.optim.Adam steps them; the packed
+weight images follow the parameters' version counters.  Under torch.no_grad() (render loops) the inference kernels run.
 """
 import torch
 
 from . import _lib
+from .render import LAYER_NAMES, LAYER_SHAPES
 
 
-def make_callables(renderer):
-    r = renderer
+# ---------------------------------------------------------------------------------------------------------------------
+# autograd glue
 
-    def sampling_pts_uniform(rays_o, rays_d, N_samples=64, near=0., far=1.05, harmony=False, perturb=False):
+class _NerfForwardFn(torch.autograd.Function):
+    """models.StyleNerf.forward (models.py:216-223) -> (rgb [N,S,3], sigma [N,S]) with the backward into the 24 parameters."""
+
+    @staticmethod
+    def forward(ctx, renderer, net, pts, dirs, *params):
+        rs, stash = renderer.nerf_forward_stash(net, pts, dirs)
+        ctx.renderer, ctx.net, ctx.stash = renderer, net, stash
+        ctx.save_for_backward(rs, dirs)
+        ctx.set_materialize_grads(False)
+        return rs[..., :3].contiguous(), rs[..., 3].contiguous()
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_sigma):
+        rs, dirs = ctx.saved_tensors
+        d = torch.zeros_like(rs)
+        if g_rgb is not None:
+            d[..., :3] = g_rgb
+        if g_sigma is not None:
+            d[..., 3] = g_sigma
+        flat = ctx.renderer.nerf_backward(ctx.net, dirs, rs, d, ctx.stash)
+        ctx.stash = None
+        grads, o = [], 0
+        for no, ni in LAYER_SHAPES:        # tgtc_set_weights order: (weight [out,in], bias [out]) per layer
+            grads.append(flat[o:o + no * ni].view(no, ni))
+            o += no * ni
+            grads.append(flat[o:o + no])
+            o += no
+        return (None, None, None, None) + tuple(grads)
+
+
+class _CompositeFn(torch.autograd.Function):
+    """utils.alpha_composition (utils.py:354-386) -> (rgb_exp, t_exp, weights); gradients w.r.t. pts_rgb and pts_sigma.
+    No gradient is defined through `weights`: the reference only feeds it to sampling_pts_fine_torch, which detaches
+    (utils.py:576-579)."""
+
+    @staticmethod
+    def forward(ctx, renderer, pts_rgb, pts_sigma, t_values, noise, white_bkgd):
+        rs = torch.cat([pts_rgb, pts_sigma.unsqueeze(-1)], -1).contiguous()
+        rgb, depth, weights, _ = renderer.composite(t_values=t_values, rgbsigma=rs, noise=noise, white_bkgd=white_bkgd)
+        ctx.renderer, ctx.white, ctx.noise, ctx.ts = renderer, white_bkgd, noise, t_values
+        ctx.save_for_backward(rs)
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(weights)
+        return rgb, depth, weights
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_weights):
+        (rs,) = ctx.saved_tensors
+        if g_rgb is None:
+            g_rgb = torch.zeros(rs.shape[0], 3, dtype=torch.float32, device=rs.device)
+        d = ctx.renderer.composite_backward(rs, ctx.ts, g_rgb.contiguous(), g_depth=g_depth, noise=ctx.noise, white_bkgd=ctx.white)
+        return None, d[..., :3], d[..., 3], None, None, None
+
+
+def _nerf_params(module):
+    named = dict(module.named_parameters())
+    return [named[n + sfx] for n in LAYER_NAMES for sfx in (".weight", ".bias")]
+
+
+class _LazyRet(dict):
+    """The reference's returned dict (models.py:113-116, :222): rgb and sigma are there; the 256-wide `base_remap` and the
+    embedded `pts` / `dirs` are produced by the general fp32 kernel only when a caller actually reads them (the reference's
+    batchify materialises them for every chunk, used or not: 132 MB per 1008-ray fine chunk)."""
+
+    def __init__(self, base, features):
+        super().__init__(base)
+        self._features = features
+
+    def _fill(self):
+        if self._features is not None:
+            f, self._features = self._features, None
+            super().update(f())
+
+    def __missing__(self, key):
+        if key in ("base_remap", "pts", "dirs") and self._features is not None:
+            self._fill()
+            return super().__getitem__(key)
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return super().__contains__(key) or (self._features is not None and key in ("base_remap", "pts", "dirs"))
+
+    def keys(self):
+        self._fill()
+        return super().keys()
+
+    def items(self):
+        self._fill()
+        return super().items()
+
+    def __iter__(self):
+        self._fill()
+        return super().__iter__()
+
+    def __len__(self):
+        self._fill()
+        return super().__len__()
+
+
+def _per_ray_dirs(dirs):
+    """the reference passes rays_d.unsqueeze(1).expand(N,S,3) (rendering.py:30): a stride-0 view -> [N,3]; None when the
+    directions genuinely differ per sample"""
+    if dirs.dim() == 2:
+        return dirs
+    if dirs.dim() == 3 and (dirs.stride(1) == 0 or dirs.shape[1] == 1):
+        return dirs[:, 0, :]
+    return None
+
+
+class Shims:
+    """The callables bound to one NerfRenderer.  Modules are registered in the order the reference wraps them: the first
+    models.StyleNerf seen by batchify is the coarse net, the second the fine net (train_tgtcs.py:27-37)."""
+
+    def __init__(self, renderer):
+        self.r = renderer
+        self.nets = {}          # id(nn.Module) -> (module, NET_COARSE / NET_FINE)
+
+    # ---- net registration / weight tracking
+    def _net_id(self, module, net=None):
+        if id(module) in self.nets:
+            return self.nets[id(module)][1]
+        if net is None:
+            used = {v[1] for v in self.nets.values()}
+            free = [i for i in (_lib.NET_COARSE, _lib.NET_FINE) if i not in used]
+            if not free:
+                # train_tgtcs.py:596-597 re-enters train() after every phase and builds fresh modules: a new generation starts
+                self.nets.clear()
+                free = [_lib.NET_COARSE]
+            net = free[0]
+        self.nets[id(module)] = (module, net)
+        return net
+
+    def _sync(self, module, net):
+        src = self.r._weights_src[net]
+        if src is not module:
+            self.r.set_weights(**{("coarse" if net == 0 else "fine"): module})
+        else:
+            self.r.refresh_weights()
+
+    # ---- the callables
+    def sampling_pts_uniform(self, rays_o, rays_d, N_samples=64, near=0., far=1.05, harmony=False, perturb=False):
         """utils.py:509-531."""
-        if harmony:
-            raise NotImplementedError("harmony=True (utils.py:516) is never used by the reference's loops")
         rand = None
         if perturb:  # same generator call as utils.py:519-520
             rand = torch.zeros([rays_o.shape[0], N_samples], device=rays_o.device)
             torch.nn.init.uniform_(rand, 0, 1)
-        return r.sample_uniform(rays_o, rays_d, N_samples, near, far, rand=rand)
+        return self.r.sample_uniform(rays_o, rays_d, N_samples, near, far, rand=rand, harmony=harmony)
 
-    def sampling_pts_fine_torch(rays_o, rays_d, ts, weights, N_samples_fine=64):
-        """utils.py:573-580."""
-        return r.sample_fine(rays_o, rays_d, ts, weights, N_samples_fine)
+    def sampling_pts_fine_torch(self, rays_o, rays_d, ts, weights, N_samples_fine=64):
+        """utils.py:573-580 (no gradient flows through it: utils.py:576-579)."""
+        return self.r.sample_fine(rays_o, rays_d, ts.detach(), weights.detach(), N_samples_fine)
 
-    def alpha_composition(pts_rgb, pts_sigma, t_values, sigma_noise_std=0., white_bkgd=False):
+    def alpha_composition(self, pts_rgb, pts_sigma, t_values, sigma_noise_std=0., white_bkgd=False):
         """utils.py:354-386.  Returns (rgb_exp, t_exp, weights) like the reference (acc is dropped there)."""
         noise = None
         if sigma_noise_std > 0:  # same generator call as utils.py:373-374
             noise = torch.randn(pts_sigma.shape, device=pts_sigma.device) * sigma_noise_std
-        rgb, depth, weights, _ = r.composite(pts_rgb, pts_sigma, t_values, noise=noise, white_bkgd=white_bkgd)
+        if torch.is_grad_enabled() and (pts_rgb.requires_grad or pts_sigma.requires_grad):
+            return _CompositeFn.apply(self.r, pts_rgb, pts_sigma, t_values, noise, bool(white_bkgd))
+        rgb, depth, weights, _ = self.r.composite(pts_rgb, pts_sigma, t_values, noise=noise, white_bkgd=white_bkgd)
         return rgb, depth, weights
 
-    def _forward(which):
+    def nerf_callable(self, module=None, net=None):
+        """batchify(lambda **kw: model(**kw), chunk) for a models.StyleNerf (utils.py:435-456, models.py:216-223)."""
+        if module is not None:
+            net = self._net_id(module, net)
+
         def model_forward(**kwargs):
-            """batchify(lambda **kw: model(**kw), chunk)(pts=..., dirs=...)  (utils.py:435-456, models.py:216-223)."""
-            r.refresh_weights()
-            return r.nerf_forward(which, kwargs["pts"], kwargs["dirs"], want_features=True)
+            pts, dirs = kwargs["pts"], kwargs["dirs"]
+            r = self.r
+            if module is not None:
+                self._sync(module, net)
+            else:
+                r.refresh_weights()
+            params = _nerf_params(module) if module is not None else []
+            if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+                d = _per_ray_dirs(dirs)
+                S = pts.shape[1]
+                if d is None or S not in (64, 128):
+                    raise _lib.TgtcError("the training kernels take per-ray view directions (a stride-0 expand of rays_d, "
+                                         "rendering.py:30) and 64 or 128 samples per ray; got dirs stride %s, S=%d" % (tuple(dirs.stride()), S))
+                rgb, sigma = _NerfForwardFn.apply(r, net, pts.detach(), d.detach().contiguous(), *params)
+                feats = lambda: {k: v for k, v in r.nerf_forward(net, pts.detach(), dirs.detach(), want_features=True).items()
+                                 if k in ("base_remap", "pts", "dirs")}
+                return _LazyRet({"rgb": rgb, "sigma": sigma}, feats)
+            # inference: the renderer's mode on the fused path; feature keys on demand (general fp32 kernel)
+            S = pts.shape[1]
+            fast = r.mode != _lib.MLP_FP32 and _per_ray_dirs(dirs) is not None and (S in (64, 128) or (S > 128 and S % 128 == 0))
+            if fast:
+                out = r.nerf_forward(net, pts, dirs, want_features=False)
+                feats = lambda: {k: v for k, v in r.nerf_forward(net, pts, dirs, want_features=True).items() if k in ("base_remap", "pts", "dirs")}
+                return _LazyRet(out, feats)
+            return r.nerf_forward(net, pts, dirs, want_features=True)
         return model_forward
 
+    def batchify(self, fn, chunk=1024 * 32):
+        """utils.batchify (utils.py:435-456).  The reference wraps `lambda **kwargs: model(**kwargs)`; when the captured module
+        is a models.StyleNerf the chunk loop disappears into the persistent kernel.  Any other callable gets the reference's
+        own chunk loop (restated)."""
+        mod = _captured_module(fn)
+        if mod is not None and type(mod).__name__ == "StyleNerf" and not getattr(mod, "is_siren", False):
+            return self.nerf_callable(mod)
+        return _chunk_loop(fn, chunk)
+
+
+def _captured_module(fn):
+    if isinstance(fn, torch.nn.Module):
+        return fn
+    for cell in (getattr(fn, "__closure__", None) or ()):
+        try:
+            v = cell.cell_contents
+        except ValueError:
+            continue
+        if isinstance(v, torch.nn.Module):
+            return v
+    return None
+
+
+def _chunk_loop(fn, chunk):
+    """utils.py:435-456, for callables the library has no kernel for"""
+    if chunk is None:
+        return fn
+
+    def ret_func(**kwargs):
+        x = kwargs[list(kwargs.keys())[0]]
+        all_ret = {}
+        for i in range(0, x.shape[0], chunk):
+            ret = fn(**{k: v[i:min(i + chunk, x.shape[0])] for k, v in kwargs.items()})
+            for k in ret:
+                all_ret.setdefault(k, []).append(ret[k])
+        return {k: torch.cat(v, 0) for k, v in all_ret.items()}
+    return ret_func
+
+
+def make_callables(renderer):
+    """The callables for a renderer whose weights were set with NerfRenderer.set_weights (modules or state_dicts): the two
+    model_forward entries use net 0 / net 1 as packed; with nn.Module sources they are autograd-capable."""
+    s = Shims(renderer)
+
+    def fwd(net):
+        src = renderer._weights_src[net]
+        if isinstance(src, torch.nn.Module):
+            return s.nerf_callable(src, net)
+        return s.nerf_callable(None, net)
     return {
-        "sampling_pts_uniform": sampling_pts_uniform,
-        "sampling_pts_fine_torch": sampling_pts_fine_torch,
-        "alpha_composition": alpha_composition,
-        "model_forward": _forward(_lib.NET_COARSE),
-        "model_forward_fine": _forward(_lib.NET_FINE),
+        "sampling_pts_uniform": s.sampling_pts_uniform,
+        "sampling_pts_fine_torch": s.sampling_pts_fine_torch,
+        "alpha_composition": s.alpha_composition,
+        "batchify": s.batchify,
+        "model_forward": fwd(_lib.NET_COARSE),
+        "model_forward_fine": fwd(_lib.NET_FINE),
+        "shims": s,
     }
 
 
+PATCHED_NAMES = ("sampling_pts_uniform", "sampling_pts_fine_torch", "alpha_composition", "batchify")
+
+
 def patch(renderer, modules):
-    """Rebinds sampling_pts_uniform / sampling_pts_fine_torch / alpha_composition in each given module
-    (the reference's `utils`, `rendering`, `train_tgtcs`).  Returns the callables dict; the two
-    model_forward entries are what train() should pass instead of its batchify wrappers."""
-    fns = make_callables(renderer)
+    """Rebinds sampling_pts_uniform / sampling_pts_fine_torch / alpha_composition / batchify in each given module (the
+    reference's `utils`, `rendering`, `train_tgtcs`; star-imports copy names, so every module's copy is patched).  After this,
+    train_tgtcs.train(args) builds model_forward / model_forward_fine through the B200 batchify and runs unchanged.
+    Returns the Shims object (its nerf_callable(module) gives a model_forward for code that does not go through batchify)."""
+    s = Shims(renderer)
     for m in modules:
-        for name in ("sampling_pts_uniform", "sampling_pts_fine_torch", "alpha_composition"):
+        for name in PATCHED_NAMES:
             if hasattr(m, name):
-                setattr(m, name, fns[name])
-    return fns
+                setattr(m, name, getattr(s, name))
+    return s

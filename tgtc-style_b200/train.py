@@ -17,7 +17,7 @@ from .render import LAYER_NAMES, LAYER_SHAPES
 
 class NerfTrainer:
     def __init__(self, renderer, coarse, fine, lr=5e-4, lr_decay_steps=100000, lr_decay_rate=0.1, group=None, max_rays_per_pass=8192,
-                 seed=None):
+                 seed=None, overlap_allreduce=True):
         """coarse / fine: state_dicts (or nn.Modules) with the reference's parameter names (models.py:75-91).
         lr schedule: lr * rate^(step/decay_steps) as train_tgtcs.py:272-276."""
         self.r = renderer
@@ -53,6 +53,10 @@ class NerfTrainer:
         self.lr = lr
         self.step_count = 0
         self.r.set_weights(self.params[0], self.params[1])
+        # data-parallel overlap: the coarse net's gradient half is all-reduced on a side stream while the fine
+        # net's forward / backward still runs; the fine half follows when the step's work is done
+        self.overlap = bool(overlap_allreduce) and hasattr(renderer, "set_coarse_event") and torch.cuda.is_available()
+        self._comm = None
 
     def world(self):
         return dist.get_world_size(self.group) if dist.is_initialized() else 1
@@ -98,9 +102,12 @@ class NerfTrainer:
             b, e = shard_range(rays_o.shape[0], self.rank(), world)
             ro, rd, gt = rays_o[b:e], rays_d[b:e], rgb_gt[b:e]
             n_total = rays_o.shape[0]
-        loss = self.forward_backward(ro, rd, gt, n_total, perturb=perturb, sigma_noise_std=sigma_noise_std)
-        if world > 1:
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.group)   # the path's only collective
+        if world > 1 and self.overlap:
+            loss = self._forward_backward_overlapped(ro, rd, gt, n_total, perturb, sigma_noise_std)
+        else:
+            loss = self.forward_backward(ro, rd, gt, n_total, perturb=perturb, sigma_noise_std=sigma_noise_std)
+            if world > 1:
+                dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.group)   # the path's only collective
         self.step_count += 1
         if self.fused:
             self.r.adam_step(self.flat, self.grads, self.exp_avg, self.exp_avg_sq, self.step_count, lr=self.lr)
@@ -111,6 +118,27 @@ class NerfTrainer:
             for g in self.opt.param_groups:
                 g["lr"] = self.lr
         self.r.set_weights(self.params[0], self.params[1])    # re-pack the bf16 / transposed images from the fp32 masters
+        return loss
+
+    def _forward_backward_overlapped(self, ro, rd, gt, n_total, perturb, sigma_noise_std):
+        """forward_backward + the gradient all-reduce in two halves: the coarse net's half starts (on a side stream) as soon as
+        the library signals that it is final, underneath the fine net's forward / backward; the fine half follows the step."""
+        dev = self.r.device
+        cur = torch.cuda.current_stream(dev)
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=dev)
+            self._ev_coarse = torch.cuda.Event()
+            self._ev_end = torch.cuda.Event()
+        P = self.grads.numel() // 2
+        self.r.set_coarse_event(self._ev_coarse)
+        loss = self.forward_backward(ro, rd, gt, n_total, perturb=perturb, sigma_noise_std=sigma_noise_std)
+        self._ev_end.record(cur)
+        self._comm.wait_event(self._ev_coarse)          # the last ray chunk's record: every chunk's coarse gradient is in
+        with torch.cuda.stream(self._comm):
+            dist.all_reduce(self.grads[:P], op=dist.ReduceOp.SUM, group=self.group)
+            self._comm.wait_event(self._ev_end)
+            dist.all_reduce(self.grads[P:], op=dist.ReduceOp.SUM, group=self.group)
+        cur.wait_stream(self._comm)                      # the optimizer step reads the reduced gradients
         return loss
 
     def state_dicts(self):
@@ -182,12 +210,13 @@ class StyleLatents:
     def forward_fused(self, style_ids, frame_ids, n_logp):
         """-> (per-ray latents [n,32] without autograd history, minus_logp SUM of the first n_logp rays [1])"""
         return self.r.style_latents_forward(self.latents.detach(), self.mu, self.logvar, style_ids, frame_ids, n_logp, self.frame_num,
-                                            self.sigma_scale)
+                                            self.sigma_scale, table_tiles=7 if self.dataset_type == "llff" else 1)
 
     def backward_fused(self, style_ids, frame_ids, n_logp, dlat, logp_scale):
         """table gradient of <dlat, lat> + logp_scale * logp_sum, written to self.latents.grad"""
         self.latents.grad = self.r.style_latents_backward(self.latents.detach(), self.mu, self.logvar, style_ids, frame_ids, n_logp,
-                                                          self.frame_num, dlat, logp_scale, self.sigma_scale)
+                                                          self.frame_num, dlat, logp_scale, self.sigma_scale,
+                                                          table_tiles=7 if self.dataset_type == "llff" else 1)
 
     def zero_grad(self):
         self.latents.grad = None
@@ -325,8 +354,10 @@ class StyleTrainer:
         else:
             d_c, d_f, _, _ = self.r.style_loss_grads(rgb_c, rgb_f, gt, scale_rgb)
         bw = self.r.style_train_backward(fw["state"], d_c, d_f, grads=self.grads, accumulate=False)
-        # latent table: the path through the style modules (d_latents) + the direct minus_logp term, one kernel
-        self.lat.backward_fused(ids[0], ids[1], n, bw["d_latents"], lam / (n * world))
+        # latent table: the path through the style modules (d_latents) + the direct minus_logp term, one kernel.  Only the
+        # shuffled batch's rows: latents_model_1.optimize(loss) backpropagates loss = loss_rgb + loss_logp
+        # (train_tgtcs.py:481, :495; models.py:544-549), never the coherence term, which reaches the style modules only (:483-493)
+        self.lat.backward_fused(sid, fid, n, bw["d_latents"][:n].contiguous(), lam / (n * world))
         if coh_batch is not None:
             self.prev = (c2, f2, org2)
         loss_rgb = self.lam_rgb * (sums[0] + sums[1]) / (3.0 * n * world)
@@ -390,9 +421,9 @@ class StyleTrainer:
         bw = self.r.style_train_backward(fw["state"], gr[0], gr[1], grads=self.grads, accumulate=False)
         roots, seeds = [loss_logp, lat1], [None, bw["d_latents"]]    # direct term + the path through the style modules
         if with_coh:
-            bw2 = self.r.style_train_backward(fw2["state"], gr[2], gr[3], grads=self.grads, accumulate=True)
-            roots.append(lat2)
-            seeds.append(bw2["d_latents"])
+            # the coherence batch's gradient reaches the two style modules only: latents_model_1.optimize(loss) backpropagates
+            # loss = loss_rgb + loss_logp (train_tgtcs.py:481, :495), not loss_for_style
+            self.r.style_train_backward(fw2["state"], gr[2], gr[3], grads=self.grads, accumulate=True)
         torch.autograd.backward(roots, seeds)                        # one engine run -> latents table
         if world > 1:
             dist.all_reduce(self.grads, op=dist.ReduceOp.SUM, group=self.group)
