@@ -1068,7 +1068,7 @@ def main():
             "dtype": {"f16": "f16", "bf16": "bf16", "fp32": "f32"}[args.mode], "data": "synthetic",
             "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n, "samples_per_ray": SAMPLES_PER_RAY,
                        "parallelism": "ray-sharded, one frame per GPU per step, one packed NCCL all-gather of the rgb/depth/acc tiles per frame on a side stream" if world > 1 else "1 GPU",
-                       "l2_policy": "per-step working set 2.4 GB (rgb-sigma workspace) >> 126 MB L2; no flush needed"},
+                       "l2_policy": "inputs larger than L2: every step reads a different frame's rays and cycles ~630 MB of per-ray state (rays 18 MB, coarse weights 195 MB, ts_fine 390 MB read + written, outputs 15 MB) through HBM >> 126 MB L2; the MLP weights (2.4 MB) are meant to stay L2-resident; no flush"},
             "mlp_samples_per_s": value * SAMPLES_PER_RAY,
             "e2e": {"value": rays_total / (ms2.item() * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 20 * n,
                     "ms_per_step": ms2.item() / args.steps, "api": "NerfRenderer.render_host -> tgtc_render_host", "checksum": checksum},

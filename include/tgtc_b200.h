@@ -138,7 +138,9 @@ int tgtc_sample_fine(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, co
 /* The fused operator (north-star surface):
  *   render(rays_o, rays_d, near, far, chunk) -> {rgb, depth, acc, weights}
  * = the loop body of rendering.py:27-51 (cal_geometry) for one batch of rays:
- * coarse MLP -> compositing -> resampling -> fine MLP -> compositing.
+ * coarse MLP -> compositing -> resampling -> fine MLP -> compositing
+ * (tensor-core modes at 64 / 128 samples: three launches -- the compositing is
+ * the last epilogue of each MLP kernel; bit-identical to tgtc_composite).
  * Any output pointer may be NULL.  All device memory. */
 typedef struct tgtc_render_out {
   float* rgb;            /* [n,3]   fine */
@@ -153,8 +155,14 @@ typedef struct tgtc_render_out {
 } tgtc_render_out;
 
 /* bytes of device workspace tgtc_render needs for a call with these sizes
- * (chunk <= 0 means "all rays in one pass") */
+ * (chunk <= 0 means "all rays in one pass").  The first form is enough for every
+ * mode; the _mode form returns what `mode` needs: in the tensor-core modes with
+ * n_samples, n_samples+n_fine in {64,128} the compositing runs inside the MLP
+ * kernel (a 128-sample tile is one fine ray / two coarse rays), the per-sample
+ * (r,g,b,sigma) never reach HBM and the workspace shrinks from 48 B/sample to
+ * ~4 B/sample (coarse weights + ts_fine). */
 size_t tgtc_render_workspace_bytes(int64_t n_rays, int n_samples, int n_fine, int64_t chunk);
+size_t tgtc_render_workspace_bytes_mode(int mode, int64_t n_rays, int n_samples, int n_fine, int64_t chunk);
 
 int tgtc_render(tgtc_ctx* ctx, int mode, const float* rays_o, const float* rays_d, int64_t n_rays, double near,
                 double far, int n_samples, int n_fine, int64_t chunk, int white_bkgd, const tgtc_render_out* out,
@@ -174,6 +182,7 @@ int tgtc_render_host(tgtc_ctx* ctx, int mode, const float* rays_o, const float* 
  * pixel_alignment as in tgtc_raygen / get_rays_np, dataset.py:33-36).
  * Device outputs; workspace as for tgtc_render plus 24*n bytes for the rays. */
 size_t tgtc_render_frame_workspace_bytes(int64_t n_rays, int n_samples, int n_fine, int64_t chunk);
+size_t tgtc_render_frame_workspace_bytes_mode(int mode, int64_t n_rays, int n_samples, int n_fine, int64_t chunk);
 int tgtc_render_frame(tgtc_ctx* ctx, int mode, int H, int W, const double* K, const double* c2w, int ndc,
                       double ndc_near, int pixel_alignment, int64_t pix_begin, int64_t n, double near, double far, int n_samples,
                       int n_fine, int64_t chunk, int white_bkgd, const tgtc_render_out* out, void* workspace,

@@ -213,3 +213,36 @@ def test_render_bf16_ragged_sizes_match_prefix_of_larger_batch(renderer_bf16, n)
     for k in ("rgb", "depth", "acc", "weights", "rgb_coarse", "ts_fine"):
         assert torch.equal(small[k], big[k][:n]), k
     assert torch.isfinite(small["rgb"]).all()
+
+
+@pytest.mark.parametrize("mode", ["f16", "bf16"])
+@pytest.mark.parametrize("n", [1, 2, 3, 129, 1001])
+def test_fused_compositing_is_bit_identical_to_the_standalone_kernel(mode, n):
+    """K5 fused into the last epilogue of the tcgen05 MLP kernel (a 128-sample tile = one fine ray / two coarse rays) against the
+    same render with the stand-alone composite kernel: every output, bit for bit -- odd ray counts (half-filled last coarse tile),
+    white background, weights requested."""
+    from tgtc_style_b200 import _lib
+    r = T.NerfRenderer(device="cuda:0", mode=mode)
+    wc, wf = weights("w1")
+    r.set_weights(wc, wf)
+    ro, rd = small_rays()
+    sel = np.linspace(0, ro.shape[0] - 1, n).astype(np.int64)
+    lib = _lib.load()
+    outs = []
+    for off in (0, 1):
+        lib.tgtc_debug_no_fused_composite(off)
+        try:
+            a = r.render(ro[sel], rd[sel], 0., 1., extras=True, want_weights=True)
+            b = r.render(ro[sel], rd[sel], 0., 1., extras=True, want_weights=True, white_bkgd=True)
+            torch.cuda.synchronize()
+            outs.append(({k: v.clone() for k, v in a.items()}, {k: v.clone() for k, v in b.items()}))
+        finally:
+            lib.tgtc_debug_no_fused_composite(0)
+    for (fa, fb), (sa, sb) in [(outs[0], outs[1])]:
+        for k in fa:
+            assert torch.equal(fa[k], sa[k]), ("plain", k)
+            assert torch.equal(fb[k], sb[k]), ("white_bkgd", k)
+    assert torch.isfinite(outs[0][0]["rgb"]).all()
+    # the fused path needs ~4 B/sample of workspace instead of 48
+    assert lib.tgtc_render_workspace_bytes_mode(r.mode, 4096, 64, 64, 0) * 8 < lib.tgtc_render_workspace_bytes(4096, 64, 64, 0)
+    r.close()

@@ -50,6 +50,8 @@ PROTOTYPES = {
     "tgtc_sample_fine": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, ctypes.c_int, ctypes.c_int,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tgtc_render_workspace_bytes": (ctypes.c_size_t, [c_i64, ctypes.c_int, ctypes.c_int, c_i64]),
+    "tgtc_render_workspace_bytes_mode": (ctypes.c_size_t, [ctypes.c_int, c_i64, ctypes.c_int, ctypes.c_int, c_i64]),
+    "tgtc_render_frame_workspace_bytes_mode": (ctypes.c_size_t, [ctypes.c_int, c_i64, ctypes.c_int, ctypes.c_int, c_i64]),
     "tgtc_render": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p, c_void_p, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                    ctypes.c_int, c_i64, ctypes.c_int, ctypes.POINTER(RenderOut), c_void_p, ctypes.c_size_t, c_void_p]),
     "tgtc_render_host": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p, c_void_p, c_i64, ctypes.c_double, ctypes.c_double,
@@ -116,6 +118,7 @@ DEBUG_PROTOTYPES = {
     "tgtc_debug_tc_layers": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p, c_void_p, c_void_p, c_i64, ctypes.c_int, ctypes.c_double,
                                             ctypes.c_double, ctypes.c_int, c_void_p, c_void_p]),
     "tgtc_debug_tc_f16": (None, [ctypes.c_int]),
+    "tgtc_debug_no_fused_composite": (None, [ctypes.c_int]),
 }
 
 _lib = None

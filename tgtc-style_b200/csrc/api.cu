@@ -292,11 +292,22 @@ struct RenderWs {
   size_t off_rs_c, off_rs_f, off_w_c, off_ts_f, off_ts_c, total;
 };
 
-static RenderWs render_ws_layout(int64_t pass_rays, int S, int F) {
+// test / A-B hook (not in the public header): 1 = keep the stand-alone compositing kernel in the tensor-core render path
+static int g_no_fused_composite = 0;
+extern "C" void tgtc_debug_no_fused_composite(int on) { g_no_fused_composite = on; }
+
+// which passes composite inside the MLP kernel (fused K5): tensor-core modes with whole rays per 128-sample tile
+static inline bool fused_pass(int mode, int samples) {
+  return (mode == TGTC_MLP_BF16 || mode == TGTC_MLP_F16) && (samples == 64 || samples == 128) && !g_no_fused_composite;
+}
+
+static RenderWs render_ws_layout(int64_t pass_rays, int S, int F, int mode) {
   RenderWs w;
   size_t o = 0;
-  w.off_rs_c = o; o = align_up(o + (size_t)pass_rays * S * 16, 256);
-  w.off_rs_f = o; o = align_up(o + (size_t)pass_rays * (S + F) * 16, 256);
+  // per-sample (r,g,b,sigma) only exists for passes that composite in a separate kernel; a fused pass keeps 12 B/ray of scratch
+  // for an rgb map the caller did not ask for
+  w.off_rs_c = o; o = align_up(o + (size_t)pass_rays * (fused_pass(mode, S) ? 12 : (size_t)S * 16), 256);
+  w.off_rs_f = o; o = align_up(o + (size_t)pass_rays * (fused_pass(mode, S + F) ? 12 : (size_t)(S + F) * 16), 256);
   w.off_w_c = o;  o = align_up(o + (size_t)pass_rays * S * 4, 256);
   w.off_ts_f = o; o = align_up(o + (size_t)pass_rays * (S + F) * 4, 256);
   w.off_ts_c = o; o = align_up(o + (size_t)S * 4, 256);
@@ -308,7 +319,11 @@ static inline int64_t pass_size(int64_t n, int64_t chunk) { return (chunk <= 0 |
 
 extern "C" size_t tgtc_render_workspace_bytes(int64_t n_rays, int n_samples, int n_fine, int64_t chunk) {
   if (n_rays <= 0 || n_samples <= 0 || n_fine < 0) return 0;
-  return render_ws_layout(pass_size(n_rays, chunk), n_samples, n_fine).total;
+  return render_ws_layout(pass_size(n_rays, chunk), n_samples, n_fine, TGTC_MLP_FP32).total;   // enough for every mode
+}
+extern "C" size_t tgtc_render_workspace_bytes_mode(int mode, int64_t n_rays, int n_samples, int n_fine, int64_t chunk) {
+  if (n_rays <= 0 || n_samples <= 0 || n_fine < 0) return 0;
+  return render_ws_layout(pass_size(n_rays, chunk), n_samples, n_fine, mode).total;
 }
 
 static int check_render_args(tgtc_ctx* ctx, int mode, int64_t n, int S, int F) {
@@ -321,13 +336,14 @@ static int check_render_args(tgtc_ctx* ctx, int mode, int64_t n, int S, int F) {
   return TGTC_OK;
 }
 
-// rendering.py:27-51 for rays [0,n): passes of `chunk` rays, six launches per pass
+// rendering.py:27-51 for rays [0,n): passes of `chunk` rays; tensor-core modes: coarse MLP(+compositing) -> resampling ->
+// fine MLP(+compositing) = three launches per pass; fp32 mode: five
 static int render_impl(tgtc_ctx* ctx, int mode, const float* rays_o, const float* rays_d, int64_t n, double near, double far,
                        int S, int F, int64_t chunk, int white_bkgd, const tgtc_render_out& out, void* workspace,
                        size_t workspace_bytes, cudaStream_t st) {
   if (n == 0) return TGTC_OK;
   const int64_t pass = pass_size(n, chunk);
-  const RenderWs ws = render_ws_layout(pass, S, F);
+  const RenderWs ws = render_ws_layout(pass, S, F, mode);
   TGTC_REQUIRE(workspace != nullptr && aligned16(workspace) && workspace_bytes >= ws.total, TGTC_ERR_STATE,
                "workspace too small or misaligned: need %zu bytes, got %zu", ws.total, workspace_bytes);
   uint8_t* base = static_cast<uint8_t*>(workspace);
@@ -349,15 +365,25 @@ static int render_impl(tgtc_ctx* ctx, int mode, const float* rays_o, const float
     ic.rays_o = o; ic.rays_d = d; ic.ts = nullptr;
     ic.t_scale = (float)(far - near); ic.t_near = (float)near;
     ic.n_rays = m; ic.S = S; ic.rgbsigma = rs_c;
+    const bool last = (F == 0);
+    float* c_rgb = out.rgb_coarse ? out.rgb_coarse + r0 * 3 : (last && out.rgb ? out.rgb + r0 * 3 : nullptr);
+    float* c_depth = out.depth_coarse ? out.depth_coarse + r0 : (last && out.depth ? out.depth + r0 : nullptr);
+    float* c_acc = out.acc_coarse ? out.acc_coarse + r0 : (last && out.acc ? out.acc + r0 : nullptr);
+    // tensor-core modes with whole rays per 128-sample tile: alpha_composition (rendering.py:36) runs inside the MLP kernel's
+    // last epilogue (fused K5) -- the per-sample (r,g,b,sigma) never reach HBM
+    const bool fuse_c = fused_pass(mode, S);
+    if (fuse_c) {
+      ic.rgbsigma = nullptr;
+      ic.comp_rgb = c_rgb != nullptr ? c_rgb : reinterpret_cast<float*>(base + ws.off_rs_c);   // rgb is always produced: scratch when unwanted
+      ic.comp_depth = c_depth; ic.comp_acc = c_acc; ic.comp_weights = w_c; ic.comp_white_bkgd = white_bkgd;
+    }
     rc = run_mlp(ctx, TGTC_NET_COARSE, mode, ic, st);
     if (rc) return rc;
-    // alpha_composition(coarse) (rendering.py:36)
-    const bool last = (F == 0);
-    rc = launch_composite(ctx, nullptr, nullptr, rs_c, ts_c, 0, nullptr, white_bkgd, m, S,
-                          out.rgb_coarse ? out.rgb_coarse + r0 * 3 : (last && out.rgb ? out.rgb + r0 * 3 : nullptr),
-                          out.depth_coarse ? out.depth_coarse + r0 : (last && out.depth ? out.depth + r0 : nullptr),
-                          out.acc_coarse ? out.acc_coarse + r0 : (last && out.acc ? out.acc + r0 : nullptr), w_c, st);
-    if (rc) return rc;
+    if (!fuse_c) {
+      // alpha_composition(coarse) (rendering.py:36)
+      rc = launch_composite(ctx, nullptr, nullptr, rs_c, ts_c, 0, nullptr, white_bkgd, m, S, c_rgb, c_depth, c_acc, w_c, st);
+      if (rc) return rc;
+    }
     if (last) {
       // coarse-only render: the coarse result IS the result; mirror it into the fine slots when both were asked for
       if (out.rgb && out.rgb_coarse) TGTC_CUDA(cudaMemcpyAsync(out.rgb + r0 * 3, out.rgb_coarse + r0 * 3, (size_t)m * 12, cudaMemcpyDeviceToDevice, st));
@@ -374,13 +400,24 @@ static int render_impl(tgtc_ctx* ctx, int mode, const float* rays_o, const float
     MlpIO fi;
     fi.rays_o = o; fi.rays_d = d; fi.ts = ts_f;
     fi.n_rays = m; fi.S = T; fi.rgbsigma = rs_f;
+    const bool fuse_f = fused_pass(mode, T);
+    if (fuse_f) {
+      fi.rgbsigma = nullptr;
+      fi.comp_rgb = out.rgb ? out.rgb + r0 * 3 : reinterpret_cast<float*>(base + ws.off_rs_f);
+      fi.comp_depth = out.depth ? out.depth + r0 : nullptr;
+      fi.comp_acc = out.acc ? out.acc + r0 : nullptr;
+      fi.comp_weights = out.weights ? out.weights + r0 * T : nullptr;
+      fi.comp_white_bkgd = white_bkgd;
+    }
     rc = run_mlp(ctx, TGTC_NET_FINE, mode, fi, st);
     if (rc) return rc;
-    // alpha_composition(fine) (rendering.py:51)
-    rc = launch_composite(ctx, nullptr, nullptr, rs_f, ts_f, T, nullptr, white_bkgd, m, T,
-                          out.rgb ? out.rgb + r0 * 3 : nullptr, out.depth ? out.depth + r0 : nullptr,
-                          out.acc ? out.acc + r0 : nullptr, out.weights ? out.weights + r0 * T : nullptr, st);
-    if (rc) return rc;
+    if (!fuse_f) {
+      // alpha_composition(fine) (rendering.py:51)
+      rc = launch_composite(ctx, nullptr, nullptr, rs_f, ts_f, T, nullptr, white_bkgd, m, T,
+                            out.rgb ? out.rgb + r0 * 3 : nullptr, out.depth ? out.depth + r0 : nullptr,
+                            out.acc ? out.acc + r0 : nullptr, out.weights ? out.weights + r0 * T : nullptr, st);
+      if (rc) return rc;
+    }
   }
   return TGTC_OK;
 }
@@ -438,7 +475,7 @@ extern "C" int tgtc_render_host(tgtc_ctx* ctx, int mode, const float* rays_o, co
     if (*s.hostp != nullptr) { s.off = o; o = align_up(o + s.bytes, 256); }
   }
   const size_t off_ws = o;
-  const size_t ws_bytes = tgtc_render_workspace_bytes(n, S, F, chunk);
+  const size_t ws_bytes = tgtc_render_workspace_bytes_mode(mode, n, S, F, chunk);
   o += ws_bytes;
   rc = ensure_arena(ctx, o, st);
   if (rc) return rc;
@@ -465,6 +502,10 @@ extern "C" size_t tgtc_render_frame_workspace_bytes(int64_t n_rays, int n_sample
   if (n_rays <= 0) return 0;
   return align_up((size_t)n_rays * 12, 256) * 2 + tgtc_render_workspace_bytes(n_rays, n_samples, n_fine, chunk);
 }
+extern "C" size_t tgtc_render_frame_workspace_bytes_mode(int mode, int64_t n_rays, int n_samples, int n_fine, int64_t chunk) {
+  if (n_rays <= 0) return 0;
+  return align_up((size_t)n_rays * 12, 256) * 2 + tgtc_render_workspace_bytes_mode(mode, n_rays, n_samples, n_fine, chunk);
+}
 
 extern "C" int tgtc_render_frame(tgtc_ctx* ctx, int mode, int H, int W, const double* K, const double* c2w, int ndc,
                                  double ndc_near, int pixel_alignment, int64_t pix_begin, int64_t n, double near, double far, int n_samples,
@@ -477,7 +518,7 @@ extern "C" int tgtc_render_frame(tgtc_ctx* ctx, int mode, int H, int W, const do
   TGTC_REQUIRE(H > 0 && W > 0 && K != nullptr && c2w != nullptr, TGTC_ERR_ARG, "bad camera");
   TGTC_REQUIRE(pix_begin >= 0 && pix_begin + n <= (int64_t)H * W, TGTC_ERR_ARG, "pixel range outside the frame");
   if (n == 0) return TGTC_OK;
-  const size_t need = tgtc_render_frame_workspace_bytes(n, n_samples, n_fine, chunk);
+  const size_t need = tgtc_render_frame_workspace_bytes_mode(mode, n, n_samples, n_fine, chunk);
   TGTC_REQUIRE(workspace != nullptr && aligned16(workspace) && workspace_bytes >= need, TGTC_ERR_STATE,
                "workspace too small or misaligned: need %zu bytes, got %zu", need, workspace_bytes);
   uint8_t* base = static_cast<uint8_t*>(workspace);

@@ -199,6 +199,15 @@ struct MlpIO {
   float* base_remap = nullptr;
   float* pts_embed = nullptr;
   float* dirs_embed = nullptr;
+  // fused K5 (mlp_tc.cu inference instantiations, ray mode, S in {64,128}: a 128-sample tile is one fine ray / two coarse rays):
+  // when comp_rgb != nullptr the last epilogue composites the tile's rays (utils.alpha_composition, utils.py:354-386, with the
+  // arithmetic of composite.cu bit for bit) and writes per-RAY outputs; rgbsigma may then be nullptr (nothing per-sample
+  // leaves the SM except the optional weights)
+  float* comp_rgb = nullptr;      // [n_rays,3]
+  float* comp_depth = nullptr;    // [n_rays] or nullptr
+  float* comp_acc = nullptr;      // [n_rays] or nullptr
+  float* comp_weights = nullptr;  // [n_rays,S] or nullptr
+  int comp_white_bkgd = 0;
 };
 
 // Activation stash of the training forward (mlp_tc.cu writes, mlp_bwd.cu reads).  Every array is a sequence of

@@ -59,16 +59,17 @@ __global__ void __launch_bounds__(32 * kWarps) composite_kernel(
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const float o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl *= o;
+        if (lane >= d) incl = __fmul_rn(incl, o);
       }
       float excl = __shfl_up_sync(0xffffffffu, incl, 1);
       if (lane == 0) excl = 1.0f;
-      const float T = carry * excl;
-      const float w = alpha * T;
-      carry = carry * __shfl_sync(0xffffffffu, incl, 31);
+      const float T = __fmul_rn(carry, excl);
+      const float w = __fmul_rn(alpha, T);
+      carry = __fmul_rn(carry, __shfl_sync(0xffffffffu, incl, 31));
       if (valid) {
         if (weights_out != nullptr) weights_out[ray * S + i] = w;
-        ar += w * cr; ag += w * cg; ab += w * cb; ad += w * t; aa += w;
+        // explicit FMAs: the fused compositing in mlp_tc.cu's last epilogue repeats this exact sequence (bit-identical results)
+        ar = __fmaf_rn(w, cr, ar); ag = __fmaf_rn(w, cg, ag); ab = __fmaf_rn(w, cb, ab); ad = __fmaf_rn(w, t, ad); aa = __fadd_rn(aa, w);
       }
     }
 #pragma unroll
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(32 * kWarps) composite_kernel(
       aa += __shfl_xor_sync(0xffffffffu, aa, d);
     }
     if (lane == 0) {
-      if (white_bkgd) { const float bg = 1.0f - aa; ar += bg; ag += bg; ab += bg; }
+      if (white_bkgd) { const float bg = __fsub_rn(1.0f, aa); ar = __fadd_rn(ar, bg); ag = __fadd_rn(ag, bg); ab = __fadd_rn(ab, bg); }
       if (rgb_out != nullptr) { rgb_out[ray * 3 + 0] = ar; rgb_out[ray * 3 + 1] = ag; rgb_out[ray * 3 + 2] = ab; }
       if (depth_out != nullptr) depth_out[ray] = ad;
       if (acc_out != nullptr) acc_out[ray] = aa;
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(32 * kWarps) composite_backward_kernel(
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const float o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl *= o;
+        if (lane >= d) incl = __fmul_rn(incl, o);
       }
       float excl = __shfl_up_sync(0xffffffffu, incl, 1);
       if (lane == 0) excl = 1.0f;

@@ -55,7 +55,8 @@ constexpr int kOffWRgb1 = kOffWSig + 256 * 4;                // 3 x 128 fp32
 constexpr int kOffDirBias = kOffWRgb1 + 384 * 4;             // [2 slots][2 bufs][2 rays][128] fp32
 constexpr int kOffSigPart = kOffDirBias + 2 * 2 * kMaxRaysPerTile * 128 * 4;  // [2 slots][128] fp32
 constexpr int kOffRgbPart = kOffSigPart + 2 * 128 * 4;       // [128][4] fp32
-constexpr int kOffBars = kOffRgbPart + 128 * 4 * 4;          // mbarriers
+constexpr int kOffCompTot = kOffRgbPart + 128 * 4 * 4;       // [4] fp32: per-warp transmittance products of the fused compositing
+constexpr int kOffBars = kOffCompTot + 4 * 4 + 16;           // mbarriers
 constexpr int kNumBars = 2 * kStages + 10;
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
@@ -598,13 +599,76 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
               const float4 o = *reinterpret_cast<const float4*>(rgbpart_s + row * 4);
               const float z0 = p0 + o.x + b_rgb[0], z1 = p1 + o.y + b_rgb[1], z2 = p2 + o.z + b_rgb[2];
               const float sg = sig_keep[t] + sigpart_s[t * 128 + row] + b_sigma;
+              const float r0 = 1.0f / (1.0f + expf(-z0)), r1 = 1.0f / (1.0f + expf(-z1)), r2 = 1.0f / (1.0f + expf(-z2));
               if (m < P.M) {
-                const float r0 = 1.0f / (1.0f + expf(-z0)), r1 = 1.0f / (1.0f + expf(-z1)), r2 = 1.0f / (1.0f + expf(-z2));
                 if (P.io.rgbsigma != nullptr) {
                   reinterpret_cast<float4*>(P.io.rgbsigma)[m] = make_float4(r0, r1, r2, sg);
-                } else {
+                } else if (P.io.rgb != nullptr) {
                   P.io.rgb[m * 3 + 0] = r0; P.io.rgb[m * 3 + 1] = r1; P.io.rgb[m * 3 + 2] = r2;
                   P.io.sigma[m] = sg;
+                }
+              }
+              if (!kTrain && P.io.comp_rgb != nullptr) {
+                // ---- fused K5: utils.alpha_composition (utils.py:354-386) for the tile's rays (S in {64,128}: rows [0,S) are one
+                // ray, a warp owns 32 consecutive samples).  Every operation and its order is composite.cu's, so the results are
+                // bit-identical to the stand-alone kernel: per-warp inclusive product scan of (1-alpha+1e-10), sequential carry
+                // over the ray's 32-sample chunks, per-lane FMA sums over the chunks, xor-butterfly.
+                const bool valid = m < P.M;
+                const int k = row & (S - 1);
+                const int c = k >> 5;                       // 32-sample chunk of this warp inside its ray
+                float tcur = 0.f, tnext = 0.f;
+                if (P.io.ts != nullptr) {
+                  if (valid) { tcur = P.io.ts[m]; if (k + 1 < S) tnext = P.io.ts[m + 1]; }
+                } else {
+                  tcur = coarse_t(k, S, P.io.t_scale, P.io.t_near);
+                  if (k + 1 < S) tnext = coarse_t(k + 1, S, P.io.t_scale, P.io.t_near);
+                }
+                const float delta = (k + 1 < S) ? __fsub_rn(tnext, tcur) : 1e10f;
+                const float act = fmaxf(sg, 0.0f);
+                const float alpha = valid ? __fsub_rn(1.0f, expf(-__fmul_rn(act, delta))) : 0.0f;
+                const float fac = valid ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;
+                float incl = fac;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                  const float up = __shfl_up_sync(0xffffffffu, incl, d);
+                  if (lane >= d) incl = __fmul_rn(incl, up);
+                }
+                float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0) excl = 1.0f;
+                float* tot_s = reinterpret_cast<float*>(smem + kOffCompTot);
+                if (lane == 31) tot_s[q] = incl;
+                named_bar_sync(4, kNumEpiThreads / 2);      // the four hc == 0 warps
+                float carry = 1.0f;
+                for (int j = 0; j < c; ++j) carry = __fmul_rn(carry, tot_s[q - c + j]);
+                const float T = __fmul_rn(carry, excl);
+                const float w = __fmul_rn(alpha, T);
+                if (valid && P.io.comp_weights != nullptr) P.io.comp_weights[m] = w;
+                *reinterpret_cast<float4*>(rgbpart_s + row * 4) = make_float4(r0, r1, r2, w);   // own row: read above, free now
+                sigpart_s[t * 128 + row] = tcur;                                                 // likewise
+                named_bar_sync(4, kNumEpiThreads / 2);
+                if (c == 0) {
+                  float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aa = 0.f;
+                  for (int j = 0; j < (S >> 5); ++j) {
+                    const float4 v = *reinterpret_cast<const float4*>(rgbpart_s + (row + 32 * j) * 4);
+                    const float tt = sigpart_s[t * 128 + row + 32 * j];
+                    ar = __fmaf_rn(v.w, v.x, ar); ag = __fmaf_rn(v.w, v.y, ag); ab = __fmaf_rn(v.w, v.z, ab);
+                    ad = __fmaf_rn(v.w, tt, ad); aa = __fadd_rn(aa, v.w);
+                  }
+#pragma unroll
+                  for (int d = 16; d > 0; d >>= 1) {
+                    ar += __shfl_xor_sync(0xffffffffu, ar, d);
+                    ag += __shfl_xor_sync(0xffffffffu, ag, d);
+                    ab += __shfl_xor_sync(0xffffffffu, ab, d);
+                    ad += __shfl_xor_sync(0xffffffffu, ad, d);
+                    aa += __shfl_xor_sync(0xffffffffu, aa, d);
+                  }
+                  const int64_t ray = m / S;                 // lane 0: the ray's first sample
+                  if (lane == 0 && ray < P.io.n_rays) {
+                    if (P.io.comp_white_bkgd) { const float bg = __fsub_rn(1.0f, aa); ar = __fadd_rn(ar, bg); ag = __fadd_rn(ag, bg); ab = __fadd_rn(ab, bg); }
+                    P.io.comp_rgb[ray * 3 + 0] = ar; P.io.comp_rgb[ray * 3 + 1] = ag; P.io.comp_rgb[ray * 3 + 2] = ab;
+                    if (P.io.comp_depth != nullptr) P.io.comp_depth[ray] = ad;
+                    if (P.io.comp_acc != nullptr) P.io.comp_acc[ray] = aa;
+                  }
                 }
               }
             }
@@ -636,6 +700,7 @@ bool mlp_tc_supports(const MlpIO& io) {
   const int S = io.S;
   if (!(S == 64 || S == 128 || (S > 128 && S % 128 == 0))) return false;
   if (io.rgbsigma != nullptr && !aligned16(io.rgbsigma)) return false;
+  if (io.comp_rgb != nullptr && !(io.rays_o != nullptr && (S == 64 || S == 128))) return false;   // fused compositing: whole rays per tile
   return true;
 }
 

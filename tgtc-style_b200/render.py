@@ -334,7 +334,7 @@ class NerfRenderer:
             if not want_weights:
                 out.pop("weights")
         ck = int(chunk) if chunk else 0
-        wsb = self.lib.tgtc_render_workspace_bytes(n, n_samples, n_fine, ck)
+        wsb = self.lib.tgtc_render_workspace_bytes_mode(mode, n, n_samples, n_fine, ck)
         ws = self._workspace(wsb)
         s = self._out_struct(out)
         _lib.check(self.lib.tgtc_render(self._h, mode, _ptr(ro), _ptr(rd), n, float(near), float(far), n_samples, n_fine, ck,
@@ -372,7 +372,7 @@ class NerfRenderer:
             if not want_weights:
                 out.pop("weights")
         ck = int(chunk) if chunk else 0
-        wsb = self.lib.tgtc_render_frame_workspace_bytes(n, n_samples, n_fine, ck)
+        wsb = self.lib.tgtc_render_frame_workspace_bytes_mode(mode, n, n_samples, n_fine, ck)
         ws = self._workspace(wsb)
         Ka, Kp = _dptr(np.asarray(K, np.float64).reshape(9))
         Ca, Cp = _dptr(np.asarray(c2w, np.float64)[:3, :4].reshape(12))
