@@ -256,6 +256,21 @@ int tgtc_render_style(tgtc_ctx* ctx, int mode, const float* rays_o, const float*
                       int n_samples, int n_fine, int64_t chunk, const float* latent1, const float* latent2,
                       const tgtc_render_out* out, void* workspace, size_t workspace_bytes, tgtc_stream stream);
 
+/* Stage entries of the per-ray style head on EXPLICIT features -- what the reference's injected callables compute
+ * (train_tgtcs.py:46, :53: batchify-wrapped modules; called at rendering.py:129 and :140):
+ *   tgtc_style_concat_forward = StyleMLP_before_concat.forward(x, latent)        -> concat_features   (models.py:137-147)
+ *   tgtc_style_forward        = StyleMLP_Wild_multilayers.forward(x, concated, latent) -> rgb         (models.py:165-180)
+ * x [M,63] = embedded points (the `pts` key of model_forward's dict), concated [M,512] = cat(base_remap, concat_features),
+ * latent: 32 device floats -- ONE latent row per call (the reference expands one (style, frame) latent over the batch's
+ * samples; a batch mixing latents is split by the caller).  concat_features [M,256], rgb [M,3] fp32.  The features are
+ * converted to the operand format of `mode` (BF16 / F16) tile images in `workspace` (tgtc_style_stage_workspace_bytes(M),
+ * 1024-byte aligned) and run through the same tcgen05 chain kernel as tgtc_render_style. */
+size_t tgtc_style_stage_workspace_bytes(int64_t n_samples_total);
+int tgtc_style_concat_forward(tgtc_ctx* ctx, int mode, const float* x, const float* latent, int64_t n_samples_total,
+                              float* concat_features, void* workspace, size_t workspace_bytes, tgtc_stream stream);
+int tgtc_style_forward(tgtc_ctx* ctx, int mode, const float* x, const float* concated, const float* latent, int64_t n_samples_total,
+                       float* rgb, void* workspace, size_t workspace_bytes, tgtc_stream stream);
+
 /* Per-kernel device timing of the MLP launches (the dominant kernel), for the roofline line of bench.py:
  * while enabled, every MLP launch is bracketed by cudaEvents on its stream (no host sync).
  * tgtc_profile_read synchronises those events and returns, since the last read/enable: the number of MLP

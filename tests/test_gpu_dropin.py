@@ -169,3 +169,45 @@ def test_harmony_sampling_matches_reference(patched):
     pts, ts = s.sampling_pts_uniform(rays_o=o.cuda(), rays_d=d.cuda(), N_samples=64, near=0.5, far=6.0, harmony=True)
     assert torch.equal(ts.cpu(), want_ts.contiguous()) and torch.equal(pts.cpu(), want_pts)
     r.close()
+
+
+@pytest.mark.parametrize("mode", ["f16", "bf16"])
+def test_style_stage_callables_on_the_kernels(patched, mode):
+    """concat_style_forward / style_forward (train_tgtcs.py:46, :53) built through the rebound batchify from the reference's own
+    StyleMLP_before_concat / StyleMLP_Wild_multilayers modules, called with the loop's shapes (rendering.py:125-142: embedded pts
+    from model_forward's dict, per-ray latents expanded over the samples, cat(base_remap, concat_features)), against the modules
+    themselves in fp32."""
+    utils, models, rendering = patched
+    r = T.NerfRenderer(device="cuda:0", mode=mode)
+    T.patch(r, [utils, rendering])
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1)
+    concat_style_model = models.StyleMLP_before_concat(ref_import.RefArgs).to(dev)
+    style_model = models.StyleMLP_Wild_multilayers(ref_import.RefArgs).to(dev)
+    concat_style_forward = rendering.batchify(lambda **kwargs: concat_style_model(**kwargs), Args.chunk)     # train_tgtcs.py:46
+    style_forward = rendering.batchify(lambda **kwargs: style_model(**kwargs), Args.chunk)                   # train_tgtcs.py:53
+    n, S = 70, 64                     # 35 tiles: a ragged last pair
+    g = torch.Generator().manual_seed(4)
+    pts = (torch.rand(n, S, 3, generator=g) * 2 - 1).to(dev)
+    pts_embed = O.embed(pts.cpu(), 10).float().to(dev)
+    base_remap = torch.relu(torch.randn(n, S, 256, generator=g)).to(dev)
+    lat2 = torch.randn(2, 32, generator=g).to(dev) * 0.7
+    first_style_latents = lat2[(torch.arange(n) >= 40).long()]              # two (style, frame) runs inside the batch
+    style_latents = torch.mean(first_style_latents, dim=1, keepdims=True)                                     # rendering.py:126
+    first_fwd = first_style_latents.unsqueeze(1).expand([n, S, 32])                                           # rendering.py:127
+    with torch.no_grad():
+        cf = concat_style_forward(x=pts_embed, latent=first_fwd)["concat_features"]
+        want_cf = concat_style_model(x=pts_embed, latent=first_fwd)["concat_features"]
+        concated = torch.concat((base_remap, cf), dim=-1)                                                     # rendering.py:132
+        second_fwd = torch.unsqueeze(style_latents, dim=2).expand([n, S, 32])                                 # rendering.py:139
+        rgb = style_forward(x=pts_embed, concated=concated, latent=second_fwd)["rgb"]
+        want_rgb = style_model(x=pts_embed, concated=concated, latent=second_fwd)["rgb"]
+    assert cf.shape == (n, S, 256) and rgb.shape == (n, S, 3)
+    e_cf = (cf - want_cf).abs().max().item() / want_cf.abs().max().item()
+    e_rgb = (rgb - want_rgb).abs().max().item()
+    print("style stages %s: concat_features rel max %.2e, rgb max %.2e" % (mode, e_cf, e_rgb))
+    assert e_cf <= (3e-3 if mode == "f16" else 2e-2) and e_rgb <= (1e-3 if mode == "f16" else 5e-3)
+    # with autograd enabled the reference's own modules run (same numbers as calling them directly)
+    out = concat_style_forward(x=pts_embed, latent=first_fwd)["concat_features"]
+    assert out.requires_grad and torch.allclose(out, concat_style_model(x=pts_embed, latent=first_fwd)["concat_features"])
+    r.close()

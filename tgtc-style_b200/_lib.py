@@ -107,6 +107,10 @@ PROTOTYPES = {
                                                ctypes.c_size_t, c_void_p]),
     "tgtc_nerf_backward": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p, c_i64, ctypes.c_int, c_void_p, c_void_p, c_void_p, ctypes.c_int,
                                           c_void_p, ctypes.c_size_t, c_void_p, ctypes.c_size_t, c_void_p]),
+    "tgtc_style_stage_workspace_bytes": (ctypes.c_size_t, [c_i64]),
+    "tgtc_style_concat_forward": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, ctypes.c_size_t, c_void_p]),
+    "tgtc_style_forward": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, ctypes.c_size_t,
+                                          c_void_p]),
     "tgtc_profile_enable": (ctypes.c_int, [c_void_p, ctypes.c_int]),
     "tgtc_profile_read": (ctypes.c_int, [c_void_p, ctypes.POINTER(c_i64), c_double_p, c_double_p]),
     "tgtc_profile_read_kind": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.POINTER(c_i64), c_double_p, c_double_p]),

@@ -945,6 +945,48 @@ extern "C" int tgtc_render_style(tgtc_ctx* ctx, int mode, const float* rays_o, c
 }
 
 // ---------------------------------------------------------------------------
+// stage entries of the per-ray style head on explicit features: what the reference's injected callables concat_style_forward /
+// style_forward compute (rendering.py:129-140), for one (style, frame) latent per call
+extern "C" size_t tgtc_style_stage_workspace_bytes(int64_t n_samples_total) {
+  return n_samples_total > 0 ? style_stage_workspace_bytes(n_samples_total) : 0;
+}
+
+static int style_stage_prologue(tgtc_ctx* ctx, int mode, int64_t M, const float* x, const float* latent, void* ws, size_t ws_bytes) {
+  TGTC_REQUIRE(ctx->style.set, TGTC_ERR_STATE, "style weights not set (tgtc_set_style_weights)");
+  TGTC_REQUIRE(mode == TGTC_MLP_BF16 || mode == TGTC_MLP_F16, TGTC_ERR_ARG, "style stages run on the tensor-core path: mode must be BF16 or F16 (got %d)", mode);
+  TGTC_REQUIRE(M >= 0, TGTC_ERR_ARG, "bad sample count %lld", (long long)M);
+  if (M == 0) return TGTC_OK;
+  CHECK_PTR(x, "x"); CHECK_PTR(latent, "latent");
+  TGTC_REQUIRE(ws != nullptr && (reinterpret_cast<uintptr_t>(ws) & 1023) == 0 && ws_bytes >= style_stage_workspace_bytes(M), TGTC_ERR_STATE,
+               "style stage workspace too small or not 1024-byte aligned: need %zu bytes, got %zu", style_stage_workspace_bytes(M), ws_bytes);
+  return TGTC_OK;
+}
+
+extern "C" int tgtc_style_concat_forward(tgtc_ctx* ctx, int mode, const float* x, const float* latent, int64_t n_samples_total,
+                                         float* concat_features, void* workspace, size_t workspace_bytes, tgtc_stream stream) {
+  CHECK_CTX(ctx);
+  int rc = style_stage_prologue(ctx, mode, n_samples_total, x, latent, workspace, workspace_bytes);
+  if (rc || n_samples_total == 0) return rc;
+  CHECK_PTR(concat_features, "concat_features");
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = style_set_latents(ctx, latent, latent, st);     // module 1's effective biases (module 2's are not used by this call)
+  if (rc) return rc;
+  return launch_style_concat_explicit(ctx, x, n_samples_total, concat_features, static_cast<uint8_t*>(workspace), mode == TGTC_MLP_F16, st);
+}
+
+extern "C" int tgtc_style_forward(tgtc_ctx* ctx, int mode, const float* x, const float* concated, const float* latent,
+                                  int64_t n_samples_total, float* rgb, void* workspace, size_t workspace_bytes, tgtc_stream stream) {
+  CHECK_CTX(ctx);
+  int rc = style_stage_prologue(ctx, mode, n_samples_total, x, latent, workspace, workspace_bytes);
+  if (rc || n_samples_total == 0) return rc;
+  CHECK_PTR(concated, "concated"); CHECK_PTR(rgb, "rgb");
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = style_set_latents(ctx, latent, latent, st);     // module 2's effective biases from ITS latent argument
+  if (rc) return rc;
+  return launch_style_wild_explicit(ctx, x, concated, n_samples_total, rgb, static_cast<uint8_t*>(workspace), mode == TGTC_MLP_F16, st);
+}
+
+// ---------------------------------------------------------------------------
 // Style_train (train_tgtcs.py:311-495): forward with per-ray latents + stash, then the backward into the
 // two style modules and the latents.  The loss lives between the two calls (it needs both rgb maps and, for the coherence
 // term, the previous batch), so the stash of both passes stays in the caller's workspace.

@@ -55,9 +55,10 @@ constexpr int kOffWRgb1 = kOffWSig + 256 * 4;                // 3 x 128 fp32
 constexpr int kOffDirBias = kOffWRgb1 + 384 * 4;             // [2 slots][2 bufs][2 rays][128] fp32
 constexpr int kOffSigPart = kOffDirBias + 2 * 2 * kMaxRaysPerTile * 128 * 4;  // [2 slots][128] fp32
 constexpr int kOffRgbPart = kOffSigPart + 2 * 128 * 4;       // [128][4] fp32
+constexpr int kCompStageOff = kActBytes - kTileM * 32;       // fused K5 staging rows: the last 4 KB of an activation buffer (K block 3, rows 96..127)
 constexpr int kOffCompTot = kOffRgbPart + 128 * 4 * 4;       // [4] fp32: per-warp transmittance products of the fused compositing
 constexpr int kOffBars = kOffCompTot + 4 * 4 + 16;           // mbarriers
-constexpr int kNumBars = 2 * kStages + 10;
+constexpr int kNumBars = 2 * kStages + 14;
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
 static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
@@ -70,8 +71,11 @@ static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 //   PeFree[t]   layer 5 of slot t retired: PE tile reusable (commit, multicast)                      count 1
 //   ActReady[t] leader only: both CTAs' epilogues stored slot t's next A operand / drained TMEM      count 16 (warps)
 //   AccFull[t]  slot t's accumulator complete (commit, multicast)                                    count 1
+//   CompReady[t] fused K5: the tile's (r,g,b,sigma) rows are staged in act[t] (local: epilogue -> producers) count 128
+//   CompDone[t]  fused K5: the producers have composited the tile, act[t] may be overwritten (local)       count 128
 constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarPeReady = 2 * kStages, kBarPeFree = kBarPeReady + 2,
-              kBarActReady = kBarPeFree + 2, kBarAccFull = kBarActReady + 2, kBarPePair = kBarAccFull + 2;
+              kBarActReady = kBarPeFree + 2, kBarAccFull = kBarActReady + 2, kBarPePair = kBarAccFull + 2,
+              kBarCompReady = kBarPePair + 2, kBarCompDone = kBarCompReady + 2;
 
 using namespace tcptx;
 
@@ -148,9 +152,11 @@ __device__ __forceinline__ void epi_block(uint32_t (&v)[32], const float* bl, co
 
 // this thread's 128 columns of one hidden layer: TMEM loads software-pipelined against the math
 // (the load of block b+1 is in flight while block b is converted and stored)
+// wait_bar != 0: an mbarrier (address, parity) to pass before this thread's LAST two blocks are stored -- the fused-compositing
+// staging rows live in the tail of the activation buffer (K block 3, rows 96..127), which only those stores overwrite.
 template <bool kSigma, bool kMask, bool kF16>
 __device__ __forceinline__ float hidden_epilogue(uint32_t tcol, const float* bl, const float* wsig, uint32_t arow, uint32_t rx,
-                                                 uint32_t* mrow) {
+                                                 uint32_t* mrow, uint32_t wait_bar = 0u, uint32_t wait_par = 0u) {
   float sig = 0.f;
   uint32_t va[32], vb[32];
   tmem_ld32(tcol, va);
@@ -162,6 +168,7 @@ __device__ __forceinline__ float hidden_epilogue(uint32_t tcol, const float* bl,
   epi_block<kSigma, kMask, kF16>(vb, bl, wsig, arow, rx, 1, sig, mrow);
   tmem_ld_wait_dep(va);
   tmem_ld32(tcol + 96, vb);
+  if (wait_bar != 0u) mbar_wait(wait_bar, wait_par);
   epi_block<kSigma, kMask, kF16>(va, bl, wsig, arow + 16384, rx, 2, sig, mrow);
   tmem_ld_wait_dep(vb);
   epi_block<kSigma, kMask, kF16>(vb, bl, wsig, arow + 16384, rx, 3, sig, mrow);
@@ -231,6 +238,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
       mbar_init(bar(kBarPeFree + t), 1);
       mbar_init(bar(kBarActReady + t), 2 * (kNumEpiThreads / 32));
       mbar_init(bar(kBarAccFull + t), 1);
+      mbar_init(bar(kBarCompReady + t), kNumEpiThreads / 2);
+      mbar_init(bar(kBarCompDone + t), kNumPeThreads);
     }
     fence_barrier_init();
   }
@@ -366,6 +375,77 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
     const MlpIO& io = P.io;
     const int S = io.S;
     const uint32_t leader_pepair = mapa_cluster(bar(kBarPePair), 0);
+    const bool comp = !kTrain && !kTrunk && io.comp_rgb != nullptr;
+    // ---- fused K5: utils.alpha_composition (utils.py:354-386) for the rays of tile (it_, t_) (S in {64,128}: rows [0,S) are one
+    // ray, a warp owns 32 consecutive samples), run by these producer warps while they would otherwise wait for the tile's PE
+    // buffer to be released.  Every operation and its order is composite.cu's, so the results are bit-identical to the
+    // stand-alone kernel: per-warp inclusive product scan of (1-alpha+1e-10), sequential carry over the ray's 32-sample
+    // chunks, per-lane FMA sums over the chunks, xor-butterfly.
+    auto composite_tile = [&](int64_t it_, int t_) {
+      const int64_t m = my_tile(it_, t_, rank) * kTileM + r;
+      const bool valid = m < P.M;
+      const int k = r & (S - 1);
+      float tcur = 0.f, tnext = 0.f;              // sample positions: fetched before the wait (L2 latency off the hand-over)
+      if (io.ts != nullptr) {
+        if (valid) { tcur = io.ts[m]; if (k + 1 < S) tnext = io.ts[m + 1]; }
+      } else {
+        tcur = coarse_t(k, S, io.t_scale, io.t_near);
+        if (k + 1 < S) tnext = coarse_t(k + 1, S, io.t_scale, io.t_near);
+      }
+      mbar_wait(bar(kBarCompReady + t_), (uint32_t)(it_ & 1));
+      uint8_t* const stg = smem + kOffAct + t_ * kActBytes + kCompStageOff;      // [128 rows][32 B]: (r,g,b,sigma) from the epilogue
+      const float4 v = *reinterpret_cast<const float4*>(stg + r * 32);
+      const int pw = r >> 5;                      // producer warp = 32-row quarter of the tile
+      const int c = k >> 5;                       // 32-sample chunk of this warp inside its ray
+      const float delta = (k + 1 < S) ? __fsub_rn(tnext, tcur) : 1e10f;
+      const float act = fmaxf(v.w, 0.0f);
+      const float alpha = valid ? __fsub_rn(1.0f, expf(-__fmul_rn(act, delta))) : 0.0f;
+      const float fac = valid ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;
+      float incl = fac;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const float up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl = __fmul_rn(incl, up);
+      }
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 1.0f;
+      float* tot_s = reinterpret_cast<float*>(smem + kOffCompTot);
+      if (lane == 31) tot_s[pw] = incl;
+      named_bar_sync(4, kNumPeThreads);
+      float carry = 1.0f;
+      for (int j = 0; j < c; ++j) carry = __fmul_rn(carry, tot_s[pw - c + j]);
+      const float T = __fmul_rn(carry, excl);
+      const float w = __fmul_rn(alpha, T);
+      if (valid && io.comp_weights != nullptr) io.comp_weights[m] = w;
+      *reinterpret_cast<float4*>(stg + r * 32) = make_float4(v.x, v.y, v.z, w);
+      *reinterpret_cast<float*>(stg + r * 32 + 16) = tcur;
+      named_bar_sync(4, kNumPeThreads);
+      if (c == 0) {
+        float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aa = 0.f;
+        for (int j = 0; j < (S >> 5); ++j) {
+          const float4 u = *reinterpret_cast<const float4*>(stg + (r + 32 * j) * 32);
+          const float tt = *reinterpret_cast<const float*>(stg + (r + 32 * j) * 32 + 16);
+          ar = __fmaf_rn(u.w, u.x, ar); ag = __fmaf_rn(u.w, u.y, ag); ab = __fmaf_rn(u.w, u.z, ab);
+          ad = __fmaf_rn(u.w, tt, ad); aa = __fadd_rn(aa, u.w);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          ar += __shfl_xor_sync(0xffffffffu, ar, d);
+          ag += __shfl_xor_sync(0xffffffffu, ag, d);
+          ab += __shfl_xor_sync(0xffffffffu, ab, d);
+          ad += __shfl_xor_sync(0xffffffffu, ad, d);
+          aa += __shfl_xor_sync(0xffffffffu, aa, d);
+        }
+        const int64_t ray = m / S;                 // lane 0: the ray's first sample
+        if (lane == 0 && ray < io.n_rays) {
+          if (io.comp_white_bkgd) { const float bg = __fsub_rn(1.0f, aa); ar = __fadd_rn(ar, bg); ag = __fadd_rn(ag, bg); ab = __fadd_rn(ab, bg); }
+          io.comp_rgb[ray * 3 + 0] = ar; io.comp_rgb[ray * 3 + 1] = ag; io.comp_rgb[ray * 3 + 2] = ab;
+          if (io.comp_depth != nullptr) io.comp_depth[ray] = ad;
+          if (io.comp_acc != nullptr) io.comp_acc[ray] = aa;
+        }
+      }
+      mbar_arrive(bar(kBarCompDone + t_));        // this thread's reads of the staging rows are done
+    };
     for (int64_t it = 0; it < iters; ++it) {
       for (int t = 0; t < 2; ++t) {
         const int64_t tile = my_tile(it, t, rank);
@@ -437,6 +517,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
         if (lane == 0) mbar_arrive_cluster(leader_pepair + 8u * t);   // pair: the leader's MMA warp
         if (r == 0) TC_TRACE(3, it, 0, t, 1);
       }
+      // fused K5: this iteration's PE tiles are out (they were released at the previous tiles' layer 5); the previous tiles' last
+      // epilogues run about now -- composite them while waiting for the next PE release
+      if (comp && it > 0) {
+        composite_tile(it - 1, 0);
+        composite_tile(it - 1, 1);
+      }
+    }
+    if (comp && iters > 0) {
+      composite_tile(iters - 1, 0);
+      composite_tile(iters - 1, 1);
     }
   } else {
     // =====================================================================
@@ -510,6 +600,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
             } else if (l == 7) {
               const float sig = hidden_epilogue<true, kTrain, kF16>(tcol, bl, wsig_s + hc * 128, arow, rx, mrow);
               if (hc == 1) sigpart_s[t * 128 + row] = sig; else sig_keep[t] = sig;
+            } else if (!kTrain && !kTrunk && l == 0 && it > 0 && hc == 1 && q == 3 && P.io.comp_rgb != nullptr) {
+              // fused K5: the previous tile's staged (r,g,b,sigma) rows occupy the tail of act[t] (K block 3, rows 96..127), which
+              // this warp's last two blocks overwrite: the producers must have composited them (long done by then)
+              hidden_epilogue<false, kTrain, kF16>(tcol, bl, nullptr, arow, rx, mrow, bar(kBarCompDone + t), (uint32_t)((it - 1) & 1));
             } else {
               hidden_epilogue<false, kTrain, kF16>(tcol, bl, nullptr, arow, rx, mrow);
             }
@@ -609,67 +703,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
                 }
               }
               if (!kTrain && P.io.comp_rgb != nullptr) {
-                // ---- fused K5: utils.alpha_composition (utils.py:354-386) for the tile's rays (S in {64,128}: rows [0,S) are one
-                // ray, a warp owns 32 consecutive samples).  Every operation and its order is composite.cu's, so the results are
-                // bit-identical to the stand-alone kernel: per-warp inclusive product scan of (1-alpha+1e-10), sequential carry
-                // over the ray's 32-sample chunks, per-lane FMA sums over the chunks, xor-butterfly.
-                const bool valid = m < P.M;
-                const int k = row & (S - 1);
-                const int c = k >> 5;                       // 32-sample chunk of this warp inside its ray
-                float tcur = 0.f, tnext = 0.f;
-                if (P.io.ts != nullptr) {
-                  if (valid) { tcur = P.io.ts[m]; if (k + 1 < S) tnext = P.io.ts[m + 1]; }
-                } else {
-                  tcur = coarse_t(k, S, P.io.t_scale, P.io.t_near);
-                  if (k + 1 < S) tnext = coarse_t(k + 1, S, P.io.t_scale, P.io.t_near);
-                }
-                const float delta = (k + 1 < S) ? __fsub_rn(tnext, tcur) : 1e10f;
-                const float act = fmaxf(sg, 0.0f);
-                const float alpha = valid ? __fsub_rn(1.0f, expf(-__fmul_rn(act, delta))) : 0.0f;
-                const float fac = valid ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.0f;
-                float incl = fac;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                  const float up = __shfl_up_sync(0xffffffffu, incl, d);
-                  if (lane >= d) incl = __fmul_rn(incl, up);
-                }
-                float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-                if (lane == 0) excl = 1.0f;
-                float* tot_s = reinterpret_cast<float*>(smem + kOffCompTot);
-                if (lane == 31) tot_s[q] = incl;
-                named_bar_sync(4, kNumEpiThreads / 2);      // the four hc == 0 warps
-                float carry = 1.0f;
-                for (int j = 0; j < c; ++j) carry = __fmul_rn(carry, tot_s[q - c + j]);
-                const float T = __fmul_rn(carry, excl);
-                const float w = __fmul_rn(alpha, T);
-                if (valid && P.io.comp_weights != nullptr) P.io.comp_weights[m] = w;
-                *reinterpret_cast<float4*>(rgbpart_s + row * 4) = make_float4(r0, r1, r2, w);   // own row: read above, free now
-                sigpart_s[t * 128 + row] = tcur;                                                 // likewise
-                named_bar_sync(4, kNumEpiThreads / 2);
-                if (c == 0) {
-                  float ar = 0.f, ag = 0.f, ab = 0.f, ad = 0.f, aa = 0.f;
-                  for (int j = 0; j < (S >> 5); ++j) {
-                    const float4 v = *reinterpret_cast<const float4*>(rgbpart_s + (row + 32 * j) * 4);
-                    const float tt = sigpart_s[t * 128 + row + 32 * j];
-                    ar = __fmaf_rn(v.w, v.x, ar); ag = __fmaf_rn(v.w, v.y, ag); ab = __fmaf_rn(v.w, v.z, ab);
-                    ad = __fmaf_rn(v.w, tt, ad); aa = __fadd_rn(aa, v.w);
-                  }
-#pragma unroll
-                  for (int d = 16; d > 0; d >>= 1) {
-                    ar += __shfl_xor_sync(0xffffffffu, ar, d);
-                    ag += __shfl_xor_sync(0xffffffffu, ag, d);
-                    ab += __shfl_xor_sync(0xffffffffu, ab, d);
-                    ad += __shfl_xor_sync(0xffffffffu, ad, d);
-                    aa += __shfl_xor_sync(0xffffffffu, aa, d);
-                  }
-                  const int64_t ray = m / S;                 // lane 0: the ray's first sample
-                  if (lane == 0 && ray < P.io.n_rays) {
-                    if (P.io.comp_white_bkgd) { const float bg = __fsub_rn(1.0f, aa); ar = __fadd_rn(ar, bg); ag = __fadd_rn(ag, bg); ab = __fadd_rn(ab, bg); }
-                    P.io.comp_rgb[ray * 3 + 0] = ar; P.io.comp_rgb[ray * 3 + 1] = ag; P.io.comp_rgb[ray * 3 + 2] = ab;
-                    if (P.io.comp_depth != nullptr) P.io.comp_depth[ray] = ad;
-                    if (P.io.comp_acc != nullptr) P.io.comp_acc[ray] = aa;
-                  }
-                }
+                // fused K5: the row's (r,g,b,sigma) is staged in the slot's activation buffer (free between the rgb0 MMA and the
+                // next tile's first epilogue) for the input-producer warps, which composite the tile off this critical path
+                *reinterpret_cast<float4*>(smem + kOffAct + t * kActBytes + kCompStageOff + row * 32) = make_float4(r0, r1, r2, sg);
+                mbar_arrive(bar(kBarCompReady + t));
               }
             }
             named_bar_sync(2, kNumEpiThreads);  // partial buffers free for the next tile

@@ -51,6 +51,7 @@ struct ChainParams {
   int S;
   int64_t M;
   int64_t ntiles;
+  const uint8_t* pe_img;     // explicit-input mode (stage shims): [ntiles][16 KB] PE tile images instead of rays (rays_o == nullptr)
   const uint8_t* img0;       // [ntiles][64 KB]
   const uint8_t* img1;
   uint8_t* img_out;          // [ntiles][64 KB]
@@ -271,13 +272,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
         if (it > 0) mbar_wait_relaxed(bar(kBarPeFree + t), (uint32_t)((it - 1) & 1), 128);
         int64_t m = tile * kTileM + r;
         if (m >= P.M) m = P.M - 1;
+        const uint32_t prow = sbase + kOffPe + t * kPeBytes + (r >> 3) * 1024 + (r & 7) * 128;
+        if (P.pe_img != nullptr) {
+          // explicit-input mode: the caller's embedded points, already converted to tile images -- copy this row's 128 bytes
+          const uint4* src = reinterpret_cast<const uint4*>(P.pe_img + (size_t)(tile < P.ntiles ? tile : P.ntiles - 1) * 16384 + (r >> 3) * 1024 + (r & 7) * 128);
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint4 q = __ldg(src + ch);
+            st_shared_v4(prow + (ch << 4), q.x, q.y, q.z, q.w);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(leader_peready + 8u * t);
+          continue;
+        }
         const int64_t ray = m / S;
         const int k = (int)(m - ray * S);
         const float tt = P.ts != nullptr ? P.ts[m] : coarse_t(k, S, P.t_scale, P.t_near);
         float x[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(P.rays_o[ray * 3 + c], __fmul_rn(tt, P.rays_d[ray * 3 + c]));
-        const uint32_t prow = sbase + kOffPe + t * kPeBytes + (r >> 3) * 1024 + (r & 7) * 128;
         float e[64];
         e[0] = x[0]; e[1] = x[1]; e[2] = x[2];
 #pragma unroll
@@ -821,6 +835,134 @@ int launch_style_wild(tgtc_ctx* ctx, const MlpIO& io, const uint8_t* remap_img, 
   P.img1 = cf_img;
   P.rgbsigma = io.rgbsigma;
   return launch_chain(ctx, P, st, false, f16);
+}
+
+// ---------------------------------------------------------------------------
+// explicit-input stage entries (the reference's concat_style_forward / style_forward callables, rendering.py:129-140): features
+// arrive as fp32 rows; two small kernels convert rows <-> the 128B-swizzled tile images the chain kernel stages
+template <typename T>
+__global__ void rows_to_images_kernel(const float* __restrict__ x, int64_t M, int C, int ld, int col0, int nblk, T* __restrict__ img) {
+  // img: [ntiles][nblk][128 rows x 64] elements; element (row, k) of block b at byte (row>>3)*1024 + (row&7)*128 + (((k>>3)^(row&7))<<4) + (k&7)*2
+  const int64_t ntiles = (M + 127) / 128;
+  const int64_t total = ntiles * nblk * 128 * 8;          // one thread per 16-byte chunk
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(idx & 7);
+    const int row = (int)((idx >> 3) & 127);
+    const int b = (int)((idx >> 10) % nblk);
+    const int64_t tile = idx / ((int64_t)nblk * 1024);
+    const int64_t m = tile * 128 + row;
+    T v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = b * 64 + ch * 8 + e;
+      v[e] = to_op<T>((m < M && c < C) ? x[m * ld + col0 + c] : 0.f);
+    }
+    uint8_t* dst = reinterpret_cast<uint8_t*>(img) + ((size_t)tile * nblk + b) * 16384 + (row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4);
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+template <typename T> __device__ __forceinline__ float from_op(T v);
+template <> __device__ __forceinline__ float from_op<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float from_op<__half>(__half v) { return __half2float(v); }
+template <typename T>
+__global__ void images_to_rows_kernel(const T* __restrict__ img, int64_t M, int nblk, float* __restrict__ out) {   // out [M][nblk*64]
+  const int64_t ntiles = (M + 127) / 128;
+  const int64_t total = ntiles * nblk * 128 * 8;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(idx & 7);
+    const int row = (int)((idx >> 3) & 127);
+    const int b = (int)((idx >> 10) % nblk);
+    const int64_t tile = idx / ((int64_t)nblk * 1024);
+    const int64_t m = tile * 128 + row;
+    if (m >= M) continue;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(img) + ((size_t)tile * nblk + b) * 16384 + (row >> 3) * 1024 + (row & 7) * 128 + ((ch ^ (row & 7)) << 4);
+    T v[8];
+    *reinterpret_cast<uint4*>(v) = *reinterpret_cast<const uint4*>(src);
+    float* o = out + m * (int64_t)(nblk * 64) + b * 64 + ch * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = from_op<T>(v[e]);
+  }
+}
+
+static int rows_to_images(tgtc_ctx* ctx, const float* x, int64_t M, int C, int ld, int col0, int nblk, uint8_t* img, bool f16, cudaStream_t st) {
+  const int64_t total = ((M + 127) / 128) * nblk * 1024;
+  const int64_t grid = (total + 255) / 256;
+  const unsigned g = (unsigned)(grid < (int64_t)ctx->num_sms * 16 ? grid : (int64_t)ctx->num_sms * 16);
+  if (f16) rows_to_images_kernel<__half><<<g, 256, 0, st>>>(x, M, C, ld, col0, nblk, reinterpret_cast<__half*>(img));
+  else rows_to_images_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(x, M, C, ld, col0, nblk, reinterpret_cast<__nv_bfloat16*>(img));
+  TGTC_LAUNCH_CHECK(ctx);
+  return TGTC_OK;
+}
+
+// workspace: pe images [ntiles][16 KB] | img0 [ntiles][64 KB] | img1 [ntiles][64 KB] | rgbsigma [M][4] fp32
+size_t style_stage_workspace_bytes(int64_t M) {
+  const size_t tiles = (size_t)((M + 127) / 128);
+  return tiles * (16384 + 2 * 65536) + (size_t)M * 16 + 1024;
+}
+
+// StyleMLP_before_concat.forward(x = embedded pts [M,63], latent) -> concat_features [M,256]   (models.py:137-147)
+int launch_style_concat_explicit(tgtc_ctx* ctx, const float* x, int64_t M, float* cf_out, uint8_t* ws, bool f16, cudaStream_t st) {
+  if (M == 0) return TGTC_OK;
+  const size_t tiles = (size_t)((M + 127) / 128);
+  uint8_t* pe = ws;
+  uint8_t* cf = ws + tiles * 16384;
+  int rc = rows_to_images(ctx, x, M, 63, 63, 0, 1, pe, f16, st);
+  if (rc) return rc;
+  ChainParams P = {};
+  P.S = 128; P.M = M; P.ntiles = (int64_t)tiles; P.img0_stride = P.img1_stride = 65536;
+  P.pe_img = pe;
+  P.nlayers = 5;
+  P.layer[0] = {{SEG_PE, 0, 0}, 1, OUT_ACT, 0};
+  for (int l = 1; l <= 3; ++l) P.layer[l] = {{SEG_ACT, 0, 0}, 1, OUT_ACT, 0};
+  P.layer[4] = {{SEG_PE, SEG_ACT, 0}, 2, OUT_ACT_IMG, 1};
+  P.blob = f16 ? ctx->style.blob_c_h : ctx->style.blob_c;
+  P.bias = ctx->style.bias_c;
+  P.img_out = cf;
+  rc = launch_chain(ctx, P, st, false, f16);
+  if (rc) return rc;
+  const int64_t total = (int64_t)tiles * 4 * 1024;
+  const unsigned g = (unsigned)((total + 255) / 256 < (int64_t)ctx->num_sms * 16 ? (total + 255) / 256 : (int64_t)ctx->num_sms * 16);
+  if (f16) images_to_rows_kernel<__half><<<g, 256, 0, st>>>(reinterpret_cast<const __half*>(cf), M, 4, cf_out);
+  else images_to_rows_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(cf), M, 4, cf_out);
+  TGTC_LAUNCH_CHECK(ctx);
+  return TGTC_OK;
+}
+
+// StyleMLP_Wild_multilayers.forward(x = embedded pts [M,63], concated = [base_remap | concat_features] [M,512], latent) -> rgb   (models.py:165-180)
+int launch_style_wild_explicit(tgtc_ctx* ctx, const float* x, const float* concated, int64_t M, float* rgb_out, uint8_t* ws, bool f16,
+                               cudaStream_t st) {
+  if (M == 0) return TGTC_OK;
+  const size_t tiles = (size_t)((M + 127) / 128);
+  uint8_t* pe = ws;
+  uint8_t* i0 = ws + tiles * 16384;
+  uint8_t* i1 = i0 + tiles * 65536;
+  float* rs = reinterpret_cast<float*>(i1 + tiles * 65536);
+  int rc = rows_to_images(ctx, x, M, 63, 63, 0, 1, pe, f16, st);
+  if (rc) return rc;
+  rc = rows_to_images(ctx, concated, M, 256, 512, 0, 4, i0, f16, st);
+  if (rc) return rc;
+  rc = rows_to_images(ctx, concated, M, 256, 512, 256, 4, i1, f16, st);
+  if (rc) return rc;
+  ChainParams P = {};
+  P.S = 128; P.M = M; P.ntiles = (int64_t)tiles; P.img0_stride = P.img1_stride = 65536;
+  P.pe_img = pe;
+  P.nlayers = 7;
+  P.layer[0] = {{SEG_PE, SEG_IMG0, SEG_IMG1}, 3, OUT_ACT, 0};
+  for (int l = 1; l <= 3; ++l) P.layer[l] = {{SEG_ACT, 0, 0}, 1, OUT_ACT, 0};
+  P.layer[4] = {{SEG_PE, SEG_ACT, 0}, 2, OUT_ACT, 1};
+  P.layer[5] = {{SEG_ACT, 0, 0}, 1, OUT_ACT, 0};
+  P.layer[6] = {{SEG_ACT, 0, 0}, 1, OUT_HEAD, 0};
+  P.blob = f16 ? ctx->style.blob_w_h : ctx->style.blob_w;
+  P.bias = ctx->style.bias_w;
+  P.head_w = ctx->style.head_w;
+  P.head_b = ctx->style.head_b;
+  P.img0 = i0;
+  P.img1 = i1;
+  P.rgbsigma = rs;
+  rc = launch_chain(ctx, P, st, false, f16);
+  if (rc) return rc;
+  TGTC_CUDA(cudaMemcpy2DAsync(rgb_out, 12, rs, 16, 12, (size_t)M, cudaMemcpyDeviceToDevice, st));
+  return TGTC_OK;
 }
 
 // ---------------------------------------------------------------------------

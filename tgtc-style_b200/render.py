@@ -461,6 +461,36 @@ class NerfRenderer:
         _lib.check(self.lib.tgtc_train_set_coarse_event(self._h, handle))
         self._coarse_event = event
 
+    # stage entries of the style head on explicit features (the injected concat_style_forward / style_forward callables)
+    def _style_stage_ws(self, M):
+        wsb = int(self.lib.tgtc_style_stage_workspace_bytes(int(M)))
+        ws = self._workspace(wsb + 1024)
+        return ctypes.c_void_p(ws.data_ptr() + ((-ws.data_ptr()) % 1024)), wsb
+
+    def style_concat_forward(self, x, latent, mode=None):
+        """StyleMLP_before_concat.forward(x=[...,63] embedded pts, latent=[32]) -> concat_features [...,256] (models.py:137-147)."""
+        mode = self.mode if mode is None else _MODES[mode]
+        mode = _lib.MLP_F16 if mode == _lib.MLP_FP32 else mode
+        xs = self._dev(x)
+        M = xs.numel() // 63
+        out = torch.empty(tuple(xs.shape[:-1]) + (256,), dtype=torch.float32, device=self.device)
+        lat = self._dev(latent).reshape(32).contiguous()
+        ws, wsb = self._style_stage_ws(M)
+        _lib.check(self.lib.tgtc_style_concat_forward(self._h, mode, _ptr(xs), _ptr(lat), M, _ptr(out), ws, wsb, self._stream))
+        return out
+
+    def style_forward(self, x, concated, latent, mode=None):
+        """StyleMLP_Wild_multilayers.forward(x=[...,63], concated=[...,512], latent=[32]) -> rgb [...,3] (models.py:165-180)."""
+        mode = self.mode if mode is None else _MODES[mode]
+        mode = _lib.MLP_F16 if mode == _lib.MLP_FP32 else mode
+        xs, cc = self._dev(x), self._dev(concated)
+        M = xs.numel() // 63
+        out = torch.empty(tuple(xs.shape[:-1]) + (3,), dtype=torch.float32, device=self.device)
+        lat = self._dev(latent).reshape(32).contiguous()
+        ws, wsb = self._style_stage_ws(M)
+        _lib.check(self.lib.tgtc_style_forward(self._h, mode, _ptr(xs), _ptr(cc), _ptr(lat), M, _ptr(out), ws, wsb, self._stream))
+        return out
+
     # ------------------------------------------------------------------ training step (a11)
     def train_step(self, rays_o, rays_d, rgb_gt, n_total=None, near=0., far=1., n_samples=64, n_fine=64, grads=None,
                    accumulate=False, rand=None, noise_coarse=None, noise_fine=None, seed=None, perturb=False, sigma_noise_std=0.):

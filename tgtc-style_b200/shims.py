@@ -5,6 +5,7 @@ The reference injects its hot path into the render / training loops as callables
   samp_func_fine   = utils.sampling_pts_fine_torch                       (train_tgtcs.py:16)
   model_forward    = utils.batchify(lambda **kw: model(**kw), chunk)     (train_tgtcs.py:30, :37)
   concat_style_forward / style_forward = utils.batchify(...) of the two style modules   (train_tgtcs.py:46, :53)
+                     -> explicit-feature stage entries of the tcgen05 style chain (tgtc_style_concat_forward / tgtc_style_forward)
   alpha_composition (module global via `from utils import *`, rendering.py:1)
 `patch(renderer, modules)` rebinds sampling_pts_uniform, sampling_pts_fine_torch, alpha_composition AND batchify in the
 reference's module globals (star-imports copy names, so each module's copy is patched).  train() then builds its wrappers
@@ -141,6 +142,8 @@ class Shims:
     def __init__(self, renderer):
         self.r = renderer
         self.nets = {}          # id(nn.Module) -> (module, NET_COARSE / NET_FINE)
+        self.style = {}         # "concat" / "wild" -> the reference's style modules, as batchify saw them
+        self._style_versions = None
 
     # ---- net registration / weight tracking
     def _net_id(self, module, net=None):
@@ -220,13 +223,63 @@ class Shims:
             return r.nerf_forward(net, pts, dirs, want_features=True)
         return model_forward
 
+    # ---- the per-ray style head (concat_style_forward / style_forward, train_tgtcs.py:46, :53; called at rendering.py:129, :140)
+    def _sync_style(self):
+        mods = (self.style["concat"], self.style["wild"])
+        ver = tuple(p._version for m in mods for p in m.parameters())
+        if ver != self._style_versions or getattr(self.r, "_style_shim_mods", None) is not mods:
+            self.r.set_style_weights(*mods)
+            self.r._style_shim_mods = mods
+            self._style_versions = ver
+
+    @staticmethod
+    def _latent_runs(latent):
+        """the reference expands per-ray latents over the samples (rendering.py:127, :139): [N,S,32] with stride 0 along S.
+        -> (per-ray rows [N,32], [(begin, end)] runs of consecutive rays with equal latents)"""
+        rows = latent[:, 0, :] if latent.dim() == 3 else latent
+        n = rows.shape[0]
+        if n <= 1:
+            return rows, [(0, n)]
+        change = (rows[1:] != rows[:-1]).any(dim=1).nonzero().flatten().add(1).tolist()
+        bounds = [0] + change + [n]
+        return rows, list(zip(bounds[:-1], bounds[1:]))
+
+    def style_callable(self, module, kind, fallback):
+        """kind "concat": StyleMLP_before_concat -> {'concat_features'};  kind "wild": StyleMLP_Wild_multilayers -> {'rgb'}.
+        Inference (no grad) runs on the tcgen05 chain kernel through the explicit-feature stage entries; with autograd enabled
+        the reference's own modules run (the B200 training path of the style head is StyleTrainer, train.py)."""
+        self.style[kind] = module
+
+        def forward(**kwargs):
+            needs_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in module.parameters())
+                                                      or any(torch.is_tensor(v) and v.requires_grad for v in kwargs.values()))
+            if needs_grad or "concat" not in self.style or "wild" not in self.style:
+                return fallback(**kwargs)
+            self._sync_style()
+            x, latent = kwargs["x"], kwargs["latent"]
+            rows, runs = self._latent_runs(latent)
+            outs = []
+            for b, e in runs:
+                if kind == "concat":
+                    outs.append(self.r.style_concat_forward(x[b:e].contiguous(), rows[b]))
+                else:
+                    outs.append(self.r.style_forward(x[b:e].contiguous(), kwargs["concated"][b:e].contiguous(), rows[b]))
+            out = outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+            return {"concat_features": out} if kind == "concat" else {"rgb": out}
+        return forward
+
     def batchify(self, fn, chunk=1024 * 32):
         """utils.batchify (utils.py:435-456).  The reference wraps `lambda **kwargs: model(**kwargs)`; when the captured module
         is a models.StyleNerf the chunk loop disappears into the persistent kernel.  Any other callable gets the reference's
         own chunk loop (restated)."""
         mod = _captured_module(fn)
-        if mod is not None and type(mod).__name__ == "StyleNerf" and not getattr(mod, "is_siren", False):
+        name = type(mod).__name__ if mod is not None else None
+        if name == "StyleNerf" and not getattr(mod, "is_siren", False):
             return self.nerf_callable(mod)
+        if name == "StyleMLP_before_concat" and hasattr(self.r, "style_concat_forward"):
+            return self.style_callable(mod, "concat", _chunk_loop(fn, chunk))
+        if name == "StyleMLP_Wild_multilayers" and hasattr(self.r, "style_forward"):
+            return self.style_callable(mod, "wild", _chunk_loop(fn, chunk))
         return _chunk_loop(fn, chunk)
 
 
