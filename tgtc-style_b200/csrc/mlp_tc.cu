@@ -71,8 +71,8 @@ static_assert(kSmemBytes <= 232448, "shared memory budget exceeded");
 //   PeFree[t]   layer 5 of slot t retired: PE tile reusable (commit, multicast)                      count 1
 //   ActReady[t] leader only: both CTAs' epilogues stored slot t's next A operand / drained TMEM      count 16 (warps)
 //   AccFull[t]  slot t's accumulator complete (commit, multicast)                                    count 1
-//   CompReady[t] fused K5: the tile's (r,g,b,sigma) rows are staged in act[t] (local: epilogue -> producers) count 128
-//   CompDone[t]  fused K5: the producers have composited the tile, act[t] may be overwritten (local)       count 128
+//   CompReady[t] fused K5: the tile's (r,g,b,sigma) rows are staged in act[t] (local: epilogue -> producers) count 4 (warps)
+//   CompDone[t]  fused K5: the producers have composited the tile, act[t] may be overwritten (local)       count 4 (warps)
 constexpr int kBarWFull = 0, kBarWEmpty = kStages, kBarPeReady = 2 * kStages, kBarPeFree = kBarPeReady + 2,
               kBarActReady = kBarPeFree + 2, kBarAccFull = kBarActReady + 2, kBarPePair = kBarAccFull + 2,
               kBarCompReady = kBarPePair + 2, kBarCompDone = kBarCompReady + 2;
@@ -238,8 +238,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
       mbar_init(bar(kBarPeFree + t), 1);
       mbar_init(bar(kBarActReady + t), 2 * (kNumEpiThreads / 32));
       mbar_init(bar(kBarAccFull + t), 1);
-      mbar_init(bar(kBarCompReady + t), kNumEpiThreads / 2);
-      mbar_init(bar(kBarCompDone + t), kNumPeThreads);
+      mbar_init(bar(kBarCompReady + t), kNumEpiThreads / 64);   // one arrival per hc == 0 epilogue warp
+      mbar_init(bar(kBarCompDone + t), kNumPeThreads / 32);     // one arrival per producer warp
     }
     fence_barrier_init();
   }
@@ -392,7 +392,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
         tcur = coarse_t(k, S, io.t_scale, io.t_near);
         if (k + 1 < S) tnext = coarse_t(k + 1, S, io.t_scale, io.t_near);
       }
-      mbar_wait(bar(kBarCompReady + t_), (uint32_t)(it_ & 1));
+      mbar_wait_relaxed(bar(kBarCompReady + t_), (uint32_t)(it_ & 1), 100);   // may be microseconds away: do not steal issue slots
       uint8_t* const stg = smem + kOffAct + t_ * kActBytes + kCompStageOff;      // [128 rows][32 B]: (r,g,b,sigma) from the epilogue
       const float4 v = *reinterpret_cast<const float4*>(stg + r * 32);
       const int pw = r >> 5;                      // producer warp = 32-row quarter of the tile
@@ -444,7 +444,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
           if (io.comp_acc != nullptr) io.comp_acc[ray] = aa;
         }
       }
-      mbar_arrive(bar(kBarCompDone + t_));        // this thread's reads of the staging rows are done
+      __syncwarp();                               // every lane's reads of the staging rows are done
+      if (lane == 0) mbar_arrive(bar(kBarCompDone + t_));
     };
     for (int64_t it = 0; it < iters; ++it) {
       for (int t = 0; t < 2; ++t) {
@@ -600,12 +601,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
             } else if (l == 7) {
               const float sig = hidden_epilogue<true, kTrain, kF16>(tcol, bl, wsig_s + hc * 128, arow, rx, mrow);
               if (hc == 1) sigpart_s[t * 128 + row] = sig; else sig_keep[t] = sig;
-            } else if (!kTrain && !kTrunk && l == 0 && it > 0 && hc == 1 && q == 3 && P.io.comp_rgb != nullptr) {
-              // fused K5: the previous tile's staged (r,g,b,sigma) rows occupy the tail of act[t] (K block 3, rows 96..127), which
-              // this warp's last two blocks overwrite: the producers must have composited them (long done by then)
-              hidden_epilogue<false, kTrain, kF16>(tcol, bl, nullptr, arow, rx, mrow, bar(kBarCompDone + t), (uint32_t)((it - 1) & 1));
             } else {
-              hidden_epilogue<false, kTrain, kF16>(tcol, bl, nullptr, arow, rx, mrow);
+              // fused K5: the previous tile's staged (r,g,b,sigma) rows occupy the tail of act[t] (K block 3, rows 96..127), which
+              // only the last two blocks of the (hc 1, quarter 3) warp overwrite at layer 0: the producers must have composited
+              // them by then (long done).  One call site: a second inlined copy of the epilogue costs more than the branch.
+              uint32_t wbar = 0u, wpar = 0u;
+              if constexpr (!kTrain && !kTrunk) {
+                if (l == 0 && it > 0 && hc == 1 && q == 3 && P.io.comp_rgb != nullptr) { wbar = bar(kBarCompDone + t); wpar = (uint32_t)((it - 1) & 1); }
+              }
+              hidden_epilogue<false, kTrain, kF16>(tcol, bl, nullptr, arow, rx, mrow, wbar, wpar);
             }
             fence_proxy_async();
             if constexpr (kTrain) {
@@ -706,7 +710,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
                 // fused K5: the row's (r,g,b,sigma) is staged in the slot's activation buffer (free between the rgb0 MMA and the
                 // next tile's first epilogue) for the input-producer warps, which composite the tile off this critical path
                 *reinterpret_cast<float4*>(smem + kOffAct + t * kActBytes + kCompStageOff + row * 32) = make_float4(r0, r1, r2, sg);
-                mbar_arrive(bar(kBarCompReady + t));
+                __syncwarp();                              // one arrival per warp (128 arrivals on one word would serialise)
+                if (lane == 0) mbar_arrive(bar(kBarCompReady + t));
               }
             }
             named_bar_sync(2, kNumEpiThreads);  // partial buffers free for the next tile
