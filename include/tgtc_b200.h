@@ -256,6 +256,15 @@ int tgtc_render_style(tgtc_ctx* ctx, int mode, const float* rays_o, const float*
                       int n_samples, int n_fine, int64_t chunk, const float* latent1, const float* latent2,
                       const tgtc_render_out* out, void* workspace, size_t workspace_bytes, tgtc_stream stream);
 
+/* tgtc_render_style with PER-RAY latents inside one call: latents [n_rays,32] = what latents_model_1(style_ids, frame_ids)
+ * returns for the batch (rendering.py:125), so a batch may mix (style, frame) pairs; module 2 sees every ray's mean(latent)
+ * broadcast to 32 dims (rendering.py:126, :139).  The latent columns of every layer are folded into per-ray effective biases
+ * (13 x 256 fp32 per ray, in the workspace) that the chain kernel's epilogue stages per half-tile. */
+size_t tgtc_render_style_rays_workspace_bytes(int64_t n_rays, int n_samples, int n_fine, int64_t chunk);
+int tgtc_render_style_rays(tgtc_ctx* ctx, int mode, const float* rays_o, const float* rays_d, int64_t n_rays, double near, double far,
+                           int n_samples, int n_fine, int64_t chunk, const float* latents, const tgtc_render_out* out, void* workspace,
+                           size_t workspace_bytes, tgtc_stream stream);
+
 /* Stage entries of the per-ray style head on EXPLICIT features -- what the reference's injected callables compute
  * (train_tgtcs.py:46, :53: batchify-wrapped modules; called at rendering.py:129 and :140):
  *   tgtc_style_concat_forward = StyleMLP_before_concat.forward(x, latent)        -> concat_features   (models.py:137-147)

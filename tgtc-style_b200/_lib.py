@@ -7,7 +7,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtgtc_b200.so")
+# TGTC_B200_LIB: another build of the same library (development A/B runs on one box: tools/ab_builds.py)
+LIB_PATH = os.environ.get("TGTC_B200_LIB") or os.path.join(HERE, "libtgtc_b200.so")
 
 c_float_p = ctypes.POINTER(ctypes.c_float)
 c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -107,6 +108,9 @@ PROTOTYPES = {
                                                ctypes.c_size_t, c_void_p]),
     "tgtc_nerf_backward": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p, c_i64, ctypes.c_int, c_void_p, c_void_p, c_void_p, ctypes.c_int,
                                           c_void_p, ctypes.c_size_t, c_void_p, ctypes.c_size_t, c_void_p]),
+    "tgtc_render_style_rays_workspace_bytes": (ctypes.c_size_t, [c_i64, ctypes.c_int, ctypes.c_int, c_i64]),
+    "tgtc_render_style_rays": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p, c_void_p, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                                              ctypes.c_int, c_i64, c_void_p, ctypes.POINTER(RenderOut), c_void_p, ctypes.c_size_t, c_void_p]),
     "tgtc_style_stage_workspace_bytes": (ctypes.c_size_t, [c_i64]),
     "tgtc_style_concat_forward": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, ctypes.c_size_t, c_void_p]),
     "tgtc_style_forward": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_void_p, ctypes.c_size_t,

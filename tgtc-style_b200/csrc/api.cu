@@ -841,9 +841,9 @@ extern "C" int tgtc_set_style_weights(tgtc_ctx* ctx, const float* const* params,
 }
 
 struct StyleWs {
-  size_t off_remap, off_cf, off_rs_c, off_rs_f, off_w_c, off_ts_f, off_ts_c, total;
+  size_t off_remap, off_cf, off_rs_c, off_rs_f, off_w_c, off_ts_f, off_ts_c, off_bias, total;
 };
-static StyleWs style_ws_layout(int64_t pass, int S, int F) {
+static StyleWs style_ws_layout(int64_t pass, int S, int F, bool per_ray = false) {
   StyleWs w;
   const size_t tiles = (size_t)((pass * (S + F) + 127) / 128);
   size_t o = 0;
@@ -854,6 +854,7 @@ static StyleWs style_ws_layout(int64_t pass, int S, int F) {
   w.off_w_c = o;   o = align_up(o + (size_t)pass * S * 4, 256);
   w.off_ts_f = o;  o = align_up(o + (size_t)pass * (S + F) * 4, 256);
   w.off_ts_c = o;  o = align_up(o + (size_t)S * 4, 256);
+  w.off_bias = o;  if (per_ray) o = align_up(o + (size_t)pass * 13 * 256 * 4, 256);   // per-ray effective biases [pass][13][256] fp32
   w.total = o;
   return w;
 }
@@ -864,9 +865,9 @@ extern "C" size_t tgtc_render_style_workspace_bytes(int64_t n_rays, int n_sample
   return style_ws_layout(style_pass(n_rays, chunk), n_samples, n_fine).total;
 }
 
-extern "C" int tgtc_render_style(tgtc_ctx* ctx, int mode, const float* rays_o, const float* rays_d, int64_t n_rays, double near, double far,
-                                 int n_samples, int n_fine, int64_t chunk, const float* latent1, const float* latent2,
-                                 const tgtc_render_out* out_p, void* workspace, size_t workspace_bytes, tgtc_stream stream) {
+static int render_style_impl(tgtc_ctx* ctx, int mode, const float* rays_o, const float* rays_d, int64_t n_rays, double near, double far,
+                             int n_samples, int n_fine, int64_t chunk, const float* latent1, const float* latent2, const float* lat_rays,
+                             const tgtc_render_out* out_p, void* workspace, size_t workspace_bytes, tgtc_stream stream) {
   CHECK_CTX(ctx);
   TGTC_REQUIRE(mode == TGTC_MLP_BF16 || mode == TGTC_MLP_F16, TGTC_ERR_ARG, "stylised render runs on the tensor-core path: mode must be BF16 or F16 (got %d)", mode);
   const bool f16 = mode == TGTC_MLP_F16;
@@ -877,11 +878,12 @@ extern "C" int tgtc_render_style(tgtc_ctx* ctx, int mode, const float* rays_o, c
   if (n_rays == 0) return TGTC_OK;
   const int S = n_samples, F = n_fine;
   TGTC_REQUIRE(S == 64 && S + F == 128, TGTC_ERR_UNSUPPORTED, "stylised render supports n_samples=64, n_fine=64; got %d+%d", S, F);
-  CHECK_PTR(rays_o, "rays_o"); CHECK_PTR(rays_d, "rays_d"); CHECK_PTR(latent1, "latent1"); CHECK_PTR(latent2, "latent2");
+  CHECK_PTR(rays_o, "rays_o"); CHECK_PTR(rays_d, "rays_d");
+  if (lat_rays == nullptr) { CHECK_PTR(latent1, "latent1"); CHECK_PTR(latent2, "latent2"); }
   TGTC_REQUIRE(out_p != nullptr, TGTC_ERR_ARG, "out is null");
   const tgtc_render_out& out = *out_p;
   const int64_t pass = style_pass(n_rays, chunk);
-  const StyleWs ws = style_ws_layout(pass, S, F);
+  const StyleWs ws = style_ws_layout(pass, S, F, lat_rays != nullptr);
   TGTC_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0 && workspace_bytes >= ws.total,
                TGTC_ERR_STATE, "style workspace too small or not 1024-byte aligned: need %zu bytes, got %zu", ws.total, workspace_bytes);
   DeviceGuard g(ctx->device);
@@ -893,14 +895,23 @@ extern "C" int tgtc_render_style(tgtc_ctx* ctx, int mode, const float* rays_o, c
   float* rs_f = reinterpret_cast<float*>(base + ws.off_rs_f);
   float* ts_c = reinterpret_cast<float*>(base + ws.off_ts_c);
   const int T = S + F;
-  int rc = style_set_latents(ctx, latent1, latent2, st);   // effective biases of both modules for this (style, frame)
-  if (rc) return rc;
+  int rc = TGTC_OK;
+  if (lat_rays == nullptr) {
+    rc = style_set_latents(ctx, latent1, latent2, st);   // effective biases of both modules for this (style, frame)
+    if (rc) return rc;
+  }
+  float* bias_rays = lat_rays != nullptr ? reinterpret_cast<float*>(base + ws.off_bias) : nullptr;
   rc = launch_sample_uniform(ctx, nullptr, nullptr, 1, S, near, far, nullptr, nullptr, ts_c, st);
   if (rc) return rc;
   for (int64_t r0 = 0; r0 < n_rays; r0 += pass) {
     const int64_t m = (n_rays - r0 < pass) ? (n_rays - r0) : pass;
     float* w_c = out.weights_coarse ? out.weights_coarse + r0 * S : reinterpret_cast<float*>(base + ws.off_w_c);
     float* ts_f = out.ts_fine ? out.ts_fine + r0 * T : reinterpret_cast<float*>(base + ws.off_ts_f);
+    if (bias_rays != nullptr) {
+      // per-ray latents (rendering.py:125-127): every layer's latent columns folded into per-ray effective biases
+      rc = launch_style_bias_rays(ctx, lat_rays + r0 * 32, m, bias_rays, st);
+      if (rc) return rc;
+    }
     for (int which = 0; which < 2; ++which) {
       MlpIO io;
       io.rays_o = rays_o + r0 * 3; io.rays_d = rays_d + r0 * 3;
@@ -918,13 +929,13 @@ extern "C" int tgtc_render_style(tgtc_ctx* ctx, int mode, const float* rays_o, c
       // style module 1 -> concat_features tile images (rendering.py:129-130)
       rc = prof_begin(ctx, 1, (double)m * io.S * 2.0 * 335360.0, st, &e1);
       if (rc) return rc;
-      rc = launch_style_concat(ctx, io, cf, st, f16);
+      rc = launch_style_concat(ctx, io, cf, st, f16, bias_rays);
       if (rc) return rc;
       if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
       // style module 2 -> stylised rgb (rendering.py:132-142)
       rc = prof_begin(ctx, 2, (double)m * io.S * 2.0 * 614752.0, st, &e1);
       if (rc) return rc;
-      rc = launch_style_wild(ctx, io, remap, cf, st, f16);
+      rc = launch_style_wild(ctx, io, remap, cf, st, f16, bias_rays);
       if (rc) return rc;
       if (e1) TGTC_CUDA(cudaEventRecord(e1, st));
       if (which == 0) {
@@ -942,6 +953,26 @@ extern "C" int tgtc_render_style(tgtc_ctx* ctx, int mode, const float* rays_o, c
     }
   }
   return TGTC_OK;
+}
+
+extern "C" int tgtc_render_style(tgtc_ctx* ctx, int mode, const float* rays_o, const float* rays_d, int64_t n_rays, double near, double far,
+                                 int n_samples, int n_fine, int64_t chunk, const float* latent1, const float* latent2,
+                                 const tgtc_render_out* out_p, void* workspace, size_t workspace_bytes, tgtc_stream stream) {
+  return render_style_impl(ctx, mode, rays_o, rays_d, n_rays, near, far, n_samples, n_fine, chunk, latent1, latent2, nullptr, out_p, workspace,
+                           workspace_bytes, stream);
+}
+
+// the same loop body with PER-RAY latents inside one call (rendering.py:125-127: latents_model_1 returns one row per ray)
+extern "C" size_t tgtc_render_style_rays_workspace_bytes(int64_t n_rays, int n_samples, int n_fine, int64_t chunk) {
+  if (n_rays <= 0 || n_samples <= 0 || n_fine < 0) return 0;
+  return style_ws_layout(style_pass(n_rays, chunk), n_samples, n_fine, true).total;
+}
+extern "C" int tgtc_render_style_rays(tgtc_ctx* ctx, int mode, const float* rays_o, const float* rays_d, int64_t n_rays, double near, double far,
+                                      int n_samples, int n_fine, int64_t chunk, const float* latents, const tgtc_render_out* out_p,
+                                      void* workspace, size_t workspace_bytes, tgtc_stream stream) {
+  if (n_rays > 0 && latents == nullptr) { tgtc_set_error("latents is null"); return TGTC_ERR_ARG; }
+  return render_style_impl(ctx, mode, rays_o, rays_d, n_rays, near, far, n_samples, n_fine, chunk, nullptr, nullptr, latents, out_p, workspace,
+                           workspace_bytes, stream);
 }
 
 // ---------------------------------------------------------------------------

@@ -261,8 +261,9 @@ int launch_style_wild_train(tgtc_ctx* ctx, const MlpIO& io, const float* bias_ra
 // style_tc.cu
 int style_set_weights(tgtc_ctx* ctx, const float* const* params, cudaStream_t st);
 int style_set_latents(tgtc_ctx* ctx, const float* latent1, const float* latent2, cudaStream_t st);
-int launch_style_concat(tgtc_ctx* ctx, const MlpIO& io, uint8_t* cf_img, cudaStream_t st, bool f16 = false);
-int launch_style_wild(tgtc_ctx* ctx, const MlpIO& io, const uint8_t* remap_img, const uint8_t* cf_img, cudaStream_t st, bool f16 = false);
+int launch_style_concat(tgtc_ctx* ctx, const MlpIO& io, uint8_t* cf_img, cudaStream_t st, bool f16 = false, const float* bias_rays = nullptr);
+int launch_style_wild(tgtc_ctx* ctx, const MlpIO& io, const uint8_t* remap_img, const uint8_t* cf_img, cudaStream_t st, bool f16 = false,
+                      const float* bias_rays = nullptr);
 
 size_t style_stage_workspace_bytes(int64_t M);
 int launch_style_concat_explicit(tgtc_ctx* ctx, const float* x, int64_t M, float* cf_out, uint8_t* ws, bool f16, cudaStream_t st);

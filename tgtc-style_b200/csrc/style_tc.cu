@@ -97,9 +97,13 @@ __device__ __forceinline__ int seg_chunks(int s) { return s == SEG_PE ? 1 : 4; }
 // global memory), every layer's output image and ReLU mask words stashed for the backward, the PE tile stashed once.
 // kF16 (inference only): fp16 instead of bf16 operands -- weights image, PE tile, activations and the feature tile images that
 // travel between the trunk / module 1 / module 2 launches (TGTC_MLP_F16).
-template <bool kTrain, bool kF16 = false>
+// kRayBias (inference): per-ray latents inside one call -- the per-ray effective-bias path of the training instantiation
+// (bias_rays) without its stash, so a batch may mix (style, frame) latents (rendering.py:125-127).
+template <bool kTrain, bool kF16 = false, bool kRayBias = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_chain_kernel(const __grid_constant__ ChainParams P) {
   static_assert(!(kTrain && kF16), "the Style_train stash / backward kernels are bf16");
+  static_assert(!(kTrain && kRayBias), "the training instantiation already takes per-ray biases");
+  constexpr bool kPerRay = kTrain || kRayBias;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5;
@@ -142,7 +146,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
   }
   {
     float* dst = reinterpret_cast<float*>(smem + kOffBias);
-    if (!kTrain)
+    if (!kPerRay)
       for (int i = threadIdx.x; i < nl * 256; i += kNumThreads) dst[i] = P.bias[i];
     if (P.head_w != nullptr) {
       float* hw = reinterpret_cast<float*>(smem + kOffHeadW);
@@ -392,7 +396,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
       b0 = __ldg(P.bias_rays + (m0 / P.S) * P.bias_ray_stride + l_ * 256 + e256);
       b1 = __ldg(P.bias_rays + (m1 / P.S) * P.bias_ray_stride + l_ * 256 + e256);
     };
-    if constexpr (kTrain) {
+    if constexpr (kPerRay) {
       if (iters > 0) {
         for (int t = 0; t < 2; ++t) {
           float b0, b1;
@@ -409,8 +413,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
           const int64_t tile = pair_tile(it, t, rank);
           const int64_t m = tile * kTileM + row;
           float nb0 = 0.f, nb1 = 0.f;
-          const bool has_next = kTrain && !(it == iters - 1 && l == nl - 1);
-          if constexpr (kTrain) {
+          const bool has_next = kPerRay && !(it == iters - 1 && l == nl - 1);
+          if constexpr (kPerRay) {
             if (has_next) bias_rows(l + 1 < nl ? it : it + 1, l + 1 < nl ? l + 1 : 0, t, nb0, nb1);
             named_bar_sync(3, kNumEpiThreads);   // this step's rows (written at the end of the slot's previous step) are visible
           }
@@ -419,11 +423,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
           const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(256 * t) + (uint32_t)(hc * 128);
           const uint32_t arow = sbase + kOffAct + t * kActBytes + (row >> 3) * 1024 + (row & 7) * 128 + hc * 2 * 16384;
           float p0 = 0.f, p1 = 0.f, p2 = 0.f;
-          if constexpr (kTrain) {
+          if constexpr (kPerRay) {
             // per-ray effective biases (the latent columns folded per ray); all 32 rows of a warp belong to one ray
             const float* bl = bias_w + ((t * 2 + (int)(use[t] & 1)) * 2 + (row >> 6)) * 256 + hc * 128;
-            uint32_t* mrow = (tile < P.ntiles && !(P.dbg_flags & 1)) ? P.mask + (((size_t)tile * P.mask_layers + P.mask_slot0 + l) * 8 + hc * 4) * 128 + row : nullptr;
-            if (!(P.dbg_flags & 8)) { mbar_wait(bar(kBarSlotFree + t), sf_par[t]); sf_par[t] ^= 1; }   // the previous image store has drained act[t]
+            uint32_t* mrow = nullptr;
+            if constexpr (kTrain) {
+              mrow = (tile < P.ntiles && !(P.dbg_flags & 1)) ? P.mask + (((size_t)tile * P.mask_layers + P.mask_slot0 + l) * 8 + hc * 4) * 128 + row : nullptr;
+              if (!(P.dbg_flags & 8)) { mbar_wait(bar(kBarSlotFree + t), sf_par[t]); sf_par[t] ^= 1; }   // the previous image store has drained act[t]
+            }
 #pragma unroll 1
             for (int blk = 0; blk < 4; ++blk) {
               uint32_t v[32];
@@ -537,7 +544,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
             named_bar_sync(1, kNumEpiThreads);
             if (hc == 0 && m < P.M) {
               const float4 o = *reinterpret_cast<const float4*>(part_s + row * 4);
-              if constexpr (kTrain) {
+              if constexpr (kPerRay) {
                 const float* hbr = P.bias_rays + (m / P.S) * P.bias_ray_stride + nl * 256;
                 hb[0] = hbr[0]; hb[1] = hbr[1]; hb[2] = hbr[2];
               }
@@ -781,7 +788,7 @@ static void fill_common(ChainParams& P, const MlpIO& io) {
 static int g_chain_dbg = 0;
 extern "C" void tgtc_debug_chain_flags(int f) { g_chain_dbg = f; }
 
-static int launch_chain(tgtc_ctx* ctx, const ChainParams& P_in, cudaStream_t st, bool train = false, bool f16 = false) {
+static int launch_chain(tgtc_ctx* ctx, const ChainParams& P_in, cudaStream_t st, bool train = false, bool f16 = false, bool ray_bias = false) {
   ChainParams P = P_in;
   P.dbg_flags = g_chain_dbg;
   static bool attr_set[64] = {};
@@ -789,12 +796,16 @@ static int launch_chain(tgtc_ctx* ctx, const ChainParams& P_in, cudaStream_t st,
     TGTC_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     TGTC_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     TGTC_CUDA((cudaFuncSetAttribute(mlp_chain_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)));
+    TGTC_CUDA((cudaFuncSetAttribute(mlp_chain_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)));
+    TGTC_CUDA((cudaFuncSetAttribute(mlp_chain_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)));
     attr_set[ctx->device & 63] = true;
   }
   const int64_t nquads = (P.ntiles + 3) / 4;
   const int64_t max_pairs = ctx->num_sms / 2;
   const int grid = 2 * (int)(nquads < max_pairs ? nquads : max_pairs);
   if (train) mlp_chain_kernel<true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
+  else if (ray_bias && f16) mlp_chain_kernel<false, true, true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
+  else if (ray_bias) mlp_chain_kernel<false, false, true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
   else if (f16) mlp_chain_kernel<false, true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
   else mlp_chain_kernel<false><<<grid, kNumThreads, kSmemBytes, st>>>(P);
   TGTC_LAUNCH_CHECK(ctx);
@@ -802,7 +813,7 @@ static int launch_chain(tgtc_ctx* ctx, const ChainParams& P_in, cudaStream_t st,
 }
 
 // module 1: concat_features tile images for the samples of io -> cf_img [ntiles][64 KB]
-int launch_style_concat(tgtc_ctx* ctx, const MlpIO& io, uint8_t* cf_img, cudaStream_t st, bool f16) {
+int launch_style_concat(tgtc_ctx* ctx, const MlpIO& io, uint8_t* cf_img, cudaStream_t st, bool f16, const float* bias_rays) {
   if (io.n_rays == 0) return TGTC_OK;
   ChainParams P = {};
   fill_common(P, io);
@@ -813,11 +824,13 @@ int launch_style_concat(tgtc_ctx* ctx, const MlpIO& io, uint8_t* cf_img, cudaStr
   P.blob = f16 ? ctx->style.blob_c_h : ctx->style.blob_c;
   P.bias = ctx->style.bias_c;
   P.img_out = cf_img;
-  return launch_chain(ctx, P, st, false, f16);
+  if (bias_rays != nullptr) { P.bias_rays = bias_rays; P.bias_ray_stride = 13 * 256; }
+  return launch_chain(ctx, P, st, false, f16, bias_rays != nullptr);
 }
 
 // module 2: stylised rgb -> rgbsigma[.].xyz from base_remap images (NeRF trunk) and concat_features images (module 1)
-int launch_style_wild(tgtc_ctx* ctx, const MlpIO& io, const uint8_t* remap_img, const uint8_t* cf_img, cudaStream_t st, bool f16) {
+int launch_style_wild(tgtc_ctx* ctx, const MlpIO& io, const uint8_t* remap_img, const uint8_t* cf_img, cudaStream_t st, bool f16,
+                      const float* bias_rays) {
   if (io.n_rays == 0) return TGTC_OK;
   ChainParams P = {};
   fill_common(P, io);
@@ -834,7 +847,8 @@ int launch_style_wild(tgtc_ctx* ctx, const MlpIO& io, const uint8_t* remap_img, 
   P.img0 = remap_img;
   P.img1 = cf_img;
   P.rgbsigma = io.rgbsigma;
-  return launch_chain(ctx, P, st, false, f16);
+  if (bias_rays != nullptr) { P.bias_rays = bias_rays + 5 * 256; P.bias_ray_stride = 13 * 256; }
+  return launch_chain(ctx, P, st, false, f16, bias_rays != nullptr);
 }
 
 // ---------------------------------------------------------------------------

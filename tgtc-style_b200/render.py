@@ -412,9 +412,8 @@ class NerfRenderer:
     def render_style(self, rays_o, rays_d, latents, near=0., far=1., chunk=None, n_samples=64, n_fine=64, extras=False,
                      want_weights=False, out=None, mode=None):
         """The loop body of render_style (rendering.py:118-178, perturb=False) for one batch of rays.
-        latents = the output of latents_model_1 (rendering.py:125): [32] for a batch that shares one (style, frame), or [N,32];
-        per-ray latents are handled as runs of consecutive rays with equal latents (the reference's loaders walk frames in
-        order, train_tgtcs.py:170), one library call per run.
+        latents = the output of latents_model_1 (rendering.py:125): [32] for a batch that shares one (style, frame), or [N,32]
+        per-ray latents (one library call either way: uniform latents fold into per-call biases, mixed ones into per-ray biases).
         -> {rgb, depth, acc} (+ weights / coarse outputs / ts_fine like render())."""
         self.refresh_weights()
         mode = self.mode if mode is None else _MODES[mode]
@@ -427,20 +426,24 @@ class NerfRenderer:
             out = self._alloc_out(n, n_samples, n_fine, extras, self.device)
             if not want_weights:
                 out.pop("weights")
+        ck = int(chunk) if chunk else 0
         if lat.dim() == 2 and n > 1 and not bool((lat == lat[:1]).all()):
+            # per-ray latents inside ONE library call (tgtc_render_style_rays): the latent columns of every layer become per-ray
+            # effective biases; batches that mix (style, frame) pairs need no host-side splitting
             if lat.shape[0] != n:
                 raise ValueError("latents must be [32] or [N,32]")
-            change = (lat[1:] != lat[:-1]).any(dim=1).nonzero().flatten().add(1).tolist()
-            bounds = [0] + change + [n]
-            for b, e in zip(bounds[:-1], bounds[1:]):
-                self.render_style(ro[b:e], rd[b:e], lat[b], near, far, chunk, n_samples, n_fine, extras, want_weights,
-                                  out={k: v[b:e] for k, v in out.items()}, mode=mode)
+            lat = lat.contiguous()
+            wsb = self.lib.tgtc_render_style_rays_workspace_bytes(n, n_samples, n_fine, ck)
+            ws = self._workspace(wsb + 1024)
+            off = (-ws.data_ptr()) % 1024
+            s = self._out_struct(out)
+            _lib.check(self.lib.tgtc_render_style_rays(self._h, mode, _ptr(ro), _ptr(rd), n, float(near), float(far), n_samples, n_fine, ck,
+                                                       _ptr(lat), ctypes.byref(s), ctypes.c_void_p(ws.data_ptr() + off), wsb, self._stream))
             return out
         if lat.dim() == 2:
             lat = lat[0]
         lat1 = lat.reshape(32).contiguous()
         lat2 = lat1.mean().expand(32).contiguous()          # rendering.py:126: mean over the latent dim, broadcast (:139)
-        ck = int(chunk) if chunk else 0
         wsb = self.lib.tgtc_render_style_workspace_bytes(n, n_samples, n_fine, ck)
         ws = self._workspace(wsb + 1024)
         off = (-ws.data_ptr()) % 1024
