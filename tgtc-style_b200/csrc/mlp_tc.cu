@@ -197,6 +197,7 @@ struct TcParams {
 };
 #define TC_TRACE(role, it, l, t, k)                                                                              \
   do {                                                                                                           \
+    if constexpr (kDbg)                                                                                          \
     if (P.dbg_trace != nullptr && blockIdx.x == 0 && (it) < 4)                                                   \
       P.dbg_trace[(((((role)*4 + (int)(it)) * 10 + (l)) * 2 + (t)) * 2) + (k)] = clock64();                      \
   } while (0)
@@ -213,9 +214,13 @@ __device__ __forceinline__ int64_t my_tile(int64_t it, int t, uint32_t rank) {
 // kTrunk (style path; implies P.trunk): the inference epilogue on L0..L7 + remap, and only the remap tile leaves as an image --
 // two barriers per tile instead of the training instantiation's one per layer.
 // kF16: fp16 instead of bf16 operands (weights image, PE tile, activations); inference only.
-template <bool kTrain, bool kTrunk = false, bool kF16 = false>
+// kDbg: the test / timing hooks (layer dump, role clock trace, work-skipping flags) -- a separate instantiation, so that the
+// production kernels carry none of that code (their instruction footprint is performance-relevant).
+template <bool kTrain, bool kTrunk = false, bool kF16 = false, bool kDbg = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_tc_kernel(const TcParams P) {
   static_assert(!(kTrain && kF16), "the training stash / backward kernels are bf16");
+  const int dbg_flags = kDbg ? P.dbg_flags : 0;
+  const int dbg_layers = kDbg ? P.dbg_layers : 0;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
   const int warp = threadIdx.x >> 5;
@@ -227,7 +232,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
   const int64_t nquads = (P.ntiles + 3) / 4;
   const int64_t ncl = gridDim.x >> 1, cid = blockIdx.x >> 1;
   const int64_t iters = nquads > cid ? (nquads - cid + ncl - 1) / ncl : 0;   // identical in both CTAs of the pair
-  const int nlayers = P.dbg_layers > 0 ? P.dbg_layers : (P.trunk ? 9 : kTcNumGemm);
+  const int nlayers = dbg_layers > 0 ? dbg_layers : (P.trunk ? 9 : kTcNumGemm);
 
   // ---- one-time setup
   if (threadIdx.x == 0) {
@@ -274,7 +279,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
     // weight producer (whole warp converged, one elected lane issues the bulk copies): this CTA's half of the rows
     int stage = 0;
     uint32_t phase = 0;
-    for (int64_t it = 0; it < ((P.dbg_flags & 16) ? 0 : iters); ++it) {
+    for (int64_t it = 0; it < ((dbg_flags & 16) ? 0 : iters); ++it) {
       for (int l = 0; l < nlayers; ++l) {
         const uint32_t hbytes = (uint32_t)tc_layer_n(l) * kTcChunkK;   // half of a [N x 64] bf16 chunk
         const uint8_t* src = P.blob + tc_layer_off_bytes(l) + (size_t)rank * hbytes;
@@ -298,7 +303,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t leader_wfull = mapa_cluster(bar(kBarWFull), 0);
-    for (int64_t it = 0; it < ((P.dbg_flags & 16) ? 0 : iters); ++it) {
+    for (int64_t it = 0; it < ((dbg_flags & 16) ? 0 : iters); ++it) {
       for (int l = 0; l < nlayers; ++l) {
         const int nch = 2 * tc_layer_chunks(l);
         for (int c = 0; c < nch; ++c) {
@@ -318,7 +323,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
     uint32_t phase = 0;
     uint32_t act_par0 = 0, act_par1 = 0, pe_par0 = 0, pe_par1 = 0;
     const uint32_t w_lo0 = (((sbase + kOffW) & 0x3FFFFu) >> 4) | (1u << 16);
-    const bool ring = !(P.dbg_flags & 16);
+    const bool ring = !(dbg_flags & 16);
     // one K=64 chunk: wait for the ring stage, four MMAs (K=16 each: +32 B inside the 128 B swizzled rows), release the stage
     auto issue_chunk = [&](uint32_t d_tmem, uint32_t a_lo, uint32_t idesc, uint32_t accumulate) {
       if (ring) { mbar_wait_uniform(bar(kBarWFull + stage), phase); tc_fence_after(); }
@@ -572,7 +577,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
             }
           }
 
-          if (P.dbg_layers > 0 && l == nlayers - 1) {
+          if (dbg_layers > 0 && l == nlayers - 1) {
             // test hook: dump the raw fp32 accumulator of the last executed layer
             const int ncols = tc_layer_n(l) / 2;
             for (int b = 0; b < ncols / 32; ++b) {
@@ -596,9 +601,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
             const uint32_t rx = (uint32_t)(row & 7) << 4;
             uint32_t* mrow = nullptr;   // training: this thread's first mask word of the layer (the image itself leaves by bulk store)
             if constexpr (kTrain) {
-              if (P.stash_mask != nullptr && tile < P.ntiles && !(P.dbg_flags & 128)) mrow = P.stash_mask + (((size_t)tile * 10 + l) * 8 + hc * 4) * 128 + row;
+              if (P.stash_mask != nullptr && tile < P.ntiles && !(dbg_flags & 128)) mrow = P.stash_mask + (((size_t)tile * 10 + l) * 8 + hc * 4) * 128 + row;
             }
-            if (P.dbg_flags & 2) {
+            if (dbg_flags & 2) {
             } else if (l == 7) {
               const float sig = hidden_epilogue<true, kTrain, kF16>(tcol, bl, wsig_s + hc * 128, arow, rx, mrow);
               if (hc == 1) sigpart_s[t * 128 + row] = sig; else sig_keep[t] = sig;
@@ -618,11 +623,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
               // previous store (the other slot, one epilogue ago) has finished reading shared memory -- that buffer is the one
               // the NEXT epilogue overwrites, and every thread passes the named barrier after this wait.
               const bool issuer = (warp == kEpiWarp0 && lane == 0);
-              if (!(P.dbg_flags & 64)) {
+              if (!(dbg_flags & 64)) {
                 if (issuer) bulk_wait_read0();
                 named_bar_sync(3, kNumEpiThreads);
               }
-              if (issuer && tile < P.ntiles && !(P.dbg_flags & 32)) {
+              if (issuer && tile < P.ntiles && !(dbg_flags & 32)) {
                 bulk_s2g(P.stash_h + ((size_t)tile * 9 + l) * 65536, sbase + kOffAct + t * kActBytes, 65536u);
                 bulk_commit_group();
               }
@@ -779,15 +784,22 @@ static int launch_tc_common(tgtc_ctx* ctx, int net, const MlpIO& io, int dbg_lay
     TGTC_CUDA((cudaFuncSetAttribute(mlp_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)));
     TGTC_CUDA((cudaFuncSetAttribute(mlp_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)));
     TGTC_CUDA((cudaFuncSetAttribute(mlp_tc_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)));
+    TGTC_CUDA((cudaFuncSetAttribute(mlp_tc_kernel<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)));
+    TGTC_CUDA((cudaFuncSetAttribute(mlp_tc_kernel<false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)));
+    TGTC_CUDA((cudaFuncSetAttribute(mlp_tc_kernel<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes)));
     attr_set[ctx->device & 63] = true;
   }
   const int64_t nquads = (P.ntiles + 3) / 4;
   const int64_t max_pairs = ctx->num_sms / 2;
   const int grid = 2 * (int)(nquads < max_pairs ? nquads : max_pairs);   // CTA pairs (clusters of 2)
+  const bool dbg = dbg_layers > 0 || g_dbg_flags != 0 || g_dbg_trace != nullptr;   // test / timing hooks: their own instantiations
   if (trunk && f16) mlp_tc_kernel<false, true, true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
   else if (trunk) mlp_tc_kernel<false, true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
+  else if (stash != nullptr && dbg) mlp_tc_kernel<true, false, false, true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
   else if (stash != nullptr) mlp_tc_kernel<true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
+  else if (f16 && dbg) mlp_tc_kernel<false, false, true, true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
   else if (f16) mlp_tc_kernel<false, false, true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
+  else if (dbg) mlp_tc_kernel<false, false, false, true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
   else mlp_tc_kernel<false><<<grid, kNumThreads, kSmemBytes, st>>>(P);
   TGTC_LAUNCH_CHECK(ctx);
   return TGTC_OK;

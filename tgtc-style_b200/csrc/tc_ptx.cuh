@@ -31,15 +31,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// the slow path of every bounded wait, out of line: a printf call inlined at ~20 wait sites per kernel costs instruction-cache
+// footprint that the hot loops pay for (removing the test hooks' code from the production kernels alone was worth 4 %)
+static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar, uint32_t parity) {
+  printf("tgtc tcgen05 kernel: mbarrier timeout (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+  __trap();
+}
 // bounded wait: a protocol bug traps (visible as a launch failure) instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s
-      printf("tgtc tcgen05 kernel: mbarrier timeout (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000LL) mbar_timeout_trap(bar, parity);  // ~2 s
   }
 }
 // warp-uniform wait for converged single-issuer warps: the loop condition is a vote, so control flow stays uniform and
@@ -48,10 +51,7 @@ __device__ __forceinline__ void mbar_wait_uniform(uint32_t bar, uint32_t parity)
   if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
   const long long t0 = clock64();
   while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
-    if (clock64() - t0 > 4000000000LL) {
-      if ((threadIdx.x & 31) == 0) printf("tgtc tcgen05 kernel: mbarrier timeout (block %d warp %d bar@%u parity %u)\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), bar, parity);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000LL) mbar_timeout_trap(bar, parity);
   }
 }
 // same, for roles that are far off the critical path: sleep between probes so the spin does not steal issue slots
@@ -60,10 +60,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity,
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     __nanosleep(ns);
-    if (clock64() - t0 > 4000000000LL) {
-      printf("tgtc tcgen05 kernel: mbarrier timeout (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar, parity);
-      __trap();
-    }
+    if (clock64() - t0 > 4000000000LL) mbar_timeout_trap(bar, parity);
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
