@@ -66,6 +66,7 @@ struct DgradParams {
 };
 #define BW_TRACE(role, it, g, t, k)                                                                        \
   do {                                                                                                     \
+    if constexpr (kDbg)                                                                                    \
     if (P.dbg_trace != nullptr && blockIdx.x == 0 && (it) < 4)                                             \
       P.dbg_trace[(((((role)*4 + (int)(it)) * 9 + (g)) * 2 + (t)) * 3) + (k)] = clock64();                 \
   } while (0)
@@ -78,6 +79,8 @@ __device__ __forceinline__ int64_t pair_tile(int64_t it, int t, uint32_t rank) {
 __host__ __device__ constexpr size_t bwd_layer_off_bytes(int g) { return g == 0 ? 0 : 65536 + (size_t)(g - 1) * 131072; }
 __host__ __device__ constexpr int bwd_layer_chunks(int g) { return g == 0 ? 2 : 4; }
 
+// kDbg: the role clock trace of tools/bwd_trace.py -- its own instantiation (the stamps sit in the issue / epilogue loops)
+template <bool kDbg>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_dgrad_kernel(const DgradParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t sbase = smem_u32(smem);
@@ -775,13 +778,15 @@ int launch_mlp_dgrad(tgtc_ctx* ctx, int net, const float* rgbsigma, const float*
   P.dbg_trace = g_bwd_trace;
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
-    TGTC_CUDA(cudaFuncSetAttribute(mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    TGTC_CUDA(cudaFuncSetAttribute(mlp_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    TGTC_CUDA(cudaFuncSetAttribute(mlp_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set[ctx->device & 63] = true;
   }
   const int64_t nquads = (P.ntiles + 3) / 4;
   const int64_t max_pairs = ctx->num_sms / 2;
   const int grid = 2 * (int)(nquads < max_pairs ? nquads : max_pairs);
-  mlp_dgrad_kernel<<<grid, kNumThreads, kSmemBytes, st>>>(P);
+  if (g_bwd_trace != nullptr) mlp_dgrad_kernel<true><<<grid, kNumThreads, kSmemBytes, st>>>(P);
+  else mlp_dgrad_kernel<false><<<grid, kNumThreads, kSmemBytes, st>>>(P);
   TGTC_LAUNCH_CHECK(ctx);
   return TGTC_OK;
 }

@@ -453,8 +453,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
       __syncwarp();                               // every lane's reads of the staging rows are done
       if (lane == 0) mbar_arrive(bar(kBarCompDone + t_));
     };
-    for (int64_t it = 0; it < iters; ++it) {
-      for (int t = 0; t < 2; ++t) {
+    for (int64_t it = 0; it <= iters; ++it) {
+#pragma unroll 1
+      for (int t = 0; t < 2 && it < iters; ++t) {
         const int64_t tile = my_tile(it, t, rank);
         if (it > 0) mbar_wait_relaxed(bar(kBarPeFree + t), (uint32_t)((it - 1) & 1), 128);
         if (r == 0) TC_TRACE(3, it, 0, t, 0);
@@ -525,15 +526,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
         if (r == 0) TC_TRACE(3, it, 0, t, 1);
       }
       // fused K5: this iteration's PE tiles are out (they were released at the previous tiles' layer 5); the previous tiles' last
-      // epilogues run about now -- composite them while waiting for the next PE release
+      // epilogues run about now -- composite them while waiting for the next PE release (the pass after the last iteration
+      // composites the last tiles).  One call site: the kernel's instruction footprint is performance-relevant.
       if (comp && it > 0) {
-        composite_tile(it - 1, 0);
-        composite_tile(it - 1, 1);
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) composite_tile(it - 1, t);
       }
-    }
-    if (comp && iters > 0) {
-      composite_tile(iters - 1, 0);
-      composite_tile(iters - 1, 1);
     }
   } else {
     // =====================================================================
