@@ -65,11 +65,16 @@ __device__ __forceinline__ double shfl_up_f64(double v, int delta) {
   hi = __shfl_up_sync(0xffffffffu, hi, delta);
   return __hiloint2double(hi, lo);
 }
+// kS / kF: compile-time sample counts (0 = runtime S_rt / F_rt).  The 64 + 64 instantiation is the reference's configuration
+// (configs/fern.txt:16-17): constant trip counts unroll every per-ray loop (the kernel is instruction-bound), same arithmetic.
+template <int kS, int kF>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_fine_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ ts_in,
-    int64_t ts_stride, const float* __restrict__ weights, int64_t n, int S, int F, int sort_n,
+    int64_t ts_stride, const float* __restrict__ weights, int64_t n, int S_rt, int F_rt, int sort_n,
     float* __restrict__ pts_out, float* __restrict__ ts_out, int64_t* __restrict__ inds_out,
     float* __restrict__ samples_out) {
+  const int S = kS ? kS : S_rt;
+  const int F = kF ? kF : F_rt;
   __shared__ FineSmem smem[kWarpsPerBlock];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -252,8 +257,12 @@ int launch_sample_fine(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, 
   const int64_t blocks_needed = (n + kWarpsPerBlock - 1) / kWarpsPerBlock;
   const int64_t cap = (int64_t)ctx->num_sms * 16;   // 16 resident 128-thread CTAs per SM
   const int64_t grid = blocks_needed < cap ? blocks_needed : cap;
-  sample_fine_kernel<<<(unsigned)grid, 32 * kWarpsPerBlock, 0, st>>>(rays_o, rays_d, ts, ts_stride, weights, n, S, n_fine,
-                                                                    sort_n, pts_out, ts_out, inds_out, samples_out);
+  if (S == 64 && n_fine == 64)
+    sample_fine_kernel<64, 64><<<(unsigned)grid, 32 * kWarpsPerBlock, 0, st>>>(rays_o, rays_d, ts, ts_stride, weights, n, S, n_fine,
+                                                                              sort_n, pts_out, ts_out, inds_out, samples_out);
+  else
+    sample_fine_kernel<0, 0><<<(unsigned)grid, 32 * kWarpsPerBlock, 0, st>>>(rays_o, rays_d, ts, ts_stride, weights, n, S, n_fine,
+                                                                            sort_n, pts_out, ts_out, inds_out, samples_out);
   TGTC_LAUNCH_CHECK(ctx);
   return TGTC_OK;
 }
