@@ -1057,9 +1057,14 @@ def main():
         rays_total = n * world * args.steps
         value = rays_total / (ms_total * 1e-3)
         achieved = (mlp_flops / (mlp_ms * 1e-3)) / 1e12 if mlp_ms > 0 else None
-        traffic = None
+        # DRAM bytes per launch cannot be measured outside a profiler: the figure comes from the committed `ncu --set full`
+        # capture of this same command, stamped with the commit / build it was taken from (profiles/mlp_tc_traffic.json)
+        traffic, traffic_src = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "mlp_tc_traffic.json"))).get("dram_bytes_per_launch")
+            prof = json.load(open(os.path.join(ROOT, "profiles", "mlp_tc_traffic.json")))
+            traffic = prof.get("dram_bytes_per_launch")
+            cap = prof.get("captured", {})
+            traffic_src = "profiles/mlp_tc_traffic.json: ncu --set full, round %s, commit %s, %s" % (cap.get("round"), cap.get("git_commit"), cap.get("build"))
         except Exception:
             pass
         res = {
@@ -1074,7 +1079,7 @@ def main():
                     "ms_per_step": ms2.item() / args.steps, "api": "NerfRenderer.render_host -> tgtc_render_host", "checksum": checksum},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-                         "traffic": traffic, "kernel": {"f16": "mlp_tc_kernel<fp16 operands>", "bf16": "mlp_tc_kernel<bf16 operands>", "fp32": "mlp_fp32_kernel"}[args.mode],
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": {"f16": "mlp_tc_kernel<fp16 operands>", "bf16": "mlp_tc_kernel<bf16 operands>", "fp32": "mlp_fp32_kernel"}[args.mode],
                          "launches_timed": int(mlp_launches), "avg_launch_ms": mlp_ms / max(mlp_launches, 1),
                          "flop_per_launch_avg": mlp_flops / max(mlp_launches, 1), "peak_source": peak_src,
                          "frac_of_burst_peak": (achieved / peaks["bf16_tflops"]) if (achieved and peaks.get("bf16_tflops")) else None,
