@@ -869,6 +869,69 @@ def run_style_train(args, sub=False):
     return _finish(args, res if rank == 0 else None, sub)
 
 
+SPIRAL_WORKLOAD = ("stylised spiral path (render_valid_style, BASELINE config 3): frames of the 120-pose spiral at 1008x756, whole frames "
+                   "round-robin over the GPUs, every frame its own (style, frame) latent, rays generated on the device, ONE packed tile "
+                   "all-gather per group of N frames on a side stream (TileGatherer)")
+
+
+def run_spiral(args, sub=False):
+    """--workload spiral (BASELINE config 3): `steps` groups of N frames of the stylised 120-pose spiral through
+    tgtc_style_b200.render_path_sharded(split="frames"); reports frames/s and the projected time of the whole 120-frame path."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import tgtc_style_b200 as T
+    rank, world, local, dev = _setup(args)
+    wc, wf = synth_nerf_weights(0)
+    cs, ws = synth_style_weights(1)
+    smode = args.mode if getattr(args, "mode", "f16") in ("f16", "bf16") else "f16"
+    r = T.NerfRenderer(device=dev, mode=smode)
+    r.set_weights(wc, wf)
+    r.set_style_weights(cs, ws)
+    K = np.array([[FOCAL, 0, 0.5 * W], [0, FOCAL, 0.5 * H], [0, 0, 1]])
+    nframes = min(120, world * args.steps)
+    poses = spiral_poses(120)
+    table = torch.randn(20, 32, generator=torch.Generator().manual_seed(3)).repeat(7, 1)[:120].to(dev)   # models.py:496 tiles 20 latents x7
+    for _ in T.render_path_sharded(r, H, W, K, poses[:world], split="frames", latents=table[:world], chunk=4096):
+        pass                                    # warm-up group
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = r.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    checksum, got = 0.0, 0
+    for i, fr in T.render_path_sharded(r, H, W, K, poses[:nframes], split="frames", latents=table[:nframes], chunk=4096):
+        got += 1
+        last = fr
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall1 = time.time()
+    checksum = float(last["rgb"].double().sum())
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    launches = r.launch_count() - l0
+    r.close()
+    res = None
+    if rank == 0:
+        clocks.stop()
+        sec = ms.item() * 1e-3
+        res = {"metric": "rays/s", "value": got * H * W / sec, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "ms_per_step": ms.item() / max(args.steps, 1),
+               "higher_is_better": True, "scaling": "weak", "dtype": smode, "data": "synthetic",
+               "config": {"workload": SPIRAL_WORKLOAD, "frames_timed": got, "rays_per_frame": H * W, "batch_rays": 4096, "samples_per_ray": SAMPLES_PER_RAY},
+               "frames_per_s": got / sec, "projected_seconds_for_120_frames": 120.0 / (got / sec),
+               "step_tflops": got * H * W * SAMPLES_PER_RAY * STYLE_FLOP_PER_SAMPLE / sec / 1e12,
+               "gpu_launches": int(launches), "checksum": checksum, "clocks": clocks.window(t_wall0, t_wall1)}
+    return _finish(args, res, sub)
+
+
 def _render_mode_quick(args, dev, rank, world, mode, steps):
     """the headline workload (device-resident rays, one frame per GPU per step + tile all-gather) in another MLP mode, a few steps"""
     import numpy as np
@@ -925,7 +988,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true",
                     help="headline only: skip the extra_workloads (configs 4/5 + Style_train) and the bf16-mode comparison")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="render", choices=["render", "train", "style", "style-train"],
+    ap.add_argument("--workload", default="render", choices=["render", "train", "style", "style-train", "spiral"],
                     help="render = BASELINE config 2 (the headline; default); train = config 5 (training step); "
                          "style = config 4 (stylised render, 4096-ray batches); style-train = one Style_train iteration "
                          "(two 4096-ray batches)")
@@ -938,7 +1001,7 @@ def main():
     if args.impl == "reference":
         if args.workload == "train":
             run_train_reference_arm(args)
-        elif args.workload == "style":
+        elif args.workload in ("style", "spiral"):
             run_style_reference_arm(args)
         elif args.workload == "style-train":
             run_style_train_reference_arm(args)
@@ -953,6 +1016,9 @@ def main():
         return
     if args.workload == "style-train":
         run_style_train(args)
+        return
+    if args.workload == "spiral":
+        run_spiral(args)
         return
 
     import numpy as np
@@ -1106,7 +1172,7 @@ def main():
                 res["other_modes"] = {"bf16": extra_bf16}
         sub = argparse.Namespace(**vars(args))
         for name, fn, steps in (("train", run_train, min(args.steps, 10)), ("style", run_style, min(args.steps, 4)),
-                                ("style_train", run_style_train, min(args.steps, 10))):
+                                ("style_train", run_style_train, min(args.steps, 10)), ("spiral", run_spiral, min(args.steps, 2))):
             sub.steps, sub.warmup = max(steps, 1), 3
             t0 = time.time()
             try:
