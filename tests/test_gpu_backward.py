@@ -95,7 +95,7 @@ def test_train_step_gradients_vs_autograd(renderer_bf16):
             print("%-6s %-32s rel %.3e cos %.6f |g| %.3e" % (name_net, k, rel, cos, denom))
             # bf16 operands (8-bit mantissa) forward and back: ~0.1 % at the rgb head growing to ~8 % at layer 0 (ReLU units
             # whose bf16 pre-activation changes sign flip their whole gradient path); direction stays within cos 0.995
-            assert rel <= 0.12 and cos >= 0.995, (name_net, k, rel, cos)
+            assert rel <= 0.10 and cos >= 0.995, (name_net, k, rel, cos)       # measured worst 8.1 % (+20 %)
     print("worst per-tensor relative gradient error: %.3e" % worst)
 
 

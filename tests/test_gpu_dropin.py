@@ -138,7 +138,7 @@ def test_origin_train_loop_body_backward_through_the_dropins(patched):
             rel = (g - g_ref).norm().item() / max(g_ref.norm().item(), 1e-12)
             cos = torch.nn.functional.cosine_similarity(g.flatten(), g_ref.flatten(), dim=0).item()
             worst = max(worst, rel)
-            assert rel <= 0.12 and cos >= 0.995, (k, rel, cos)
+            assert rel <= 0.08 and cos >= 0.995, (k, rel, cos)       # measured worst 6.2 % (+20 %)
     print("Origin_train loop body through the drop-ins: loss %.5f (oracle %.5f), worst per-tensor gradient error %.3e" % (loss.item(), loss_ref.item(), worst))
     # ---- optimizer.step() (train_tgtcs.py:255) moves the reference's own parameters; the next forward sees the new weights
     before = model.net.sigma_layer.weight.detach().clone()
