@@ -218,8 +218,9 @@ def test_render_bf16_ragged_sizes_match_prefix_of_larger_batch(renderer_bf16, n)
 @pytest.mark.parametrize("mode", ["f16", "bf16"])
 @pytest.mark.parametrize("n", [1, 2, 3, 129, 1001])
 def test_fused_compositing_is_bit_identical_to_the_standalone_kernel(mode, n):
-    """K5 fused into the last epilogue of the tcgen05 MLP kernel (a 128-sample tile = one fine ray / two coarse rays) against the
-    same render with the stand-alone composite kernel: every output, bit for bit -- odd ray counts (half-filled last coarse tile),
+    """K5 fused into the tcgen05 MLP kernel (a 128-sample tile = one fine ray / two coarse rays) and K6+K7 fused into the fine
+    kernel's producer warps, against the same render with the stand-alone composite / sample_fine kernels: every output (incl.
+    ts_fine), bit for bit -- odd ray counts (half-filled last coarse tile),
     white background, weights requested."""
     from tgtc_style_b200 import _lib
     r = T.NerfRenderer(device="cuda:0", mode=mode)
@@ -231,6 +232,7 @@ def test_fused_compositing_is_bit_identical_to_the_standalone_kernel(mode, n):
     outs = []
     for off in (0, 1):
         lib.tgtc_debug_no_fused_composite(off)
+        lib.tgtc_debug_no_fused_sample_fine(off)     # likewise the resampling: fused into the fine kernel's producers vs its own kernel
         try:
             a = r.render(ro[sel], rd[sel], 0., 1., extras=True, want_weights=True)
             b = r.render(ro[sel], rd[sel], 0., 1., extras=True, want_weights=True, white_bkgd=True)
@@ -238,6 +240,7 @@ def test_fused_compositing_is_bit_identical_to_the_standalone_kernel(mode, n):
             outs.append(({k: v.clone() for k, v in a.items()}, {k: v.clone() for k, v in b.items()}))
         finally:
             lib.tgtc_debug_no_fused_composite(0)
+            lib.tgtc_debug_no_fused_sample_fine(0)
     for (fa, fb), (sa, sb) in [(outs[0], outs[1])]:
         for k in fa:
             assert torch.equal(fa[k], sa[k]), ("plain", k)

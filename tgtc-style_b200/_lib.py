@@ -127,6 +127,7 @@ DEBUG_PROTOTYPES = {
                                             ctypes.c_double, ctypes.c_int, c_void_p, c_void_p]),
     "tgtc_debug_tc_f16": (None, [ctypes.c_int]),
     "tgtc_debug_no_fused_composite": (None, [ctypes.c_int]),
+    "tgtc_debug_no_fused_sample_fine": (None, [ctypes.c_int]),
 }
 
 _lib = None
@@ -146,10 +147,15 @@ def load():
             "libtgtc_b200.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
-    for name, (res, args) in list(PROTOTYPES.items()) + list(DEBUG_PROTOTYPES.items()):
+    for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
+    for name, (res, args) in DEBUG_PROTOTYPES.items():      # test hooks: an older build under TGTC_B200_LIB may lack the newest
+        fn = getattr(lib, name, None)
+        if fn is not None:
+            fn.restype = res
+            fn.argtypes = args
     if lib.tgtc_abi_version() != 2:
         raise TgtcError("libtgtc_b200.so ABI version mismatch")
     _lib = lib

@@ -295,6 +295,8 @@ struct RenderWs {
 // test / A-B hook (not in the public header): 1 = keep the stand-alone compositing kernel in the tensor-core render path
 static int g_no_fused_composite = 0;
 extern "C" void tgtc_debug_no_fused_composite(int on) { g_no_fused_composite = on; }
+static int g_no_fused_sample_fine = 0;     // 1 = keep the stand-alone resampling kernel between the coarse and the fine launch
+extern "C" void tgtc_debug_no_fused_sample_fine(int on) { g_no_fused_sample_fine = on; }
 
 // which passes composite inside the MLP kernel (fused K5): tensor-core modes with whole rays per 128-sample tile
 static inline bool fused_pass(int mode, int samples) {
@@ -393,14 +395,22 @@ static int render_impl(tgtc_ctx* ctx, int mode, const float* rays_o, const float
       if (out.ts_fine) { rc = launch_sample_uniform(ctx, nullptr, nullptr, m, S, near, far, nullptr, nullptr, out.ts_fine + r0 * S, st); if (rc) return rc; }
       continue;
     }
-    // sampling_pts_fine_torch (rendering.py:43)
-    rc = launch_sample_fine(ctx, nullptr, nullptr, ts_c, 0, w_c, m, S, F, nullptr, ts_f, nullptr, nullptr, st);
-    if (rc) return rc;
+    // sampling_pts_fine_torch (rendering.py:43): its own kernel, or -- tensor-core modes at 64 + 64 samples -- run by the fine MLP
+    // kernel's input-producer warps one iteration ahead of each tile (fused K6+K7, same code: sample_fine.cuh)
+    const bool fuse_f = fused_pass(mode, T);
+    const bool fuse_sf = fuse_f && S == 64 && F == 64 && !g_no_fused_sample_fine;
+    if (!fuse_sf) {
+      rc = launch_sample_fine(ctx, nullptr, nullptr, ts_c, 0, w_c, m, S, F, nullptr, ts_f, nullptr, nullptr, st);
+      if (rc) return rc;
+    }
     // fine MLP on the sorted union (rendering.py:44-46)
     MlpIO fi;
     fi.rays_o = o; fi.rays_d = d; fi.ts = ts_f;
     fi.n_rays = m; fi.S = T; fi.rgbsigma = rs_f;
-    const bool fuse_f = fused_pass(mode, T);
+    if (fuse_sf) {
+      fi.fine_weights = w_c; fi.fine_ts = ts_f;
+      fi.fine_t_scale = (float)(far - near); fi.fine_t_near = (float)near;
+    }
     if (fuse_f) {
       fi.rgbsigma = nullptr;
       fi.comp_rgb = out.rgb ? out.rgb + r0 * 3 : reinterpret_cast<float*>(base + ws.off_rs_f);

@@ -208,6 +208,13 @@ struct MlpIO {
   float* comp_acc = nullptr;      // [n_rays] or nullptr
   float* comp_weights = nullptr;  // [n_rays,S] or nullptr
   int comp_white_bkgd = 0;
+  // fused K6+K7 (mlp_tc.cu inference instantiation of the FINE pass, 64 coarse + 64 new samples): when fine_weights != nullptr
+  // the input-producer warps run sample_pdf + the sorted union (sample_fine.cuh, the stand-alone kernel's arithmetic) for every
+  // ray one iteration ahead of its tile, write the row to fine_ts (== ts, [n_rays,128]) and read it back when they form the
+  // tile's sample positions: no resampling kernel between the coarse and the fine launch
+  const float* fine_weights = nullptr;   // [n_rays,64] coarse weights
+  float* fine_ts = nullptr;              // [n_rays,128], the same buffer as ts
+  float fine_t_scale = 1.f, fine_t_near = 0.f;   // the coarse ts row: linspace(0,1,64) * scale + near
 };
 
 // Activation stash of the training forward (mlp_tc.cu writes, mlp_bwd.cu reads).  Every array is a sequence of

@@ -31,6 +31,7 @@
 // 24 B/ray in + 16 B/sample out.
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "sample_fine.cuh"
 
 namespace {
 
@@ -57,7 +58,8 @@ constexpr int kOffSigPart = kOffDirBias + 2 * 2 * kMaxRaysPerTile * 128 * 4;  //
 constexpr int kOffRgbPart = kOffSigPart + 2 * 128 * 4;       // [128][4] fp32
 constexpr int kCompStageOff = kActBytes - kTileM * 32;       // fused K5 staging rows: the last 4 KB of an activation buffer (K block 3, rows 96..127)
 constexpr int kOffCompTot = kOffRgbPart + 128 * 4 * 4;       // [4] fp32: per-warp transmittance products of the fused compositing
-constexpr int kOffBars = kOffCompTot + 4 * 4 + 16;           // mbarriers
+constexpr int kOffTsRow = kOffCompTot + 4 * 4 + 16;          // [64] fp32: the coarse ts row of the fused resampling (K6+K7)
+constexpr int kOffBars = kOffTsRow + 64 * 4;                 // mbarriers
 constexpr int kNumBars = 2 * kStages + 14;
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kSmemBytes = kOffTmemPtr + 16;
@@ -393,7 +395,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
       const int k = r & (S - 1);
       float tcur = 0.f, tnext = 0.f;              // sample positions: fetched before the wait (L2 latency off the hand-over)
       if (io.ts != nullptr) {
-        if (valid) { tcur = io.ts[m]; if (k + 1 < S) tnext = io.ts[m + 1]; }
+        if (valid) { tcur = __ldcg(io.ts + m); if (k + 1 < S) tnext = __ldcg(io.ts + m + 1); }
       } else {
         tcur = coarse_t(k, S, io.t_scale, io.t_near);
         if (k + 1 < S) tnext = coarse_t(k + 1, S, io.t_scale, io.t_near);
@@ -453,6 +455,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
       __syncwarp();                               // every lane's reads of the staging rows are done
       if (lane == 0) mbar_arrive(bar(kBarCompDone + t_));
     };
+    // ---- fused K6+K7 (fine pass, S == 128: one ray per tile): producer warp t runs utils.sample_pdf + the sorted union
+    // (sample_fine.cuh: the stand-alone kernel's code, bit-identical) for the ray of tile (it_, t) and writes its ts_fine row; the
+    // rows of iteration it+1 are computed at the end of iteration it, while these warps would otherwise wait for the next PE
+    // release.  Scratch: the second-ray halves of the view-direction buffers (unused when a tile holds one ray) + a shared ts row.
+    const bool fuse_sf = !kTrain && !kTrunk && io.fine_weights != nullptr;
+    struct FinePtrs { float* ts; float* w; float* cdf; float* out; float* smp; };
+    auto sample_tile = [&](int64_t it_, int t_) {
+      const int64_t tile = my_tile(it_, t_, rank);
+      if (tile >= P.ntiles) return;
+      float* const spare = reinterpret_cast<float*>(smem + kOffDirBias) + (t_ * 2 * kMaxRaysPerTile + 1) * 128;   // (slot t_, buffer 0, ray 1)
+      FinePtrs fs;
+      fs.ts = reinterpret_cast<float*>(smem + kOffTsRow);
+      fs.w = spare;                                  // 62 values; the cdf (63) takes its place once the pdf is in registers
+      fs.cdf = spare;
+      fs.smp = spare + 64;
+      fs.out = spare + kMaxRaysPerTile * 128;        // (slot t_, buffer 1, ray 1): 128 floats
+      const float* wsrc = io.fine_weights + tile * 64;   // one ray per tile
+      if (lane >= 1) fs.w[lane - 1] = __fadd_rn(__ldcg(wsrc + lane), 1e-5f);
+      if (lane + 32 <= 62) fs.w[lane + 31] = __fadd_rn(__ldcg(wsrc + lane + 32), 1e-5f);
+      __syncwarp();
+      sample_fine_core<64, 64>(fs, lane, 64, 64, 128, nullptr, nullptr);
+      float* dst = io.fine_ts + tile * 128;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dst[lane + 32 * i] = fs.out[lane + 32 * i];
+      __syncwarp();
+    };
+    if (fuse_sf) {
+      if (r < 64) reinterpret_cast<float*>(smem + kOffTsRow)[r] = coarse_t(r, 64, io.fine_t_scale, io.fine_t_near);
+      named_bar_sync(4, kNumPeThreads);
+      if ((r >> 5) < 2 && iters > 0) sample_tile(0, r >> 5);
+      named_bar_sync(4, kNumPeThreads);          // the rows are visible to every producer thread (CTA-scope ordering)
+    }
     for (int64_t it = 0; it <= iters; ++it) {
 #pragma unroll 1
       for (int t = 0; t < 2 && it < iters; ++t) {
@@ -466,7 +500,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
         float x[3];
         if (io.rays_o != nullptr) {
           const int k = (int)(m - ray * S);
-          const float tt = io.ts != nullptr ? io.ts[m] : coarse_t(k, S, io.t_scale, io.t_near);
+          const float tt = io.ts != nullptr ? __ldcg(io.ts + m) : coarse_t(k, S, io.t_scale, io.t_near);   // (.cg: fused K6+K7 rows come from another warp)
 #pragma unroll
           for (int c = 0; c < 3; ++c) x[c] = __fadd_rn(io.rays_o[ray * 3 + c], __fmul_rn(tt, io.rays_d[ray * 3 + c]));
         } else {
@@ -531,6 +565,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
       if (comp && it > 0) {
 #pragma unroll 1
         for (int t = 0; t < 2; ++t) composite_tile(it - 1, t);
+      }
+      // fused K6+K7: the next iteration's ts_fine rows
+      if (fuse_sf && it + 1 < iters) {
+        if ((r >> 5) < 2) sample_tile(it + 1, r >> 5);
+        named_bar_sync(4, kNumPeThreads);
       }
     }
   } else {
@@ -747,6 +786,7 @@ bool mlp_tc_supports(const MlpIO& io) {
   if (!(S == 64 || S == 128 || (S > 128 && S % 128 == 0))) return false;
   if (io.rgbsigma != nullptr && !aligned16(io.rgbsigma)) return false;
   if (io.comp_rgb != nullptr && !(io.rays_o != nullptr && (S == 64 || S == 128))) return false;   // fused compositing: whole rays per tile
+  if (io.fine_weights != nullptr && !(io.rays_o != nullptr && S == 128 && io.fine_ts != nullptr && io.fine_ts == io.ts)) return false;   // fused resampling
   return true;
 }
 
