@@ -353,9 +353,13 @@ static int render_impl(tgtc_ctx* ctx, int mode, const float* rays_o, const float
   float* rs_f = reinterpret_cast<float*>(base + ws.off_rs_f);
   float* ts_c = reinterpret_cast<float*>(base + ws.off_ts_c);
   const int T = S + F;
-  // the shared coarse t row (utils.py:512-516; the reference expands it with stride 0 over rays)
-  int rc = launch_sample_uniform(ctx, nullptr, nullptr, 1, S, near, far, nullptr, nullptr, ts_c, st);
-  if (rc) return rc;
+  // the shared coarse t row (utils.py:512-516; the reference expands it with stride 0 over rays): only the stand-alone
+  // compositing / resampling kernels read it -- the fused passes form it in-kernel
+  int rc = TGTC_OK;
+  if (!(fused_pass(mode, S) && (F == 0 || (fused_pass(mode, T) && S == 64 && F == 64 && !g_no_fused_sample_fine)))) {
+    rc = launch_sample_uniform(ctx, nullptr, nullptr, 1, S, near, far, nullptr, nullptr, ts_c, st);
+    if (rc) return rc;
+  }
   for (int64_t r0 = 0; r0 < n; r0 += pass) {
     const int64_t m = (n - r0 < pass) ? (n - r0) : pass;
     const float* o = rays_o + r0 * 3;
