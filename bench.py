@@ -208,7 +208,38 @@ class ClockSampler:
             self.proc.terminate()
 
 
-def _reference_chain_fn():
+def eager_gpu_reference_rays_per_s(dev, rays_per_step=32768, steps=2, chunk=8192):
+    """The like-for-like comparator: the reference's OWN modules (oracle/_ref) in eager fp32 (TF32 off)
+    on the same B200 -- what a user of the reference runs today.  None when the staged copy is missing."""
+    import numpy as np
+    import torch
+    try:
+        fn, kind = _reference_chain_fn(dev)
+    except Exception:
+        return None
+    if kind != "reference":
+        return None
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sel = np.linspace(0, H * W - 1, rays_per_step).astype(np.int64)
+        fn(sel[:chunk], chunk)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            for b in range(0, rays_per_step, chunk):
+                fn(sel[b:b + chunk], chunk)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+    return {"value": rays_per_step * steps / (ms * 1e-3), "unit": "rays/s", "kind": "reference modules, eager torch fp32 (TF32 off) on this GPU",
+            "sample": "%d steps of %d rays in batches of %d" % (steps, rays_per_step, chunk)}
+
+
+def _reference_chain_fn(device="cpu"):
     """-> (fn(ray index array) running one batch through the CPU chain, kind).  kind = "reference": the reference's OWN modules
     (utils / models from /root/reference or the staged copy oracle/_ref, see oracle/stage_ref.py), driven as rendering.py:27-51
     drives them; kind = "port": the oracle restatement (bit-identical on the golden vectors) when no copy is available."""
@@ -222,7 +253,8 @@ def _reference_chain_fn():
         try:
             utils, models, _, _ = ref_import.import_reference()
             mc, mf = ref_import.reference_nets(models, 0)
-            ro_t, rd_t = torch.from_numpy(ro), torch.from_numpy(rd)
+            mc, mf = mc.to(device), mf.to(device)
+            ro_t, rd_t = torch.from_numpy(ro).to(device), torch.from_numpy(rd).to(device)
 
             def fn(sel, chunk=1024):
                 return ref_import.reference_chain(utils, mc, mf, ro_t[sel], rd_t[sel], 0., 1., N_SAMPLES, N_FINE, chunk)
@@ -1155,6 +1187,11 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample, kind = cpu_chain_rays_per_s(16 * 1024)
             res["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": kind, "sample": sample}
+            # the like-for-like comparator: the reference's own code on this same GPU (the CPU ratio says little about the kernels)
+            eg = eager_gpu_reference_rays_per_s(dev)
+            if eg is not None:
+                res["eager_gpu_reference"] = eg
+                res["speedup_vs_eager_gpu_reference"] = value / eg["value"]
     else:
         res = None
 
