@@ -27,14 +27,14 @@ def main():
     K = np.array([[FOCAL, 0, 0.5 * W], [0, FOCAL, 0.5 * H], [0, 0, 1]])
     poses = spiral_poses(120)[:nframes]
     table = torch.randn(20, 32, generator=torch.Generator().manual_seed(3)).repeat(7, 1)[:nframes].to(dev)   # models.py:496 tiles 20 latents x7
-    for _ in T.render_path_sharded(r, H, W, K, poses[:world], split="frames", latents=table[:world], chunk=4096):
+    for _ in T.render_path_sharded(r, H, W, K, poses[:world], split="frames", latents=table[:world], chunk=32768):
         pass                                    # warm-up group
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.time()
     checksum, got = 0.0, 0
-    for i, fr in T.render_path_sharded(r, H, W, K, poses, split="frames", latents=table, chunk=4096):
+    for i, fr in T.render_path_sharded(r, H, W, K, poses, split="frames", latents=table, chunk=32768):
         got += 1
         if i % 40 == 0:
             checksum += float(fr["rgb"].double().sum())
