@@ -85,9 +85,14 @@ using namespace tcptx;
 // blk = 32-column block index inside this thread's 128 columns; kb = row base of the 64-column K block.
 // mrow: when training, the block's ReLU mask word (bit 31-c = sign of pre-activation c, i.e. 1 = gradient blocked) goes to the
 // mask stash in HBM that mlp_dgrad_kernel reads instead of the 16x larger activation image; nullptr otherwise.
+// nb0 / nb1 (inference form): the bias values of this block's FIRST 8-column group, loaded by the caller; on return they hold the
+// next block's first group.  Every group's bias (and sigma-head weight) loads are issued BEFORE the previous group's activation
+// store: ptxas cannot tell the bias table from the activation buffer, so a load written after the store is issued after it and
+// the packed add that needs it waits out the full shared-memory latency -- 16 exposed round trips per layer and slot, 40 % of
+// the epilogue warps' time in the round-2 ncu source view (stall_short_sb on the FADD2s).
 template <bool kSigma, bool kMask, bool kF16>
 __device__ __forceinline__ void epi_block(uint32_t (&v)[32], const float* bl, const float* wsig, uint32_t kb, uint32_t rx, int blk,
-                                          float& sig, uint32_t* mrow) {
+                                          float& sig, uint32_t* mrow, float4& nb0, float4& nb1) {
   if constexpr (kMask) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -101,15 +106,28 @@ __device__ __forceinline__ void epi_block(uint32_t (&v)[32], const float* bl, co
     }
     if (mrow != nullptr) mrow[blk * 128] = sign_mask32(v);
   }
+  float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+  if constexpr (kSigma) {
+    w0 = *reinterpret_cast<const float4*>(wsig + blk * 32);
+    w1 = *reinterpret_cast<const float4*>(wsig + blk * 32 + 4);
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int c = blk * 32 + 8 * j;
     const uint32_t coff = (uint32_t)((((blk & 1) * 4) + j) << 4) ^ rx;
     const uint32_t dst = kb + coff;
     if constexpr (!kMask) {
-      const float4 b0 = *reinterpret_cast<const float4*>(bl + c);
-      const float4 b1 = *reinterpret_cast<const float4*>(bl + c + 4);
+      const float4 b0 = nb0, b1 = nb1;
+      if (c + 8 < 128) {   // the next group's bias: in flight while this group is converted and stored
+        nb0 = *reinterpret_cast<const float4*>(bl + c + 8);
+        nb1 = *reinterpret_cast<const float4*>(bl + c + 12);
+      }
       if constexpr (kSigma) {
+        const float ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        if (j < 3) {
+          w0 = *reinterpret_cast<const float4*>(wsig + c + 8);
+          w1 = *reinterpret_cast<const float4*>(wsig + c + 12);
+        }
         float h[8];
         h[0] = fmaxf(__uint_as_float(v[8 * j + 0]) + b0.x, 0.f);
         h[1] = fmaxf(__uint_as_float(v[8 * j + 1]) + b0.y, 0.f);
@@ -120,10 +138,8 @@ __device__ __forceinline__ void epi_block(uint32_t (&v)[32], const float* bl, co
         h[6] = fmaxf(__uint_as_float(v[8 * j + 6]) + b1.z, 0.f);
         h[7] = fmaxf(__uint_as_float(v[8 * j + 7]) + b1.w, 0.f);
         // fp32 sigma head on the un-rounded activations (models.py:103)
-        const float4 w0 = *reinterpret_cast<const float4*>(wsig + c);
-        const float4 w1 = *reinterpret_cast<const float4*>(wsig + c + 4);
-        sig = fmaf(h[0], w0.x, sig); sig = fmaf(h[1], w0.y, sig); sig = fmaf(h[2], w0.z, sig); sig = fmaf(h[3], w0.w, sig);
-        sig = fmaf(h[4], w1.x, sig); sig = fmaf(h[5], w1.y, sig); sig = fmaf(h[6], w1.z, sig); sig = fmaf(h[7], w1.w, sig);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sig = fmaf(h[e], ws[e], sig);
         const uint32_t q0 = pack_op<kF16>(h[0], h[1]), q1 = pack_op<kF16>(h[2], h[3]), q2 = pack_op<kF16>(h[4], h[5]), q3 = pack_op<kF16>(h[6], h[7]);
         st_shared_v4(dst, q0, q1, q2, q3);
       } else {
@@ -139,9 +155,9 @@ __device__ __forceinline__ void epi_block(uint32_t (&v)[32], const float* bl, co
       // bias already added above (the mask wants the pre-activations)
       if constexpr (kSigma) {
         // fp32 sigma head on the un-rounded activations (models.py:103)
-        const float4 w0 = *reinterpret_cast<const float4*>(wsig + c);
-        const float4 w1 = *reinterpret_cast<const float4*>(wsig + c + 4);
-        const float ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const float4 s0 = *reinterpret_cast<const float4*>(wsig + c);
+        const float4 s1 = *reinterpret_cast<const float4*>(wsig + c + 4);
+        const float ws[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) sig = fmaf(fmaxf(__uint_as_float(v[8 * j + e]), 0.f), ws[e], sig);
       }
@@ -161,20 +177,25 @@ __device__ __forceinline__ float hidden_epilogue(uint32_t tcol, const float* bl,
                                                  uint32_t* mrow, uint32_t wait_bar = 0u, uint32_t wait_par = 0u) {
   float sig = 0.f;
   uint32_t va[32], vb[32];
+  float4 nb0 = make_float4(0.f, 0.f, 0.f, 0.f), nb1 = nb0;
+  if constexpr (!kMask) {
+    nb0 = *reinterpret_cast<const float4*>(bl);
+    nb1 = *reinterpret_cast<const float4*>(bl + 4);
+  }
   tmem_ld32(tcol, va);
   tmem_ld_wait_dep(va);
   // (four unrolled blocks: a two-pass loop over block pairs halves the code but measured 2.3 % slower, A/B on one box)
   tmem_ld32(tcol + 32, vb);
-  epi_block<kSigma, kMask, kF16>(va, bl, wsig, arow, rx, 0, sig, mrow);
+  epi_block<kSigma, kMask, kF16>(va, bl, wsig, arow, rx, 0, sig, mrow, nb0, nb1);
   tmem_ld_wait_dep(vb);
   tmem_ld32(tcol + 64, va);
-  epi_block<kSigma, kMask, kF16>(vb, bl, wsig, arow, rx, 1, sig, mrow);
+  epi_block<kSigma, kMask, kF16>(vb, bl, wsig, arow, rx, 1, sig, mrow, nb0, nb1);
   tmem_ld_wait_dep(va);
   tmem_ld32(tcol + 96, vb);
   if (wait_bar != 0u) mbar_wait(wait_bar, wait_par);
-  epi_block<kSigma, kMask, kF16>(va, bl, wsig, arow + 16384, rx, 2, sig, mrow);
+  epi_block<kSigma, kMask, kF16>(va, bl, wsig, arow + 16384, rx, 2, sig, mrow, nb0, nb1);
   tmem_ld_wait_dep(vb);
-  epi_block<kSigma, kMask, kF16>(vb, bl, wsig, arow + 16384, rx, 3, sig, mrow);
+  epi_block<kSigma, kMask, kF16>(vb, bl, wsig, arow + 16384, rx, 3, sig, mrow, nb0, nb1);
   return sig;
 }
 

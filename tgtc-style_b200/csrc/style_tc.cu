@@ -469,13 +469,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
           } else if (okind != OUT_HEAD) {
             // hidden layer: packed bias add + ReLU + bf16 pack, the TMEM load of block b+1 in flight while block b is processed
             const float* bl = bias_s + l * 256 + hc * 128;
+            // every group's bias loads are issued BEFORE the previous group's activation store (ptxas cannot tell the bias table
+            // from the activation buffer: a load written after the store waits behind it and its latency is exposed -- mlp_tc.cu)
+            float4 pb0 = *reinterpret_cast<const float4*>(bl), pb1 = *reinterpret_cast<const float4*>(bl + 4);
             auto blk_store = [&](uint32_t (&v)[32], int blk) {
               const uint32_t kb = arow + (uint32_t)(blk >> 1) * 16384u;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const int c = blk * 32 + 8 * j;
-                const float4 b0 = *reinterpret_cast<const float4*>(bl + c);
-                const float4 b1 = *reinterpret_cast<const float4*>(bl + c + 4);
+                const float4 b0 = pb0, b1 = pb1;
+                if (c + 8 < 128) {
+                  pb0 = *reinterpret_cast<const float4*>(bl + c + 8);
+                  pb1 = *reinterpret_cast<const float4*>(bl + c + 12);
+                }
                 add2(v[8 * j + 0], v[8 * j + 1], b0.x, b0.y);
                 add2(v[8 * j + 2], v[8 * j + 3], b0.z, b0.w);
                 add2(v[8 * j + 4], v[8 * j + 5], b1.x, b1.y);
