@@ -89,7 +89,8 @@ def test_style_train_gradients_vs_autograd(renderer_bf16):
     g2 = bw["grads"].clone()
     bw2 = r.style_train_backward(fw["state"], g_c, g_f, grads=g2, accumulate=True)
     torch.cuda.synchronize()
-    assert torch.allclose(bw2["grads"], 2 * bw["grads"], rtol=1e-6, atol=1e-12)
+    # (g + g_coarse) + g_fine against 2 * (g_coarse + g_fine): equal up to one rounding of the largest term
+    assert (bw2["grads"] - 2 * bw["grads"]).abs().max().item() <= 4e-7 * bw["grads"].abs().max().item()
     assert torch.equal(bw2["d_latents"], bw["d_latents"])
     # a fresh forward + backward of the same batch reproduces everything bit for bit (ordered reductions, no atomics)
     fw3 = r.style_train_forward(ro, rd, lat, rand=rand)
