@@ -267,7 +267,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
       mbar_init(bar(kBarPeFree + t), 1);
       mbar_init(bar(kBarActReady + t), 2 * (kNumEpiThreads / 32));
       mbar_init(bar(kBarAccFull + t), 1);
-      mbar_init(bar(kBarCompReady + t), kNumEpiThreads / 64);   // one arrival per hc == 0 epilogue warp
+      // fused K5: one arrival per epilogue warp that stages partial sums (tail_off: all eight; otherwise the four hc == 0 warps)
+      mbar_init(bar(kBarCompReady + t), (!kTrain && !kTrunk && P.io.comp_rgb != nullptr && P.io.rgbsigma == nullptr && P.io.rgb == nullptr)
+                                            ? kNumEpiThreads / 32 : kNumEpiThreads / 64);
       mbar_init(bar(kBarCompDone + t), kNumPeThreads / 32);     // one arrival per producer warp
     }
     fence_barrier_init();
@@ -405,6 +407,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
     const int S = io.S;
     const uint32_t leader_pepair = mapa_cluster(bar(kBarPePair), 0);
     const bool comp = !kTrain && !kTrunk && io.comp_rgb != nullptr;
+    // tail_off: nothing per-sample is asked for, so the epilogue warps hand the rgb1 head's partial sums over and these warps finish
+    // the sample (sum, biases, sigmoid) before compositing it
+    const bool tail_off = comp && io.rgbsigma == nullptr && io.rgb == nullptr;
+    const float comp_b_sigma = P.smalls[kSmBSigma];
+    const float comp_b_rgb[3] = {P.smalls[kSmBRgb1 + 0], P.smalls[kSmBRgb1 + 1], P.smalls[kSmBRgb1 + 2]};
     // ---- fused K5: utils.alpha_composition (utils.py:354-386) for the rays of tile (it_, t_) (S in {64,128}: rows [0,S) are one
     // ray, a warp owns 32 consecutive samples), run by these producer warps while they would otherwise wait for the tile's PE
     // buffer to be released.  Every operation and its order is composite.cu's, so the results are bit-identical to the
@@ -423,7 +430,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
       }
       mbar_wait_relaxed(bar(kBarCompReady + t_), (uint32_t)(it_ & 1), 100);   // may be microseconds away: do not steal issue slots
       uint8_t* const stg = smem + kOffAct + t_ * kActBytes + kCompStageOff;      // [128 rows][32 B]: (r,g,b,sigma) from the epilogue
-      const float4 v = *reinterpret_cast<const float4*>(stg + r * 32);
+      float4 v = *reinterpret_cast<const float4*>(stg + r * 32);
+      if (tail_off) {
+        // the epilogue warps staged the two column halves' partial sums of the rgb1 head (and the first half's share of sigma)
+        // instead of the finished sample: the sum, biases and sigmoid (models.py:103, :111) run here, off the epilogue's
+        // critical loop -- the same expressions in the same order as the epilogue's own tail, so the results are bit-identical
+        const float4 o = *reinterpret_cast<const float4*>(stg + r * 32 + 16);
+        const float z0 = v.x + o.x + comp_b_rgb[0], z1 = v.y + o.y + comp_b_rgb[1], z2 = v.z + o.z + comp_b_rgb[2];
+        const float sg = v.w + reinterpret_cast<const float*>(smem + kOffSigPart)[t_ * 128 + r] + comp_b_sigma;
+        v = make_float4(1.0f / (1.0f + expf(-z0)), 1.0f / (1.0f + expf(-z1)), 1.0f / (1.0f + expf(-z2)), sg);
+      }
       const int pw = r >> 5;                      // producer warp = 32-row quarter of the tile
       const int c = k >> 5;                       // 32-sample chunk of this warp inside its ray
       const float delta = (k + 1 < S) ? __fsub_rn(tnext, tcur) : 1e10f;
@@ -755,6 +771,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
             tc_fence_before();
             act_arrive(t);  // accumulator drained: the next tile's layer 0 may start
             if (lane == 0 && q == 2) TC_TRACE(1 + hc, it, l, t, 1);
+            if (!kTrain && !kTrunk && P.io.comp_rgb != nullptr && P.io.rgbsigma == nullptr && P.io.rgb == nullptr) {
+              // fused K5, nothing per-sample requested (tail_off): stage this column half's partial sums of the rgb1 head (hc 0: + its
+              // share of sigma) in the row's 32 staging bytes and go on -- the producer warps sum the halves, add the biases and
+              // take the sigmoid before they composite.  No barrier among the epilogue warps, no expf on this critical loop.
+              *reinterpret_cast<float4*>(smem + kOffAct + t * kActBytes + kCompStageOff + row * 32 + hc * 16) =
+                  make_float4(p0, p1, p2, hc == 0 ? sig_keep[t] : 0.f);
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar(kBarCompReady + t));
+              continue;
+            }
             if (hc == 1) *reinterpret_cast<float4*>(rgbpart_s + row * 4) = make_float4(p0, p1, p2, 0.f);
             named_bar_sync(1, kNumEpiThreads);
             if (hc == 0) {
