@@ -486,7 +486,6 @@ def run_style(args, sub=False):
     for s in range(args.warmup):
         step_dev(s)
     sync_all()
-    r.profile_enable(True)
     l0 = r.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
@@ -501,6 +500,14 @@ def run_style(args, sub=False):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     launches = r.launch_count() - l0
+    # per-kernel times (roofline of the dominant kernel): a separate pass with the library's per-launch timers on.  The timed
+    # steps above run the 4096-ray batches alternately on two streams (one batch's kernel prologues / tails fill under the
+    # other's kernels), where launches overlap and cannot be timed one by one; with the timers on the library keeps one stream.
+    prof_steps = min(args.steps, 2)
+    r.profile_enable(True)
+    for s in range(prof_steps):
+        step_dev(s)
+    sync_all()
     kinds = {name: r.profile_read_kind(k) for name, k in (("mlp_tc_kernel<trunk>", 0), ("mlp_chain_kernel<module 1>", 1),
                                                             ("mlp_chain_kernel<module 2>", 2))}
     r.profile_enable(False)
@@ -558,8 +565,10 @@ def run_style(args, sub=False):
                          "kernel": "mlp_chain_kernel (style module 2)", "launches_timed": int(n2),
                          "avg_launch_ms": ms2k / max(n2, 1), "flop_per_sample": STYLE_M2_FLOP_PER_SAMPLE,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"},
-            "kernels": {k: {"launches": int(v[0]), "ms_per_step": v[1] / args.steps,
+            "kernels": {k: {"launches": int(v[0]), "ms_per_step": v[1] / prof_steps,
                             "tflops": (v[2] / (v[1] * 1e-3) / 1e12) if v[1] > 0 else None} for k, v in kinds.items()},
+            "kernels_note": "per-kernel times from %d extra single-stream steps with the library's launch timers on; the timed steps "
+                            "alternate the 4096-ray batches over two streams" % prof_steps,
             "clocks": clocks.window(t_wall0, t_wall1),
         }
     return _finish(args, res if rank == 0 else None, sub)

@@ -72,6 +72,9 @@ extern "C" int tgtc_destroy(tgtc_ctx* ctx) {
   }
   if (ctx->arena) cudaFree(ctx->arena);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
+  if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   delete ctx;
   return TGTC_OK;
 }
@@ -874,9 +877,14 @@ static StyleWs style_ws_layout(int64_t pass, int S, int F, bool per_ray = false)
 }
 static inline int64_t style_pass(int64_t n, int64_t chunk) { return pass_size(n, chunk <= 0 ? 32768 : chunk); }
 
+// several passes: two workspace sets, even passes on the caller's stream, odd passes on the context's side stream
+static inline size_t style_ws_sets(int64_t n_rays, int64_t pass) { return n_rays > pass ? 2 : 1; }
+static inline size_t style_ws_set_bytes(const StyleWs& w) { return align_up(w.total, 1024); }
+
 extern "C" size_t tgtc_render_style_workspace_bytes(int64_t n_rays, int n_samples, int n_fine, int64_t chunk) {
   if (n_rays <= 0 || n_samples <= 0 || n_fine < 0) return 0;
-  return style_ws_layout(style_pass(n_rays, chunk), n_samples, n_fine).total;
+  const int64_t pass = style_pass(n_rays, chunk);
+  return style_ws_set_bytes(style_ws_layout(pass, n_samples, n_fine)) * style_ws_sets(n_rays, pass);
 }
 
 static int render_style_impl(tgtc_ctx* ctx, int mode, const float* rays_o, const float* rays_d, int64_t n_rays, double near, double far,
@@ -898,26 +906,46 @@ static int render_style_impl(tgtc_ctx* ctx, int mode, const float* rays_o, const
   const tgtc_render_out& out = *out_p;
   const int64_t pass = style_pass(n_rays, chunk);
   const StyleWs ws = style_ws_layout(pass, S, F, lat_rays != nullptr);
-  TGTC_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0 && workspace_bytes >= ws.total,
-               TGTC_ERR_STATE, "style workspace too small or not 1024-byte aligned: need %zu bytes, got %zu", ws.total, workspace_bytes);
+  const size_t nsets_ws = style_ws_sets(n_rays, pass), set_bytes = style_ws_set_bytes(ws);
+  TGTC_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0 && workspace_bytes >= set_bytes * nsets_ws,
+               TGTC_ERR_STATE, "style workspace too small or not 1024-byte aligned: need %zu bytes, got %zu", set_bytes * nsets_ws, workspace_bytes);
+  // with the per-launch timers on (tgtc_profile_enable) everything stays on the caller's stream: overlapping launches of two
+  // streams cannot be timed one by one
+  const size_t nsets = ctx->profile ? 1 : nsets_ws;
   DeviceGuard g(ctx->device);
-  cudaStream_t st = (cudaStream_t)stream;
-  uint8_t* base = static_cast<uint8_t*>(workspace);
-  uint8_t* remap = base + ws.off_remap;
-  uint8_t* cf = base + ws.off_cf;
-  float* rs_c = reinterpret_cast<float*>(base + ws.off_rs_c);
-  float* rs_f = reinterpret_cast<float*>(base + ws.off_rs_f);
-  float* ts_c = reinterpret_cast<float*>(base + ws.off_ts_c);
+  cudaStream_t st0 = (cudaStream_t)stream;
+  uint8_t* base0 = static_cast<uint8_t*>(workspace);
+  float* ts_c = reinterpret_cast<float*>(base0 + ws.off_ts_c);   // the shared coarse positions: set 0's row, read by both streams
   const int T = S + F;
   int rc = TGTC_OK;
+  if (nsets > 1 && ctx->aux_stream == nullptr) {
+    TGTC_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    TGTC_CUDA(cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming));
+    TGTC_CUDA(cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming));
+  }
   if (lat_rays == nullptr) {
-    rc = style_set_latents(ctx, latent1, latent2, st);   // effective biases of both modules for this (style, frame)
+    rc = style_set_latents(ctx, latent1, latent2, st0);   // effective biases of both modules for this (style, frame)
     if (rc) return rc;
   }
-  float* bias_rays = lat_rays != nullptr ? reinterpret_cast<float*>(base + ws.off_bias) : nullptr;
-  rc = launch_sample_uniform(ctx, nullptr, nullptr, 1, S, near, far, nullptr, nullptr, ts_c, st);
+  rc = launch_sample_uniform(ctx, nullptr, nullptr, 1, S, near, far, nullptr, nullptr, ts_c, st0);
   if (rc) return rc;
-  for (int64_t r0 = 0; r0 < n_rays; r0 += pass) {
+  if (nsets > 1) {   // fork: the side stream starts after everything queued so far on the caller's stream
+    TGTC_CUDA(cudaEventRecord(ctx->aux_fork, st0));
+    TGTC_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
+  }
+  int64_t pass_idx = 0;
+  for (int64_t r0 = 0; r0 < n_rays; r0 += pass, ++pass_idx) {
+    // Passes are independent (different rays): even passes run on the caller's stream with workspace set 0, odd passes on the side
+    // stream with set 1 -- one pass's kernel prologues / tails (TMEM allocation, barrier set-up, the last partial wave of tiles)
+    // fill under the other pass's kernels instead of idling the SMs between ~10 dependent launches per pass.
+    const int set = (nsets > 1) ? (int)(pass_idx & 1) : 0;
+    cudaStream_t st = set ? ctx->aux_stream : st0;
+    uint8_t* base = base0 + (size_t)set * set_bytes;
+    uint8_t* remap = base + ws.off_remap;
+    uint8_t* cf = base + ws.off_cf;
+    float* rs_c = reinterpret_cast<float*>(base + ws.off_rs_c);
+    float* rs_f = reinterpret_cast<float*>(base + ws.off_rs_f);
+    float* bias_rays = lat_rays != nullptr ? reinterpret_cast<float*>(base + ws.off_bias) : nullptr;
     const int64_t m = (n_rays - r0 < pass) ? (n_rays - r0) : pass;
     float* w_c = out.weights_coarse ? out.weights_coarse + r0 * S : reinterpret_cast<float*>(base + ws.off_w_c);
     float* ts_f = out.ts_fine ? out.ts_fine + r0 * T : reinterpret_cast<float*>(base + ws.off_ts_f);
@@ -966,6 +994,10 @@ static int render_style_impl(tgtc_ctx* ctx, int mode, const float* rays_o, const
       }
     }
   }
+  if (nsets > 1) {   // join: the caller's stream continues after the side stream's passes
+    TGTC_CUDA(cudaEventRecord(ctx->aux_join, ctx->aux_stream));
+    TGTC_CUDA(cudaStreamWaitEvent(st0, ctx->aux_join, 0));
+  }
   return TGTC_OK;
 }
 
@@ -979,7 +1011,8 @@ extern "C" int tgtc_render_style(tgtc_ctx* ctx, int mode, const float* rays_o, c
 // the same loop body with PER-RAY latents inside one call (rendering.py:125-127: latents_model_1 returns one row per ray)
 extern "C" size_t tgtc_render_style_rays_workspace_bytes(int64_t n_rays, int n_samples, int n_fine, int64_t chunk) {
   if (n_rays <= 0 || n_samples <= 0 || n_fine < 0) return 0;
-  return style_ws_layout(style_pass(n_rays, chunk), n_samples, n_fine, true).total;
+  const int64_t pass = style_pass(n_rays, chunk);
+  return style_ws_set_bytes(style_ws_layout(pass, n_samples, n_fine, true)) * style_ws_sets(n_rays, pass);
 }
 extern "C" int tgtc_render_style_rays(tgtc_ctx* ctx, int mode, const float* rays_o, const float* rays_d, int64_t n_rays, double near, double far,
                                       int n_samples, int n_fine, int64_t chunk, const float* latents, const tgtc_render_out* out_p,

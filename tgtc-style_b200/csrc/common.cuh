@@ -106,6 +106,10 @@ struct tgtc_ctx {
   double prof_flops = 0.0;            // forward MLP (kind 0) algorithmic FLOPs since the last read
   double prof_work[4] = {0, 0, 0, 0}; // algorithmic FLOPs per kind
   cudaEvent_t coarse_done = nullptr;  // caller-owned: recorded by tgtc_train_step when the coarse net's gradient half is final
+  // stylised render in several passes: odd passes run on this library-owned side stream (forked from / joined to the caller's
+  // stream by events), so that one pass's kernel prologues and tails fill under the other's kernels
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
   // Style_train: which workspaces hold a forward stash (tgtc_style_train_backward refuses anything else)
   struct StyleFwdRec { const void* ws; int64_t n; int S, F, has_rand; };
   std::vector<StyleFwdRec> style_fwd;
