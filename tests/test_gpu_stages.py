@@ -151,3 +151,38 @@ def test_sample_fine_bit_exact_random(renderer_fp32, S, F):
     ts2 = renderer_fp32.sample_fine(None, None, row, w, F, want_pts=False)[1]
     assert torch.equal(ts2.cpu(), ref_ts2)
     assert (ts2[:, 0] == 0).all() and (ts2[:, -1] == 1).all() and (ts2[:, 1:] >= ts2[:, :-1]).all()
+
+
+@pytest.mark.gpu
+def test_sample_fine_lean_64_kernel_equals_general_kernel_and_oracle(renderer_fp32):
+    """The 64 + 64 ts_fine-only kernel (registers + shuffles, fixed-trip searches, occupancy-mask merge; sampling.cu) against the
+    general kernel and the oracle, bit for bit: random and adversarial weights (all zero, one-hot, two spikes, tiny, saturated),
+    per-ray sorted positions, the shared row, and position rows with duplicates (the merge's check-and-fall-back path)."""
+    from tgtc_style_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(7)
+    n, S, F = 4099, 64, 64
+    w = torch.rand(n, S) ** 6 * (torch.rand(n, 1) < 0.8)
+    w[0] = 0
+    w[1] = 0; w[1, 17] = 1.0
+    w[2] = 0; w[2, 1] = 0.5; w[2, 62] = 0.5
+    w[3] = 1e-12
+    w[4] = 1.0
+    w[5] = 0; w[5, 31] = 1e-6; w[5, 32] = 1.0
+    w[6] = torch.rand(S) * 1e-7
+    ts_row = torch.from_numpy(O.linspace_f32(0., 1., S))
+    ts_ray = torch.sort(torch.rand(n, S), -1)[0]
+    ts_dup = ts_ray.clone()
+    ts_dup[:, 10:14] = ts_dup[:, 10:11]            # runs of equal positions
+    ts_dup[::3, 40:64] = ts_dup[::3, 40:41]
+    for name, ts in (("row", ts_row), ("ray", ts_ray), ("dup", ts_dup)):
+        ts_full = ts.unsqueeze(0).expand(n, S) if ts.dim() == 1 else ts
+        ref = O.sample_fine(torch.zeros(n, 3), torch.ones(n, 3), ts_full, w, F)[1]
+        lean = renderer_fp32.sample_fine(None, None, ts, w, F, want_pts=False)[1].cpu()
+        lib.tgtc_debug_sample_fine_general(1)
+        try:
+            general = renderer_fp32.sample_fine(None, None, ts, w, F, want_pts=False)[1].cpu()
+        finally:
+            lib.tgtc_debug_sample_fine_general(0)
+        assert torch.equal(general, ref), name
+        assert torch.equal(lean, ref), name

@@ -128,6 +128,7 @@ DEBUG_PROTOTYPES = {
     "tgtc_debug_tc_f16": (None, [ctypes.c_int]),
     "tgtc_debug_no_fused_composite": (None, [ctypes.c_int]),
     "tgtc_debug_no_fused_sample_fine": (None, [ctypes.c_int]),
+    "tgtc_debug_sample_fine_general": (None, [ctypes.c_int]),
 }
 
 _lib = None
