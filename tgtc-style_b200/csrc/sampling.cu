@@ -102,8 +102,9 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_fine_kernel(
 // bin midpoints below/above it, so the number of coarse positions <= it is below+1 (+1, +2) -- checked against the neighbours,
 // with the full bitonic sort as the fallback for anything unexpected -- and the union is written by a 128-bit occupancy mask:
 // slot p holds a new sample if its bit is set, otherwise the (p - popc(bits below p))-th coarse position.
-constexpr int kFastWarps = 1;   // one warp = one CTA = one ray per loop trip: `ray` is block-uniform, so ptxas sees every shuffle / vote /
-                                // reduction as convergent (with several warps per CTA each collective cost a WARPSYNC + ENDCOLLECTIVE pair)
+constexpr int kFastWarps = 4;   // one ray per warp, no ray loop and no early exit (index clamped, stores predicated): straight-line code, so
+                                // ptxas sees every shuffle / vote / reduction as convergent (inside a grid-stride loop over a thread-derived
+                                // ray index each collective cost a WARPSYNC + ENDCOLLECTIVE pair and a duplicated shuffle)
 // out of line and not unrolled: the rare path must not sit in the common path's instruction stream
 __device__ __noinline__ void bitonic_sort128(float* out, int lane) {
 #pragma unroll 1
@@ -123,7 +124,7 @@ __device__ __noinline__ void bitonic_sort128(float* out, int lane) {
     }
   }
 }
-__global__ void __launch_bounds__(32 * kFastWarps) sample_fine64_kernel(const float* __restrict__ ts_in, int64_t ts_stride,
+__global__ void __launch_bounds__(32 * kFastWarps, 12) sample_fine64_kernel(const float* __restrict__ ts_in, int64_t ts_stride,
                                                                         const float* __restrict__ weights, int64_t n,
                                                                         float* __restrict__ ts_out) {
   __shared__ __align__(16) float s_ts[kFastWarps][64];
@@ -134,7 +135,10 @@ __global__ void __launch_bounds__(32 * kFastWarps) sample_fine64_kernel(const fl
   float* const cdf = s_cdf[wib];
   float* const out = s_out[wib];
   const unsigned full = 0xffffffffu;
-  for (int64_t ray = (int64_t)blockIdx.x * kFastWarps + wib; ray < n; ray += (int64_t)gridDim.x * kFastWarps) {
+  const int64_t ray_raw = (int64_t)blockIdx.x * kFastWarps + wib;
+  const bool live = ray_raw < n;                 // a padding warp of the last CTA recomputes the last ray and stores nothing
+  const int64_t ray = live ? ray_raw : n - 1;
+  {
     // ---- this lane's two coarse positions and raw weights (elements 2*lane, 2*lane+1)
     const float2 t2 = *reinterpret_cast<const float2*>(ts_in + ray * ts_stride + 2 * lane);
     const float2 x2 = *reinterpret_cast<const float2*>(weights + ray * 64 + 2 * lane);
@@ -249,9 +253,10 @@ __global__ void __launch_bounds__(32 * kFastWarps) sample_fine64_kernel(const fl
 #pragma unroll
       for (int w = 0; w < 4; ++w) r[w] = out[lane + 32 * w];
     }
+    if (live) {
 #pragma unroll
-    for (int w = 0; w < 4; ++w) ts_out[ray * 128 + lane + 32 * w] = r[w];
-    __syncwarp();   // the scratch rows are rewritten by the next ray
+      for (int w = 0; w < 4; ++w) ts_out[ray * 128 + lane + 32 * w] = r[w];
+    }
   }
 }
 
@@ -292,9 +297,9 @@ int launch_sample_fine(tgtc_ctx* ctx, const float* rays_o, const float* rays_d, 
   // the lean 64 + 64 kernel when only ts_fine is asked for and the rows are 8-byte aligned (float2 loads)
   if (S == 64 && n_fine == 64 && pts_out == nullptr && inds_out == nullptr && samples_out == nullptr && (ts_stride % 2) == 0 &&
       (reinterpret_cast<uintptr_t>(ts) & 7) == 0 && (reinterpret_cast<uintptr_t>(weights) & 7) == 0 && !g_force_general_sample_fine) {
-    const int64_t fb = (n + kFastWarps - 1) / kFastWarps;
-    const int64_t fcap = (int64_t)ctx->num_sms * 32 * 8;   // 32 resident one-warp CTAs per SM, 8 waves
-    sample_fine64_kernel<<<(unsigned)(fb < fcap ? fb : fcap), 32 * kFastWarps, 0, st>>>(ts, ts_stride, weights, n, ts_out);
+    const int64_t fb = (n + kFastWarps - 1) / kFastWarps;   // one ray per warp
+    TGTC_REQUIRE(fb <= 0x7fffffff, TGTC_ERR_UNSUPPORTED, "sample_fine: too many rays in one call");
+    if (n > 0) sample_fine64_kernel<<<(unsigned)fb, 32 * kFastWarps, 0, st>>>(ts, ts_stride, weights, n, ts_out);
     TGTC_LAUNCH_CHECK(ctx);
     return TGTC_OK;
   }
