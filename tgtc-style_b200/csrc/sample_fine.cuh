@@ -31,6 +31,27 @@ __device__ __forceinline__ double fine_shfl_up_f64(double v, int delta) {
   return __hiloint2double(hi, lo);
 }
 
+// the rare fallback of the sorted union: out of line and not unrolled, so that it does not sit in the instruction stream of the
+// kernels that inline sample_fine_core (the fine MLP kernel's producer warps among them)
+static __device__ __noinline__ void fine_bitonic_sort(float* out, int sort_n, int lane) {
+#pragma unroll 1
+  for (int k = 2; k <= sort_n; k <<= 1) {
+#pragma unroll 1
+    for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll 1
+      for (int i = lane; i < sort_n; i += 32) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const float a = out[i], b = out[ixj];
+          const bool up = ((i & k) == 0);
+          if ((a > b) == up) { out[i] = b; out[ixj] = a; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // in: sm.ts[0..S), sm.w[0..S-2) filled and visible to the warp.  out: sm.out[0..S+F) = sorted union, sm.smp[0..F) = the new
 // samples; inds_row / samples_row (may be nullptr): this ray's rows of the optional outputs.
 template <int kS, int kF, typename Smem>
@@ -148,19 +169,7 @@ __device__ __forceinline__ void sample_fine_core(Smem& sm, const int lane, const
     for (int k = lane; k < F; k += 32) sm.out[S + k] = sm.smp[k];
     for (int i = total + lane; i < sort_n; i += 32) sm.out[i] = __int_as_float(0x7f800000);  // +inf padding
     __syncwarp();
-    for (int k = 2; k <= sort_n; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = lane; i < sort_n; i += 32) {
-          const int ixj = i ^ j;
-          if (ixj > i) {
-            const float a = sm.out[i], b = sm.out[ixj];
-            const bool up = ((i & k) == 0);
-            if ((a > b) == up) { sm.out[i] = b; sm.out[ixj] = a; }
-          }
-        }
-        __syncwarp();
-      }
-    }
+    fine_bitonic_sort(sm.out, sort_n, lane);
   }
 
 }

@@ -105,25 +105,6 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) sample_fine_kernel(
 constexpr int kFastWarps = 4;   // one ray per warp, no ray loop and no early exit (index clamped, stores predicated): straight-line code, so
                                 // ptxas sees every shuffle / vote / reduction as convergent (inside a grid-stride loop over a thread-derived
                                 // ray index each collective cost a WARPSYNC + ENDCOLLECTIVE pair and a duplicated shuffle)
-// out of line and not unrolled: the rare path must not sit in the common path's instruction stream
-__device__ __noinline__ void bitonic_sort128(float* out, int lane) {
-#pragma unroll 1
-  for (int k = 2; k <= 128; k <<= 1) {
-#pragma unroll 1
-    for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll 1
-      for (int i = lane; i < 128; i += 32) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const float a = out[i], b = out[ixj];
-          const bool up = ((i & k) == 0);
-          if ((a > b) == up) { out[i] = b; out[ixj] = a; }
-        }
-      }
-      __syncwarp();
-    }
-  }
-}
 __global__ void __launch_bounds__(32 * kFastWarps, 12) sample_fine64_kernel(const float* __restrict__ ts_in, int64_t ts_stride,
                                                                         const float* __restrict__ weights, int64_t n,
                                                                         float* __restrict__ ts_out) {
@@ -249,7 +230,7 @@ __global__ void __launch_bounds__(32 * kFastWarps, 12) sample_fine64_kernel(cons
       out[2 * lane] = t2.x; out[2 * lane + 1] = t2.y;
       out[64 + 2 * lane] = smp[0]; out[64 + 2 * lane + 1] = smp[1];
       __syncwarp();
-      bitonic_sort128(out, lane);
+      fine_bitonic_sort(out, 128, lane);
 #pragma unroll
       for (int w = 0; w < 4; ++w) r[w] = out[lane + 32 * w];
     }
