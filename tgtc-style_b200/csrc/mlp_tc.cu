@@ -509,13 +509,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1) mlp_
       fs.smp = spare + 64;
       fs.out = spare + kMaxRaysPerTile * 128;        // (slot t_, buffer 1, ray 1): 128 floats
       const float* wsrc = io.fine_weights + tile * 64;   // one ray per tile
-      if (lane >= 1) fs.w[lane - 1] = __fadd_rn(__ldcg(wsrc + lane), 1e-5f);
-      if (lane + 32 <= 62) fs.w[lane + 31] = __fadd_rn(__ldcg(wsrc + lane + 32), 1e-5f);
-      __syncwarp();
-      sample_fine_core<64, 64>(fs, lane, 64, 64, 128, nullptr, nullptr);
+      // the lean 64 + 64 form of sample_fine_core (sample_fine.cuh; bit-identical, a third of the instructions): this lane's two raw
+      // weights / coarse positions in registers, the shared coarse row in fs.ts, cdf and union scratch in the spare rows
+      const float2 x2 = __ldcg(reinterpret_cast<const float2*>(wsrc) + lane);
+      const float2 t2 = *reinterpret_cast<const float2*>(fs.ts + 2 * lane);
+      float rr[4];
+      sample_fine64_lean_core(fs.ts, fs.cdf, fs.out, x2, t2, lane, rr);
       float* dst = io.fine_ts + tile * 128;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) dst[lane + 32 * i] = fs.out[lane + 32 * i];
+      for (int i = 0; i < 4; ++i) dst[lane + 32 * i] = rr[i];
       __syncwarp();
     };
     if (fuse_sf) {

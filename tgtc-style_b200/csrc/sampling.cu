@@ -124,116 +124,9 @@ __global__ void __launch_bounds__(32 * kFastWarps, 12) sample_fine64_kernel(cons
     const float2 t2 = *reinterpret_cast<const float2*>(ts_in + ray * ts_stride + 2 * lane);
     const float2 x2 = *reinterpret_cast<const float2*>(weights + ray * 64 + 2 * lane);
     *reinterpret_cast<float2*>(ts + 2 * lane) = t2;
-    // w[m] = weights[m + 1] + 1e-5 for m = 0..61 lives at raw index r = m + 1: lane r >> 1, slot r & 1
-    const float x0 = __fadd_rn(x2.x, 1e-5f), x1 = __fadd_rn(x2.y, 1e-5f);
-    // ---- torch.sum(-1) in ATen's order (8 lanes, 4-way ILP over the first 4 vectors, then vectors 4..6, then a1 a2 a3):
-    // lane k < 8 needs w[k + off] for off = 0, 32, 40, 48, 8, 16, 24, i.e. raw k + 1 + off in lane ((k+1) >> 1) + off/2
-    const int src0 = (lane + 1) >> 1;
-    const bool odd = (lane + 1) & 1;
-    auto w_at = [&](int off) {
-      const float a = __shfl_sync(full, x0, src0 + (off >> 1)), b = __shfl_sync(full, x1, src0 + (off >> 1));
-      return odd ? b : a;
-    };
-    float acc = w_at(0);
-    acc = __fadd_rn(acc, w_at(32));
-    acc = __fadd_rn(acc, w_at(40));
-    acc = __fadd_rn(acc, w_at(48));
-    acc = __fadd_rn(acc, w_at(8));
-    acc = __fadd_rn(acc, w_at(16));
-    acc = __fadd_rn(acc, w_at(24));
-    // tail w[56..61] = raw 57..62, then the eight lane sums in lane order
-    float fin = __shfl_sync(full, x1, 28);
-    fin = __fadd_rn(fin, __shfl_sync(full, x0, 29));
-    fin = __fadd_rn(fin, __shfl_sync(full, x1, 29));
-    fin = __fadd_rn(fin, __shfl_sync(full, x0, 30));
-    fin = __fadd_rn(fin, __shfl_sync(full, x1, 30));
-    fin = __fadd_rn(fin, __shfl_sync(full, x0, 31));
-#pragma unroll
-    for (int l = 0; l < 8; ++l) fin = __fadd_rn(fin, __shfl_sync(full, acc, l));
-    // ---- pdf, exact fp64 prefix (every partial sum is representable: any order gives torch's bits), cdf[r] for raw r = 0..62
-    const float d0 = __fdiv_rn(x0, fin), d1 = __fdiv_rn(x1, fin);
-    const float p0 = lane >= 1 ? d0 : 0.f;      // raw 2*lane     (raw 0 is not part of the pdf)
-    const float p1 = lane <= 30 ? d1 : 0.f;     // raw 2*lane + 1 (raw 63 is not part of the pdf)
-    const double run = (double)p0 + (double)p1;
-    double incl = run;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const double o = fine_shfl_up_f64(incl, d);
-      if (lane >= d) incl += o;
-    }
-    const double c0 = (incl - run) + (double)p0;
-    const double c1 = c0 + (double)p1;
-    *reinterpret_cast<float2*>(cdf + 2 * lane) = make_float2((float)c0, (float)c1);   // cdf[0] = 0; cdf[63] is never read
     __syncwarp();
-    // ---- inverse CDF at u_k, k = 2*lane + e: ind = #{cdf[0..62] <= u} by a fixed-trip branch-free search
-    float smp[2];
-    int cnt[2];          // #{coarse positions <= sample}
-    bool ok = true;
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int k = 2 * lane + e;
-      const float u = linspace01(k, 64);
-      int pos = 0;   // pos + step <= 63 at every step of 32, 16, ..., 1: no bound check, no branch
-#pragma unroll
-      for (int step = 32; step > 0; step >>= 1) pos += (cdf[pos + step - 1] <= u) ? step : 0;
-      const int ind = pos;                       // >= 1: cdf[0] = 0 <= u
-      const int below = max(0, ind - 1);
-      const int above = min(62, ind);
-      const float cb = cdf[below], ca = cdf[above];
-      const float tb0 = ts[below], tb1 = ts[below + 1], ta0 = ts[above], ta1 = ts[above + 1];
-      const float bb = __fmul_rn(0.5f, __fadd_rn(tb1, tb0));
-      const float ba = __fmul_rn(0.5f, __fadd_rn(ta1, ta0));
-      float denom = __fsub_rn(ca, cb);
-      if (denom < 1e-5f) denom = 1.0f;
-      const float t = __fdiv_rn(__fsub_rn(u, cb), denom);
-      const float sv = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
-      smp[e] = sv;
-      // coarse positions <= sv: everything up to `below` (ts[below] <= its midpoint <= sv), then the next one or two by comparison
-      const bool in1 = tb1 <= sv, in2 = in1 && above != below && ta1 <= sv;
-      const int c = below + 1 + (in1 ? 1 : 0) + (in2 ? 1 : 0);
-      cnt[e] = c;
-      // the count must be exact for the mask merge: ts[c-1] <= sv < ts[c]
-      const float tlo = ts[c - 1], thi = ts[min(c, 63)];
-      ok = ok & (tlo <= sv) & ((c >= 64) | (thi > sv));
-    }
-    // both lists ascending?  (the new samples are, except in rare fp32 corner cases; the coarse positions by construction)
-    {
-      const float s_next = __shfl_down_sync(full, smp[0], 1), t_next = __shfl_down_sync(full, t2.x, 1);
-      ok = ok & (smp[0] <= smp[1]) & ((lane == 31) | (smp[1] <= s_next));
-      ok = ok & (t2.x <= t2.y) & ((lane == 31) | (t2.y <= t_next));
-    }
     float r[4];
-    if (__all_sync(full, ok)) {
-      // ---- sorted union through a 128-bit occupancy mask: sample k goes to slot k + cnt_k
-      const int q0 = 2 * lane + cnt[0], q1 = 2 * lane + 1 + cnt[1];
-      out[q0] = smp[0];
-      out[q1] = smp[1];
-      unsigned m[4];
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const unsigned mine = ((q0 >> 5) == w ? 1u << (q0 & 31) : 0u) | ((q1 >> 5) == w ? 1u << (q1 & 31) : 0u);
-        m[w] = __reduce_or_sync(full, mine);
-      }
-      __syncwarp();
-      int before = 0;      // new samples in the words below
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const int pslot = lane + 32 * w;
-        const bool taken = (m[w] >> lane) & 1u;
-        const int i = pslot - (before + __popc(m[w] & ((1u << lane) - 1u)));   // coarse index for a free slot
-        const float* src = taken ? out + pslot : ts + min(i, 63);     // one load from the selected row
-        r[w] = *src;
-        before += __popc(m[w]);
-      }
-    } else {
-      // anything unexpected: torch.sort of the concatenation (values only) by the bitonic network, as sample_fine_core does
-      out[2 * lane] = t2.x; out[2 * lane + 1] = t2.y;
-      out[64 + 2 * lane] = smp[0]; out[64 + 2 * lane + 1] = smp[1];
-      __syncwarp();
-      fine_bitonic_sort(out, 128, lane);
-#pragma unroll
-      for (int w = 0; w < 4; ++w) r[w] = out[lane + 32 * w];
-    }
+    sample_fine64_lean_core(ts, cdf, out, x2, t2, lane, r);
     if (live) {
 #pragma unroll
       for (int w = 0; w < 4; ++w) ts_out[ray * 128 + lane + 32 * w] = r[w];
