@@ -115,7 +115,6 @@ __global__ void __launch_bounds__(32 * kFastWarps, 12) sample_fine64_kernel(cons
   float* const ts = s_ts[wib];
   float* const cdf = s_cdf[wib];
   float* const out = s_out[wib];
-  const unsigned full = 0xffffffffu;
   const int64_t ray_raw = (int64_t)blockIdx.x * kFastWarps + wib;
   const bool live = ray_raw < n;                 // a padding warp of the last CTA recomputes the last ray and stores nothing
   const int64_t ray = live ? ray_raw : n - 1;
